@@ -1,0 +1,19 @@
+"""Drop-in ``MinkowskiEngine`` module surface for DPCR-AGB's MSENet14 / MSENet50, B200-native.
+
+Usage from unchanged reference code::
+
+    import dpcr_agb_b200
+    dpcr_agb_b200.install()            # registers this package as ``MinkowskiEngine``
+    import MinkowskiEngine as ME       # torch_points3d/modules/MinkowskiEngine/*.py now run on libb200sparse
+
+Everything underneath is hand-written sm_100a CUDA behind the C ABI of ``include/b200sparse.h``;
+there is no CPU path (SparseTensor creation raises on CPU tensors).
+"""
+from .coordinate_manager import CoordinateManager, CoordinateMapKey, KernelMap  # noqa: F401
+from .sparse_tensor import SparseTensor  # noqa: F401
+from .modules import *  # noqa: F401,F403
+from .modules import (KernelGenerator, MinkowskiNetwork, PoolingMode, RegionType, cat)  # noqa: F401
+from . import MinkowskiNonlinearity, MinkowskiNormalization, utils  # noqa: F401
+from . import functional as MinkowskiFunctional  # noqa: F401
+
+__version__ = "0.5.4+b200"

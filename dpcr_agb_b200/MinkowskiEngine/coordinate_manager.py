@@ -1,0 +1,211 @@
+"""Coordinate manager: GPU coordinate hash, strided maps, kernel maps, per-plot row info.
+
+Mirrors what ``ME.SparseTensor(...)`` / strided ops create inside MinkowskiEngine's
+``CoordinateManager`` (call sites: ``torch_points3d/models/instance/minkowski.py:74``,
+``modules/MinkowskiEngine/SENet.py:53,94-97``, ``resnet_block.py:48-54`` of the reference).
+All state lives in torch CUDA tensors owned by this object; every kernel is a C-ABI call
+(``include/b200sparse.h``).  Host syncs: one per new coordinate map (its row count).
+"""
+from __future__ import annotations
+
+import torch
+
+from dpcr_agb_b200 import lib as L
+
+
+def _triple(v):
+    if isinstance(v, torch.Tensor):
+        v = v.tolist()
+    if isinstance(v, (list, tuple)):
+        if len(v) == 1:
+            return (int(v[0]),) * 3
+        assert len(v) == 3, "only D=3 is supported"
+        return tuple(int(a) for a in v)
+    return (int(v),) * 3
+
+
+class CoordinateMapKey:
+    """(tensor_stride, tag) -- hashable identity of a coordinate map inside one manager."""
+
+    __slots__ = ("tensor_stride", "tag")
+
+    def __init__(self, tensor_stride, tag=""):
+        self.tensor_stride = _triple(tensor_stride)
+        self.tag = tag
+
+    def get_tensor_stride(self):
+        return list(self.tensor_stride)
+
+    def get_key(self):
+        return (list(self.tensor_stride), self.tag)
+
+    def __eq__(self, other):
+        return isinstance(other, CoordinateMapKey) and self.tensor_stride == other.tensor_stride \
+            and self.tag == other.tag
+
+    def __hash__(self):
+        return hash((self.tensor_stride, self.tag))
+
+    def __repr__(self):
+        return f"CoordinateMapKey(tensor_stride={list(self.tensor_stride)}, tag={self.tag!r})"
+
+
+class CoordMap:
+    """One coordinate map: rows ``int32 [N,4]`` (batch,x,y,z) + its open-addressing hash table."""
+
+    __slots__ = ("coords", "table", "capacity", "n", "_inv_counts", "_counts_host")
+
+    def __init__(self, coords, table, capacity):
+        self.coords = coords
+        self.table = table
+        self.capacity = capacity
+        self.n = coords.shape[0]
+        self._inv_counts = None
+        self._counts_host = None
+
+
+class KernelMap:
+    """Neighbour table ``nbr int32 [K^3, N_out]`` (+ lazily the transposed table for dgrad)."""
+
+    def __init__(self, manager, in_key, out_key, kernel_size, step, nbr, n_in, n_out):
+        self.manager, self.in_key, self.out_key = manager, in_key, out_key
+        self.kernel_size, self.step = kernel_size, step
+        self.nbr, self.n_in, self.n_out = nbr, n_in, n_out
+        self.k3 = kernel_size[0] * kernel_size[1] * kernel_size[2]
+        # stride-1 odd kernels are point-symmetric: the transposed table is nbr with k reversed
+        self.symmetric = in_key == out_key and all(k % 2 == 1 for k in kernel_size)
+        self._inv = None
+
+    @property
+    def inv(self):
+        """Transposed table ``[K^3, N_in]``: ``inv[k, i] = o`` iff ``nbr[k, o] = i`` (strided maps only)."""
+        if self._inv is None:
+            cm = self.manager
+            self._inv = cm._probe(cm.maps[self.in_key].coords, cm.maps[self.out_key], self.kernel_size, self.step, -1)
+        return self._inv
+
+    def pairs(self):
+        """MinkowskiEngine's pair-list form: (in_idx, out_idx, offsets[K^3+1]); sorted by out row per offset."""
+        counts = torch.empty(self.k3, dtype=torch.int32, device=self.nbr.device)
+        L.call("b2s_kernel_map_pair_counts", self.nbr, self.k3, self.n_out, counts)
+        offsets = torch.zeros(self.k3 + 1, dtype=torch.int64, device=self.nbr.device)
+        offsets[1:] = torch.cumsum(counts.long(), 0)
+        total = int(offsets[-1].item())
+        in_idx = torch.empty(total, dtype=torch.int32, device=self.nbr.device)
+        out_idx = torch.empty(total, dtype=torch.int32, device=self.nbr.device)
+        if total:
+            L.call("b2s_kernel_map_pairs_fill", self.nbr, self.k3, self.n_out, offsets, in_idx, out_idx)
+        return in_idx, out_idx, offsets
+
+
+class CoordinateManager:
+    def __init__(self, D=3, device=None):
+        assert D == 3, "the B200 path implements the D=3 case the reference uses"
+        self.D = D
+        self.device = device
+        self.maps = {}
+        self.kernel_maps = {}
+        self.num_batches = 0
+
+    # ------------------------------------------------------------------ map construction
+    def _build(self, coords: torch.Tensor, ts_floor, want_in2out=True):
+        """Hash-insert ``coords`` floored to ``ts_floor``; returns (CoordMap, in2out or None, n_unique)."""
+        n = coords.shape[0]
+        dev = coords.device
+        cap = L.query("b2s_hash_capacity", n)
+        table = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
+        slot = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        rank = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        info = torch.empty(4, dtype=torch.int32, device=dev)
+        scan_ws = torch.empty(L.query("b2s_scan_workspace_bytes", n), dtype=torch.uint8, device=dev)
+        ts = L.host_i32(*ts_floor)
+        L.call("b2s_coordmap_insert", coords, n, ts, table, cap, slot, rank, info, scan_ws)
+        n_unique, overflow, max_batch, _ = info.tolist()          # the one host sync of a new map
+        if overflow:
+            raise L.B2SError("coordinate outside the packed 16-bit range (|c| < 32000, 0 <= batch < 65535): "
+                             "B2S_EOVERFLOW")
+        self.num_batches = max(self.num_batches, max_batch + 1)
+        if n_unique == n and tuple(ts_floor) == (1, 1, 1):
+            return CoordMap(coords, table, cap), None, n       # already unique: table values are the rows
+        out = torch.empty((n_unique, 4), dtype=torch.int32, device=dev)
+        in2out = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_in2out else None
+        L.call("b2s_coordmap_fill", coords, n, ts, table, cap, slot, rank, out, in2out)
+        return CoordMap(out, table, cap), (in2out[:n] if want_in2out else None), n_unique
+
+    def insert(self, coords: torch.Tensor, tensor_stride=(1, 1, 1), tag=""):
+        """Create the map of a new SparseTensor.  Returns (key, unique_index or None)."""
+        coords = coords.to(torch.int32).contiguous()
+        assert coords.dim() == 2 and coords.shape[1] == 4, "coordinates must be [N, 1+3] (batch first)"
+        key = CoordinateMapKey(tensor_stride, tag)
+        cmap, in2out, n_unique = self._build(coords, (1, 1, 1))
+        self.maps[key] = cmap
+        self.device = coords.device
+        unique_index = None
+        if in2out is not None:                                  # duplicates: keep the first occurrence
+            n = coords.shape[0]
+            first = torch.full((n_unique,), n, dtype=torch.int64, device=coords.device)
+            first.scatter_reduce_(0, in2out.long(), torch.arange(n, device=coords.device), reduce="amin")
+            unique_index = first
+        return key, unique_index
+
+    def stride(self, in_key: CoordinateMapKey, stride):
+        stride = _triple(stride)
+        ts = tuple(a * b for a, b in zip(in_key.tensor_stride, stride))
+        out_key = CoordinateMapKey(ts, in_key.tag)
+        if out_key not in self.maps:
+            cmap, _, _ = self._build(self.maps[in_key].coords, ts, want_in2out=False)
+            self.maps[out_key] = cmap
+        return out_key
+
+    def origin(self, key=None):
+        """Key of the per-plot origin map (one row per batch id), as MinkowskiGlobalPooling returns."""
+        key = CoordinateMapKey((0, 0, 0), "origin")
+        if key not in self.maps:
+            c = torch.zeros((self.num_batches, 4), dtype=torch.int32, device=self.device)
+            c[:, 0] = torch.arange(self.num_batches, device=self.device, dtype=torch.int32)
+            self.maps[key] = CoordMap(c, None, 0)
+        return key
+
+    # ------------------------------------------------------------------ kernel maps
+    def _probe(self, query_coords, table_map: CoordMap, kernel_size, step, sign):
+        n = query_coords.shape[0]
+        k3 = kernel_size[0] * kernel_size[1] * kernel_size[2]
+        nbr = torch.empty((k3, n), dtype=torch.int32, device=query_coords.device)
+        L.call("b2s_kernel_map", query_coords, n, table_map.table, table_map.capacity, L.host_i32(*kernel_size),
+               L.host_i32(*step), sign, nbr)
+        return nbr
+
+    def kernel_map(self, in_key, out_key, kernel_size, dilation=(1, 1, 1)) -> KernelMap:
+        kernel_size, dilation = _triple(kernel_size), _triple(dilation)
+        ck = (in_key, out_key, kernel_size, dilation)
+        km = self.kernel_maps.get(ck)
+        if km is None:
+            step = tuple(d * t for d, t in zip(dilation, in_key.tensor_stride))
+            imap, omap = self.maps[in_key], self.maps[out_key]
+            nbr = self._probe(omap.coords, imap, kernel_size, step, +1)
+            km = KernelMap(self, in_key, out_key, kernel_size, step, nbr, imap.n, omap.n)
+            self.kernel_maps[ck] = km
+        return km
+
+    # ------------------------------------------------------------------ per-plot info (origin map)
+    def coords(self, key):
+        return self.maps[key].coords
+
+    def inv_counts(self, key):
+        """float32 [B]: 1 / (rows of each plot) -- the average-pooling scale."""
+        m = self.maps[key]
+        if m._inv_counts is None:
+            counts = torch.empty(self.num_batches, dtype=torch.int32, device=m.coords.device)
+            L.call("b2s_batch_counts", m.coords, 4, m.n, self.num_batches, counts)
+            m._inv_counts = 1.0 / counts.clamp(min=1).float()
+            m._counts_host = None
+        return m._inv_counts
+
+    def rows_per_batch(self, key):
+        """Host list of row counts per plot (syncs once per map; used by decomposed_coordinates)."""
+        m = self.maps[key]
+        if m._counts_host is None:
+            counts = torch.empty(self.num_batches, dtype=torch.int32, device=m.coords.device)
+            L.call("b2s_batch_counts", m.coords, 4, m.n, self.num_batches, counts)
+            m._counts_host = counts.tolist()
+        return m._counts_host

@@ -1,0 +1,233 @@
+"""torch.autograd Functions over the C ABI -- one per MinkowskiEngine op on the MSENet hot path.
+
+Every forward/backward here is a call into ``libb200sparse.so`` on the current CUDA stream; there is
+no torch fallback.  Functions are declared fp32 (``custom_fwd(cast_inputs=float32)``) so a stray
+half tensor under autocast never reaches the C ABI (SURVEY.md 8b "autocast interaction").
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from dpcr_agb_b200 import lib as L
+
+# 0 = auto (tcgen05 where the shape qualifies, SIMT otherwise), 1 = force SIMT, 2 = force tcgen05
+CONV_IMPL = int(os.environ.get("B2S_CONV_IMPL", "0"))
+
+_fwd = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_bwd = custom_bwd(device_type="cuda")
+
+
+def _ws(n_in, n_out, c_in, c_out, k3, device):
+    nbytes = L.query("b2s_conv_workspace_bytes", n_in, n_out, c_in, c_out, k3)
+    if nbytes < 0:
+        raise L.B2SError("b2s_conv_workspace_bytes rejected the shape")
+    return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device), nbytes
+
+
+def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None):
+    """y[o] = bias + sum_k x[nbr[k,o]] @ B_k  (C ABI ``b2s_conv_gather_gemm``)."""
+    y = torch.empty((n_out, c_out), dtype=torch.float32, device=x.device)
+    ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device)
+    L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, y, ws, nbytes,
+           CONV_IMPL if impl is None else impl)
+    return y
+
+
+def wgrad(x, gy, nbr, n_in, n_out, c_in, c_out, k3, impl=None):
+    gw = torch.empty((k3, c_in, c_out), dtype=torch.float32, device=x.device)
+    L.call("b2s_conv_wgrad", x, gy, nbr, n_in, n_out, c_in, c_out, k3, gw, None, 0,
+           CONV_IMPL if impl is None else impl)
+    return gw
+
+
+class ConvolutionFunction(torch.autograd.Function):
+    """MinkowskiConvolution fwd / dgrad / wgrad (reference call sites: SENet.py:49-52,94-97;
+    resnet_block.py:48-54,95-107).  ``kmap`` is None for the K=1, stride=1 ``use_mm`` case."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, feats, kernel, bias, kmap):
+        feats = feats.contiguous()
+        kernel = kernel.contiguous()
+        c_in, c_out = kernel.shape[-2], kernel.shape[-1]
+        if kmap is None:
+            n_in = n_out = feats.shape[0]
+            nbr, k3 = None, 1
+        else:
+            n_in, n_out, nbr, k3 = kmap.n_in, kmap.n_out, kmap.nbr, kmap.k3
+        assert feats.shape == (n_in, c_in), f"feature shape {tuple(feats.shape)} does not match the map ({n_in},{c_in})"
+        b = bias.contiguous().view(-1) if bias is not None else None
+        out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0)
+        ctx.kmap = kmap
+        ctx.dims = (n_in, n_out, c_in, c_out, k3)
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(feats, kernel)
+        return out
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy):
+        feats, kernel = ctx.saved_tensors
+        kmap = ctx.kmap
+        n_in, n_out, c_in, c_out, k3 = ctx.dims
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if kmap is None:
+                gx = gather_gemm(gy, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1)
+            elif kmap.symmetric:      # transposed map == same table with the kernel index reversed
+                gx = gather_gemm(gy, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2)
+            else:
+                gx = gather_gemm(gy, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1)
+        if ctx.needs_input_grad[1]:
+            gw = wgrad(feats, gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out, k3).view(kernel.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = torch.empty((1, c_out), dtype=torch.float32, device=gy.device)
+            L.call("b2s_colsum", gy, n_out, c_out, gb)
+        return gx, gw, gb, None
+
+
+class MaxPoolFunction(torch.autograd.Function):
+    """MinkowskiMaxPooling (SENet.py:53)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, feats, kmap):
+        feats = feats.contiguous()
+        c = feats.shape[1]
+        y = torch.empty((kmap.n_out, c), dtype=torch.float32, device=feats.device)
+        arg = torch.empty((kmap.n_out, c), dtype=torch.int32, device=feats.device)
+        L.call("b2s_maxpool_fwd", feats, kmap.nbr, kmap.n_out, c, kmap.k3, y, arg)
+        ctx.save_for_backward(arg)
+        ctx.dims = (kmap.n_in, kmap.n_out, c)
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy):
+        (arg,) = ctx.saved_tensors
+        n_in, n_out, c = ctx.dims
+        gx = torch.empty((n_in, c), dtype=torch.float32, device=gy.device)
+        L.call("b2s_maxpool_bwd", gy.contiguous(), arg, n_in, n_out, c, gx)
+        return gx, None
+
+
+class GlobalPoolFunction(torch.autograd.Function):
+    """MinkowskiGlobal{Sum,Avg}Pooling / MinkowskiGlobalPooling (senet_block.py:43; common.py:44-48)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, feats, coords, num_batches, scale):
+        feats = feats.contiguous()
+        n, c = feats.shape
+        y = torch.empty((num_batches, c), dtype=torch.float32, device=feats.device)
+        L.call("b2s_segment_sum", feats, coords, 4, n, c, num_batches, scale, y)
+        ctx.coords, ctx.scale, ctx.dims = coords, scale, (n, c)
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy):
+        n, c = ctx.dims
+        gx = torch.empty((n, c), dtype=torch.float32, device=gy.device)
+        L.call("b2s_segment_bcast", gy.contiguous(), ctx.coords, 4, n, c, ctx.scale, gx)
+        return gx, None, None, None
+
+
+class BroadcastMulFunction(torch.autograd.Function):
+    """MinkowskiBroadcastMultiplication (senet_block.py:44,50): out[i] = x[i] * y[batch(i)]."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, y, coords, num_batches):
+        x, y = x.contiguous(), y.contiguous()
+        n, c = x.shape
+        assert y.shape[0] == num_batches and y.shape[1] in (1, c)
+        out = torch.empty_like(x)
+        L.call("b2s_bcast_mul_fwd", x, y, coords, 4, n, c, y.shape[1], out)
+        ctx.save_for_backward(x, y)
+        ctx.coords, ctx.nb = coords, num_batches
+        return out
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        n, c = x.shape
+        g = g.contiguous()
+        need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if y.shape[1] != c:                      # per-plot scalar (drop-path mask): no gradient to the mask
+            gx = torch.empty_like(x)
+            L.call("b2s_bcast_mul_fwd", g, y, ctx.coords, 4, n, c, 1, gx)
+            return gx, None, None, None
+        gx = torch.empty_like(x) if need_x else None
+        gy = torch.empty_like(y) if need_y else None
+        L.call("b2s_bcast_mul_bwd", g, x, y, ctx.coords, 4, n, c, ctx.nb, gx, gy)
+        return gx, gy, None, None
+
+
+class BatchNormFunction(torch.autograd.Function):
+    """MinkowskiBatchNorm == nn.BatchNorm1d over all rows (SENet.py:35,51,98); act=1 fuses exact GELU."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act):
+        x = x.contiguous()
+        n, c = x.shape
+        dev = x.device
+        if training:
+            mean = torch.empty(c, dtype=torch.float32, device=dev)
+            invstd = torch.empty(c, dtype=torch.float32, device=dev)
+            ws = torch.empty(2 * c, dtype=torch.float64, device=dev)
+            L.call("b2s_bn_stats", x, n, c, float(eps), float(momentum), running_mean, running_var, ws, mean, invstd)
+        else:
+            mean = running_mean
+            invstd = torch.rsqrt(running_var + eps)
+        y = torch.empty_like(x)
+        L.call("b2s_bn_apply", x, mean, invstd, weight, bias, n, c, act, y)
+        ctx.save_for_backward(x, mean, invstd, weight, bias)
+        ctx.training, ctx.act = training, act
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy):
+        x, mean, invstd, weight, bias = ctx.saved_tensors
+        n, c = x.shape
+        gy = gy.contiguous()
+        dev = x.device
+        sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        ws = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        L.call("b2s_bn_bwd_reduce", gy, x, mean, invstd, weight, bias, n, c, ctx.act, ws, sums)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            L.call("b2s_bn_bwd_apply", gy, x, mean, invstd, weight, bias, sums, n, c, ctx.act, 1 if ctx.training else 0,
+                   gx)
+        gw = sums[c:].clone() if (weight is not None and ctx.needs_input_grad[1]) else None
+        gb = sums[:c].clone() if (bias is not None and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+class GELUFunction(torch.autograd.Function):
+    """NL.MinkowskiGELU: exact-erf GELU (common.py:41)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        L.call("b2s_gelu_fwd", x, x.numel(), y)
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gx = torch.empty_like(x)
+        L.call("b2s_gelu_bwd", gy.contiguous(), x, x.numel(), gx)
+        return gx

@@ -1,0 +1,315 @@
+// conv_tc.cu -- tcgen05 (kind::tf32, fp32 accumulate in TMEM) kernels for the sparse convolution.
+//
+// Forward / dgrad: OUTPUT-STATIONARY implicit GEMM over the neighbour table.
+//   CTA tile = 128 out rows x BN out channels, accumulator = 128 TMEM lanes x BN fp32 columns.
+//   K loop   = (kernel offset k) x (32-channel chunk of c_in): per step
+//       A [128 x 32] = rows x[nbr[k, o], chunk]   gathered by 128 producer threads with 16-byte LDGSTS
+//                      (zero-fill when nbr = -1) straight into the 128B-swizzled K-major UMMA layout,
+//       B [BN  x 32] = a pre-swizzled image of W[k] (built once per call by prep_weights_kernel), fetched
+//                      with ONE 1-D bulk copy (UBLKCP) whose bytes complete on the stage's mbarrier,
+//       4 x tcgen05.mma (M=128, N=BN, K=8) issued by one elected thread; tcgen05.commit frees the stage.
+//   Epilogue: tcgen05.ld 32x32b -> + bias -> fp32 rows of y.  No atomics, deterministic.
+//   SMALL mode (c_in <= 4, the k7 stem with c_in = 3): x is padded to 4 floats per row so that one
+//   16-byte chunk is one (row, offset) gather; a K step covers 8 kernel offsets.
+//
+// Reference call sites: R:modules/MinkowskiEngine/SENet.py:49-52,94-97; resnet_block.py:48-54,95-107.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <stdlib.h>
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128;            // out rows per CTA == UMMA M
+constexpr int BK = 32;             // fp32 per K step == one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int PRODUCERS = 128;     // warps 0..3 gather A and run the epilogue; warp 4 issues MMA
+constexpr int TC_THREADS = 160;
+constexpr int LAG = 2;             // a producer publishes stage (it - LAG) after issuing stage it
+
+// ---------------------------------------------------------------------------------------------
+// weight image: img[it][n][32] (128 bytes per n, 16-byte chunks XOR-swizzled by n & 7)
+//   general: it = k * (c_in/32) + cc, element kk = ci - 32*cc
+//   small  : it = k / 8, element kk = (k % 8) * 4 + ci      (ci < c_in <= 4, rest zero)
+// B_k[ci, co] = w[(k*c_in + ci)*c_out + co] (layout bit0 = 0) or w[(k*c_out + co)*c_in + ci] (bit0 = 1);
+// layout bit1 reverses the kernel index (k -> k3-1-k)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restrict__ w, int c_in, int c_out, int k3,
+                                                           int w_layout, int small, int T,
+                                                           float* __restrict__ img) {
+  const int64_t total = (int64_t)T * c_out * BK;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int pos = (int)(e % BK);             // physical position inside the 128-byte row
+    const int64_t rn = e / BK;
+    const int n = (int)(rn % c_out);
+    const int it = (int)(rn / c_out);
+    const int chunk = (pos >> 2) ^ (n & 7);     // logical 16-byte chunk stored at this physical slot
+    const int kk = chunk * 4 + (pos & 3);
+    int k, ci;
+    if (small) {
+      k = it * 8 + (kk >> 2);
+      ci = kk & 3;
+    } else {
+      const int kc = c_in / BK;
+      k = it / kc;
+      ci = (it % kc) * BK + kk;
+    }
+    float v = 0.f;
+    if (k < k3 && ci < c_in) {
+      const int kw = (w_layout & 2) ? k3 - 1 - k : k;  // bit 1: kernel index reversed (symmetric maps)
+      v = !(w_layout & 1) ? w[((int64_t)kw * c_in + ci) * c_out + n] : w[((int64_t)kw * c_out + n) * c_in + ci];
+    }
+    img[e] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) pad_rows4_kernel(const float* __restrict__ x, int64_t n, int c,
+                                                        float4* __restrict__ x4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < c; ++j) v[j] = x[i * c + j];
+    x4[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;  // full[S], empty[S], accum, tmem slot
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 2) * 8;
+  static constexpr int DYN_BYTES = TOTAL + 1024;                   // slack for manual 1024-byte alignment
+};
+
+template <int BN, int STAGES, bool SMALL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
+                          const int* __restrict__ nbr, int64_t n_out, int c_in, int c_out, int k3, int T,
+                          float* __restrict__ y) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base + L::A_OFF, b_base = base + L::B_OFF;
+  const uint32_t bar_base = base + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + 8 * (2 * STAGES + 1));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), PRODUCERS + 1);  // 128 gather arrivals + 1 arrive.expect_tx for the B bulk copy
+      mbar_init(empty_bar(s), 1);             // one tcgen05.commit
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    // ===================== producers: gather A, fetch B =====================
+    const int chunk = tid & 7;   // 16-byte chunk inside the 128-byte row
+    const int rsub = tid >> 3;   // rows rsub + 16 p
+    const int kc = SMALL ? 1 : c_in / BK;
+    int idx[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) idx[p] = -1;
+
+    auto publish = [&](int it_done) {  // all of this thread's LDGSTS for it_done have landed
+      fence_proxy_async();
+      mbar_arrive(full_bar(it_done % STAGES));
+    };
+
+    for (int it = 0; it < T; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (tid == 0) {
+        mbar_arrive_expect_tx(full_bar(s), L::B_STAGE_BYTES);
+        bulk_g2s(b_base + s * L::B_STAGE_BYTES, wimg + ((int64_t)it * c_out + n0) * BK, L::B_STAGE_BYTES,
+                 full_bar(s));
+      }
+      const uint32_t a_stage = a_base + s * A_STAGE_BYTES;
+      if (SMALL) {
+        const int k = it * 8 + chunk;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const int row = rsub + 16 * p;
+          const int64_t o = m0 + row;
+          int i = -1;
+          if (k < k3 && o < n_out) i = nbr ? __ldg(&nbr[(int64_t)k * n_out + o]) : (int)o;
+          const float* src = x + (int64_t)(i >= 0 ? i : 0) * 4;
+          cp_async16(a_stage + sw128_offset(row, chunk), src, i >= 0 ? 16u : 0u);
+        }
+      } else {
+        const int k = it / kc, cc = it - k * kc;
+        if (cc == 0) {
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const int64_t o = m0 + rsub + 16 * p;
+            idx[p] = o < n_out ? (nbr ? __ldg(&nbr[(int64_t)k * n_out + o]) : (int)o) : -1;
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const int row = rsub + 16 * p;
+          const int i = idx[p];
+          const float* src = x + (int64_t)(i >= 0 ? i : 0) * c_in + cc * BK + chunk * 4;
+          cp_async16(a_stage + sw128_offset(row, chunk), src, i >= 0 ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (it >= LAG) {
+        cp_async_wait<LAG>();
+        publish(it - LAG);
+      }
+    }
+    // drain the last LAG stages
+    if (T >= 2) {
+      cp_async_wait<1>();
+      publish(T - 2);
+    }
+    cp_async_wait<0>();
+    publish(T - 1);
+
+    // ===================== epilogue: TMEM -> registers -> y =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int64_t o = m0 + warp * 32 + lane;
+    const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (o < n_out) {
+        float* dst = y + o * c_out + n0 + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 r;
+          r.x = __uint_as_float(v[j]) + (bias ? __ldg(&bias[n0 + c0 + j]) : 0.f);
+          r.y = __uint_as_float(v[j + 1]) + (bias ? __ldg(&bias[n0 + c0 + j + 1]) : 0.f);
+          r.z = __uint_as_float(v[j + 2]) + (bias ? __ldg(&bias[n0 + c0 + j + 2]) : 0.f);
+          r.w = __uint_as_float(v[j + 3]) + (bias ? __ldg(&bias[n0 + c0 + j + 3]) : 0.f);
+          *reinterpret_cast<float4*>(dst + j) = r;
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ===================== MMA issuer: warp 4 stays converged, lane 0 issues =====================
+    constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0);
+    for (int it = 0; it < T; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t a_desc = smem_desc_sw128(a_base + s * A_STAGE_BYTES, 16, 1024);
+        const uint64_t b_desc = smem_desc_sw128(b_base + s * L::B_STAGE_BYTES, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk)  // advance 32 bytes (8 tf32) inside the swizzle row per MMA
+          mma_tf32(tmem_d, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC, (it | kk) ? 1u : 0u);
+        mma_commit(empty_bar(s));
+      }
+      __syncwarp();
+    }
+    if (lane == 0) mma_commit(accum_bar);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_d);
+  }
+}
+
+bool tc_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2S_DISABLE_TC");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int BN, int STAGES, bool SMALL>
+int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, int c_in, int c_out,
+              int k3, int T, float* y, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
+      b2s_set_error("conv_tc: cannot opt in to %d bytes of shared memory", L::DYN_BYTES);
+      return -1;
+    }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN));
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, c_in, c_out, k3, T, y);
+  return 0;
+}
+
+}  // namespace
+
+bool b2s_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_out) {
+  (void)k3;
+  if (tc_disabled() || n_out <= 0) return false;
+  if (c_out % 64 != 0) return false;
+  return c_in <= 4 || c_in % BK == 0;
+}
+
+static inline int64_t align256(int64_t b) { return (b + 255) & ~(int64_t)255; }
+
+static int iterations(int c_in, int k3) { return c_in <= 4 ? (k3 + 7) / 8 : k3 * (c_in / BK); }
+
+int64_t b2s_conv_tc_image_bytes(int32_t c_in, int32_t c_out, int32_t k3) {
+  return align256((int64_t)iterations(c_in, k3) * c_out * 128);
+}
+
+int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_in) {
+  return b2s_conv_tc_image_bytes(c_in, c_out, k3) + (c_in <= 4 ? align256(n_in * 16) : 0);
+}
+
+int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
+                            int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
+                            void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  (void)workspace_bytes;
+  const bool small = c_in <= 4;
+  const int T = iterations(c_in, k3);
+  float* img = reinterpret_cast<float*>(workspace);
+  prep_weights_kernel<<<grid_for((int64_t)T * c_out * BK, 256), 256, 0, st>>>(w, c_in, c_out, k3, w_layout, small ? 1 : 0,
+                                                                             T, img);
+  const float* xin = x;
+  if (small) {
+    float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + b2s_conv_tc_image_bytes(c_in, c_out, k3));
+    pad_rows4_kernel<<<grid_for(n_in, 256), 256, 0, st>>>(x, n_in, c_in, x4);
+    xin = reinterpret_cast<const float*>(x4);
+  }
+  const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
+  if (small) {
+    if (bn == 256) return launch_tc<256, 4, true>(xin, img, bias, nbr, n_out, 4, c_out, k3, T, y, st);
+    if (bn == 128) return launch_tc<128, 3, true>(xin, img, bias, nbr, n_out, 4, c_out, k3, T, y, st);
+    return launch_tc<64, 4, true>(xin, img, bias, nbr, n_out, 4, c_out, k3, T, y, st);
+  }
+  if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, c_in, c_out, k3, T, y, st);
+  if (bn == 128) return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, c_in, c_out, k3, T, y, st);
+  return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, c_in, c_out, k3, T, y, st);
+}
+
+// wgrad on tensor cores: see wgrad_tc.cu

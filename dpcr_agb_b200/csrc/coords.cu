@@ -1,0 +1,590 @@
+// coords.cu -- integer stages of the hot path: voxel quantisation (a1), coordinate hash and strided
+// maps (a2, a3), kernel maps (a4).  All HBM / L2-latency bound; no tensor cores here by design.
+//
+// Reference call sites (R: = /root/reference/torch-points3d/torch_points3d/):
+//   a1  R:core/data_transform/grid_transform.py:112-128
+//   a2  R:models/instance/minkowski.py:74
+//   a3/a4  implicit in R:modules/MinkowskiEngine/SENet.py:53,94-97 and resnet_block.py:48-54
+#include "common.cuh"
+#include <limits.h>
+
+// =============================================================================================
+// exclusive scan of int32 (three small kernels; n is at most a few 10^7 here)
+// =============================================================================================
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) >= d) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread across a block of SCAN_THREADS; returns exclusive prefix,
+// writes the block total to *total
+__device__ __forceinline__ int block_excl_scan(int v, int* total) {
+  __shared__ int warp_sums[SCAN_THREADS / 32];
+  __shared__ int block_total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = warp_incl_scan(v);
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+    int si = warp_incl_scan(s);
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = si - s;
+    if (lane == SCAN_THREADS / 32 - 1) block_total = si;
+  }
+  __syncthreads();
+  int res = incl - v + warp_sums[wid];
+  *total = block_total;
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int* __restrict__ in, int64_t n,
+                                                                   int* __restrict__ block_sums) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    int64_t i = base + j;
+    if (i < n) s += in[i];
+  }
+  int total;
+  block_excl_scan(s, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(int* __restrict__ block_sums, int nb,
+                                                                       int* __restrict__ total_out) {
+  int carry = 0;
+  for (int base = 0; base < nb; base += SCAN_THREADS) {
+    int i = base + threadIdx.x;
+    int v = i < nb ? block_sums[i] : 0;
+    int total;
+    int ex = block_excl_scan(v, &total);
+    if (i < nb) block_sums[i] = ex + carry;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                                  int64_t n, const int* __restrict__ block_sums) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    int64_t i = base + j;
+    v[j] = i < n ? in[i] : 0;
+    s += v[j];
+  }
+  int total;
+  int ex = block_excl_scan(s, &total) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    int64_t i = base + j;
+    if (i < n) out[i] = ex;
+    ex += v[j];
+  }
+}
+
+// in-place capable exclusive scan; total (device int) may be null
+int launch_exclusive_scan(const int* in, int* out, int64_t n, int* total_dev, void* ws, cudaStream_t st) {
+  if (n <= 0) {
+    if (total_dev) cudaMemsetAsync(total_dev, 0, sizeof(int), st);
+    return 0;
+  }
+  int nb = (int)ceil_div64(n, SCAN_TILE);
+  int* block_sums = reinterpret_cast<int*>(ws);
+  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, block_sums);
+  scan_block_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, nb, total_dev);
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, block_sums);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t b2s_scan_workspace_bytes(int64_t n) {
+  return (ceil_div64(n > 0 ? n : 1, SCAN_TILE) + 1) * (int64_t)sizeof(int);
+}
+
+// =============================================================================================
+// (a1) voxel quantisation
+// =============================================================================================
+namespace {
+
+__global__ void init_bounds_kernel(int* bounds) {
+  if (threadIdx.x < 3) bounds[threadIdx.x] = INT_MAX;
+  else if (threadIdx.x < 6) bounds[threadIdx.x] = INT_MIN;
+}
+
+// q = rint(pos / size) in fp32 (IEEE divide, round-half-even) -- grid_transform.py:116
+__global__ void __launch_bounds__(256) quantize_points_kernel(const float* __restrict__ pos, int64_t n, float size,
+                                                              int* __restrict__ q, int* __restrict__ bounds) {
+  int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+  const int64_t total = n * 3;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    float v = rintf(__fdiv_rn(pos[e], size));
+    int iv = (int)v;
+    q[e] = iv;
+    int d = (int)(e % 3);
+    // branch-free select keeps lo/hi in registers
+    lo[0] = d == 0 ? min(lo[0], iv) : lo[0];
+    lo[1] = d == 1 ? min(lo[1], iv) : lo[1];
+    lo[2] = d == 2 ? min(lo[2], iv) : lo[2];
+    hi[0] = d == 0 ? max(hi[0], iv) : hi[0];
+    hi[1] = d == 1 ? max(hi[1], iv) : hi[1];
+    hi[2] = d == 2 ? max(hi[2], iv) : hi[2];
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = min(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = max(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (lo[d] != INT_MAX) atomicMin(&bounds[d], lo[d]);
+      if (hi[d] != INT_MIN) atomicMax(&bounds[3 + d], hi[d]);
+    }
+  }
+}
+
+struct QBox {
+  int lo[3];
+  int dim[3];  // nx, ny, nz
+};
+
+__device__ __forceinline__ int64_t cell_of(const int* __restrict__ q, const int* __restrict__ plot, int64_t p,
+                                           const QBox& box) {
+  int x = q[3 * p] - box.lo[0], y = q[3 * p + 1] - box.lo[1], z = q[3 * p + 2] - box.lo[2];
+  if ((unsigned)x >= (unsigned)box.dim[0] || (unsigned)y >= (unsigned)box.dim[1] || (unsigned)z >= (unsigned)box.dim[2])
+    return -1;
+  return (((int64_t)plot[p] * box.dim[2] + z) * box.dim[1] + y) * box.dim[0] + x;
+}
+
+__global__ void __launch_bounds__(256) quantize_mark_kernel(const int* __restrict__ q, const int* __restrict__ plot,
+                                                            int64_t n, int num_plots, QBox box,
+                                                            unsigned* __restrict__ bitmap, int* __restrict__ oob) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t cell = ((unsigned)plot[p] < (unsigned)num_plots) ? cell_of(q, plot, p, box) : -1;
+    if (cell < 0) {
+      *oob = 1;
+      continue;
+    }
+    atomicOr(&bitmap[cell >> 5], 1u << (cell & 31));
+  }
+}
+
+__global__ void __launch_bounds__(256) popc_kernel(const unsigned* __restrict__ bitmap, int64_t words,
+                                                   int* __restrict__ pc) {
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (int64_t)gridDim.x * blockDim.x)
+    pc[w] = __popc(bitmap[w]);
+}
+
+__global__ void quantize_total_kernel(const int* __restrict__ oob, int* __restrict__ num_voxels) {
+  if (*oob) *num_voxels = -1;
+}
+
+__global__ void __launch_bounds__(256) quantize_rep_kernel(const int* __restrict__ q, const int* __restrict__ plot,
+                                                           const int* __restrict__ order, int64_t n, QBox box,
+                                                           const unsigned* __restrict__ bitmap,
+                                                           const int* __restrict__ prefix, int* __restrict__ rep) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = order ? order[j] : j;
+    int64_t cell = cell_of(q, plot, p, box);
+    if (cell < 0) continue;
+    int64_t w = cell >> 5;
+    unsigned bit = (unsigned)(cell & 31);
+    int r = prefix[w] + __popc(bitmap[w] & ((1u << bit) - 1u));
+    atomicMax(&rep[r], (int)j);  // last position in the shuffled order wins
+  }
+}
+
+__global__ void __launch_bounds__(256) quantize_emit_kernel(const int* __restrict__ q, const int* __restrict__ plot,
+                                                            const int* __restrict__ order, int64_t m,
+                                                            int* __restrict__ out_coords, int* __restrict__ rep_src) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (int64_t)gridDim.x * blockDim.x) {
+    int j = rep_src[r];
+    int p = order ? order[j] : j;
+    int4 c = make_int4(plot[p], q[3 * (int64_t)p], q[3 * (int64_t)p + 1], q[3 * (int64_t)p + 2]);
+    reinterpret_cast<int4*>(out_coords)[r] = c;
+    rep_src[r] = p;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ in, const int* __restrict__ idx,
+                                                          int64_t m, int c, float* __restrict__ out) {
+  const int64_t total = m * c;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = e / c;
+    int ch = (int)(e - r * c);
+    out[e] = in[(int64_t)idx[r] * c + ch];
+  }
+}
+
+struct QWs {
+  unsigned* bitmap;
+  int* prefix;
+  int* oob;
+  void* scan_ws;
+  int64_t words;
+  int64_t bytes;
+};
+
+bool quantize_layout(int64_t num_plots, const int32_t* dims, void* ws, QWs* out) {
+  if (num_plots <= 0 || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return false;
+  int64_t cells = num_plots * (int64_t)dims[0] * dims[1] * dims[2];
+  if (cells <= 0 || cells > ((int64_t)1 << 36)) return false;
+  int64_t words = ceil_div64(cells, 32);
+  auto align = [](int64_t b) { return (b + 255) & ~(int64_t)255; };
+  char* p = reinterpret_cast<char*>(ws);
+  int64_t off = 0;
+  out->bitmap = reinterpret_cast<unsigned*>(p + off);
+  off += align(words * 4);
+  out->prefix = reinterpret_cast<int*>(p + off);
+  off += align(words * 4);
+  out->oob = reinterpret_cast<int*>(p + off);
+  off += 256;
+  out->scan_ws = p + off;
+  off += align(b2s_scan_workspace_bytes(words));
+  out->words = words;
+  out->bytes = off;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int32_t b2s_quantize_points(const float* pos, int64_t n, float size, int32_t* qcoords, int32_t* bounds,
+                                       b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && size > 0.f, "n >= 0 and size > 0");
+  B2S_CHECK_ARG(bounds && (n == 0 || (pos && qcoords)), "null pointer");
+  cudaStream_t st = as_stream(stream);
+  init_bounds_kernel<<<1, 32, 0, st>>>(bounds);
+  if (n > 0) quantize_points_kernel<<<grid_for(n * 3, 256), 256, 0, st>>>(pos, n, size, qcoords, bounds);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int64_t b2s_quantize_workspace_bytes(int64_t num_plots, const int32_t* dims_host) {
+  QWs l;
+  if (!dims_host || !quantize_layout(num_plots, dims_host, nullptr, &l)) return -1;
+  return l.bytes;
+}
+
+extern "C" int32_t b2s_quantize_count(const int32_t* qcoords, const int32_t* plot_of_point, int64_t n,
+                                      int32_t num_plots, const int32_t* lo_host, const int32_t* dims_host,
+                                      void* workspace, int64_t workspace_bytes, int32_t* num_voxels_dev,
+                                      b2s_stream_t stream) {
+  B2S_CHECK_ARG(lo_host && dims_host && workspace && num_voxels_dev, "null pointer");
+  QWs l;
+  if (!quantize_layout(num_plots, dims_host, workspace, &l)) {
+    b2s_set_error("b2s_quantize_count: voxel box %d x %d x %d x %d plots is empty or above 2^36 cells", dims_host[0],
+                  dims_host[1], dims_host[2], num_plots);
+    return B2S_EOVERFLOW;
+  }
+  B2S_CHECK_ARG(workspace_bytes >= l.bytes, "workspace too small");
+  cudaStream_t st = as_stream(stream);
+  QBox box{{lo_host[0], lo_host[1], lo_host[2]}, {dims_host[0], dims_host[1], dims_host[2]}};
+  B2S_CUDA(cudaMemsetAsync(l.bitmap, 0, l.words * 4, st));
+  B2S_CUDA(cudaMemsetAsync(l.oob, 0, 4, st));
+  if (n > 0)
+    quantize_mark_kernel<<<grid_for(n, 256), 256, 0, st>>>(qcoords, plot_of_point, n, num_plots, box, l.bitmap, l.oob);
+  popc_kernel<<<grid_for(l.words, 256), 256, 0, st>>>(l.bitmap, l.words, l.prefix);
+  launch_exclusive_scan(l.prefix, l.prefix, l.words, num_voxels_dev, l.scan_ws, st);
+  quantize_total_kernel<<<1, 1, 0, st>>>(l.oob, num_voxels_dev);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_quantize_fill(const int32_t* qcoords, const int32_t* plot_of_point, const int32_t* order,
+                                     int64_t n, int32_t num_plots, const int32_t* lo_host, const int32_t* dims_host,
+                                     void* workspace, int64_t num_voxels, int32_t* out_coords, int32_t* out_src,
+                                     b2s_stream_t stream) {
+  B2S_CHECK_ARG(lo_host && dims_host && workspace, "null pointer");
+  B2S_CHECK_ARG(num_voxels >= 0 && num_voxels <= n, "num_voxels out of range");
+  if (num_voxels == 0) return B2S_OK;
+  B2S_CHECK_ARG(out_coords && out_src, "null output");
+  QWs l;
+  B2S_CHECK_ARG(quantize_layout(num_plots, dims_host, workspace, &l), "bad voxel box");
+  cudaStream_t st = as_stream(stream);
+  QBox box{{lo_host[0], lo_host[1], lo_host[2]}, {dims_host[0], dims_host[1], dims_host[2]}};
+  B2S_CUDA(cudaMemsetAsync(out_src, 0xFF, num_voxels * 4, st));  // -1
+  quantize_rep_kernel<<<grid_for(n, 256), 256, 0, st>>>(qcoords, plot_of_point, order, n, box, l.bitmap, l.prefix,
+                                                        out_src);
+  quantize_emit_kernel<<<grid_for(num_voxels, 256), 256, 0, st>>>(qcoords, plot_of_point, order, num_voxels,
+                                                                   out_coords, out_src);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t m, int32_t c, float* out,
+                                   b2s_stream_t stream) {
+  B2S_CHECK_ARG(m >= 0 && c > 0, "m >= 0 and c > 0");
+  if (m == 0) return B2S_OK;
+  B2S_CHECK_ARG(in && idx && out, "null pointer");
+  gather_rows_kernel<<<grid_for(m * c, 256), 256, 0, as_stream(stream)>>>(in, idx, m, c, out);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+// =============================================================================================
+// (a2, a3) coordinate hash + strided maps
+// =============================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256) coordmap_insert_kernel(const int4* __restrict__ coords, int64_t n, int tsx,
+                                                              int tsy, int tsz, B2sEntry* __restrict__ table,
+                                                              uint64_t mask, int* __restrict__ slot,
+                                                              int* __restrict__ info) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    if (c.x < 0 || c.x >= 65535 || abs(c.y) >= B2S_COORD_LIMIT || abs(c.z) >= B2S_COORD_LIMIT ||
+        abs(c.w) >= B2S_COORD_LIMIT) {
+      info[1] = 1;
+      slot[i] = -1;
+      continue;
+    }
+    if (c.x > info[2]) atomicMax(&info[2], c.x);  // largest batch id (rows are batch-sorted: few atomics)
+    const uint64_t key = b2s_pack_key(c.x, b2s_floor_to(c.y, tsx), b2s_floor_to(c.z, tsy), b2s_floor_to(c.w, tsz));
+    uint64_t s = b2s_hash64(key) & mask;
+    for (;;) {
+      unsigned long long old = atomicCAS(&table[s].key, (unsigned long long)B2S_KEY_EMPTY, (unsigned long long)key);
+      if (old == B2S_KEY_EMPTY || old == key) {
+        atomicMin(reinterpret_cast<unsigned*>(&table[s].val), (unsigned)i);  // first occurrence wins
+        slot[i] = (int)s;
+        break;
+      }
+      s = (s + 1) & mask;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) coordmap_flag_kernel(const B2sEntry* __restrict__ table,
+                                                            const int* __restrict__ slot, int64_t n,
+                                                            int* __restrict__ flag) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int s = slot[i];
+    flag[i] = (s >= 0 && table[s].val == (int)i) ? 1 : 0;
+  }
+}
+
+// firsts: emit floored coordinate at their rank and rewrite the table value to that rank.
+// A non-first row i' can never pass the (val == i') test: val is either first(i') < i' or rank <= first.
+__global__ void __launch_bounds__(256) coordmap_emit_kernel(const int4* __restrict__ coords, int64_t n, int tsx,
+                                                            int tsy, int tsz, B2sEntry* __restrict__ table,
+                                                            const int* __restrict__ slot,
+                                                            const int* __restrict__ rank, int4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int s = slot[i];
+    if (s < 0) continue;
+    if (table[s].val == (int)i) {
+      int r = rank[i];
+      int4 c = coords[i];
+      out[r] = make_int4(c.x, b2s_floor_to(c.y, tsx), b2s_floor_to(c.z, tsy), b2s_floor_to(c.w, tsz));
+      table[s].val = r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) coordmap_in2out_kernel(const B2sEntry* __restrict__ table,
+                                                              const int* __restrict__ slot, int64_t n,
+                                                              int* __restrict__ in2out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int s = slot[i];
+    in2out[i] = s >= 0 ? table[s].val : -1;
+  }
+}
+
+bool is_pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+extern "C" int64_t b2s_hash_capacity(int64_t n) {
+  int64_t cap = 1024;
+  while (cap < 2 * n) cap <<= 1;
+  return cap;
+}
+
+extern "C" int32_t b2s_coordmap_insert(const int32_t* coords, int64_t n, const int32_t* ts_host, void* table,
+                                       int64_t capacity, int32_t* slot, int32_t* rank, int32_t* info_dev,
+                                       void* scan_workspace, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && n < INT_MAX, "0 <= n < 2^31");
+  B2S_CHECK_ARG(is_pow2(capacity) && capacity >= 2 * n, "capacity must be a power of two >= 2n");
+  B2S_CHECK_ARG(table && info_dev && ts_host && scan_workspace, "null pointer");
+  B2S_CHECK_ARG(ts_host[0] > 0 && ts_host[1] > 0 && ts_host[2] > 0, "tensor stride must be positive");
+  B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(coords) & 15) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0,
+                "coords and table must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  B2S_CUDA(cudaMemsetAsync(table, 0xFF, capacity * sizeof(B2sEntry), st));
+  B2S_CUDA(cudaMemsetAsync(info_dev, 0, 4 * sizeof(int), st));
+  B2S_CUDA(cudaMemsetAsync(info_dev + 2, 0xFF, sizeof(int), st));  // max batch id starts at -1
+  if (n > 0) {
+    B2S_CHECK_ARG(coords && slot && rank, "null pointer");
+    coordmap_insert_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, ts_host[0],
+                                                             ts_host[1], ts_host[2],
+                                                             reinterpret_cast<B2sEntry*>(table),
+                                                             (uint64_t)capacity - 1, slot, info_dev);
+    coordmap_flag_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const B2sEntry*>(table), slot, n, rank);
+    launch_exclusive_scan(rank, rank, n, info_dev, scan_workspace, st);
+  }
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_coordmap_fill(const int32_t* coords, int64_t n, const int32_t* ts_host, void* table,
+                                     int64_t capacity, const int32_t* slot, const int32_t* rank, int32_t* out_coords,
+                                     int32_t* in2out, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && is_pow2(capacity), "bad sizes");
+  if (n == 0) return B2S_OK;
+  B2S_CHECK_ARG(coords && table && slot && rank && out_coords && ts_host, "null pointer");
+  B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(out_coords) & 15) == 0, "out_coords must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  coordmap_emit_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, ts_host[0],
+                                                         ts_host[1], ts_host[2], reinterpret_cast<B2sEntry*>(table),
+                                                         slot, rank, reinterpret_cast<int4*>(out_coords));
+  if (in2out)
+    coordmap_in2out_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const B2sEntry*>(table), slot, n,
+                                                             in2out);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+// =============================================================================================
+// (a4) kernel maps
+// =============================================================================================
+namespace {
+
+struct KmParams {
+  int K[3];
+  int step[3];
+  int sign;
+  int k3;
+  int group;  // offsets handled per blockIdx.y
+};
+
+// One thread per query row, blockIdx.y selects a group of kernel offsets.  Writes of nbr[k, q] are
+// coalesced across the warp for every k; the 16-byte coordinate is loaded once per group.
+__global__ void __launch_bounds__(256) kernel_map_kernel(const int4* __restrict__ query, int64_t n,
+                                                         const B2sEntry* __restrict__ table, uint64_t mask,
+                                                         KmParams p, int* __restrict__ nbr) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int4 c = query[q];
+  const int k0 = blockIdx.y * p.group;
+  const int k1 = min(k0 + p.group, p.k3);
+  const int hx = (p.K[0] & 1) ? p.K[0] / 2 : 0, hy = (p.K[1] & 1) ? p.K[1] / 2 : 0, hz = (p.K[2] & 1) ? p.K[2] / 2 : 0;
+  int ix = k0 % p.K[0], iy = (k0 / p.K[0]) % p.K[1], iz = k0 / (p.K[0] * p.K[1]);
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    const int x = c.y + p.sign * (ix - hx) * p.step[0];
+    const int y = c.z + p.sign * (iy - hy) * p.step[1];
+    const int z = c.w + p.sign * (iz - hz) * p.step[2];
+    nbr[(int64_t)k * n + q] = b2s_table_find(table, mask, b2s_pack_key(c.x, x, y, z));
+    if (++ix == p.K[0]) {
+      ix = 0;
+      if (++iy == p.K[1]) {
+        iy = 0;
+        ++iz;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pair_count_kernel(const int* __restrict__ nbr, int64_t n,
+                                                         int* __restrict__ counts) {
+  const int k = blockIdx.y;
+  int c = 0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    c += nbr[(int64_t)k * n + q] >= 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counts[k], c);
+}
+
+// one CTA per kernel offset walks the row of the table in order, so pairs come out sorted by out row
+__global__ void __launch_bounds__(SCAN_THREADS) pair_fill_kernel(const int* __restrict__ nbr, int64_t n,
+                                                                 const int64_t* __restrict__ offsets,
+                                                                 int* __restrict__ in_idx, int* __restrict__ out_idx) {
+  const int k = blockIdx.x;
+  int64_t base_out = offsets[k];
+  for (int64_t q0 = 0; q0 < n; q0 += SCAN_THREADS) {
+    int64_t q = q0 + threadIdx.x;
+    int v = q < n ? nbr[(int64_t)k * n + q] : -1;
+    int total;
+    int ex = block_excl_scan(v >= 0 ? 1 : 0, &total);
+    if (v >= 0) {
+      in_idx[base_out + ex] = v;
+      out_idx[base_out + ex] = (int)q;
+    }
+    base_out += total;
+  }
+}
+
+}  // namespace
+
+extern "C" int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, const void* table, int64_t capacity,
+                                  const int32_t* kernel_size_host, const int32_t* step_host, int32_t sign,
+                                  int32_t* nbr, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n_query >= 0 && is_pow2(capacity), "bad sizes");
+  B2S_CHECK_ARG(kernel_size_host && step_host && table, "null pointer");
+  B2S_CHECK_ARG(sign == 1 || sign == -1, "sign must be +1 or -1");
+  KmParams p;
+  for (int d = 0; d < 3; ++d) {
+    B2S_CHECK_ARG(kernel_size_host[d] >= 1 && kernel_size_host[d] <= 15 && step_host[d] >= 1, "kernel size 1..15");
+    p.K[d] = kernel_size_host[d];
+    p.step[d] = step_host[d];
+    B2S_CHECK_ARG((int64_t)p.K[d] * p.step[d] < (B2S_COORD_BIAS - B2S_COORD_LIMIT), "kernel reach too large");
+  }
+  p.sign = sign;
+  p.k3 = p.K[0] * p.K[1] * p.K[2];
+  if (n_query == 0) return B2S_OK;
+  B2S_CHECK_ARG(query_coords && nbr, "null pointer");
+  // enough CTAs for >= 2 waves of 148 SMs x 8 even when the map is small
+  int64_t row_blocks = ceil_div64(n_query, 256);
+  int groups = 1;
+  while (row_blocks * groups < 2 * B2S_NUM_SMS * 8 && groups < p.k3) ++groups;
+  p.group = (p.k3 + groups - 1) / groups;
+  groups = (p.k3 + p.group - 1) / p.group;
+  dim3 grid((unsigned)row_blocks, (unsigned)groups);
+  kernel_map_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const int4*>(query_coords), n_query,
+                                                         reinterpret_cast<const B2sEntry*>(table),
+                                                         (uint64_t)capacity - 1, p, nbr);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_kernel_map_pair_counts(const int32_t* nbr, int32_t k3, int64_t n_query, int32_t* counts,
+                                              b2s_stream_t stream) {
+  B2S_CHECK_ARG(k3 > 0 && n_query >= 0 && counts, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  B2S_CUDA(cudaMemsetAsync(counts, 0, k3 * sizeof(int), st));
+  if (n_query == 0) return B2S_OK;
+  B2S_CHECK_ARG(nbr, "null pointer");
+  dim3 grid((unsigned)grid_for(n_query, 256, 2), (unsigned)k3);
+  pair_count_kernel<<<grid, 256, 0, st>>>(nbr, n_query, counts);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_t n_query, const int64_t* offsets,
+                                             int32_t* in_idx, int32_t* out_idx, b2s_stream_t stream) {
+  B2S_CHECK_ARG(k3 > 0 && n_query >= 0, "bad arguments");
+  if (n_query == 0) return B2S_OK;
+  B2S_CHECK_ARG(nbr && offsets && in_idx && out_idx, "null pointer");
+  pair_fill_kernel<<<k3, SCAN_THREADS, 0, as_stream(stream)>>>(nbr, n_query, offsets, in_idx, out_idx);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}

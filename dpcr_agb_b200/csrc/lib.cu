@@ -1,0 +1,108 @@
+// lib.cu -- library plumbing (errors, version, device check) and the convolution dispatch of the C ABI.
+#include "common.cuh"
+#include <string.h>
+
+static thread_local char g_last_error[512] = "";
+
+void b2s_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* b2s_last_error(void) { return g_last_error; }
+extern "C" int32_t b2s_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" int32_t b2s_device_check(void) {
+  int dev = 0;
+  B2S_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  B2S_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  B2S_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    b2s_set_error("b2s_device_check: device %d is sm_%d%d; libb200sparse is built for sm_100a (B200) only", dev, major,
+                  minor);
+    return B2S_ECUDA;
+  }
+  return B2S_OK;
+}
+
+// implemented in conv_simt.cu / conv_tc.cu
+int b2s_conv_gather_gemm_simt(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_out,
+                              int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y, cudaStream_t st);
+int b2s_conv_wgrad_simt(const float* x, const float* gy, const int32_t* nbr, int64_t n_out, int32_t c_in,
+                        int32_t c_out, int32_t k3, float* gw, cudaStream_t st);
+bool b2s_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_out);
+int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_in);
+int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
+                            int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
+                            void* workspace, int64_t workspace_bytes, cudaStream_t st);
+bool b2s_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_out);
+int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_out, int32_t c_in, int32_t c_out,
+                      int32_t k3, float* gw, cudaStream_t st);
+
+extern "C" int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3) {
+  if (c_in <= 0 || c_out <= 0 || k3 <= 0 || n_in < 0 || n_out < 0) return -1;
+  return b2s_conv_tc_supported(c_in, c_out, k3, n_out) ? b2s_conv_tc_workspace_bytes(c_in, c_out, k3, n_in) : 0;
+}
+
+extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr,
+                                        int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3,
+                                        int32_t w_layout, float* y, void* workspace, int64_t workspace_bytes,
+                                        int32_t impl, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0, "bad sizes");
+  B2S_CHECK_ARG(w_layout >= 0 && w_layout <= 3, "w_layout must be in 0..3");
+  B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
+  B2S_CHECK_ARG(nbr || (k3 == 1 && n_in == n_out), "nbr may be null only for the identity map (k3 == 1)");
+  if (n_out == 0) return B2S_OK;
+  B2S_CHECK_ARG(x && w && y, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  const bool tc_ok = b2s_conv_tc_supported(c_in, c_out, k3, n_out);
+  if (impl == 2 && !tc_ok) {
+    b2s_set_error("b2s_conv_gather_gemm: tcgen05 kernel does not cover c_in=%d c_out=%d k3=%d", c_in, c_out, k3);
+    return B2S_EINVAL;
+  }
+  if (impl == 2 || (impl == 0 && tc_ok)) {
+    B2S_CHECK_ARG(workspace && workspace_bytes >= b2s_conv_tc_workspace_bytes(c_in, c_out, k3, n_in),
+                  "workspace too small (see b2s_conv_workspace_bytes)");
+    B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                  "workspace must be 256-byte aligned, x and y 16-byte aligned");
+    if (b2s_conv_gather_gemm_tc(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, y, workspace, workspace_bytes,
+                                st))
+      return B2S_ECUDA;
+  } else {
+    b2s_conv_gather_gemm_simt(x, w, bias, nbr, n_out, c_in, c_out, k3, w_layout, y, st);
+  }
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
+                                  int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace,
+                                  int64_t workspace_bytes, int32_t impl, b2s_stream_t stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0 && gw, "bad sizes");
+  B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
+  B2S_CHECK_ARG(nbr || (k3 == 1 && n_in == n_out), "nbr may be null only for the identity map (k3 == 1)");
+  cudaStream_t st = as_stream(stream);
+  if (n_out == 0) {
+    B2S_CUDA(cudaMemsetAsync(gw, 0, (size_t)k3 * c_in * c_out * sizeof(float), st));
+    return B2S_OK;
+  }
+  B2S_CHECK_ARG(x && gy, "null pointer");
+  const bool tc_ok = b2s_wgrad_tc_supported(c_in, c_out, k3, n_out);
+  if (impl == 2 && !tc_ok) {
+    b2s_set_error("b2s_conv_wgrad: tcgen05 kernel does not cover c_in=%d c_out=%d k3=%d", c_in, c_out, k3);
+    return B2S_EINVAL;
+  }
+  if (impl == 2 || (impl == 0 && tc_ok)) {
+    if (b2s_conv_wgrad_tc(x, gy, nbr, n_out, c_in, c_out, k3, gw, st)) return B2S_ECUDA;
+  } else {
+    b2s_conv_wgrad_simt(x, gy, nbr, n_out, c_in, c_out, k3, gw, st);
+  }
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}

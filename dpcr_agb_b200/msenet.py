@@ -1,0 +1,198 @@
+"""MSENet14 / MSENet50 (and the sibling depths) written against a MinkowskiEngine-shaped namespace.
+
+This restates the network *definitions* of the reference --
+``torch_points3d/modules/MinkowskiEngine/SENet.py:14-118,151-188`` (ResNetBase / SENet14 / SENet50),
+``senet_block.py:33-147`` (SELayer, SEBasicBlock, SEBottleneck), ``resnet_block.py:31-133``,
+``common.py:215-226,344-366`` (ConvNormActivation, MinkowskiDropPath) and the ``SeparateLinear`` head of
+``models/instance/minkowski.py:15-26,39-46`` -- because ``/root/reference`` does not exist where the GPU
+tests and the benchmark run.  Module attribute names are kept identical, so ``state_dict()`` keys match
+the reference's and its checkpoints load (tests/test_api_surface.py checks key-by-key equality against
+the unchanged reference classes when the reference tree is present).
+
+``ME`` is passed in: ``dpcr_agb_b200.MinkowskiEngine`` for the CUDA product path, ``oracle.me_cpu`` for
+the CPU checker.  The unchanged reference classes run over the same namespaces via ``install()``.
+"""
+from __future__ import annotations
+
+import random
+
+import torch
+import torch.nn as nn
+
+ARCH = {
+    #  name        (bottleneck, layers,          init_dim, planes)
+    "SENet14": (False, (1, 1, 1, 1), 64, (64, 128, 256, 512)),
+    "SENet18": (False, (2, 2, 2, 2), 64, (64, 128, 256, 512)),
+    "SENet34": (False, (3, 4, 6, 3), 64, (64, 128, 256, 512)),
+    "SENet50": (True, (3, 4, 6, 3), 64, (64, 128, 256, 512)),
+    "SENet101": (True, (3, 4, 23, 3), 64, (64, 128, 256, 512)),
+}
+ACTIVATION_NAMES = {"relu": "MinkowskiReLU", "gelu": "MinkowskiGELU", "silu": "MinkowskiSiLU",
+                    "swish": "MinkowskiSiLU", "sigmoid": "MinkowskiSigmoid", "tanh": "MinkowskiTanh"}
+POOL_NAMES = {"sum": "MinkowskiGlobalSumPooling", "mean": "MinkowskiGlobalAvgPooling",
+              "max": "MinkowskiGlobalMaxPooling"}
+
+
+def _rewrap(ME, x, feats):
+    return ME.SparseTensor(feats, coordinate_map_key=x.coordinate_map_key, coordinate_manager=x.coordinate_manager)
+
+
+class DropPath(nn.Module):
+    """Per-plot stochastic depth, same draws as ``common.py:353-366``: one ``random.uniform(0, 1)`` per
+    plot in batch order, kept plots scaled by 1/keep.  The mask is a [B,1] tensor applied with the
+    broadcast-multiply op instead of a host-built per-row mask (no device->host sync)."""
+
+    def __init__(self, ME, drop_prob=0.0, scale_by_keep=True):
+        super().__init__()
+        self.drop_prob, self.scale_by_keep = drop_prob, scale_by_keep
+        self._ME = [ME]                      # list: keep the namespace out of nn.Module registration
+        self.mul = ME.MinkowskiBroadcastMultiplication()
+
+    def forward(self, x):
+        if not self.training:
+            return x
+        ME = self._ME[0]
+        cm = x.coordinate_manager
+        nb = cm.num_batches if isinstance(cm.num_batches, int) else cm.num_batches()
+        keep = 1.0 - self.drop_prob
+        scale = 1.0 / keep if (keep > 0.0 and self.scale_by_keep) else 1.0
+        vals = [scale if random.uniform(0, 1) > self.drop_prob else 0.0 for _ in range(nb)]
+        mask = torch.tensor(vals, dtype=x.F.dtype).view(nb, 1).to(x.F.device, non_blocking=True)
+        glob = ME.SparseTensor(mask, coordinate_map_key=cm.origin(x.coordinate_map_key), coordinate_manager=cm)
+        return self.mul(x, glob)
+
+
+class ConvNormAct(nn.Module):
+    def __init__(self, ME, cin, cout, kernel_size, stride, norm_layer, act, bias):
+        super().__init__()
+        self.conv = ME.MinkowskiConvolution(cin, cout, kernel_size=kernel_size, stride=stride, dimension=3, bias=bias)
+        self.norm = norm_layer(cout)
+        self.act = nn.Identity() if act is None else act
+
+    def forward(self, x):
+        return self.act(self.norm(self.conv(x)))
+
+
+class SqueezeExcite(nn.Module):
+    def __init__(self, ME, channels, act, reduction=16):
+        super().__init__()
+        self.fc = nn.Sequential(ME.MinkowskiLinear(channels, channels // reduction), act,
+                                ME.MinkowskiLinear(channels // reduction, channels), ME.MinkowskiSigmoid())
+        self.pooling = ME.MinkowskiGlobalPooling()
+        self.broadcast_mul = ME.MinkowskiBroadcastMultiplication()
+
+    def forward(self, x):
+        return self.broadcast_mul(x, self.fc(self.pooling(x)))
+
+
+class SEResidualBlock(nn.Module):
+    """SEBasicBlock (expansion 1: k3 - k3) or SEBottleneck (expansion 4: k1 - k3 - k1), + SE + residual."""
+
+    def __init__(self, ME, inplanes, planes, act, norm_layer, bottleneck, stride=1, downsample=None,
+                 drop_path=0.0, bias=True):
+        super().__init__()
+        self.expansion = 4 if bottleneck else 1
+        if bottleneck:
+            spec = [(inplanes, planes, 1, 1), (planes, planes, 3, stride), (planes, planes * 4, 1, 1)]
+        else:
+            spec = [(inplanes, planes, 3, stride), (planes, planes, 3, 1)]
+        self.num_convs = len(spec)
+        for i, (ci, co, k, s) in enumerate(spec, 1):
+            setattr(self, f"conv{i}", ME.MinkowskiConvolution(ci, co, kernel_size=k, stride=s, dilation=1,
+                                                              dimension=3, bias=bias))
+            setattr(self, f"norm{i}", norm_layer(co))
+        self.relu = act
+        self.downsample = downsample if downsample is not None else nn.Identity()
+        self.drop_path = DropPath(ME, drop_path) if drop_path > 0.0 else nn.Identity()
+        self.se = SqueezeExcite(ME, planes * self.expansion, act)
+
+    def forward(self, x):
+        out = x
+        for i in range(1, self.num_convs + 1):
+            out = getattr(self, f"norm{i}")(getattr(self, f"conv{i}")(out))
+            if i < self.num_convs:
+                out = self.relu(out)
+        out = self.se(out)
+        out = self.drop_path(out) + self.downsample(x)
+        return self.relu(out)
+
+
+class SeparateLinear(nn.Module):
+    """One ``Linear(C, 1)`` per regression target (``minkowski.py:15-26``)."""
+
+    def __init__(self, in_channel, num_reg_classes):
+        super().__init__()
+        self.linears = nn.ModuleList([nn.Linear(in_channel, 1, bias=True) for _ in range(num_reg_classes)])
+
+    def forward(self, x):
+        return torch.cat([lin(x.F) for lin in self.linears], 1)
+
+
+class MSENet(nn.Module):
+    def __init__(self, ME, name="SENet14", in_channels=3, out_channels=2, activation="gelu", first_stride=1,
+                 dropout=0.0, drop_path=0.0, bn_momentum=0.1, global_pool="sum", bias=True, separate_head=True):
+        super().__init__()
+        bottleneck, layers, init_dim, planes_list = ARCH[name]
+        self.name = name
+        self.act_fn = getattr(ME.MinkowskiNonlinearity, ACTIVATION_NAMES[activation])()
+        norm_layer = lambda c: ME.MinkowskiNormalization.MinkowskiBatchNorm(c, momentum=bn_momentum)  # noqa: E731
+        self.inplanes = init_dim
+        stages = [nn.Sequential(
+            ConvNormAct(ME, in_channels, init_dim, 7, first_stride, norm_layer, self.act_fn, bias),
+            ME.MinkowskiMaxPooling(kernel_size=3, stride=2, dimension=3))]
+        expansion = 4 if bottleneck else 1
+        for planes, count, stride in zip(planes_list, layers, (1, 2, 2, 2)):
+            blocks = []
+            for j in range(count):
+                s = stride if j == 0 else 1
+                down = None
+                if j == 0 and (s != 1 or self.inplanes != planes * expansion):
+                    down = nn.Sequential(
+                        ME.MinkowskiConvolution(self.inplanes, planes * expansion, kernel_size=1, stride=s,
+                                                dimension=3, dilation=1, bias=bias),
+                        norm_layer(planes * expansion))
+                blocks.append(SEResidualBlock(ME, self.inplanes, planes, self.act_fn, norm_layer, bottleneck,
+                                              stride=s, downsample=down, drop_path=drop_path, bias=bias))
+                self.inplanes = planes * expansion
+            stages.append(nn.Sequential(*blocks))
+        self.blocks = nn.ModuleList(stages)
+        self.glob_avg = getattr(ME, POOL_NAMES[global_pool])()
+        if dropout > 0:
+            self.glob_avg = nn.Sequential(self.glob_avg, ME.MinkowskiDropout(dropout))
+        if separate_head:
+            self.final = SeparateLinear(self.inplanes, out_channels)
+        else:
+            self.final = ME.MinkowskiLinear(self.inplanes, out_channels, bias=True)
+        self._init_weights(ME)
+
+    def _init_weights(self, ME):
+        """``ResNetBase.init_weights`` (SENet.py:74-87) + head init of ``minkowski.py:43-46``."""
+        for m in self.modules():
+            if isinstance(m, ME.MinkowskiBatchNorm):
+                nn.init.constant_(m.bn.weight, 1)
+                nn.init.constant_(m.bn.bias, 0)
+            elif isinstance(m, ME.MinkowskiConvolution):
+                nn.init.trunc_normal_(m.kernel, std=0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, ME.MinkowskiLinear):
+                nn.init.trunc_normal_(m.linear.weight, std=0.02)
+                if m.linear.bias is not None:
+                    nn.init.constant_(m.linear.bias, 0)
+            elif isinstance(m, SeparateLinear):
+                for lin in m.linears:
+                    nn.init.trunc_normal_(lin.weight, std=0.02)
+                    nn.init.constant_(lin.bias, 0)
+
+    def forward(self, x):
+        for stage in self.blocks:
+            x = stage(x)
+        return self.final(self.glob_avg(x))
+
+
+def build(ME, name="SENet14", **kw):
+    """README configuration of the reference (``conf/models/instance/minkowski_baseline.yaml:71-80``)."""
+    cfg = dict(in_channels=3, out_channels=2, activation="gelu", first_stride=1, dropout=0.0, drop_path=0.01,
+               global_pool="sum", bias=True)
+    cfg.update(kw)
+    return MSENet(ME, name, **cfg)

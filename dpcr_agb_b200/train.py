@@ -1,0 +1,143 @@
+"""Training step for the MSENet regression models: loss, fused AdaBelief, data-parallel wiring.
+
+Mirrors ``BaseModel.optimize_parameters`` of the reference (``torch_points3d/models/base_model.py:230-256``):
+forward -> ``0.5 * smooth_l1`` on z-scored targets (``models/instance/base.py:154-179``) -> backward ->
+``clip_grad_value_(100)`` -> AdaBelief step (``core/optimizer/adabelief.py:90-201``) -> LR schedule.
+The reference's single-process ``nn.DataParallel`` (``trainer.py:149-150``) is replaced by one process per
+GPU with a NCCL all-reduce of ONE flat gradient buffer: every plot is an independent
+sample, so the only exchange step of the path is that gradient sum.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import lib as L
+
+
+def reg_loss(pred, target, center, scale, weight=0.5):
+    """``compute_reg_loss`` (base.py:154-179): smooth-L1 on z-scored targets, NaN targets masked,
+    weighted by ``reg_weights.mean()`` = 0.5 (conf/data/instance/NFI/reg.yaml:21-24)."""
+    labels = (target - center) / scale
+    mask = ~torch.isnan(labels)
+    labels = torch.where(mask, labels, pred.detach())          # masked entries contribute zero loss/grad
+    denom = mask.sum().clamp(min=1).to(pred.dtype)
+    return weight * F.smooth_l1_loss(pred, labels, reduction="sum") / denom
+
+
+class FlatAdaBelief:
+    """AdaBelief over ONE flat fp32 buffer: parameters and gradients of the model are re-pointed to views
+    of two contiguous tensors so that the whole update (plus unscale / clip / inf-skip) is a single
+    ``b2s_adabelief_step`` launch and the data-parallel exchange is a single all-reduce."""
+
+    def __init__(self, params, lr=5e-3, betas=(0.9, 0.999), eps=1e-16, weight_decay=1e-2, grad_clip=100.0):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.numel = n
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_var = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.reshape(-1))
+                p.data = self.flat_param[off:off + k].view_as(p)
+                p.grad = self.flat_grad[off:off + k].view_as(p)
+                off += k
+        self.lr, self.betas, self.eps, self.weight_decay, self.grad_clip = lr, betas, eps, weight_decay, grad_clip
+        self.step_count = 0
+        self.found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    @staticmethod
+    def rectified_step(step, beta1, beta2):
+        """adabelief.py:169-187 -> (num_sma, step_size); degenerated_to_sgd=True."""
+        beta2_t = beta2 ** step
+        sma_max = 2.0 / (1.0 - beta2) - 1.0
+        sma = sma_max - 2.0 * step * beta2_t / (1.0 - beta2_t)
+        if sma >= 5:
+            step_size = math.sqrt((1 - beta2_t) * (sma - 4) / (sma_max - 4) * (sma - 2) / sma
+                                  * sma_max / (sma_max - 2)) / (1 - beta1 ** step)
+        else:
+            step_size = 1.0 / (1 - beta1 ** step)
+        return sma, step_size
+
+    def step(self, inv_scale=1.0, check_inf=False):
+        self.step_count += 1
+        b1, b2 = self.betas
+        sma, step_size = self.rectified_step(self.step_count, b1, b2)
+        found = None
+        if check_inf:
+            L.call("b2s_grad_check", self.flat_grad, self.numel, float(inv_scale), self.found_inf)
+            found = self.found_inf
+        hyper = L.host_f32(self.lr, b1, b2, self.eps, self.weight_decay, step_size, 1.0 if sma >= 5 else 0.0,
+                           inv_scale, self.grad_clip, 0, 0, 0, 0, 0, 0, 0)
+        L.call("b2s_adabelief_step", self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_var, self.numel,
+               hyper, found)
+
+
+class CosineAnnealingWarmRestarts:
+    """torch's CosineAnnealingWarmRestarts(T_0, T_mult) evaluated at a fractional epoch, as the reference
+    steps it per batch (``base_model.py:219-226``; conf/lr_scheduler/cosineawr.yaml:2-5)."""
+
+    def __init__(self, base_lr, T_0=10, T_mult=2, eta_min=0.0):
+        self.base_lr, self.T_0, self.T_mult, self.eta_min = base_lr, T_0, T_mult, eta_min
+
+    def lr_at(self, epoch: float) -> float:
+        if epoch >= self.T_0 and self.T_mult > 1:
+            n = int(math.log(epoch / self.T_0 * (self.T_mult - 1) + 1, self.T_mult))
+            t_cur = epoch - self.T_0 * (self.T_mult ** n - 1) / (self.T_mult - 1)
+            t_i = self.T_0 * self.T_mult ** n
+        elif epoch >= self.T_0:
+            t_cur, t_i = epoch % self.T_0, self.T_0
+        else:
+            t_cur, t_i = epoch, self.T_0
+        return self.eta_min + (self.base_lr - self.eta_min) * (1 + math.cos(math.pi * t_cur / t_i)) / 2
+
+
+class Trainer:
+    """One optimisation step of MSENet on one GPU (rank); gradients are averaged across ranks."""
+
+    def __init__(self, model, ME, lr=5e-3, weight_decay=1e-2, grad_clip=100.0, batches_per_epoch=133,
+                 target_center=(107.0, 200.0), target_scale=(103.0, 194.0)):
+        self.model, self.ME = model, ME
+        self.opt = FlatAdaBelief(model.parameters(), lr=lr, weight_decay=weight_decay, grad_clip=grad_clip)
+        self.sched = CosineAnnealingWarmRestarts(lr)
+        self.batches_per_epoch = batches_per_epoch
+        dev = self.opt.flat_param.device
+        self.center = torch.tensor(target_center, dtype=torch.float32, device=dev)
+        self.scale = torch.tensor(target_scale, dtype=torch.float32, device=dev)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.num_batches = 0
+
+    def broadcast_parameters(self):
+        if self.world > 1:
+            dist.broadcast(self.opt.flat_param, src=0)
+
+    def step(self, coords, feats, target):
+        """coords int32 [N,4] (plot,x,y,z), feats fp32 [N,3], target fp32 [B,2] -- all on this rank's GPU.
+        Returns the (detached, on-device) loss."""
+        self.model.train()
+        self.opt.zero_grad()
+        x = self.ME.SparseTensor(features=feats, coordinates=coords)
+        pred = self.model(x)
+        loss = reg_loss(pred, target, self.center, self.scale)
+        loss.backward()
+        if self.world > 1:
+            # the one exchange step of the path: sum the flat gradient over ranks (NCCL over NVLink), then
+            # average -- equivalent to DDP's bucketed all-reduce with a single bucket
+            dist.all_reduce(self.opt.flat_grad, op=dist.ReduceOp.SUM)
+            self.opt.flat_grad.mul_(1.0 / self.world)
+        self.num_batches += 1
+        self.opt.lr = self.sched.lr_at(self.num_batches / self.batches_per_epoch)
+        self.opt.step()
+        return loss.detach()

@@ -1,0 +1,198 @@
+/*
+ * b200sparse.h -- C ABI of libb200sparse.so, the B200 (sm_100a) sparse-convolution library behind
+ * the MinkowskiEngine-shaped Python surface in dpcr_agb_b200/MinkowskiEngine.
+ *
+ * This is the drop-in boundary for the hot path of StefOe/DPCR-AGB's MSENet14 / MSENet50.  The
+ * reference has no native code for this path: it calls the third-party MinkowskiEngine library
+ * through `import MinkowskiEngine as ME` (torch-points3d/torch_points3d/modules/MinkowskiEngine/
+ * SENet.py:3, common.py:6, models/instance/minkowski.py:3).  Every entry point below cites the
+ * reference call site whose work it performs ("R:" = /root/reference/torch-points3d/torch_points3d/).
+ *
+ * Conventions
+ *   - every function returns 0 (B2S_OK) or a negative error code; b2s_last_error() gives the text
+ *     (thread-local).  No exceptions, no caller-visible allocation: the caller owns every buffer.
+ *   - all pointers are device pointers on the CURRENT device unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; the library never touches the default stream and
+ *     never synchronises, so it is safe from autograd / DDP worker threads.
+ *   - coordinates are int32 [N,4] = (batch, x, y, z)  (R:models/instance/minkowski.py:69).
+ *   - a kernel map is a neighbour table nbr int32 [K3, N_out]: nbr[k*N_out + o] = in-row i with
+ *     coords_in[i] == coords_out[o] + delta_k, or -1.  k = ix + K*iy + K*K*iz (x fastest).
+ *   - features are fp32 row-major [N, C].
+ */
+#ifndef B200SPARSE_H_
+#define B200SPARSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_OK 0
+#define B2S_EINVAL (-1)
+#define B2S_ENOMEM (-2)
+#define B2S_ECUDA (-3)
+#define B2S_EOVERFLOW (-4)
+
+#if defined(__GNUC__)
+#define B2S_API __attribute__((visibility("default")))
+#else
+#define B2S_API
+#endif
+
+typedef void* b2s_stream_t;
+
+/* ---------------------------------------------------------------- library ------------------- */
+B2S_API const char* b2s_last_error(void);
+B2S_API int32_t b2s_version(void);
+/* 0 iff the current device is compute capability 10.x (B200); B2S_ECUDA otherwise. */
+B2S_API int32_t b2s_device_check(void);
+
+/* ---------------------------------------------------------------- (a1) voxel quantisation ----
+ * R:core/data_transform/grid_transform.py:112-128 (GridSampling3D._process, mode="last").
+ * b2s_quantize_points : q = rint_half_even(fp32(pos) / fp32(size)) as int32 [n,3]   (:116)
+ *                       and bounds[0..2] = min(q), bounds[3..5] = max(q) over the batch.
+ * b2s_quantize_count  : marks the occupied cells (plot, z, y, x) of the box lo..lo+dims in a bitmap
+ *                       held in `workspace` and ranks them; *num_voxels_dev = number of voxels, or
+ *                       -1 if a point falls outside the box.  Row order of the result is the order
+ *                       of torch.unique(cluster) per plot, plots concatenated (:117-121).
+ * b2s_quantize_fill   : representative of a voxel = the point with the largest position in the
+ *                       shuffled order (`order[j]` = original index of the j-th shuffled point, NULL =
+ *                       identity): consecutive_cluster's last-write-wins (:121).  Writes
+ *                       out_coords int32 [M,4] (plot, x, y, z) and out_src int32 [M] (original index).
+ */
+B2S_API int32_t b2s_quantize_points(const float* pos, int64_t n, float size, int32_t* qcoords, int32_t* bounds,
+                            b2s_stream_t stream);
+B2S_API int64_t b2s_quantize_workspace_bytes(int64_t num_plots, const int32_t* dims_host);
+B2S_API int32_t b2s_quantize_count(const int32_t* qcoords, const int32_t* plot_of_point, int64_t n, int32_t num_plots,
+                           const int32_t* lo_host, const int32_t* dims_host, void* workspace,
+                           int64_t workspace_bytes, int32_t* num_voxels_dev, b2s_stream_t stream);
+B2S_API int32_t b2s_quantize_fill(const int32_t* qcoords, const int32_t* plot_of_point, const int32_t* order, int64_t n,
+                          int32_t num_plots, const int32_t* lo_host, const int32_t* dims_host, void* workspace,
+                          int64_t num_voxels, int32_t* out_coords, int32_t* out_src, b2s_stream_t stream);
+/* out[r, :] = in[idx[r], :]  -- the per-point tensors gathered at the representative (:64-66). */
+B2S_API int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t m, int32_t c, float* out, b2s_stream_t stream);
+
+/* ---------------------------------------------------------------- (a2,a3) coordinate maps ----
+ * R:models/instance/minkowski.py:74 (ME.SparseTensor -> hash build) and every stride-2 op
+ * (R:modules/MinkowskiEngine/SENet.py:53,94-97; resnet_block.py:48-50).
+ * The table is an open-addressing hash of `capacity` 16-byte entries {uint64 key, int32 row, pad}.
+ * insert : key = pack(batch, floor(c / ts) * ts); value = smallest inserting row (first occurrence).
+ *          info_dev (int32[4]): [0] number of unique keys, [1] 1 if a coordinate is out of range,
+ *          [2] largest batch id seen (-1 if n == 0), [3] reserved.
+ *          rank[i] = out row of in-row i if i is the first occurrence of its key, else -1;
+ *          slot[i] = table slot of row i's key (scratch for _fill).
+ * fill   : writes out_coords [M,4] in first-occurrence order, rewrites table values to out rows and
+ *          (optionally) in2out[i] = out row of in-row i.
+ */
+B2S_API int64_t b2s_hash_capacity(int64_t n);
+B2S_API int64_t b2s_scan_workspace_bytes(int64_t n);
+B2S_API int32_t b2s_coordmap_insert(const int32_t* coords, int64_t n, const int32_t* ts_host, void* table, int64_t capacity,
+                            int32_t* slot, int32_t* rank, int32_t* info_dev, void* scan_workspace,
+                            b2s_stream_t stream);
+B2S_API int32_t b2s_coordmap_fill(const int32_t* coords, int64_t n, const int32_t* ts_host, void* table, int64_t capacity,
+                          const int32_t* slot, const int32_t* rank, int32_t* out_coords, int32_t* in2out,
+                          b2s_stream_t stream);
+
+/* ---------------------------------------------------------------- (a4) kernel maps -----------
+ * Implicit in every MinkowskiConvolution / MinkowskiMaxPooling call (same call sites).
+ * nbr[k*n_query + q] = table row of (query[q] + sign * delta_k) or -1;
+ * delta = (i - K/2) * step for odd K, i * step for even K; step = dilation * tensor_stride_in.
+ * sign=+1: forward map (query = out coords, table = in map).  sign=-1 with query = in coords and the
+ * table of the OUT map gives the transposed map (dgrad of strided convs, ConvolutionTranspose).
+ * pair_counts / pairs_fill derive MinkowskiEngine's pair-list form (per offset, sorted by out row).
+ */
+B2S_API int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, const void* table, int64_t capacity,
+                       const int32_t* kernel_size_host, const int32_t* step_host, int32_t sign, int32_t* nbr,
+                       b2s_stream_t stream);
+B2S_API int32_t b2s_kernel_map_pair_counts(const int32_t* nbr, int32_t k3, int64_t n_query, int32_t* counts,
+                                   b2s_stream_t stream);
+B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_t n_query, const int64_t* offsets,
+                                  int32_t* in_idx, int32_t* out_idx, b2s_stream_t stream);
+
+/* ---------------------------------------------------------------- (a6-a8) convolution --------
+ * R:modules/MinkowskiEngine/SENet.py:49-52,94-97; resnet_block.py:48-54,95-107; common.py:219-221.
+ * b2s_conv_gather_gemm : y[o,:] = bias + sum_k x[nbr[k,o],:] * B_k          (output-stationary)
+ *     w_layout bit 0 clear: w is [K3, c_in, c_out]  (forward with the stored kernel)
+ *     w_layout bit 0 set  : w is [K3, c_out, c_in]  (dgrad: x = grad_out, nbr = transposed map, w = kernel)
+ *     w_layout bit 1 set  : B_k is taken from w[K3-1-k] -- for point-symmetric maps (stride 1, odd K) the
+ *                           transposed table is the forward table with k reversed, so dgrad reuses nbr.
+ *     k3 == 1 and nbr == NULL means the identity map (the K=1, stride=1 `use_mm` case).
+ *     impl: 0 = auto, 1 = SIMT fp32 reference kernel, 2 = tcgen05 kind::tf32 kernel.
+ * b2s_conv_wgrad       : gw[k] = sum_o x[nbr[k,o],:]^T gy[o,:]   (gw fp32 [K3, c_in, c_out])
+ * b2s_colsum           : out[c] = sum_rows x[r,c]                (bias gradient)
+ */
+B2S_API int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3);
+B2S_API int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
+                             int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
+                             void* workspace, int64_t workspace_bytes, int32_t impl, b2s_stream_t stream);
+B2S_API int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
+                       int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace,
+                       int64_t workspace_bytes, int32_t impl, b2s_stream_t stream);
+B2S_API int32_t b2s_colsum(const float* x, int64_t n, int32_t c, float* out, b2s_stream_t stream);
+
+/* ---------------------------------------------------------------- (a9) max pooling -----------
+ * R:modules/MinkowskiEngine/SENet.py:53.  y[o,c] = max_k x[nbr[k,o],c]; arg[o,c] = winning in-row
+ * (lowest row on ties, -1 if the out row has no neighbour -> y = 0).  bwd: gx[arg] += gy.
+ */
+B2S_API int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_out, int32_t c, int32_t k3, float* y,
+                        int32_t* arg, b2s_stream_t stream);
+B2S_API int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t n_in, int64_t n_out, int32_t c, float* gx,
+                        b2s_stream_t stream);
+
+/* ---------------------------------------------------------------- (a5,a10,a11) per-plot ops --
+ * R:modules/MinkowskiEngine/senet_block.py:43-50; common.py:44-48; SENet.py:63,117.
+ * row_batch points at the batch id of row 0 and is read with `row_batch_stride` int32s per row (the
+ * coords array itself: stride 4).  scale (nullable) is a per-plot factor, e.g. 1/count for average.
+ */
+B2S_API int32_t b2s_batch_counts(const int32_t* row_batch, int32_t row_batch_stride, int64_t n, int32_t num_batches,
+                         int32_t* counts, b2s_stream_t stream);
+B2S_API int32_t b2s_segment_sum(const float* x, const int32_t* row_batch, int32_t row_batch_stride, int64_t n, int32_t c,
+                        int32_t num_batches, const float* scale, float* y, b2s_stream_t stream);
+B2S_API int32_t b2s_segment_bcast(const float* y, const int32_t* row_batch, int32_t row_batch_stride, int64_t n, int32_t c,
+                          const float* scale, float* x_out, b2s_stream_t stream);
+B2S_API int32_t b2s_bcast_mul_fwd(const float* x, const float* y, const int32_t* row_batch, int32_t row_batch_stride,
+                          int64_t n, int32_t c, int32_t y_c, float* out, b2s_stream_t stream);
+B2S_API int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float* y, const int32_t* row_batch,
+                          int32_t row_batch_stride, int64_t n, int32_t c, int32_t num_batches, float* gx, float* gy,
+                          b2s_stream_t stream);
+
+/* ---------------------------------------------------------------- (a13,a14,a16) norm / act ---
+ * R:modules/MinkowskiEngine/SENet.py:35,51,98; resnet_block.py:51-56,65,73; common.py:41.
+ * bn_stats      : batch mean[c] and invstd[c] = 1/sqrt(biased var + eps) over n rows, and (if the
+ *                 pointers are non-null) the nn.BatchNorm1d running-statistics update
+ *                 running = (1-momentum)*running + momentum*stat with the UNBIASED variance.
+ *                 stats_ws = 2*c doubles of scratch.
+ * bn_apply      : y = (x-mean)*invstd*gamma+beta, act 0 = none, 1 = exact-erf GELU (fused).
+ *                 gamma / beta may be null (affine=False).
+ * bn_bwd_reduce : sums[0..c) = sum gy', sums[c..2c) = sum gy'*xhat  (gy' = gy through the fused act);
+ *                 these are also grad_beta and grad_gamma.
+ * bn_bwd_apply  : training: gx = gamma*invstd*(gy' - sums0/n - xhat*sums1/n); eval: gx = gamma*invstd*gy'.
+ * gelu_fwd/bwd  : exact erf GELU on a flat array.
+ */
+B2S_API int32_t b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
+                     float* running_var, double* stats_ws, float* mean, float* invstd, b2s_stream_t stream);
+B2S_API int32_t b2s_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                     int64_t n, int32_t c, int32_t act, float* y, b2s_stream_t stream);
+B2S_API int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const float* mean, const float* invstd,
+                          const float* gamma, const float* beta, int64_t n, int32_t c, int32_t act, double* stats_ws,
+                          float* sums, b2s_stream_t stream);
+B2S_API int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, const float* sums, int64_t n, int32_t c, int32_t act, int32_t training,
+                         float* gx, b2s_stream_t stream);
+B2S_API int32_t b2s_gelu_fwd(const float* x, int64_t numel, float* y, b2s_stream_t stream);
+B2S_API int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t numel, float* gx, b2s_stream_t stream);
+
+/* ---------------------------------------------------------------- optimiser ----
+ * R:core/optimizer/adabelief.py:90-201 over one flat fp32 parameter buffer, with GradScaler
+ * unscale (R:models/base_model.py:241), clip_grad_value_ (:243) and the inf/nan skip fused in.
+ * found_inf_dev[0] != 0 -> the step is skipped (GradScaler semantics).  hyper_host: see csrc/optim.cu.
+ */
+B2S_API int32_t b2s_grad_check(const float* grad, int64_t numel, float inv_scale, float* found_inf_dev, b2s_stream_t stream);
+B2S_API int32_t b2s_adabelief_step(float* param, const float* grad, float* exp_avg, float* exp_avg_var, int64_t numel,
+                           const float* hyper_host, const float* found_inf_dev, b2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPARSE_H_ */
