@@ -16,6 +16,23 @@ from dpcr_agb_b200 import lib as L
 # 0 = auto (tcgen05 where the shape qualifies, SIMT otherwise), 1 = force SIMT, 2 = force tcgen05
 CONV_IMPL = int(os.environ.get("B2S_CONV_IMPL", "0"))
 
+# bench.py sets this to a dict to collect ALGORITHMIC work per conv launch kind (pairs come from the neighbour
+# table: one device reduction + host sync per launch, so only ever enabled in an untimed statistics pass)
+WORK_STATS = None
+
+
+def _account(kind, nbr, n_rows, c_in, c_out, k3):
+    if WORK_STATS is None:
+        return
+    pairs = int((nbr >= 0).sum().item()) if nbr is not None else int(n_rows)
+    st = WORK_STATS.setdefault(kind, {"launches": 0, "pairs": 0, "flops": 0, "bytes": 0})
+    st["launches"] += 1
+    st["pairs"] += pairs
+    st["flops"] += 2 * pairs * c_in * c_out
+    # compulsory traffic: inputs + outputs + weights + int32 pair indices, each touched once
+    st["bytes"] += 4 * (n_rows * (c_in + c_out)) + 4 * k3 * c_in * c_out + 8 * pairs
+
+
 _fwd = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _bwd = custom_bwd(device_type="cuda")
 
@@ -30,6 +47,7 @@ def _ws(n_in, n_out, c_in, c_out, k3, device):
 def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None):
     """y[o] = bias + sum_k x[nbr[k,o]] @ B_k  (C ABI ``b2s_conv_gather_gemm``)."""
     y = torch.empty((n_out, c_out), dtype=torch.float32, device=x.device)
+    _account("dgrad" if (w_layout & 1) else "fwd", nbr, n_out, c_in, c_out, k3)
     ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device)
     L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, y, ws, nbytes,
            CONV_IMPL if impl is None else impl)
@@ -38,6 +56,7 @@ def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=No
 
 def wgrad(x, gy, nbr, n_in, n_out, c_in, c_out, k3, impl=None):
     gw = torch.empty((k3, c_in, c_out), dtype=torch.float32, device=x.device)
+    _account("wgrad", nbr, n_out, c_in, c_out, k3)
     L.call("b2s_conv_wgrad", x, gy, nbr, n_in, n_out, c_in, c_out, k3, gw, None, 0,
            CONV_IMPL if impl is None else impl)
     return gw

@@ -56,7 +56,27 @@ SIGNATURES = {
 
 _lib = None
 _checked_devices = set()
-launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it as gpu_launches' lower bound)
+launch_count = 0  # number of C-ABI compute calls issued (each launches >= 1 kernel of libb200sparse)
+
+# Optional per-entry-point CUDA-event timing (bench.py): name -> list of (start, end) events recorded on the
+# stream the kernels are launched on.  ``_profile_names`` None = every entry point.
+_profile = None
+_profile_names = None
+
+
+def profile_start(names=None):
+    global _profile, _profile_names
+    _profile, _profile_names = {}, (set(names) if names is not None else None)
+
+
+def profile_stop():
+    """Returns {key: (num_calls, total_ms)}; synchronises the device."""
+    global _profile
+    prof, _profile = _profile, None
+    if not prof:
+        return {}
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in prof.items()}
 
 
 class B2SError(RuntimeError):
@@ -121,7 +141,17 @@ def call(name: str, *args):
     lib = load()
     fn = getattr(lib, name)
     conv = [ptr(a) if (a is None or isinstance(a, (torch.Tensor, ctypes.Array))) else a for a in args]
-    rc = fn(*conv, stream())
+    if _profile is not None and (_profile_names is None or name in _profile_names):
+        key = name
+        if name == "b2s_conv_gather_gemm":            # w_layout bit 0 set == dgrad
+            key = name + (":dgrad" if (args[9] & 1) else ":fwd")
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = fn(*conv, stream())
+        ev1.record()
+        _profile.setdefault(key, []).append((ev0, ev1))
+    else:
+        rc = fn(*conv, stream())
     launch_count += 1
     if rc != 0:
         raise B2SError(f"{name} failed ({rc}): {lib.b2s_last_error().decode()}")

@@ -104,6 +104,30 @@ class CosineAnnealingWarmRestarts:
         return self.eta_min + (self.base_lr - self.eta_min) * (1 + math.cos(math.pi * t_cur / t_i)) / 2
 
 
+def shard_plots(weights, rank, world):
+    """Data-parallel partition of a global batch of plots: plots are independent samples, so
+    each rank takes a disjoint subset.  ``weights`` are per-plot work estimates (point or voxel counts);
+    plots are dealt heaviest-first to the currently lightest rank so per-rank work stays within a few %.
+    Returns the sorted list of plot indices owned by ``rank``."""
+    order = sorted(range(len(weights)), key=lambda i: (-float(weights[i]), i))
+    load = [0.0] * world
+    owner = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda j: (len(owner[j]) >= -(-len(weights) // world), load[j], j))
+        owner[r].append(i)
+        load[r] += float(weights[i])
+    return sorted(owner[rank])
+
+
+def allreduce_mean_(flat: torch.Tensor, world: int):
+    """The one exchange step of the path: sum a flat gradient buffer over ranks and average in place
+    (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.mul_(1.0 / world)
+    return flat
+
+
 class Trainer:
     """One optimisation step of MSENet on one GPU (rank); gradients are averaged across ranks."""
 
@@ -132,11 +156,7 @@ class Trainer:
         pred = self.model(x)
         loss = reg_loss(pred, target, self.center, self.scale)
         loss.backward()
-        if self.world > 1:
-            # the one exchange step of the path: sum the flat gradient over ranks (NCCL over NVLink), then
-            # average -- equivalent to DDP's bucketed all-reduce with a single bucket
-            dist.all_reduce(self.opt.flat_grad, op=dist.ReduceOp.SUM)
-            self.opt.flat_grad.mul_(1.0 / self.world)
+        allreduce_mean_(self.opt.flat_grad, self.world)   # == DDP's all-reduce with a single bucket
         self.num_batches += 1
         self.opt.lr = self.sched.lr_at(self.num_batches / self.batches_per_epoch)
         self.opt.step()

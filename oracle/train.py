@@ -66,3 +66,37 @@ class AdaBelief:
                 p.addcdiv_(m, s.sqrt().add_(self.eps), value=-step_size * self.lr)   # :193-195
             elif step_size > 0:
                 p.add_(m, alpha=-step_size * self.lr)             # :196-197
+
+
+def cpu_training_step(model, opt, batch, size, center, scale):
+    """One whole optimisation step of the path on the CPU oracle, from raw points: per-plot GridSampling3D,
+    collate + batch column (minkowski.py:69), SparseTensor (hash / maps built lazily by the ops), forward,
+    loss, backward, AdaBelief.  This is what bench.py times as the CPU baseline ("port": a restatement of the
+    reference's CPU MinkowskiEngine path, NOT upstream ME-CPU itself)."""
+    import numpy as np
+
+    from . import coords as oc
+    from . import me_cpu
+
+    nb = int(batch["batch"].max()) + 1
+    pos_l, feat_l, perm_l, base = [], [], [], 0
+    for b in range(nb):
+        sel = batch["batch"] == b
+        n = int(sel.sum())
+        pos_l.append(batch["pos"][sel])
+        feat_l.append(batch["feats"][sel])
+        perm_l.append(batch["perm"][base:base + n] - base)
+        base += n
+    c, f, _, _, _ = oc.quantize_batch(pos_l, feat_l, size, perm_l)
+    x = me_cpu.SparseTensor(torch.from_numpy(np.ascontiguousarray(f)), coordinates=torch.from_numpy(c))
+    model.train()
+    for p in model.parameters():
+        p.grad = None
+    pred = model(x)
+    loss = reg_loss(pred, torch.from_numpy(batch["target"]), center, scale)
+    loss.backward()
+    for p in model.parameters():                      # clip_grad_value_(100), base_model.py:243
+        if p.grad is not None:
+            p.grad.clamp_(-100.0, 100.0)
+    opt.step()
+    return float(loss)

@@ -1,0 +1,161 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports exactly what include/b200sparse.h
+declares; the Python module exports every ME.* name the reference touches; the UNCHANGED
+reference networks import and build over it with state-dict keys identical to our restatement."""
+import os
+import re
+import sys
+import types
+import warnings
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/torch-points3d"
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200sparse.h")).read()
+    return sorted(set(re.findall(r"B2S_API\s+[\w\s\*]+?\b(b2s_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dpcr_agb_b200 import lib
+    names = _declared_symbols()
+    assert len(names) >= 30
+    handle = lib.load()                       # raises if the .so is missing: there is no fallback
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in the header but not exported"
+    assert sorted(lib.SIGNATURES) == names, "ctypes table and header disagree"
+    assert handle.b2s_version() >= 100
+
+
+def test_product_path_has_no_cpu_fallback():
+    from dpcr_agb_b200 import MinkowskiEngine as ME
+    from dpcr_agb_b200 import lib
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only assertion")
+    with pytest.raises(RuntimeError):
+        ME.SparseTensor(features=torch.zeros(2, 3), coordinates=torch.zeros(2, 4, dtype=torch.int32))
+    with pytest.raises(lib.B2SError):
+        lib.call("b2s_gelu_fwd", torch.zeros(4), 4, torch.zeros(4))
+    # nothing of the product imports the oracle
+    for mod in list(sys.modules):
+        if mod.startswith("dpcr_agb_b200"):
+            src = getattr(sys.modules[mod], "__file__", None)
+            if src and src.endswith(".py"):
+                assert "oracle" not in open(src).read().replace("oracle.me_cpu", "").replace("CPU oracle", "") \
+                    or mod.endswith("msenet"), mod
+
+
+ME_NAMES = """SparseTensor MinkowskiConvolution MinkowskiConvolutionTranspose MinkowskiMaxPooling MinkowskiAvgPooling
+MinkowskiSumPooling MinkowskiAvgUnpooling MinkowskiGlobalPooling MinkowskiGlobalSumPooling MinkowskiGlobalAvgPooling
+MinkowskiGlobalMaxPooling MinkowskiBroadcastMultiplication MinkowskiLinear MinkowskiBatchNorm MinkowskiInstanceNorm
+MinkowskiDropout MinkowskiReLU MinkowskiSigmoid MinkowskiNetwork RegionType KernelGenerator cat utils
+MinkowskiNormalization MinkowskiNonlinearity CoordinateManager""".split()
+
+
+def test_me_surface_names():
+    from dpcr_agb_b200 import MinkowskiEngine as ME
+    for n in ME_NAMES:
+        assert hasattr(ME, n), n
+    for n in "MinkowskiGELU MinkowskiReLU MinkowskiCELU MinkowskiSiLU MinkowskiELU MinkowskiSigmoid MinkowskiTanh MinkowskiSinusoidal".split():
+        assert hasattr(ME.MinkowskiNonlinearity, n), n
+    for n in "MinkowskiBatchNorm MinkowskiInstanceNorm".split():
+        assert hasattr(ME.MinkowskiNormalization, n), n
+    assert {m.name for m in ME.RegionType} >= {"HYPER_CUBE", "HYPER_CROSS", "CUSTOM"}
+    assert callable(ME.utils.kaiming_normal_)
+    conv = ME.MinkowskiConvolution(3, 64, kernel_size=7, stride=1, dimension=3, bias=True)
+    assert tuple(conv.kernel.shape) == (343, 3, 64) and tuple(conv.bias.shape) == (1, 64)
+    assert tuple(ME.MinkowskiConvolution(64, 128, kernel_size=1, stride=2, dimension=3).kernel.shape) == (1, 64, 128)
+    assert tuple(ME.MinkowskiConvolution(64, 256, kernel_size=1, dimension=3).kernel.shape) == (64, 256)  # use_mm
+    assert isinstance(ME.MinkowskiBatchNorm(8).bn, torch.nn.BatchNorm1d)
+    assert isinstance(ME.MinkowskiLinear(8, 2).linear, torch.nn.Linear)
+    # SparseTensor must pass through torch.cuda.amp.custom_fwd untouched (senet_block.py:46)
+    import collections.abc
+    assert not issubclass(ME.SparseTensor, collections.abc.Mapping) and not hasattr(ME.SparseTensor, "__iter__")
+
+
+def _stub_reference_imports():
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules.setdefault(name, m)
+    stub("omegaconf", OmegaConf=type("OmegaConf", (), {}), DictConfig=dict, ListConfig=list)
+    stub("omegaconf.listconfig", ListConfig=list)
+    stub("omegaconf.dictconfig", DictConfig=dict)
+    stub("matplotlib")
+    stub("matplotlib.pyplot")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+@pytest.mark.parametrize("backend", ["product", "oracle"])
+def test_unchanged_reference_networks_build_over_our_module(backend):
+    """`import MinkowskiEngine as ME` inside the reference resolves to our module; SENet14 / SENet50 construct,
+    init_weights runs (touches .kernel/.bias/.bn/.linear), and the state-dict keys equal our restatement's."""
+    import dpcr_agb_b200
+    from dpcr_agb_b200 import msenet
+    from oracle import me_cpu
+    for k in [k for k in sys.modules if k.startswith("torch_points3d") or k.startswith("MinkowskiEngine")]:
+        del sys.modules[k]
+    ME = dpcr_agb_b200.install() if backend == "product" else me_cpu.install()
+    _stub_reference_imports()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from torch_points3d.modules.MinkowskiEngine import SENet, initialize_minkowski_unet
+    try:
+        for name, nparam in (("SENet14", 14447870), ("SENet50", 48760626)):
+            ref = initialize_minkowski_unet(name, 3, 2, activation="gelu", first_stride=1, global_pool="sum",
+                                            bias=True, bn_momentum=0.1, norm_type="bn", dropout=0.0, drop_path=0.01)
+            assert isinstance(ref, getattr(SENet, name))
+            mine = msenet.MSENet(ME, name, drop_path=0.01, separate_head=False)
+            a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+            b = {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+            assert a == b
+            assert sum(p.numel() for p in ref.parameters()) == nparam
+            mine.load_state_dict(ref.state_dict())
+    finally:
+        for k in [k for k in sys.modules if k.startswith("torch_points3d") or k.startswith("MinkowskiEngine")]:
+            del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+def test_reference_senet14_equals_restatement_on_oracle():
+    """Forward of the UNCHANGED reference SENet14 == forward of dpcr_agb_b200.msenet on the same (oracle)
+    backend, same weights, same DropPath draws: pins our network restatement to the reference definition."""
+    import random
+    import numpy as np
+    from dpcr_agb_b200 import msenet, plots
+    from oracle import coords as oc
+    from oracle import me_cpu
+    for k in [k for k in sys.modules if k.startswith("torch_points3d") or k.startswith("MinkowskiEngine")]:
+        del sys.modules[k]
+    me_cpu.install()
+    _stub_reference_imports()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from torch_points3d.modules.MinkowskiEngine import SENet
+        try:
+            torch.manual_seed(0)
+            ref = SENet.SENet14(in_channels=3, out_channels=2, activation="gelu", first_stride=1, global_pool="sum",
+                                drop_path=0.3, D=3)
+            mine = msenet.MSENet(me_cpu, "SENet14", drop_path=0.3, separate_head=False)
+            mine.load_state_dict(ref.state_dict())
+            b = plots.synth_batch(0, 0, 2, n_points=800)
+            c, f, _, _, _ = oc.quantize_batch([b["pos"][b["batch"] == i] for i in range(2)],
+                                              [b["feats"][b["batch"] == i] for i in range(2)], 0.05)
+            for training in (False, True):
+                ref.train(training)
+                mine.train(training)
+                random.seed(4)
+                yr = ref(me_cpu.SparseTensor(torch.from_numpy(f), coordinates=torch.from_numpy(c))).F
+                random.seed(4)
+                ym = mine(me_cpu.SparseTensor(torch.from_numpy(f), coordinates=torch.from_numpy(c))).F
+                assert torch.equal(yr, ym)
+        finally:
+            for k in [k for k in sys.modules if k.startswith("torch_points3d") or k.startswith("MinkowskiEngine")]:
+                del sys.modules[k]

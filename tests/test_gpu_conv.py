@@ -1,0 +1,127 @@
+"""GPU parity of the convolution kernels (a6-a8) against the oracle, SIMT and tcgen05 paths, through
+the C ABI.  Tolerance: 1e-3 relative (max|a-b| / max|b|), the fp32/TF32 bar of BASELINE.json."""
+import numpy as np
+import pytest
+import torch
+
+from dpcr_agb_b200 import lib as L
+from dpcr_agb_b200.MinkowskiEngine import functional as Fn
+from oracle import coords as oc
+from oracle import ops as oo
+import b2s_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+SIMT, TC = 1, 2
+
+
+def _maps(n, nb=2, extent=9, seed=0, K=3, strided=False):
+    rng = np.random.default_rng(seed)
+    c = util.random_coords(rng, n, nb=nb, extent=extent)
+    if strided:
+        out, _ = oc.stride_map(c, (2, 2, 2))
+    else:
+        out = c
+    nbr = oc.kernel_map_table(c, out, K, (1, 1, 1))
+    return c, out, nbr
+
+
+def _run_fwd(x, w, b, nbr, n_in, n_out, impl, dev):
+    xg, wg = torch.from_numpy(x).to(dev), torch.from_numpy(w).to(dev)
+    bg = torch.from_numpy(b).to(dev) if b is not None else None
+    ng = torch.from_numpy(nbr).to(dev) if nbr is not None else None
+    k3 = 1 if nbr is None else nbr.shape[0]
+    return Fn.gather_gemm(xg, wg, bg, ng, n_in, n_out, w.shape[-2], w.shape[-1], k3, 0, impl=impl)
+
+
+@pytest.mark.parametrize("impl", [SIMT, TC])
+@pytest.mark.parametrize("n,cin,cout,K,strided", [
+    (700, 64, 64, 3, False),       # layer1 shape
+    (1500, 64, 128, 3, True),      # strided conv
+    (300, 128, 256, 3, False),
+    (130, 256, 512, 3, False),     # two N tiles of 256
+    (1000, 3, 64, 7, False),       # the k7 stem (SMALL mode)
+    (129, 32, 64, 1, False),       # one row past a tile boundary
+])
+def test_conv_forward(cuda, impl, n, cin, cout, K, strided):
+    c, out, nbr = _maps(n, K=K, strided=strided, extent=7 if K == 7 else 9)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((c.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((K ** 3, cin, cout)) * 0.05).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    ref = oo.conv(torch.from_numpy(x).double(), torch.from_numpy(w).double(), nbr, torch.from_numpy(b).double())
+    got = _run_fwd(x, w, b, nbr, c.shape[0], out.shape[0], impl, cuda)
+    util.assert_close(got, ref, what=f"conv fwd impl={impl}")
+    if impl == SIMT:   # fp32 SIMT must be far tighter than the TF32 bar
+        util.assert_close(got, ref, tol=2e-5, what="conv fwd simt fp32")
+
+
+@pytest.mark.parametrize("impl", [SIMT, TC])
+def test_conv_use_mm_identity_map(cuda, impl):
+    rng = np.random.default_rng(2)
+    n, cin, cout = 777, 256, 64
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    w = (rng.standard_normal((1, cin, cout)) * 0.05).astype(np.float32)
+    got = _run_fwd(x, w, None, None, n, n, impl, cuda)
+    util.assert_close(got, torch.from_numpy(x).double() @ torch.from_numpy(w[0]).double(), what="use_mm")
+
+
+@pytest.mark.parametrize("impl", [SIMT, TC])
+@pytest.mark.parametrize("n,cin,cout,strided", [(900, 64, 64, False), (1200, 64, 128, True), (200, 128, 256, False)])
+def test_conv_backward(cuda, impl, n, cin, cout, strided):
+    """dgrad and wgrad through the autograd Function, against autograd of the oracle."""
+    from dpcr_agb_b200.MinkowskiEngine.coordinate_manager import CoordinateManager
+    c, out, nbr = _maps(n, strided=strided, seed=5)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((c.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) * 0.05).astype(np.float32)
+    b = rng.standard_normal((1, cout)).astype(np.float32)
+    gy = rng.standard_normal((out.shape[0], cout)).astype(np.float32)
+
+    xr = torch.from_numpy(x).double().requires_grad_()
+    wr = torch.from_numpy(w).double().requires_grad_()
+    br = torch.from_numpy(b).double().requires_grad_()
+    oo.conv(xr, wr, nbr, br).backward(torch.from_numpy(gy).double())
+
+    cm = CoordinateManager(D=3, device=cuda)
+    key, _ = cm.insert(torch.from_numpy(c).to(cuda))
+    out_key = cm.stride(key, 2) if strided else key
+    assert np.array_equal(cm.coords(out_key).cpu().numpy(), out)
+    km = cm.kernel_map(key, out_key, 3)
+    old = Fn.CONV_IMPL
+    Fn.CONV_IMPL = impl if impl == SIMT else 0     # auto: tcgen05 where covered (wgrad may still be SIMT)
+    try:
+        xg = torch.from_numpy(x).to(cuda).requires_grad_()
+        wg = torch.from_numpy(w).to(cuda).requires_grad_()
+        bg = torch.from_numpy(b).to(cuda).requires_grad_()
+        y = Fn.ConvolutionFunction.apply(xg, wg, bg, km)
+        y.backward(torch.from_numpy(gy).to(cuda))
+    finally:
+        Fn.CONV_IMPL = old
+    util.assert_close(xg.grad, xr.grad, what="dgrad")
+    util.assert_close(wg.grad, wr.grad, what="wgrad")
+    util.assert_close(bg.grad, br.grad, what="bias grad")
+
+
+def test_stem_wgrad_small_cin(cuda):
+    c, out, nbr = _maps(1500, K=7, extent=7, seed=8)
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((c.shape[0], 3)).astype(np.float32)
+    gy = rng.standard_normal((c.shape[0], 64)).astype(np.float32)
+    xr = torch.from_numpy(x).double()
+    wr = torch.zeros((343, 3, 64), dtype=torch.float64, requires_grad=True)
+    oo.conv(xr, wr, nbr).backward(torch.from_numpy(gy).double())
+    n = c.shape[0]
+    got = Fn.wgrad(torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda), torch.from_numpy(nbr).to(cuda),
+                   n, n, 3, 64, 343)
+    util.assert_close(got, wr.grad, what="stem wgrad")
+
+
+def test_conv_rejects_bad_arguments(cuda):
+    x = torch.zeros((4, 8), device=cuda)
+    w = torch.zeros((27, 8, 8), device=cuda)
+    y = torch.zeros((4, 8), device=cuda)
+    with pytest.raises(L.B2SError):   # nbr may be null only for k3 == 1
+        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, 8, 8, 27, 0, y, None, 0, 1)
+    with pytest.raises(L.B2SError):   # tcgen05 kernel does not cover c_out = 8
+        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, 8, 8, 1, 0, y, None, 0, 2)

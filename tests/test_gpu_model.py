@@ -1,0 +1,163 @@
+"""End-to-end GPU parity: MSENet14 / MSENet50 forward + backward through the ME-shaped surface against the
+same network over the CPU oracle; fused AdaBelief against the oracle's restatement; full-size
+(16 000-point plots, batch of 4) size-independent properties."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from dpcr_agb_b200 import MinkowskiEngine as ME
+from dpcr_agb_b200 import msenet, plots, train
+from dpcr_agb_b200.quantize import GridSampling3D
+from oracle import me_cpu
+from oracle import train as otrain
+import b2s_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(name, seed=0, **kw):
+    torch.manual_seed(seed)
+    ref = msenet.MSENet(me_cpu, name, **kw)
+    mine = msenet.MSENet(ME, name, **kw)
+    mine.load_state_dict(ref.state_dict())
+    return ref, mine
+
+
+def _grad_check(mine, ref):
+    gmax = max(p.grad.abs().max().item() for p in ref.parameters() if p.grad is not None)
+    worst = 0.0
+    for (n1, p1), (n2, p2) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert n1 == n2
+        if p2.grad is None:
+            assert p1.grad is None or p1.grad.abs().max().item() == 0.0, n1
+            continue
+        err = (p1.grad.detach().cpu().double() - p2.grad.double()).abs().max().item()
+        bound = util.REL_TOL * p2.grad.abs().max().item() + 2e-5 * gmax
+        assert err <= bound, f"grad of {n1}: abs err {err:.3e} > {bound:.3e}"
+        worst = max(worst, err / (p2.grad.abs().max().item() + 1e-30))
+    return worst
+
+
+@pytest.mark.parametrize("name,n_points,size", [("SENet14", 1500, 0.05), ("SENet50", 1200, 0.05)])
+@pytest.mark.parametrize("training", [True, False])
+def test_msenet_forward_backward(cuda, name, n_points, size, training):
+    batch = util.make_points(3, n_points)
+    c, f, _, _, _ = util.oracle_quantize(batch, size)
+    ref, mine = _pair(name, drop_path=0.2)
+    mine = mine.to(cuda)
+    ref.train(training)
+    mine.train(training)
+    target = torch.from_numpy(batch["target"])
+    center, scale = torch.tensor([107.0, 200.0]), torch.tensor([103.0, 194.0])
+
+    random.seed(11)
+    yr = ref(me_cpu.SparseTensor(torch.from_numpy(f), coordinates=torch.from_numpy(c)))
+    lr = otrain.reg_loss(yr, target, center, scale)
+    lr.backward()
+    random.seed(11)
+    ym = mine(ME.SparseTensor(features=torch.from_numpy(f), coordinates=torch.from_numpy(c), device=cuda))
+    lm = train.reg_loss(ym, target.to(cuda), center.to(cuda), scale.to(cuda))
+    lm.backward()
+    util.assert_close(ym, yr, what=f"{name} output")
+    util.assert_close(lm, lr, what=f"{name} loss")
+    _grad_check(mine, ref)
+    if training:   # BN running statistics followed the same batches
+        for (n1, b1), (n2, b2) in zip(mine.named_buffers(), ref.named_buffers()):
+            if b2.dtype.is_floating_point:
+                util.assert_close(b1, b2, what=f"buffer {n1}")
+            else:
+                assert int(b1) == int(b2)
+
+
+def test_state_dict_round_trip_and_names(cuda):
+    ref, mine = _pair("SENet14")
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    assert "blocks.0.0.conv.kernel" in mine.state_dict() and "blocks.2.0.downsample.1.bn.weight" in mine.state_dict()
+    assert tuple(mine.state_dict()["blocks.0.0.conv.kernel"].shape) == (343, 3, 64)
+    assert tuple(mine.state_dict()["blocks.2.0.downsample.0.kernel"].shape) == (1, 64, 128)
+
+
+def test_fused_adabelief_matches_oracle(cuda):
+    torch.manual_seed(0)
+    shapes = [(27, 8, 16), (1, 16), (16,), (5, 7)]
+    ps_ref = [torch.randn(s) for s in shapes]
+    ps_gpu = [p.clone().to(cuda).requires_grad_() for p in ps_ref]
+    for p in ps_ref:
+        p.requires_grad_()
+    oref = otrain.AdaBelief(ps_ref, lr=5e-3, weight_decay=1e-2)
+    ogpu = train.FlatAdaBelief(ps_gpu, lr=5e-3, weight_decay=1e-2, grad_clip=100.0)
+    for step in range(12):        # crosses the num_sma >= 5 switch (step 6)
+        for pr, pg in zip(ps_ref, ps_gpu):
+            g = torch.randn(pr.shape) * (200.0 if step == 3 else 1.0)     # step 3 exercises the clip
+            pr.grad = g.clamp(-100.0, 100.0)
+            pg.grad.copy_(g.to(cuda))
+        oref.step()
+        ogpu.step()
+        for pr, pg in zip(ps_ref, ps_gpu):
+            util.assert_close(pg, pr, tol=2e-6, what=f"param after step {step}")
+    # inf skip (GradScaler semantics)
+    before = ogpu.flat_param.clone()
+    ogpu.flat_grad[3] = float("inf")
+    ogpu.step(check_inf=True)
+    assert torch.equal(before, ogpu.flat_param)
+
+
+def test_trainer_steps_reduce_loss(cuda):
+    """Three optimisation steps on one small batch through the public Trainer; loss must go down and stay
+    finite (the functional smoke of the whole path: quantise -> hash -> maps -> convs -> optimiser)."""
+    batch = util.make_points(4, 2000, cfg=9)
+    gs = GridSampling3D(0.0125)
+    out = gs(torch.from_numpy(batch["pos"]).to(cuda), torch.from_numpy(batch["batch"]).to(cuda),
+             tensors=(torch.from_numpy(batch["feats"]).to(cuda),), order=torch.from_numpy(batch["perm"]).to(cuda))
+    torch.manual_seed(0)
+    model = msenet.build(ME, "SENet14", drop_path=0.0).to(cuda)
+    tr = train.Trainer(model, ME, lr=2e-4)
+    before = tr.opt.flat_param.clone()
+    target = torch.from_numpy(batch["target"]).to(cuda)
+    losses = [float(tr.step(out["coords"], out["tensors"][0], target)) for _ in range(6)]
+    assert all(np.isfinite(losses)), losses
+    assert min(losses[1:]) < losses[0], losses
+    assert not torch.equal(before, tr.opt.flat_param)
+
+
+def test_full_size_properties(cuda):
+    """BASELINE-size plots (16 000 points, 0.0125 grid): properties that need no oracle run."""
+    batch = util.make_points(4, 16000, cfg=2)
+    gs = GridSampling3D(0.0125)
+    out = gs(torch.from_numpy(batch["pos"]).to(cuda), torch.from_numpy(batch["batch"]).to(cuda),
+             tensors=(torch.from_numpy(batch["feats"]).to(cuda),), order=torch.from_numpy(batch["perm"]).to(cuda))
+    coords = out["coords"]
+    # (1) quantise is idempotent on its own representatives and sorted by (plot, z, y, x)
+    c = coords.cpu().numpy().astype(np.int64)
+    key = ((c[:, 0] * 4096 + c[:, 3]) * 4096 + c[:, 2]) * 4096 + c[:, 1]
+    assert np.all(np.diff(key) > 0)
+    # (2) every voxel's representative maps back to the voxel
+    q = np.rint(batch["pos"][out["src"].cpu().numpy()] / np.float32(0.0125)).astype(np.int32)
+    assert np.array_equal(q, coords.cpu().numpy()[:, 1:])
+    x = ME.SparseTensor(features=out["tensors"][0], coordinates=coords)
+    cm = x.coordinate_manager
+    k1 = x.coordinate_map_key
+    k2 = cm.stride(k1, 2)
+    # (3) strided map: floor of every fine row exists exactly once in the coarse map
+    fine = cm.coords(k1)
+    coarse = cm.coords(k2)
+    fl = fine.clone()
+    fl[:, 1:] = torch.div(fine[:, 1:], 2, rounding_mode="floor") * 2
+    assert torch.unique(fl, dim=0).shape[0] == coarse.shape[0]
+    assert torch.unique(coarse, dim=0).shape[0] == coarse.shape[0]
+    # (4) kernel-map symmetry and centre tap on the stem map (343 offsets)
+    km = cm.kernel_map(k1, k1, 7)
+    n = km.n_out
+    assert torch.equal(km.nbr[171], torch.arange(n, device=cuda, dtype=torch.int32))      # centre offset
+    for k in (0, 100, 250):
+        o = torch.nonzero(km.nbr[k] >= 0).squeeze(1)
+        assert torch.equal(km.nbr[342 - k][km.nbr[k][o].long()].long(), o)
+    # (5) conv linearity on the full-size map: conv(a x1 + x2) = a conv(x1) + conv(x2)
+    conv = ME.MinkowskiConvolution(3, 64, kernel_size=7, stride=1, dimension=3, bias=False).to(cuda)
+    f1, f2 = out["tensors"][0], torch.randn_like(out["tensors"][0])
+    y1 = conv(ME.SparseTensor(f1, coordinate_map_key=k1, coordinate_manager=cm)).F
+    y2 = conv(ME.SparseTensor(f2, coordinate_map_key=k1, coordinate_manager=cm)).F
+    y3 = conv(ME.SparseTensor(2.0 * f1 + f2, coordinate_map_key=k1, coordinate_manager=cm)).F
+    util.assert_close(y3, 2.0 * y1 + y2, tol=2e-3, what="linearity")

@@ -1,0 +1,148 @@
+"""CPU tests of the oracle itself: hand-derived small cases, the golden fixtures, and hypothesis
+properties of the integer stages (SURVEY.md section 4 test plan (i) and (iii))."""
+import os
+
+import numpy as np
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import coords as oc
+from oracle import me_cpu
+from oracle import ops as oo
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_quantize_matches_torch_expression_fixture():
+    """grid_transform.py:116 evaluated by torch CPU (fixture made by tests/golden/make_golden.py)."""
+    d = np.load(os.path.join(GOLD, "gridsampling_ref.npz"))
+    got = oc.quantize_points(d["pos"], float(d["size"]))
+    assert np.array_equal(got, d["coords"])
+    # and live against torch, including half-way cases in both directions
+    pos = torch.tensor([[0.00625, 0.01875, 0.03125], [0.04375, -0.00625, 1.0]], dtype=torch.float32)
+    assert np.array_equal(oc.quantize_points(pos.numpy(), 0.0125), torch.round(pos / 0.0125).numpy())
+
+
+def test_quantize_plot_hand_case():
+    # size 1: points 0,1 share voxel (0,0,0); 2 alone in (1,0,0); 3,4 share (0,0,1)
+    pos = np.array([[0.1, 0.2, 0.0], [0.4, -0.3, 0.2], [1.2, 0.0, 0.1], [0.0, 0.1, 0.9], [-0.2, 0.3, 1.1]], np.float32)
+    feats = np.arange(5, dtype=np.float32)[:, None]
+    coords, f, p, src = oc.quantize_plot(pos, feats, 1.0, None)
+    # sorted by (z, y, x); representative = last point of the voxel in the (identity) shuffled order
+    assert coords.tolist() == [[0, 0, 0], [1, 0, 0], [0, 0, 1]]
+    assert src.tolist() == [1, 2, 4] and f[:, 0].tolist() == [1.0, 2.0, 4.0]
+    # with a permutation the representative is the last in SHUFFLED order: perm = [4,3,2,1,0] -> 0 wins over 1
+    coords2, f2, _, src2 = oc.quantize_plot(pos, feats, 1.0, np.array([4, 3, 2, 1, 0]))
+    assert coords2.tolist() == coords.tolist() and src2.tolist() == [0, 2, 3]
+
+
+def test_stride_map_hand_case():
+    c = np.array([[0, 0, 0, 0], [0, 1, 0, 0], [0, 2, 0, 0], [0, -1, 0, 0], [1, 3, 3, -3], [0, 3, 0, 0]], np.int32)
+    out, inv = oc.stride_map(c, (2, 2, 2))
+    # floor toward -inf: -1 -> -2, -3 -> -4; first-occurrence order
+    assert out.tolist() == [[0, 0, 0, 0], [0, 2, 0, 0], [0, -2, 0, 0], [1, 2, 2, -4]]
+    assert inv.tolist() == [0, 0, 1, 2, 3, 1]
+
+
+def test_kernel_map_and_conv_hand_case():
+    # three voxels in a row along x (batch 0) and one isolated voxel in batch 1
+    c = np.array([[0, 0, 0, 0], [0, 1, 0, 0], [0, 2, 0, 0], [1, 1, 0, 0]], np.int32)
+    nbr = oc.kernel_map_table(c, c, 3, (1, 1, 1))
+    assert nbr.shape == (27, 4)
+    centre, left, right = 13, 12, 14                       # k = ix + 3 iy + 9 iz with (dx,dy,dz) = (ix-1, ...)
+    assert nbr[centre].tolist() == [0, 1, 2, 3]
+    assert nbr[left].tolist() == [-1, 0, 1, -1]            # in = out + (-1,0,0)
+    assert nbr[right].tolist() == [1, 2, -1, -1]
+    assert (nbr >= 0).sum() == 4 + 2 + 2
+    i, o, off = oc.table_to_pairs(nbr)
+    assert off[-1] == 8 and off[left] == 0 and off[centre] == 2 and off[right] == 6
+    assert i[:2].tolist() == [0, 1] and o[:2].tolist() == [1, 2]
+    # conv with W[k] = k * I : out[o] = sum_k k * x[nbr[k,o]]
+    x = torch.tensor([[1.0], [10.0], [100.0], [7.0]])
+    w = torch.arange(27, dtype=torch.float32).view(27, 1, 1)
+    y = oo.conv(x, w, nbr)
+    assert y[:, 0].tolist() == [13 * 1 + 14 * 10, 12 * 1 + 13 * 10 + 14 * 100, 12 * 10 + 13 * 100, 13 * 7]
+    # strided map: out coords floor to multiples of 2; the k1 s2 "downsample" map has pairs only where the out
+    # coordinate itself exists in the in map
+    out, _ = oc.stride_map(c, (2, 2, 2))
+    k1 = oc.kernel_map_table(c, out, 1, (1, 1, 1))
+    assert out.tolist() == [[0, 0, 0, 0], [0, 2, 0, 0], [1, 0, 0, 0]] and k1.tolist() == [[0, 2, -1]]
+
+
+def test_max_pool_ties_and_gradient():
+    nbr = np.array([[0, 2], [1, -1]], np.int32)            # out0 <- {0,1}, out1 <- {2}
+    x = torch.tensor([[1.0, 5.0], [1.0, 7.0], [3.0, 4.0]], requires_grad=True)
+    y = oo.max_pool(x, nbr)
+    assert y.tolist() == [[1.0, 7.0], [3.0, 4.0]]
+    y.sum().backward()
+    assert x.grad.tolist() == [[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]]   # tie in column 0 -> lowest in-row
+
+
+def test_msenet14_oracle_fixture():
+    """The committed golden input/output pair still reproduces (guards the oracle against drift)."""
+    from dpcr_agb_b200 import msenet
+    d = np.load(os.path.join(GOLD, "msenet14_oracle.npz"))
+    pos_l = [d["pos"][d["batch"] == b] for b in range(2)]
+    feat_l = [d["feats"][d["batch"] == b] for b in range(2)]
+    perm_l = [d["perm"][:1200], d["perm"][1200:] - 1200]
+    c, f, _, s, _ = oc.quantize_batch(pos_l, feat_l, 0.05, perm_l)
+    assert np.array_equal(c, d["coords"]) and np.array_equal(s, d["src"]) and np.array_equal(f, d["vox_feats"])
+    cur = c
+    for ts in (2, 4, 8, 16):
+        cur, _ = oc.stride_map(cur, (ts,) * 3)
+        assert np.array_equal(cur, d[f"ts{ts}"])
+    assert np.array_equal((oc.kernel_map_table(c, c, 7, (1, 1, 1)) >= 0).sum(1), d["stem_pairs"])
+    assert np.array_equal(oc.kernel_map_table(c, d["ts2"], 3, (1, 1, 1)), d["pool_nbr"])
+    torch.manual_seed(0)
+    net = msenet.MSENet(me_cpu, "SENet14", drop_path=0.0).eval()
+    with torch.no_grad():
+        y = net(me_cpu.SparseTensor(torch.from_numpy(f), coordinates=torch.from_numpy(c))).numpy()
+    assert np.allclose(y, d["output"], rtol=1e-4, atol=1e-5)
+
+
+coord_lists = st.lists(st.tuples(st.integers(0, 2), st.integers(-9, 9), st.integers(-9, 9), st.integers(-9, 9)),
+                       min_size=1, max_size=60, unique=True)
+
+
+@settings(max_examples=60, deadline=None)
+@given(coord_lists, st.sampled_from([1, 2, 3, 5]))
+def test_kernel_map_properties(rows, K):
+    c = np.asarray(rows, np.int32)
+    nbr = oc.kernel_map_table(c, c, K, (1, 1, 1))
+    offs = oc.kernel_offsets(K, (1, 1, 1))
+    k3 = K ** 3
+    for k in range(k3):
+        o = np.nonzero(nbr[k] >= 0)[0]
+        # definition: in = out + delta, same batch
+        assert np.array_equal(c[nbr[k, o]][:, 1:], c[o][:, 1:] + offs[k])
+        assert np.array_equal(c[nbr[k, o]][:, 0], c[o][:, 0])
+        if K % 2 == 1:   # point symmetry of stride-1 odd kernels (used by dgrad)
+            assert np.array_equal(nbr[k3 - 1 - k][nbr[k, o]], o)
+    if K % 2 == 1:
+        assert np.array_equal(nbr[k3 // 2], np.arange(c.shape[0]))
+    # brute-force pair count
+    keys = {tuple(r) for r in rows}
+    want = sum((r[0], r[1] + d[0], r[2] + d[1], r[3] + d[2]) in keys for r in rows for d in offs.tolist())
+    assert int((nbr >= 0).sum()) == want
+
+
+@settings(max_examples=60, deadline=None)
+@given(coord_lists, st.sampled_from([2, 4]))
+def test_stride_map_properties(rows, ts):
+    c = np.asarray(rows, np.int32)
+    out, inv = oc.stride_map(c, (ts,) * 3)
+    assert np.all(out[:, 1:] % ts == 0)
+    assert len({tuple(r) for r in out.tolist()}) == out.shape[0]
+    fl = c.copy()
+    fl[:, 1:] = np.floor_divide(c[:, 1:], ts) * ts
+    assert np.array_equal(out[inv], fl)
+    first = [np.nonzero(inv == j)[0][0] for j in range(out.shape[0])]
+    assert first == sorted(first)                            # first-occurrence order
+    # transposed table is the inverse relation of the forward strided table
+    fwd = oc.kernel_map_table(c, out, 3, (ts // 2 if ts > 1 else 1,) * 3)
+    tr = oc.kernel_map_table(out, c, 3, (ts // 2 if ts > 1 else 1,) * 3, sign=-1)
+    for k in range(27):
+        o = np.nonzero(fwd[k] >= 0)[0]
+        assert np.array_equal(tr[k][fwd[k, o]], o)
+    assert int((fwd >= 0).sum()) == int((tr >= 0).sum())
