@@ -18,6 +18,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "roundup_power2_divisions:8")  # row counts differ every step: bucket sizes so cached blocks are reused
 import subprocess
 import sys
 import tempfile

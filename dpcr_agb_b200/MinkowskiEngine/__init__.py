@@ -17,3 +17,15 @@ from . import MinkowskiNonlinearity, MinkowskiNormalization, utils  # noqa: F401
 from . import functional as MinkowskiFunctional  # noqa: F401
 
 __version__ = "0.5.4+b200"
+
+# Extensions beyond the MinkowskiEngine surface, used by dpcr_agb_b200.msenet when present (the unchanged
+# reference networks never touch them): MinkowskiBatchNorm.forward(x, act=1) fuses the exact GELU into the
+# batch-norm apply kernel, fused_add_gelu(x, y) is the residual join act(x + y) as one kernel.
+B200_FUSED_OPS = True
+
+
+def fused_add_gelu(x, y):
+    assert x._same_map(y), "fused_add_gelu needs both tensors on the same coordinate map"
+    if x.F.numel() % 4:
+        return x._wrap(MinkowskiFunctional.GELUFunction.apply(x.F + y.F))
+    return x._wrap(MinkowskiFunctional.AddGELUFunction.apply(x.F, y.F))

@@ -57,7 +57,8 @@ def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=No
 def wgrad(x, gy, nbr, n_in, n_out, c_in, c_out, k3, impl=None):
     gw = torch.empty((k3, c_in, c_out), dtype=torch.float32, device=x.device)
     _account("wgrad", nbr, n_out, c_in, c_out, k3)
-    L.call("b2s_conv_wgrad", x, gy, nbr, n_in, n_out, c_in, c_out, k3, gw, None, 0,
+    ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device) if c_in <= 4 else (None, 0)
+    L.call("b2s_conv_wgrad", x, gy, nbr, n_in, n_out, c_in, c_out, k3, gw, ws, nbytes,
            CONV_IMPL if impl is None else impl)
     return gw
 
@@ -250,3 +251,25 @@ class GELUFunction(torch.autograd.Function):
         gx = torch.empty_like(x)
         L.call("b2s_gelu_bwd", gy.contiguous(), x, x.numel(), gx)
         return gx
+
+
+class AddGELUFunction(torch.autograd.Function):
+    """Residual join ``act(a + b)`` of every block (senet_block.py:93-94) as one kernel; the sum is kept for the
+    backward, which is a single GELU-gradient kernel shared by both addends."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        s, y = torch.empty_like(a), torch.empty_like(a)
+        L.call("b2s_add_gelu_fwd", a, b, a.numel(), s, y)
+        ctx.save_for_backward(s)
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy):
+        (s,) = ctx.saved_tensors
+        g = torch.empty_like(s)
+        L.call("b2s_gelu_bwd", gy.contiguous(), s, s.numel(), g)
+        return g, g

@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
       const int kw = (w_layout & 2) ? k3 - 1 - k : k;  // bit 1: kernel index reversed (symmetric maps)
       v = !(w_layout & 1) ? w[((int64_t)kw * c_in + ci) * c_out + n] : w[((int64_t)kw * c_out + n) * c_in + ci];
     }
-    img[e] = v;
+    // round-to-nearest to TF32 here: whatever the tensor core does with the low 13 mantissa bits of B is then a no-op
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    img[e] = __uint_as_float(r);
   }
 }
 

@@ -38,13 +38,16 @@ int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                             int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
                             void* workspace, int64_t workspace_bytes, cudaStream_t st);
-bool b2s_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_out);
-int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_out, int32_t c_in, int32_t c_out,
-                      int32_t k3, float* gw, cudaStream_t st);
+bool b2s_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_out, bool has_map);
+int64_t b2s_wgrad_tc_workspace_bytes(int32_t c_in, int64_t n_in);
+int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out, int32_t c_in,
+                      int32_t c_out, int32_t k3, float* gw, void* workspace, cudaStream_t st);
 
 extern "C" int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3) {
   if (c_in <= 0 || c_out <= 0 || k3 <= 0 || n_in < 0 || n_out < 0) return -1;
-  return b2s_conv_tc_supported(c_in, c_out, k3, n_out) ? b2s_conv_tc_workspace_bytes(c_in, c_out, k3, n_in) : 0;
+  int64_t fwd = b2s_conv_tc_supported(c_in, c_out, k3, n_out) ? b2s_conv_tc_workspace_bytes(c_in, c_out, k3, n_in) : 0;
+  int64_t wg = b2s_wgrad_tc_supported(c_in, c_out, k3, n_out, true) ? b2s_wgrad_tc_workspace_bytes(c_in, n_in) : 0;
+  return fwd > wg ? fwd : wg;
 }
 
 extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr,
@@ -82,8 +85,6 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
 extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
                                   int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace,
                                   int64_t workspace_bytes, int32_t impl, b2s_stream_t stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0 && gw, "bad sizes");
   B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
   B2S_CHECK_ARG(nbr || (k3 == 1 && n_in == n_out), "nbr may be null only for the identity map (k3 == 1)");
@@ -93,13 +94,16 @@ extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t
     return B2S_OK;
   }
   B2S_CHECK_ARG(x && gy, "null pointer");
-  const bool tc_ok = b2s_wgrad_tc_supported(c_in, c_out, k3, n_out);
+  const bool tc_ok = b2s_wgrad_tc_supported(c_in, c_out, k3, n_out, nbr != nullptr);
   if (impl == 2 && !tc_ok) {
     b2s_set_error("b2s_conv_wgrad: tcgen05 kernel does not cover c_in=%d c_out=%d k3=%d", c_in, c_out, k3);
     return B2S_EINVAL;
   }
   if (impl == 2 || (impl == 0 && tc_ok)) {
-    if (b2s_conv_wgrad_tc(x, gy, nbr, n_out, c_in, c_out, k3, gw, st)) return B2S_ECUDA;
+    const int64_t need = b2s_wgrad_tc_workspace_bytes(c_in, n_in);
+    B2S_CHECK_ARG(need == 0 || (workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0),
+                  "workspace too small (see b2s_conv_workspace_bytes)");
+    if (b2s_conv_wgrad_tc(x, gy, nbr, n_in, n_out, c_in, c_out, k3, gw, workspace, st)) return B2S_ECUDA;
   } else {
     b2s_conv_wgrad_simt(x, gy, nbr, n_out, c_in, c_out, k3, gw, st);
   }

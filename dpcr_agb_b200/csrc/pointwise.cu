@@ -263,6 +263,18 @@ __global__ void __launch_bounds__(PW_THREADS) gelu_bwd_kernel(const float* __res
     gx[e] = gy[e] * gelu_grad_f(x[e]);
 }
 
+// s = a + b (kept for the backward), y = gelu(s): the residual join of every block (senet_block.py:93-94)
+__global__ void __launch_bounds__(PW_THREADS) add_gelu_fwd_kernel(const float4* __restrict__ a,
+                                                                  const float4* __restrict__ b, int64_t n4,
+                                                                  float4* __restrict__ s, float4* __restrict__ y) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+    const float4 av = a[e], bv = b[e];
+    const float4 sv = make_float4(av.x + bv.x, av.y + bv.y, av.z + bv.z, av.w + bv.w);
+    s[e] = sv;
+    y[e] = make_float4(gelu_f(sv.x), gelu_f(sv.y), gelu_f(sv.z), gelu_f(sv.w));
+  }
+}
+
 dim3 colgrid(int64_t n, int c) { return dim3((unsigned)ceil_div64(n, ROWS_PER_CTA), (unsigned)((c + 31) / 32)); }
 
 }  // namespace
@@ -439,6 +451,18 @@ extern "C" int32_t b2s_gelu_fwd(const float* x, int64_t numel, float* y, b2s_str
   if (numel == 0) return B2S_OK;
   B2S_CHECK_ARG(x && y, "null pointer");
   gelu_fwd_kernel<<<grid_for(numel, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(x, numel, y);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t numel, float* sum, float* y,
+                                    b2s_stream_t stream) {
+  B2S_CHECK_ARG(numel >= 0 && numel % 4 == 0, "numel must be a non-negative multiple of 4");
+  if (numel == 0) return B2S_OK;
+  B2S_CHECK_ARG(a && b && sum && y, "null pointer");
+  add_gelu_fwd_kernel<<<grid_for(numel / 4, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), numel / 4,
+      reinterpret_cast<float4*>(sum), reinterpret_cast<float4*>(y));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -116,6 +116,20 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   return d;
 }
 
+// MN-major operands of 32-bit types (tf32) must use the "128-byte swizzle with 32-byte base" layout (type 1,
+// Swizzle<2,5,2>): atoms of 4 K-rows x 128 bytes, the four 32-byte units of a row XOR-ed with (row & 3).
+// LBO = byte stride between atoms along M/N (next 32 elements), SBO = stride between atoms along K (next 4
+// rows).  Plain SWIZZLE_128B (type 2) with MN-major tf32 silently yields zeros (measured, tools/umma_probe.cu).
+__device__ __forceinline__ uint64_t smem_desc_sw128_base32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+
 // Instruction descriptor (32-bit) for kind::tf32, fp32 accumulate:
 //   [4,6) D format: 1 = F32     [7,10) A format: 2 = TF32     [10,13) B format: 2 = TF32
 //   [15] A major (0 = K, 1 = MN)   [16] B major   [17,23) N >> 3   [24,29) M >> 4

@@ -50,6 +50,7 @@ SIGNATURES = {
     "b2s_bn_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "b2s_gelu_fwd": (_i32, [_vp, _i64, _vp, _vp]),
     "b2s_gelu_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "b2s_add_gelu_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "b2s_grad_check": (_i32, [_vp, _i64, _f32, _vp, _vp]),
     "b2s_adabelief_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
 }
@@ -117,12 +118,22 @@ def host_f32(*vals):
     return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cuda_ok = None
+_fn_cache = {}
+
+
 def stream() -> int:
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
 def _ensure_device():
-    if not torch.cuda.is_available():
+    global _cuda_ok
+    if _cuda_ok is None:
+        _cuda_ok = torch.cuda.is_available()
+    if not _cuda_ok:
         raise B2SError("libb200sparse needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     dev = torch.cuda.current_device()
     if dev not in _checked_devices:
@@ -130,6 +141,7 @@ def _ensure_device():
         if lib.b2s_device_check() != 0:
             raise B2SError(lib.b2s_last_error().decode())
         _checked_devices.add(dev)
+    return dev
 
 
 def call(name: str, *args):
@@ -137,10 +149,15 @@ def call(name: str, *args):
 
     The trailing ``stream`` argument of the C function is appended automatically."""
     global launch_count
-    _ensure_device()
-    lib = load()
-    fn = getattr(lib, name)
-    conv = [ptr(a) if (a is None or isinstance(a, (torch.Tensor, ctypes.Array))) else a for a in args]
+    dev = _ensure_device()
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
+    lib = _lib
+    conv = [a.data_ptr() if isinstance(a, torch.Tensor) else (a if (a is None or not isinstance(a, ctypes.Array))
+                                                              else ctypes.cast(a, ctypes.c_void_p).value)
+            for a in args]
+    stream = (lambda: _raw_stream(dev)) if _raw_stream is not None else globals()["stream"]
     if _profile is not None and (_profile_names is None or name in _profile_names):
         key = name
         if name == "b2s_conv_gather_gemm":            # w_layout bit 0 set == dgrad

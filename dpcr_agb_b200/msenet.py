@@ -62,14 +62,21 @@ class DropPath(nn.Module):
         return self.mul(x, glob)
 
 
+def _is_gelu(ME, act):
+    return isinstance(act, ME.MinkowskiNonlinearity.MinkowskiGELU)
+
+
 class ConvNormAct(nn.Module):
-    def __init__(self, ME, cin, cout, kernel_size, stride, norm_layer, act, bias):
+    def __init__(self, ME, cin, cout, kernel_size, stride, norm_layer, act, bias, fuse=False):
         super().__init__()
         self.conv = ME.MinkowskiConvolution(cin, cout, kernel_size=kernel_size, stride=stride, dimension=3, bias=bias)
         self.norm = norm_layer(cout)
         self.act = nn.Identity() if act is None else act
+        self._fuse = fuse and act is not None and _is_gelu(ME, act)
 
     def forward(self, x):
+        if self._fuse:                                   # batch norm + exact GELU in one kernel (same arithmetic)
+            return self.norm(self.conv(x), act=1)
         return self.act(self.norm(self.conv(x)))
 
 
@@ -89,8 +96,10 @@ class SEResidualBlock(nn.Module):
     """SEBasicBlock (expansion 1: k3 - k3) or SEBottleneck (expansion 4: k1 - k3 - k1), + SE + residual."""
 
     def __init__(self, ME, inplanes, planes, act, norm_layer, bottleneck, stride=1, downsample=None,
-                 drop_path=0.0, bias=True):
+                 drop_path=0.0, bias=True, fuse=False):
         super().__init__()
+        self._fuse = fuse and _is_gelu(ME, act)
+        self._add_act = [ME.fused_add_gelu] if self._fuse else None
         self.expansion = 4 if bottleneck else 1
         if bottleneck:
             spec = [(inplanes, planes, 1, 1), (planes, planes, 3, stride), (planes, planes * 4, 1, 1)]
@@ -109,10 +118,14 @@ class SEResidualBlock(nn.Module):
     def forward(self, x):
         out = x
         for i in range(1, self.num_convs + 1):
-            out = getattr(self, f"norm{i}")(getattr(self, f"conv{i}")(out))
+            conv, norm = getattr(self, f"conv{i}"), getattr(self, f"norm{i}")
             if i < self.num_convs:
-                out = self.relu(out)
+                out = norm(conv(out), act=1) if self._fuse else self.relu(norm(conv(out)))
+            else:
+                out = norm(conv(out))
         out = self.se(out)
+        if self._fuse:
+            return self._add_act[0](self.drop_path(out), self.downsample(x))
         out = self.drop_path(out) + self.downsample(x)
         return self.relu(out)
 
@@ -130,15 +143,17 @@ class SeparateLinear(nn.Module):
 
 class MSENet(nn.Module):
     def __init__(self, ME, name="SENet14", in_channels=3, out_channels=2, activation="gelu", first_stride=1,
-                 dropout=0.0, drop_path=0.0, bn_momentum=0.1, global_pool="sum", bias=True, separate_head=True):
+                 dropout=0.0, drop_path=0.0, bn_momentum=0.1, global_pool="sum", bias=True, separate_head=True,
+                 fuse=True):
         super().__init__()
+        fuse = bool(fuse and getattr(ME, "B200_FUSED_OPS", False))   # product-only kernels, same arithmetic
         bottleneck, layers, init_dim, planes_list = ARCH[name]
         self.name = name
         self.act_fn = getattr(ME.MinkowskiNonlinearity, ACTIVATION_NAMES[activation])()
         norm_layer = lambda c: ME.MinkowskiNormalization.MinkowskiBatchNorm(c, momentum=bn_momentum)  # noqa: E731
         self.inplanes = init_dim
         stages = [nn.Sequential(
-            ConvNormAct(ME, in_channels, init_dim, 7, first_stride, norm_layer, self.act_fn, bias),
+            ConvNormAct(ME, in_channels, init_dim, 7, first_stride, norm_layer, self.act_fn, bias, fuse=fuse),
             ME.MinkowskiMaxPooling(kernel_size=3, stride=2, dimension=3))]
         expansion = 4 if bottleneck else 1
         for planes, count, stride in zip(planes_list, layers, (1, 2, 2, 2)):
@@ -152,7 +167,7 @@ class MSENet(nn.Module):
                                                 dimension=3, dilation=1, bias=bias),
                         norm_layer(planes * expansion))
                 blocks.append(SEResidualBlock(ME, self.inplanes, planes, self.act_fn, norm_layer, bottleneck,
-                                              stride=s, downsample=down, drop_path=drop_path, bias=bias))
+                                              stride=s, downsample=down, drop_path=drop_path, bias=bias, fuse=fuse))
                 self.inplanes = planes * expansion
             stages.append(nn.Sequential(*blocks))
         self.blocks = nn.ModuleList(stages)

@@ -181,6 +181,10 @@ B2S_API int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* m
                          const float* beta, const float* sums, int64_t n, int32_t c, int32_t act, int32_t training,
                          float* gx, b2s_stream_t stream);
 B2S_API int32_t b2s_gelu_fwd(const float* x, int64_t numel, float* y, b2s_stream_t stream);
+/* sum = a + b, y = gelu(sum): the residual join out = act(drop_path(out) + residual); backward = gelu_bwd(gy, sum)
+ * for both addends (R:modules/MinkowskiEngine/senet_block.py:93-94, resnet_block.py:72-73). */
+B2S_API int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t numel, float* sum, float* y,
+                                 b2s_stream_t stream);
 B2S_API int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t numel, float* gx, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- optimiser ----

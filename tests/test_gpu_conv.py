@@ -103,7 +103,8 @@ def test_conv_backward(cuda, impl, n, cin, cout, strided):
     util.assert_close(bg.grad, br.grad, what="bias grad")
 
 
-def test_stem_wgrad_small_cin(cuda):
+@pytest.mark.parametrize("impl", [SIMT, TC])
+def test_stem_wgrad_small_cin(cuda, impl):
     c, out, nbr = _maps(1500, K=7, extent=7, seed=8)
     rng = np.random.default_rng(4)
     x = rng.standard_normal((c.shape[0], 3)).astype(np.float32)
@@ -113,8 +114,8 @@ def test_stem_wgrad_small_cin(cuda):
     oo.conv(xr, wr, nbr).backward(torch.from_numpy(gy).double())
     n = c.shape[0]
     got = Fn.wgrad(torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda), torch.from_numpy(nbr).to(cuda),
-                   n, n, 3, 64, 343)
-    util.assert_close(got, wr.grad, what="stem wgrad")
+                   n, n, 3, 64, 343, impl=impl)
+    util.assert_close(got, wr.grad, what=f"stem wgrad impl={impl}")
 
 
 def test_conv_rejects_bad_arguments(cuda):
@@ -125,3 +126,35 @@ def test_conv_rejects_bad_arguments(cuda):
         L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, 8, 8, 27, 0, y, None, 0, 1)
     with pytest.raises(L.B2SError):   # tcgen05 kernel does not cover c_out = 8
         L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, 8, 8, 1, 0, y, None, 0, 2)
+
+
+@pytest.mark.parametrize("n,cin,cout,K,strided", [
+    (5000, 64, 64, 3, False),      # many row splits, atomics
+    (3000, 64, 128, 3, True),
+    (700, 128, 256, 3, False),
+    (100, 512, 512, 3, False),     # single split: plain stores, 4 ci tiles x 2 co tiles
+    (1000, 256, 64, 1, False),     # use_mm shape (identity map passed explicitly)
+])
+def test_wgrad_tcgen05(cuda, n, cin, cout, K, strided):
+    c, out, nbr = _maps(n, K=K, strided=strided, seed=12)
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((c.shape[0], cin)).astype(np.float32)
+    gy = rng.standard_normal((out.shape[0], cout)).astype(np.float32)
+    xr = torch.from_numpy(x).double()
+    wr = torch.zeros((K ** 3, cin, cout), dtype=torch.float64, requires_grad=True)
+    oo.conv(xr, wr, nbr).backward(torch.from_numpy(gy).double())
+    args = (torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda), torch.from_numpy(nbr).to(cuda),
+            c.shape[0], out.shape[0], cin, cout, K ** 3)
+    got_tc = Fn.wgrad(*args, impl=TC)
+    got_simt = Fn.wgrad(*args, impl=SIMT)
+    util.assert_close(got_simt, wr.grad, tol=2e-5, what="wgrad simt")
+    util.assert_close(got_tc, wr.grad, what="wgrad tcgen05")
+
+
+def test_wgrad_tcgen05_null_map(cuda):
+    rng = np.random.default_rng(7)
+    n, cin, cout = 900, 64, 256
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    gy = rng.standard_normal((n, cout)).astype(np.float32)
+    got = Fn.wgrad(torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda), None, n, n, cin, cout, 1, impl=TC)
+    util.assert_close(got[0], torch.from_numpy(x).double().T @ torch.from_numpy(gy).double(), what="wgrad use_mm")
