@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) pad_rows4_kernel(const float* __restrict_
                                                         float4* __restrict__ x4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < c; ++j) v[j] = x[i * c + j];
+    for (int j = 0; j < c; ++j) v[j] = __uint_as_float(rna_tf32(__float_as_uint(x[i * c + j])));
     x4[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
@@ -132,6 +132,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int p = 0; p < 8; ++p) idx[p] = -1;
 
     auto publish = [&](int it_done) {  // all of this thread's LDGSTS for it_done have landed
+      if (!SMALL) {                    // round the chunks this thread gathered to tf32 (SMALL: x4 is pre-rounded)
+        const uint32_t st = a_base + (it_done % STAGES) * A_STAGE_BYTES;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) round_chunk_tf32(st + sw128_offset(rsub + 16 * p, chunk));
+      }
       fence_proxy_async();
       mbar_arrive(full_bar(it_done % STAGES));
     };

@@ -50,6 +50,22 @@ __device__ __forceinline__ void cp_async_wait() {
 // make generic-proxy smem writes (cp.async / st.shared) visible to the async proxy (tensor core reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// round-to-nearest (ties away) fp32 -> tf32 bit pattern.  tcgen05 kind::tf32 TRUNCATES the low 13 mantissa bits of
+// its fp32 operands (measured: tools/umma_probe.cu, "rounding probe"), which biases every product towards zero;
+// operands are therefore rounded explicitly before the tensor core sees them.
+__device__ __forceinline__ uint32_t rna_tf32(uint32_t v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(__uint_as_float(v)));
+  return r;
+}
+// in-place rna rounding of one 16-byte chunk of shared memory (a chunk this thread's own LDGSTS has filled)
+__device__ __forceinline__ void round_chunk_tf32(uint32_t saddr) {
+  uint32_t a, b, c, d;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr) : "memory");
+  a = rna_tf32(a); b = rna_tf32(b); c = rna_tf32(c); d = rna_tf32(d);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),

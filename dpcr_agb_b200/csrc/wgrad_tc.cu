@@ -98,11 +98,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   const uint32_t tmem_d = *tmem_slot_ptr;
 
   if (warp < 4) {
-    auto publish = [&](int it_done) {
+    const int a_chunks = ci_valid >> 2;  // 16-byte chunks of the A row piece (multiple of 8)
+    auto publish = [&](int it_done) {    // round this thread's own chunks of stage it_done to tf32, then hand over
+      const uint32_t a_st = a_base + (it_done % STAGES) * WG_A_STAGE, b_st = b_base + (it_done % STAGES) * L::B_STAGE;
+#pragma unroll
+      for (int p = 0; p < WG_ROWS / 4; ++p) {
+        const int row = p * 4 + warp;
+        if (lane < a_chunks) round_chunk_tf32(a_st + mn_offset(row, lane));
+#pragma unroll
+        for (int q = 0; q < (BN + 127) / 128; ++q) {
+          const int chunk = q * 32 + lane;
+          if (chunk < BN / 4) round_chunk_tf32(b_st + mn_offset(row, chunk));
+        }
+      }
       fence_proxy_async();
       mbar_arrive(full_bar(it_done % STAGES));
     };
-    const int a_chunks = ci_valid >> 2;  // 16-byte chunks of the A row piece (multiple of 8)
     for (int it = 0; it < T; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -250,11 +261,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   const uint32_t tmem_d = *tmem_slot_ptr;
 
   if (warp < 4) {
-    auto publish = [&](int it_done) {
+    const int a_chunks = co_valid >> 2;
+    auto publish = [&](int it_done) {    // gy chunks are rounded here; x4 was rounded by the padding kernel
+      const uint32_t a_st = a_base + (it_done % STAGES) * WG_A_STAGE;
+#pragma unroll
+      for (int p = 0; p < WG_ROWS / 4; ++p)
+        if (lane < a_chunks) round_chunk_tf32(a_st + mn_offset(p * 4 + warp, lane));
       fence_proxy_async();
       mbar_arrive(full_bar(it_done % STAGES));
     };
-    const int a_chunks = co_valid >> 2;
     const int kA = k0 + lane, kB = k0 + 32 + lane;       // the two kernel offsets this lane gathers
     for (int it = 0; it < T; ++it) {
       const int s = it % STAGES;
@@ -340,7 +355,7 @@ __global__ void __launch_bounds__(256) wg_pad_rows4_kernel(const float* __restri
                                                            float4* __restrict__ x4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < c; ++j) v[j] = x[i * c + j];
+    for (int j = 0; j < c; ++j) v[j] = __uint_as_float(rna_tf32(__float_as_uint(x[i * c + j])));
     x4[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }

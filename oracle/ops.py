@@ -20,23 +20,71 @@ def _as_long(a):
     return a.long()
 
 
+# Precision model of the convolution.  "fp32" is the reference arithmetic (MinkowskiEngine computes these
+# products in fp32).  "tf32" restates what the B200 kernels compute: both operands of every product rounded to
+# TF32 (10-bit mantissa, round-to-nearest, ties away from zero == PTX cvt.rna.tf32.f32), products and sums in
+# fp32 -- in the forward (x, W), in dgrad (grad_out, W) and in wgrad (x, grad_out).  The parity tests hold the
+# CUDA path to 1e-3 against "fp32" per op (the north_star tolerance) and to a much tighter bound against "tf32".
+CONV_PRECISION = "fp32"
+
+
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32 on every element (fp32 in, fp32 out with the low 13 mantissa bits cleared)."""
+    if t.dtype != torch.float32:
+        return t
+    bits = t.detach().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _conv_fp32(x, weight, nbr):
+    if weight.dim() == 2:
+        return x @ weight
+    n_out = nbr.shape[1]
+    out = x.new_zeros((n_out, weight.shape[2]))
+    for k in range(nbr.shape[0]):
+        o = torch.nonzero(nbr[k] >= 0).squeeze(1)
+        if o.numel() == 0:
+            continue
+        out = out.index_add(0, o, x[nbr[k, o]] @ weight[k])
+    return out
+
+
+class _ConvTF32(torch.autograd.Function):
+    """The same sum with operands rounded to TF32 in all three passes (see CONV_PRECISION)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, nbr):
+        ctx.save_for_backward(x, weight)
+        ctx.nbr = nbr
+        return _conv_fp32(round_tf32(x), round_tf32(weight), nbr)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gyr = round_tf32(gy)
+        gx = gw = None
+        with torch.enable_grad():
+            if ctx.needs_input_grad[0]:
+                xv = torch.zeros_like(x).requires_grad_()
+                (gx,) = torch.autograd.grad(_conv_fp32(xv, round_tf32(weight), ctx.nbr), xv, gyr)
+            if ctx.needs_input_grad[1]:
+                wv = torch.zeros_like(weight).requires_grad_()
+                (gw,) = torch.autograd.grad(_conv_fp32(round_tf32(x), wv, ctx.nbr), wv, gyr)
+        return gx, gw, None
+
+
 def conv(x: torch.Tensor, weight: torch.Tensor, nbr, bias: torch.Tensor | None = None) -> torch.Tensor:
     """MinkowskiConvolution forward: ``out[o] = bias + sum_k sum_{(i->o) in M_k} x[i] @ W[k]``.
 
     Call sites in the reference: ``modules/MinkowskiEngine/SENet.py:49-52,94-97``,
     ``resnet_block.py:48-54,95-107``, ``common.py:219-221``.  ``weight`` is ``[K^3, Cin, Cout]``
     (or ``[Cin, Cout]`` for the K=1, stride=1 ``use_mm`` case, where ``nbr`` is ignored)."""
-    if weight.dim() == 2:
-        out = x @ weight
-    else:
+    if weight.dim() != 2:
         nbr = _as_long(nbr)
-        n_out = nbr.shape[1]
-        out = x.new_zeros((n_out, weight.shape[2]))
-        for k in range(nbr.shape[0]):
-            o = torch.nonzero(nbr[k] >= 0).squeeze(1)
-            if o.numel() == 0:
-                continue
-            out = out.index_add(0, o, x[nbr[k, o]] @ weight[k])
+    if CONV_PRECISION == "tf32" and x.dtype == torch.float32:
+        out = _ConvTF32.apply(x, weight, nbr)
+    else:
+        out = _conv_fp32(x, weight, nbr)
     if bias is not None:
         out = out + bias
     return out

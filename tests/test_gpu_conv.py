@@ -1,5 +1,8 @@
 """GPU parity of the convolution kernels (a6-a8) against the oracle, SIMT and tcgen05 paths, through
-the C ABI.  Tolerance: 1e-3 relative (max|a-b| / max|b|), the fp32/TF32 bar of BASELINE.json."""
+the C ABI.  Two bars for the tcgen05 kernels: 1e-3 relative (max|a-b| / max|b|) against the fp32/fp64 oracle --
+the fp32/TF32 tolerance of BASELINE.json -- and TF32_MODEL_TOL against the oracle's "tf32" precision model
+(operands rounded to TF32 with round-to-nearest, fp32 accumulation), which restates exactly what the kernels
+compute and leaves only the summation order free."""
 import numpy as np
 import pytest
 import torch
@@ -13,6 +16,17 @@ import b2s_testutil as util
 pytestmark = pytest.mark.gpu
 
 SIMT, TC = 1, 2
+TF32_MODEL_TOL = 2e-5
+
+
+class tf32_model:
+    """Context manager: evaluate the oracle convolution under its "tf32" precision model (fp32 tensors)."""
+
+    def __enter__(self):
+        self.old, oo.CONV_PRECISION = oo.CONV_PRECISION, "tf32"
+
+    def __exit__(self, *a):
+        oo.CONV_PRECISION = self.old
 
 
 def _maps(n, nb=2, extent=9, seed=0, K=3, strided=False):
@@ -54,6 +68,10 @@ def test_conv_forward(cuda, impl, n, cin, cout, K, strided):
     util.assert_close(got, ref, what=f"conv fwd impl={impl}")
     if impl == SIMT:   # fp32 SIMT must be far tighter than the TF32 bar
         util.assert_close(got, ref, tol=2e-5, what="conv fwd simt fp32")
+    else:
+        with tf32_model():
+            ref32 = oo.conv(torch.from_numpy(x), torch.from_numpy(w), nbr, torch.from_numpy(b))
+        util.assert_close(got, ref32, tol=TF32_MODEL_TOL, what="conv fwd tcgen05 vs tf32 model")
 
 
 @pytest.mark.parametrize("impl", [SIMT, TC])
@@ -101,6 +119,13 @@ def test_conv_backward(cuda, impl, n, cin, cout, strided):
     util.assert_close(xg.grad, xr.grad, what="dgrad")
     util.assert_close(wg.grad, wr.grad, what="wgrad")
     util.assert_close(bg.grad, br.grad, what="bias grad")
+    if impl == TC:
+        x32 = torch.from_numpy(x).requires_grad_()
+        w32 = torch.from_numpy(w).requires_grad_()
+        with tf32_model():
+            oo.conv(x32, w32, nbr, torch.from_numpy(b)).backward(torch.from_numpy(gy))
+        util.assert_close(xg.grad, x32.grad, tol=TF32_MODEL_TOL, what="dgrad vs tf32 model")
+        util.assert_close(wg.grad, w32.grad, tol=TF32_MODEL_TOL, what="wgrad vs tf32 model")
 
 
 @pytest.mark.parametrize("impl", [SIMT, TC])
@@ -116,6 +141,11 @@ def test_stem_wgrad_small_cin(cuda, impl):
     got = Fn.wgrad(torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda), torch.from_numpy(nbr).to(cuda),
                    n, n, 3, 64, 343, impl=impl)
     util.assert_close(got, wr.grad, what=f"stem wgrad impl={impl}")
+    if impl == TC:
+        w32 = torch.zeros((343, 3, 64), requires_grad=True)
+        with tf32_model():
+            oo.conv(torch.from_numpy(x), w32, nbr).backward(torch.from_numpy(gy))
+        util.assert_close(got, w32.grad, tol=TF32_MODEL_TOL, what="stem wgrad vs tf32 model")
 
 
 def test_conv_rejects_bad_arguments(cuda):
@@ -149,6 +179,10 @@ def test_wgrad_tcgen05(cuda, n, cin, cout, K, strided):
     got_simt = Fn.wgrad(*args, impl=SIMT)
     util.assert_close(got_simt, wr.grad, tol=2e-5, what="wgrad simt")
     util.assert_close(got_tc, wr.grad, what="wgrad tcgen05")
+    w32 = torch.zeros((K ** 3, cin, cout), requires_grad=True)
+    with tf32_model():
+        oo.conv(torch.from_numpy(x), w32, nbr).backward(torch.from_numpy(gy))
+    util.assert_close(got_tc, w32.grad, tol=TF32_MODEL_TOL, what="wgrad tcgen05 vs tf32 model")
 
 
 def test_wgrad_tcgen05_null_map(cuda):
