@@ -170,7 +170,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     from dpcr_agb_b200 import MinkowskiEngine as ME
-    from dpcr_agb_b200 import lib, msenet, plots, train
+    from dpcr_agb_b200 import graph_step, lib, msenet, plots, train
     from dpcr_agb_b200.MinkowskiEngine import functional as Fn
     from dpcr_agb_b200.quantize import GridSampling3D
 
@@ -201,7 +201,197 @@ def run_b200(args):
         host.append(h)
         devb.append({k: v.to(dev) for k, v in h.items()})
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
-    staging = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()}
+
+    def eager_step(d):
+        vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=B, bounds=BOUNDS)
+        return trainer.step(vox["coords"], vox["tensors"][0], d["target"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- algorithmic work per step (untimed statistics pass over every distinct batch, eager exact-size path)
+    Fn.WORK_STATS = {}
+    for d in devb:
+        eager_step(d)
+    torch.cuda.synchronize()
+    work = {k: {kk: vv / len(devb) for kk, vv in v.items()} for k, v in Fn.WORK_STATS.items()}
+    Fn.WORK_STATS = None
+
+    # ---- the product path: the whole step captured as one CUDA graph at fixed row capacities (graph_step.py)
+    caps = graph_step.plan_capacities(gs, ME, model, devb, B, BOUNDS)
+    if world > 1:                                       # same capacities on every rank (max over ranks)
+        keys = sorted(caps)
+        t = torch.tensor([caps[k] for k in keys], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        caps = {k: int(v) for k, v in zip(keys, t.tolist())}
+    gstep = graph_step.GraphStep(trainer, gs, B, B * POINTS_PER_PLOT, BOUNDS, caps).capture()
+
+    def step_from_device(d):
+        gstep.load(d)
+        return gstep.step()
+
+    def step_from_host(h):
+        gstep.load(h)                                             # pinned host -> device copies of this step's inputs
+        return float(gstep.step())                                # device -> host read of the step's result
+
+    def timed(fn, items, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(items[i % len(items)])
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # max over ranks, timed on the device
+        return float(ms.item())
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step_from_device(devb[i % nb])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    clocks = ClockSampler(local)
+    ms_total = timed(step_from_device, devb, args.steps)
+    clk = clocks.stop()
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    calls = gstep.launches_per_step * args.steps
+    gstep.verify()
+
+    # ---- timed region 2: end to end from pinned host buffers
+    for i in range(min(2, args.warmup)):
+        step_from_host(host[i % nb])
+    ms_e2e = timed(step_from_host, host, args.steps)
+    e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+    gstep.verify()
+
+    # ---- per-entry-point CUDA-event timing on the launching stream (eager exact-size path, same kernels, same
+    #      batches): conv kernels alone first (their events do not perturb each other much), then everything
+    for d in devb[:2]:
+        eager_step(d)
+    lib.profile_start(["b2s_conv_gather_gemm", "b2s_conv_wgrad"])
+    psteps = min(args.steps, 6)
+    for i in range(psteps):
+        eager_step(devb[i % nb])
+    prof = {k: (n * args.steps / psteps, t * args.steps / psteps) for k, (n, t) in lib.profile_stop().items()}
+    lib.profile_start(None)
+    bsteps = min(3, args.steps)
+    for i in range(bsteps):
+        eager_step(devb[i % nb])
+    breakdown = {k: {"calls_per_step": n / bsteps, "ms_per_step": t / bsteps} for k, (n, t) in lib.profile_stop().items()}
+
+    if rank != 0:
+        return
+    sample = max(1, args.cpu_sample_plots)
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    cb = cpu_arm(args, steps, warmup, sample)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference MinkowskiEngine (CPU build, env_cpu.yml) is an un-vendored pip dependency and cannot "
+                    "be built offline; this arm is the oracle port of its algorithm on the host cores"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.path = tempfile.mktemp(prefix="b2s_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(device_index)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+
+    from dpcr_agb_b200 import MinkowskiEngine as ME
+    from dpcr_agb_b200 import graph_step, lib, msenet, plots, train
+    from dpcr_agb_b200.MinkowskiEngine import functional as Fn
+    from dpcr_agb_b200.quantize import GridSampling3D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    B = args.plots_per_gpu
+
+    torch.manual_seed(0)
+    model = msenet.build(ME, args.model, drop_path=0.01).to(dev)
+    trainer = train.Trainer(model, ME)
+    trainer.broadcast_parameters()
+    gs = GridSampling3D(GRID)
+
+    # ---- synthetic input: NUM_DISTINCT_BATCHES different batches per rank, cycled (pinned host + device copies)
+    nb = min(NUM_DISTINCT_BATCHES, args.steps + args.warmup)
+    host, devb = [], []
+    for i in range(nb):
+        b = plots.synth_batch(2, (rank * nb + i) * B, B, n_points=POINTS_PER_PLOT)
+        h = {k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in ("pos", "feats", "batch", "perm", "target")}
+        host.append(h)
+        devb.append({k: v.to(dev) for k, v in h.items()})
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
 
     def step_from_device(d):
         vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=B, bounds=BOUNDS)
@@ -315,8 +505,9 @@ def run_b200(args):
             "config": workload(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": calls, "gpu_launches_note": "C-ABI calls into libb200sparse.so inside the timed region "
-                                                        "(each launches 1-4 kernels of ours)",
+            "gpu_launches": calls, "gpu_launches_note": "C-ABI calls into libb200sparse.so recorded in the captured "
+                                                        "step graph x steps (each launches 1-4 kernels of ours)",
+            "row_capacities": caps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "breakdown_ms_per_step": breakdown}
     print(json.dumps(line), flush=True)
     if world > 1:

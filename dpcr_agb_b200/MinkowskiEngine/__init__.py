@@ -26,6 +26,4 @@ B200_FUSED_OPS = True
 
 def fused_add_gelu(x, y):
     assert x._same_map(y), "fused_add_gelu needs both tensors on the same coordinate map"
-    if x.F.numel() % 4:
-        return x._wrap(MinkowskiFunctional.GELUFunction.apply(x.F + y.F))
-    return x._wrap(MinkowskiFunctional.AddGELUFunction.apply(x.F, y.F))
+    return x._wrap(MinkowskiFunctional.AddGELUFunction.apply(x.F, y.F, x.n_dev))

@@ -1,5 +1,11 @@
 """Coordinate manager: GPU coordinate hash, strided maps, kernel maps, per-plot row info.
 
+Two modes.  DYNAMIC (default): every map is sized exactly; creating a map costs one host sync (its row count).
+STATIC (``capacities=...``): every map is allocated at a fixed row capacity per tensor stride and its actual row
+count stays on the device (``CoordMap.n_dev``); no call synchronises, so a whole training step can be captured
+into one CUDA graph (``dpcr_agb_b200.graph_step``).  The kernels take both (capacity, device count), see
+``include/b200sparse.h`` "row counts".
+
 Mirrors what ``ME.SparseTensor(...)`` / strided ops create inside MinkowskiEngine's
 ``CoordinateManager`` (call sites: ``torch_points3d/models/instance/minkowski.py:74``,
 ``modules/MinkowskiEngine/SENet.py:53,94-97``, ``resnet_block.py:48-54`` of the reference).
@@ -53,13 +59,15 @@ class CoordinateMapKey:
 class CoordMap:
     """One coordinate map: rows ``int32 [N,4]`` (batch,x,y,z) + its open-addressing hash table."""
 
-    __slots__ = ("coords", "table", "capacity", "n", "_inv_counts", "_counts_host")
+    __slots__ = ("coords", "table", "capacity", "n", "n_dev", "info", "_inv_counts", "_counts_host")
 
-    def __init__(self, coords, table, capacity):
+    def __init__(self, coords, table, capacity, n_dev=None, info=None):
         self.coords = coords
         self.table = table
         self.capacity = capacity
-        self.n = coords.shape[0]
+        self.n = coords.shape[0]          # rows allocated: the exact count (dynamic) or the capacity (static)
+        self.n_dev = n_dev                # int32 [1] device tensor with the live row count, or None
+        self.info = info                  # int32 [4] device tensor of b2s_coordmap_insert (static mode checks)
         self._inv_counts = None
         self._counts_host = None
 
@@ -67,10 +75,11 @@ class CoordMap:
 class KernelMap:
     """Neighbour table ``nbr int32 [K^3, N_out]`` (+ lazily the transposed table for dgrad)."""
 
-    def __init__(self, manager, in_key, out_key, kernel_size, step, nbr, n_in, n_out):
+    def __init__(self, manager, in_key, out_key, kernel_size, step, nbr, n_in, n_out, n_in_dev=None, n_out_dev=None):
         self.manager, self.in_key, self.out_key = manager, in_key, out_key
         self.kernel_size, self.step = kernel_size, step
         self.nbr, self.n_in, self.n_out = nbr, n_in, n_out
+        self.n_in_dev, self.n_out_dev = n_in_dev, n_out_dev
         self.k3 = kernel_size[0] * kernel_size[1] * kernel_size[2]
         # stride-1 odd kernels are point-symmetric: the transposed table is nbr with k reversed
         self.symmetric = in_key == out_key and all(k % 2 == 1 for k in kernel_size)
@@ -81,11 +90,12 @@ class KernelMap:
         """Transposed table ``[K^3, N_in]``: ``inv[k, i] = o`` iff ``nbr[k, o] = i`` (strided maps only)."""
         if self._inv is None:
             cm = self.manager
-            self._inv = cm._probe(cm.maps[self.in_key].coords, cm.maps[self.out_key], self.kernel_size, self.step, -1)
+            self._inv = cm._probe(cm.maps[self.in_key], cm.maps[self.out_key], self.kernel_size, self.step, -1)
         return self._inv
 
     def pairs(self):
         """MinkowskiEngine's pair-list form: (in_idx, out_idx, offsets[K^3+1]); sorted by out row per offset."""
+        assert self.n_out_dev is None, "pairs() needs exact row counts (dynamic mode)"
         counts = torch.empty(self.k3, dtype=torch.int32, device=self.nbr.device)
         L.call("b2s_kernel_map_pair_counts", self.nbr, self.k3, self.n_out, counts)
         offsets = torch.zeros(self.k3 + 1, dtype=torch.int64, device=self.nbr.device)
@@ -99,13 +109,47 @@ class KernelMap:
 
 
 class CoordinateManager:
-    def __init__(self, D=3, device=None):
+    def __init__(self, D=3, device=None, capacities=None, num_batches=None):
+        """``capacities``: {tensor_stride (int, the x stride): row capacity} switches the manager to STATIC mode;
+        ``num_batches`` must then be given too (it cannot be read back without a sync)."""
         assert D == 3, "the B200 path implements the D=3 case the reference uses"
         self.D = D
         self.device = device
         self.maps = {}
         self.kernel_maps = {}
-        self.num_batches = 0
+        self.capacities = dict(capacities) if capacities is not None else None
+        self.static = capacities is not None
+        if self.static:
+            assert num_batches is not None, "static mode needs num_batches"
+        self.num_batches = int(num_batches) if num_batches is not None else 0
+        self.checks = []     # static mode: (description, capacity, int32 device tensor [>=1]) to verify after a replay
+
+    def capacity_of(self, tensor_stride):
+        ts = tensor_stride[0]
+        if ts not in self.capacities:
+            raise L.B2SError(f"no row capacity planned for tensor stride {ts} (have {sorted(self.capacities)})")
+        return int(self.capacities[ts])
+
+    def insert_static(self, coords: torch.Tensor, n_dev: torch.Tensor, tensor_stride=(1, 1, 1), tag=""):
+        """STATIC mode: register ``coords`` int32 [capacity, 4] whose first ``n_dev[0]`` rows are live, unique and
+        batch-sorted (the quantiser's output contract) -- hash build only, no host sync."""
+        assert self.static and coords.dtype == torch.int32 and coords.is_contiguous() and coords.shape[1] == 4
+        cap_rows = coords.shape[0]
+        dev = coords.device
+        hcap = L.query("b2s_hash_capacity", cap_rows)
+        table = torch.empty(hcap * 16, dtype=torch.uint8, device=dev)
+        slot = torch.empty(max(cap_rows, 1), dtype=torch.int32, device=dev)
+        rank = torch.empty(max(cap_rows, 1), dtype=torch.int32, device=dev)
+        info = torch.empty(4, dtype=torch.int32, device=dev)
+        scan_ws = torch.empty(L.query("b2s_scan_workspace_bytes", cap_rows), dtype=torch.uint8, device=dev)
+        L.call("b2s_coordmap_insert", coords, cap_rows, n_dev, L.host_i32(1, 1, 1), table, hcap, slot, rank, info,
+               scan_ws)
+        key = CoordinateMapKey(tensor_stride, tag)
+        self.maps[key] = CoordMap(coords, table, hcap, n_dev=n_dev, info=info)   # unique rows: table values == rows
+        self.device = dev
+        self.checks.append((f"rows at tensor stride {key.tensor_stride[0]}", cap_rows, n_dev))
+        self.checks.append(("coordinate range flag", 0, info[1:2]))
+        return key
 
     # ------------------------------------------------------------------ map construction
     def _build(self, coords: torch.Tensor, ts_floor, want_in2out=True):
@@ -119,7 +163,7 @@ class CoordinateManager:
         info = torch.empty(4, dtype=torch.int32, device=dev)
         scan_ws = torch.empty(L.query("b2s_scan_workspace_bytes", n), dtype=torch.uint8, device=dev)
         ts = L.host_i32(*ts_floor)
-        L.call("b2s_coordmap_insert", coords, n, ts, table, cap, slot, rank, info, scan_ws)
+        L.call("b2s_coordmap_insert", coords, n, None, ts, table, cap, slot, rank, info, scan_ws)
         n_unique, overflow, max_batch, _ = info.tolist()          # the one host sync of a new map
         if overflow:
             raise L.B2SError("coordinate outside the packed 16-bit range (|c| < 32000, 0 <= batch < 65535): "
@@ -129,7 +173,7 @@ class CoordinateManager:
             return CoordMap(coords, table, cap), None, n       # already unique: table values are the rows
         out = torch.empty((n_unique, 4), dtype=torch.int32, device=dev)
         in2out = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_in2out else None
-        L.call("b2s_coordmap_fill", coords, n, ts, table, cap, slot, rank, out, in2out)
+        L.call("b2s_coordmap_fill", coords, n, None, ts, table, cap, slot, rank, out, n_unique, in2out)
         return CoordMap(out, table, cap), (in2out[:n] if want_in2out else None), n_unique
 
     def insert(self, coords: torch.Tensor, tensor_stride=(1, 1, 1), tag=""):
@@ -153,9 +197,29 @@ class CoordinateManager:
         ts = tuple(a * b for a, b in zip(in_key.tensor_stride, stride))
         out_key = CoordinateMapKey(ts, in_key.tag)
         if out_key not in self.maps:
-            cmap, _, _ = self._build(self.maps[in_key].coords, ts, want_in2out=False)
-            self.maps[out_key] = cmap
+            if self.static:
+                self.maps[out_key] = self._build_static(self.maps[in_key], ts)
+            else:
+                cmap, _, _ = self._build(self.maps[in_key].coords, ts, want_in2out=False)
+                self.maps[out_key] = cmap
         return out_key
+
+    def _build_static(self, imap: CoordMap, ts):
+        """Strided map at fixed capacity: the unique count stays on the device (info[0])."""
+        n, dev = imap.n, imap.coords.device
+        cap_out = self.capacity_of(ts)
+        hcap = L.query("b2s_hash_capacity", n)
+        table = torch.empty(hcap * 16, dtype=torch.uint8, device=dev)
+        slot = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        rank = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        info = torch.empty(4, dtype=torch.int32, device=dev)
+        scan_ws = torch.empty(L.query("b2s_scan_workspace_bytes", n), dtype=torch.uint8, device=dev)
+        tsh = L.host_i32(*ts)
+        L.call("b2s_coordmap_insert", imap.coords, n, imap.n_dev, tsh, table, hcap, slot, rank, info, scan_ws)
+        out = torch.empty((cap_out, 4), dtype=torch.int32, device=dev)
+        L.call("b2s_coordmap_fill", imap.coords, n, imap.n_dev, tsh, table, hcap, slot, rank, out, cap_out, None)
+        self.checks.append((f"rows at tensor stride {ts[0]}", cap_out, info[0:1]))
+        return CoordMap(out, table, hcap, n_dev=info[0:1], info=info)
 
     def origin(self, key=None):
         """Key of the per-plot origin map (one row per batch id), as MinkowskiGlobalPooling returns."""
@@ -167,12 +231,12 @@ class CoordinateManager:
         return key
 
     # ------------------------------------------------------------------ kernel maps
-    def _probe(self, query_coords, table_map: CoordMap, kernel_size, step, sign):
-        n = query_coords.shape[0]
+    def _probe(self, query_map: CoordMap, table_map: CoordMap, kernel_size, step, sign):
+        n = query_map.n
         k3 = kernel_size[0] * kernel_size[1] * kernel_size[2]
-        nbr = torch.empty((k3, n), dtype=torch.int32, device=query_coords.device)
-        L.call("b2s_kernel_map", query_coords, n, table_map.table, table_map.capacity, L.host_i32(*kernel_size),
-               L.host_i32(*step), sign, nbr)
+        nbr = torch.empty((k3, n), dtype=torch.int32, device=query_map.coords.device)
+        L.call("b2s_kernel_map", query_map.coords, n, query_map.n_dev, table_map.table, table_map.capacity,
+               L.host_i32(*kernel_size), L.host_i32(*step), sign, nbr)
         return nbr
 
     def kernel_map(self, in_key, out_key, kernel_size, dilation=(1, 1, 1)) -> KernelMap:
@@ -182,8 +246,8 @@ class CoordinateManager:
         if km is None:
             step = tuple(d * t for d, t in zip(dilation, in_key.tensor_stride))
             imap, omap = self.maps[in_key], self.maps[out_key]
-            nbr = self._probe(omap.coords, imap, kernel_size, step, +1)
-            km = KernelMap(self, in_key, out_key, kernel_size, step, nbr, imap.n, omap.n)
+            nbr = self._probe(omap, imap, kernel_size, step, +1)
+            km = KernelMap(self, in_key, out_key, kernel_size, step, nbr, imap.n, omap.n, imap.n_dev, omap.n_dev)
             self.kernel_maps[ck] = km
         return km
 
@@ -191,12 +255,32 @@ class CoordinateManager:
     def coords(self, key):
         return self.maps[key].coords
 
+    def n_dev(self, key):
+        """Device row count of a map (None in dynamic mode and for the origin map)."""
+        return self.maps[key].n_dev
+
+    def verify(self):
+        """STATIC mode: one host read of every recorded device count; raises if a capacity was exceeded or a
+        coordinate was out of the packed range.  Call after the step (or replay) has been enqueued."""
+        if not self.checks:
+            return {}
+        vals = torch.cat([t.reshape(-1)[:1] for _, _, t in self.checks]).tolist()
+        out = {}
+        for (what, cap, _), v in zip(self.checks, vals):
+            out[what] = v
+            if cap == 0:
+                if v != 0:
+                    raise L.B2SError(f"{what} raised on the device (B2S_EOVERFLOW)")
+            elif v > cap:
+                raise L.B2SError(f"{what}: {v} exceeds the planned capacity {cap}; re-plan with larger capacities")
+        return out
+
     def inv_counts(self, key):
         """float32 [B]: 1 / (rows of each plot) -- the average-pooling scale."""
         m = self.maps[key]
         if m._inv_counts is None:
             counts = torch.empty(self.num_batches, dtype=torch.int32, device=m.coords.device)
-            L.call("b2s_batch_counts", m.coords, 4, m.n, self.num_batches, counts)
+            L.call("b2s_batch_counts", m.coords, 4, m.n, m.n_dev, self.num_batches, counts)
             m._inv_counts = 1.0 / counts.clamp(min=1).float()
             m._counts_host = None
         return m._inv_counts
@@ -206,6 +290,6 @@ class CoordinateManager:
         m = self.maps[key]
         if m._counts_host is None:
             counts = torch.empty(self.num_batches, dtype=torch.int32, device=m.coords.device)
-            L.call("b2s_batch_counts", m.coords, 4, m.n, self.num_batches, counts)
+            L.call("b2s_batch_counts", m.coords, 4, m.n, m.n_dev, self.num_batches, counts)
             m._counts_host = counts.tolist()
         return m._counts_host

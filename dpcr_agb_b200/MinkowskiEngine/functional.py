@@ -21,10 +21,12 @@ CONV_IMPL = int(os.environ.get("B2S_CONV_IMPL", "0"))
 WORK_STATS = None
 
 
-def _account(kind, nbr, n_rows, c_in, c_out, k3):
+def _account(kind, nbr, n_rows, c_in, c_out, k3, n_dev=None):
     if WORK_STATS is None:
         return
-    pairs = int((nbr >= 0).sum().item()) if nbr is not None else int(n_rows)
+    if n_dev is not None:
+        n_rows = min(int(n_rows), int(n_dev.item()))
+    pairs = int((nbr[:, :n_rows] >= 0).sum().item()) if nbr is not None else int(n_rows)
     st = WORK_STATS.setdefault(kind, {"launches": 0, "pairs": 0, "flops": 0, "bytes": 0})
     st["launches"] += 1
     st["pairs"] += pairs
@@ -44,21 +46,22 @@ def _ws(n_in, n_out, c_in, c_out, k3, device):
     return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device), nbytes
 
 
-def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None):
-    """y[o] = bias + sum_k x[nbr[k,o]] @ B_k  (C ABI ``b2s_conv_gather_gemm``)."""
+def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None, n_out_dev=None):
+    """y[o] = bias + sum_k x[nbr[k,o]] @ B_k  (C ABI ``b2s_conv_gather_gemm``).  ``n_out_dev``: device row count
+    (then ``n_out`` is the capacity / pitch of ``nbr``)."""
     y = torch.empty((n_out, c_out), dtype=torch.float32, device=x.device)
-    _account("dgrad" if (w_layout & 1) else "fwd", nbr, n_out, c_in, c_out, k3)
+    _account("dgrad" if (w_layout & 1) else "fwd", nbr, n_out, c_in, c_out, k3, n_out_dev)
     ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device)
-    L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, y, ws, nbytes,
+    L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout, y, ws, nbytes,
            CONV_IMPL if impl is None else impl)
     return y
 
 
-def wgrad(x, gy, nbr, n_in, n_out, c_in, c_out, k3, impl=None):
+def wgrad(x, gy, nbr, n_in, n_out, c_in, c_out, k3, impl=None, n_out_dev=None):
     gw = torch.empty((k3, c_in, c_out), dtype=torch.float32, device=x.device)
-    _account("wgrad", nbr, n_out, c_in, c_out, k3)
+    _account("wgrad", nbr, n_out, c_in, c_out, k3, n_out_dev)
     ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device) if c_in <= 4 else (None, 0)
-    L.call("b2s_conv_wgrad", x, gy, nbr, n_in, n_out, c_in, c_out, k3, gw, ws, nbytes,
+    L.call("b2s_conv_wgrad", x, gy, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, gw, ws, nbytes,
            CONV_IMPL if impl is None else impl)
     return gw
 
@@ -69,19 +72,24 @@ class ConvolutionFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, feats, kernel, bias, kmap):
+    def forward(ctx, feats, kernel, bias, kmap, n_dev=None):
+        """``n_dev``: device row count of the (identity-map) input when ``kmap`` is None; a KernelMap carries its
+        own device counts."""
         feats = feats.contiguous()
         kernel = kernel.contiguous()
         c_in, c_out = kernel.shape[-2], kernel.shape[-1]
         if kmap is None:
             n_in = n_out = feats.shape[0]
             nbr, k3 = None, 1
+            nd_in = nd_out = n_dev
         else:
             n_in, n_out, nbr, k3 = kmap.n_in, kmap.n_out, kmap.nbr, kmap.k3
+            nd_in, nd_out = kmap.n_in_dev, kmap.n_out_dev
         assert feats.shape == (n_in, c_in), f"feature shape {tuple(feats.shape)} does not match the map ({n_in},{c_in})"
         b = bias.contiguous().view(-1) if bias is not None else None
-        out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0)
+        out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0, n_out_dev=nd_out)
         ctx.kmap = kmap
+        ctx.nd = (nd_in, nd_out)
         ctx.dims = (n_in, n_out, c_in, c_out, k3)
         ctx.has_bias = bias is not None
         ctx.save_for_backward(feats, kernel)
@@ -94,20 +102,22 @@ class ConvolutionFunction(torch.autograd.Function):
         kmap = ctx.kmap
         n_in, n_out, c_in, c_out, k3 = ctx.dims
         gy = gy.contiguous()
+        nd_in, nd_out = ctx.nd
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             if kmap is None:
-                gx = gather_gemm(gy, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1)
+                gx = gather_gemm(gy, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1, n_out_dev=nd_in)
             elif kmap.symmetric:      # transposed map == same table with the kernel index reversed
-                gx = gather_gemm(gy, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2)
+                gx = gather_gemm(gy, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2, n_out_dev=nd_in)
             else:
-                gx = gather_gemm(gy, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1)
+                gx = gather_gemm(gy, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1, n_out_dev=nd_in)
         if ctx.needs_input_grad[1]:
-            gw = wgrad(feats, gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out, k3).view(kernel.shape)
+            gw = wgrad(feats, gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out, k3,
+                       n_out_dev=nd_out).view(kernel.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = torch.empty((1, c_out), dtype=torch.float32, device=gy.device)
-            L.call("b2s_colsum", gy, n_out, c_out, gb)
-        return gx, gw, gb, None
+            L.call("b2s_colsum", gy, n_out, nd_out, c_out, gb)
+        return gx, gw, gb, None, None
 
 
 class MaxPoolFunction(torch.autograd.Function):
@@ -120,8 +130,9 @@ class MaxPoolFunction(torch.autograd.Function):
         c = feats.shape[1]
         y = torch.empty((kmap.n_out, c), dtype=torch.float32, device=feats.device)
         arg = torch.empty((kmap.n_out, c), dtype=torch.int32, device=feats.device)
-        L.call("b2s_maxpool_fwd", feats, kmap.nbr, kmap.n_out, c, kmap.k3, y, arg)
+        L.call("b2s_maxpool_fwd", feats, kmap.nbr, kmap.n_out, kmap.n_out_dev, c, kmap.k3, y, arg)
         ctx.save_for_backward(arg)
+        ctx.nd_out = kmap.n_out_dev
         ctx.dims = (kmap.n_in, kmap.n_out, c)
         return y
 
@@ -131,7 +142,7 @@ class MaxPoolFunction(torch.autograd.Function):
         (arg,) = ctx.saved_tensors
         n_in, n_out, c = ctx.dims
         gx = torch.empty((n_in, c), dtype=torch.float32, device=gy.device)
-        L.call("b2s_maxpool_bwd", gy.contiguous(), arg, n_in, n_out, c, gx)
+        L.call("b2s_maxpool_bwd", gy.contiguous(), arg, n_in, n_out, ctx.nd_out, c, gx)
         return gx, None
 
 
@@ -140,12 +151,12 @@ class GlobalPoolFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, feats, coords, num_batches, scale):
+    def forward(ctx, feats, coords, num_batches, scale, n_dev=None):
         feats = feats.contiguous()
         n, c = feats.shape
         y = torch.empty((num_batches, c), dtype=torch.float32, device=feats.device)
-        L.call("b2s_segment_sum", feats, coords, 4, n, c, num_batches, scale, y)
-        ctx.coords, ctx.scale, ctx.dims = coords, scale, (n, c)
+        L.call("b2s_segment_sum", feats, coords, 4, n, n_dev, c, num_batches, scale, y)
+        ctx.coords, ctx.scale, ctx.dims, ctx.nd = coords, scale, (n, c), n_dev
         return y
 
     @staticmethod
@@ -153,8 +164,8 @@ class GlobalPoolFunction(torch.autograd.Function):
     def backward(ctx, gy):
         n, c = ctx.dims
         gx = torch.empty((n, c), dtype=torch.float32, device=gy.device)
-        L.call("b2s_segment_bcast", gy.contiguous(), ctx.coords, 4, n, c, ctx.scale, gx)
-        return gx, None, None, None
+        L.call("b2s_segment_bcast", gy.contiguous(), ctx.coords, 4, n, ctx.nd, c, ctx.scale, gx)
+        return gx, None, None, None, None
 
 
 class BroadcastMulFunction(torch.autograd.Function):
@@ -162,14 +173,14 @@ class BroadcastMulFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, x, y, coords, num_batches):
+    def forward(ctx, x, y, coords, num_batches, n_dev=None):
         x, y = x.contiguous(), y.contiguous()
         n, c = x.shape
         assert y.shape[0] == num_batches and y.shape[1] in (1, c)
         out = torch.empty_like(x)
-        L.call("b2s_bcast_mul_fwd", x, y, coords, 4, n, c, y.shape[1], out)
+        L.call("b2s_bcast_mul_fwd", x, y, coords, 4, n, n_dev, c, y.shape[1], out)
         ctx.save_for_backward(x, y)
-        ctx.coords, ctx.nb = coords, num_batches
+        ctx.coords, ctx.nb, ctx.nd = coords, num_batches, n_dev
         return out
 
     @staticmethod
@@ -181,12 +192,12 @@ class BroadcastMulFunction(torch.autograd.Function):
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if y.shape[1] != c:                      # per-plot scalar (drop-path mask): no gradient to the mask
             gx = torch.empty_like(x)
-            L.call("b2s_bcast_mul_fwd", g, y, ctx.coords, 4, n, c, 1, gx)
-            return gx, None, None, None
+            L.call("b2s_bcast_mul_fwd", g, y, ctx.coords, 4, n, ctx.nd, c, 1, gx)
+            return gx, None, None, None, None
         gx = torch.empty_like(x) if need_x else None
         gy = torch.empty_like(y) if need_y else None
-        L.call("b2s_bcast_mul_bwd", g, x, y, ctx.coords, 4, n, c, ctx.nb, gx, gy)
-        return gx, gy, None, None
+        L.call("b2s_bcast_mul_bwd", g, x, y, ctx.coords, 4, n, ctx.nd, c, ctx.nb, gx, gy)
+        return gx, gy, None, None, None
 
 
 class BatchNormFunction(torch.autograd.Function):
@@ -194,7 +205,7 @@ class BatchNormFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act):
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act, n_dev=None):
         x = x.contiguous()
         n, c = x.shape
         dev = x.device
@@ -202,14 +213,15 @@ class BatchNormFunction(torch.autograd.Function):
             mean = torch.empty(c, dtype=torch.float32, device=dev)
             invstd = torch.empty(c, dtype=torch.float32, device=dev)
             ws = torch.empty(2 * c, dtype=torch.float64, device=dev)
-            L.call("b2s_bn_stats", x, n, c, float(eps), float(momentum), running_mean, running_var, ws, mean, invstd)
+            L.call("b2s_bn_stats", x, n, n_dev, c, float(eps), float(momentum), running_mean, running_var, ws, mean,
+                   invstd)
         else:
             mean = running_mean
             invstd = torch.rsqrt(running_var + eps)
         y = torch.empty_like(x)
-        L.call("b2s_bn_apply", x, mean, invstd, weight, bias, n, c, act, y)
+        L.call("b2s_bn_apply", x, mean, invstd, weight, bias, n, n_dev, c, act, y)
         ctx.save_for_backward(x, mean, invstd, weight, bias)
-        ctx.training, ctx.act = training, act
+        ctx.training, ctx.act, ctx.nd = training, act, n_dev
         return y
 
     @staticmethod
@@ -221,15 +233,15 @@ class BatchNormFunction(torch.autograd.Function):
         dev = x.device
         sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
         ws = torch.empty(2 * c, dtype=torch.float64, device=dev)
-        L.call("b2s_bn_bwd_reduce", gy, x, mean, invstd, weight, bias, n, c, ctx.act, ws, sums)
+        L.call("b2s_bn_bwd_reduce", gy, x, mean, invstd, weight, bias, n, ctx.nd, c, ctx.act, ws, sums)
         gx = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            L.call("b2s_bn_bwd_apply", gy, x, mean, invstd, weight, bias, sums, n, c, ctx.act, 1 if ctx.training else 0,
-                   gx)
+            L.call("b2s_bn_bwd_apply", gy, x, mean, invstd, weight, bias, sums, n, ctx.nd, c, ctx.act,
+                   1 if ctx.training else 0, gx)
         gw = sums[c:].clone() if (weight is not None and ctx.needs_input_grad[1]) else None
         gb = sums[:c].clone() if (bias is not None and ctx.needs_input_grad[2]) else None
-        return gx, gw, gb, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None
 
 
 class GELUFunction(torch.autograd.Function):
@@ -237,11 +249,13 @@ class GELUFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, x):
+    def forward(ctx, x, n_dev=None):
         x = x.contiguous()
         y = torch.empty_like(x)
-        L.call("b2s_gelu_fwd", x, x.numel(), y)
+        n = x.shape[0] if x.dim() > 1 else 1
+        L.call("b2s_gelu_fwd", x, n, n_dev if x.dim() > 1 else None, x.numel() // max(n, 1), y)
         ctx.save_for_backward(x)
+        ctx.nd = n_dev if x.dim() > 1 else None
         return y
 
     @staticmethod
@@ -249,8 +263,9 @@ class GELUFunction(torch.autograd.Function):
     def backward(ctx, gy):
         (x,) = ctx.saved_tensors
         gx = torch.empty_like(x)
-        L.call("b2s_gelu_bwd", gy.contiguous(), x, x.numel(), gx)
-        return gx
+        n = x.shape[0] if x.dim() > 1 else 1
+        L.call("b2s_gelu_bwd", gy.contiguous(), x, n, ctx.nd, x.numel() // max(n, 1), gx)
+        return gx, None
 
 
 class AddGELUFunction(torch.autograd.Function):
@@ -259,11 +274,13 @@ class AddGELUFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, n_dev=None):
         a, b = a.contiguous(), b.contiguous()
         s, y = torch.empty_like(a), torch.empty_like(a)
-        L.call("b2s_add_gelu_fwd", a, b, a.numel(), s, y)
+        n = a.shape[0]
+        L.call("b2s_add_gelu_fwd", a, b, n, n_dev, a.numel() // max(n, 1), s, y)
         ctx.save_for_backward(s)
+        ctx.nd = n_dev
         return y
 
     @staticmethod
@@ -271,5 +288,6 @@ class AddGELUFunction(torch.autograd.Function):
     def backward(ctx, gy):
         (s,) = ctx.saved_tensors
         g = torch.empty_like(s)
-        L.call("b2s_gelu_bwd", gy.contiguous(), s, s.numel(), g)
-        return g, g
+        n = s.shape[0]
+        L.call("b2s_gelu_bwd", gy.contiguous(), s, n, ctx.nd, s.numel() // max(n, 1), g)
+        return g, g, None

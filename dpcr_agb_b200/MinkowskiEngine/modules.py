@@ -106,7 +106,7 @@ class MinkowskiConvolution(MinkowskiModuleBase):
     def forward(self, input: SparseTensor, coordinates=None):
         cm = input.coordinate_manager
         if self.use_mm:
-            out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, None)
+            out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, None, input.n_dev)
             return SparseTensor(out, coordinate_map_key=input.coordinate_map_key, coordinate_manager=cm)
         out_key = _out_key(input, self.stride)
         kmap = cm.kernel_map(input.coordinate_map_key, out_key, self.kernel_size, self.dilation)
@@ -177,7 +177,7 @@ class _GlobalPoolBase(MinkowskiModuleBase):
         cm = input.coordinate_manager
         key = input.coordinate_map_key
         scale = cm.inv_counts(key) if self.AVERAGE else None
-        out = Fn.GlobalPoolFunction.apply(input.F, cm.coords(key), cm.num_batches, scale)
+        out = Fn.GlobalPoolFunction.apply(input.F, cm.coords(key), cm.num_batches, scale, cm.n_dev(key))
         return SparseTensor(out, coordinate_map_key=cm.origin(), coordinate_manager=cm)
 
     def __repr__(self):
@@ -215,7 +215,8 @@ class MinkowskiGlobalMaxPooling(MinkowskiModuleBase):
 class MinkowskiBroadcastMultiplication(MinkowskiModuleBase):
     def forward(self, input: SparseTensor, input_glob: SparseTensor):
         cm = input.coordinate_manager
-        out = Fn.BroadcastMulFunction.apply(input.F, input_glob.F, cm.coords(input.coordinate_map_key), cm.num_batches)
+        out = Fn.BroadcastMulFunction.apply(input.F, input_glob.F, cm.coords(input.coordinate_map_key), cm.num_batches,
+                                            input.n_dev)
         return input._wrap(out)
 
     def __repr__(self):
@@ -274,7 +275,8 @@ class MinkowskiBatchNorm(nn.Module):
         out = Fn.BatchNormFunction.apply(input.F, bn.weight, bn.bias,
                                          bn.running_mean if (update or not use_batch_stats) else None,
                                          bn.running_var if (update or not use_batch_stats) else None,
-                                         use_batch_stats, 0.0 if momentum is None else momentum, bn.eps, act)
+                                         use_batch_stats, 0.0 if momentum is None else momentum, bn.eps, act,
+                                         input.n_dev)
         return input._wrap(out)
 
     def __repr__(self):
@@ -366,7 +368,7 @@ class MinkowskiGELU(MinkowskiNonlinearityBase):
     def forward(self, input):
         if getattr(self.module, "approximate", "none") != "none":
             return input._wrap(self.module(input.F))
-        return input._wrap(Fn.GELUFunction.apply(input.F))
+        return input._wrap(Fn.GELUFunction.apply(input.F, input.n_dev))
 
 
 class MinkowskiSinusoidal(MinkowskiModuleBase):

@@ -15,11 +15,20 @@ from .coordinate_manager import CoordinateManager, CoordinateMapKey, _triple
 class SparseTensor:
     def __init__(self, features, coordinates=None, tensor_stride=1, coordinate_map_key=None,
                  coordinate_manager=None, quantization_mode=None, allocator_type=None,
-                 minkowski_algorithm=None, requires_grad=None, device=None):
+                 minkowski_algorithm=None, requires_grad=None, device=None, num_rows=None, capacities=None,
+                 num_batches=None):
+        """Beyond the MinkowskiEngine signature: ``num_rows`` (int32 [1] device tensor), ``capacities`` and
+        ``num_batches`` create the tensor in STATIC mode -- ``features`` / ``coordinates`` are allocated at a fixed
+        capacity, only the first ``num_rows[0]`` rows are live (unique, batch-sorted), and nothing synchronises."""
         assert isinstance(features, torch.Tensor), "features must be a torch.Tensor"
         if device is not None:
             features = features.to(device, non_blocking=True)
-        if coordinate_manager is None:
+        if coordinate_manager is None and num_rows is not None:
+            assert coordinates is not None and capacities is not None and num_batches is not None
+            coordinate_manager = CoordinateManager(D=3, device=features.device, capacities=capacities,
+                                                   num_batches=num_batches)
+            coordinate_map_key = coordinate_manager.insert_static(coordinates, num_rows, _triple(tensor_stride))
+        elif coordinate_manager is None:
             assert coordinates is not None, "either coordinates or (coordinate_map_key, coordinate_manager)"
             coordinates = coordinates.to(features.device, non_blocking=True)
             if not features.is_cuda:
@@ -53,6 +62,11 @@ class SparseTensor:
     @property
     def coordinates(self):
         return self.C
+
+    @property
+    def n_dev(self):
+        """Device row count of this tensor's map (None in dynamic mode)."""
+        return self.coordinate_manager.n_dev(self.coordinate_map_key)
 
     @property
     def tensor_stride(self):

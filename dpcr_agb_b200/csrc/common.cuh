@@ -52,6 +52,18 @@ static inline int grid_for(int64_t work_items, int block, int ctas_per_sm = 8) {
   return (int)(need < cap ? need : cap);
 }
 
+// ------------------------------------------------------------------ device-side row counts --
+// Every entry point that takes a row count n also takes `const int32_t* n_dev`.  NULL: n is exact.  Otherwise n is
+// the CAPACITY (array pitch, launch bound) and the kernel reads the actual count from device memory, clamped to
+// [0, n].  Launch shapes then do not depend on the data, so a whole training step can be captured in a CUDA graph.
+__device__ __forceinline__ int64_t b2s_rows(int64_t n, const int* __restrict__ n_dev) {
+  if (n_dev) {
+    const int64_t v = (int64_t)__ldg(n_dev);
+    n = v < 0 ? 0 : (v < n ? v : n);
+  }
+  return n;
+}
+
 // ------------------------------------------------------------------ coordinate keys ---------
 // 64-bit key: batch | z | y | x, 16 bits each, spatial fields biased by 2^15 so that kernel
 // offsets may reach below zero.  Key order == lexicographic (batch, z, y, x).

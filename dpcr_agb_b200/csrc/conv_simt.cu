@@ -18,8 +18,12 @@ __global__ void __launch_bounds__(THREADS) gather_gemm_simt_kernel(const float* 
                                                                    const float* __restrict__ w,
                                                                    const float* __restrict__ bias,
                                                                    const int* __restrict__ nbr, int64_t n_out,
-                                                                   int c_in, int c_out, int k3, int w_layout,
+                                                                   const int* __restrict__ n_out_dev, int c_in,
+                                                                   int c_out, int k3, int w_layout,
                                                                    float* __restrict__ y) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
+  if ((int64_t)blockIdx.x * BM >= n_out) return;
   __shared__ int idx_s[BM];
   __shared__ float a_s[BK][BM + 4];
   __shared__ float b_s[BK][BN + 4];
@@ -37,7 +41,7 @@ __global__ void __launch_bounds__(THREADS) gather_gemm_simt_kernel(const float* 
     int my = -1;
     if (t < BM) {
       const int64_t o = m0 + t;
-      my = o < n_out ? (nbr ? nbr[(int64_t)k * n_out + o] : (int)o) : -1;
+      my = o < n_out ? (nbr ? nbr[(int64_t)k * pitch + o] : (int)o) : -1;
       idx_s[t] = my;
     }
     if (!__syncthreads_or(my >= 0)) continue;  // no row of this tile has a neighbour at offset k
@@ -98,9 +102,12 @@ __global__ void __launch_bounds__(THREADS) gather_gemm_simt_kernel(const float* 
 constexpr int WG_ROWS = 16;
 __global__ void __launch_bounds__(THREADS) wgrad_simt_kernel(const float* __restrict__ x,
                                                              const float* __restrict__ gy,
-                                                             const int* __restrict__ nbr, int64_t n_out, int c_in,
-                                                             int c_out, int co_tiles, int64_t rows_per_split,
+                                                             const int* __restrict__ nbr, int64_t n_out,
+                                                             const int* __restrict__ n_out_dev, int c_in, int c_out,
+                                                             int co_tiles, int64_t rows_per_split,
                                                              float* __restrict__ gw) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
   __shared__ int idx_s[WG_ROWS];
   __shared__ float a_s[WG_ROWS][BM + 4];  // [row][ci]
   __shared__ float b_s[WG_ROWS][BN + 4];  // [row][co]
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(THREADS) wgrad_simt_kernel(const float* __rest
     int my = -1;
     if (t < WG_ROWS) {
       const int64_t o = r0 + t;
-      my = o < r_end ? (nbr ? nbr[(int64_t)k * n_out + o] : (int)o) : -1;
+      my = o < r_end ? (nbr ? nbr[(int64_t)k * pitch + o] : (int)o) : -1;
       idx_s[t] = my;
     }
     if (!__syncthreads_or(my >= 0)) continue;
@@ -168,9 +175,11 @@ constexpr int SC_WARPS = 8;
 __global__ void __launch_bounds__(SC_WARPS * 32) wgrad_smallcin_kernel(const float* __restrict__ x,
                                                                       const float* __restrict__ gy,
                                                                       const int* __restrict__ nbr, int64_t n_out,
-                                                                      int c_in, int c_out,
-                                                                      int64_t rows_per_split,
+                                                                      const int* __restrict__ n_out_dev, int c_in,
+                                                                      int c_out, int64_t rows_per_split,
                                                                       float* __restrict__ gw) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
   __shared__ float red[SC_WARPS][4][64];
   const int k = blockIdx.x;
   const int co0 = blockIdx.y * 64;
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32) wgrad_smallcin_kernel(const flo
   const int coA = co0 + lane, coB = co0 + 32 + lane;
   for (int64_t r0 = r_begin + warp * 32; r0 < r_end; r0 += SC_WARPS * 32) {
     const int64_t o_l = r0 + lane;
-    const int mine = o_l < r_end ? nbr[(int64_t)k * n_out + o_l] : -1;
+    const int mine = o_l < r_end ? nbr[(int64_t)k * pitch + o_l] : -1;
     unsigned live = __ballot_sync(0xffffffffu, mine >= 0);
     while (live) {
       const int src = __ffs(live) - 1;
@@ -221,18 +230,18 @@ __global__ void __launch_bounds__(SC_WARPS * 32) wgrad_smallcin_kernel(const flo
 }  // namespace
 
 int b2s_conv_gather_gemm_simt(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_out,
-                              int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
-                              cudaStream_t st) {
+                              const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout,
+                              float* y, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)((c_out + BN - 1) / BN));
   if (c_in <= 4)
-    gather_gemm_simt_kernel<4><<<grid, THREADS, 0, st>>>(x, w, bias, nbr, n_out, c_in, c_out, k3, w_layout, y);
+    gather_gemm_simt_kernel<4><<<grid, THREADS, 0, st>>>(x, w, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, w_layout, y);
   else
-    gather_gemm_simt_kernel<16><<<grid, THREADS, 0, st>>>(x, w, bias, nbr, n_out, c_in, c_out, k3, w_layout, y);
+    gather_gemm_simt_kernel<16><<<grid, THREADS, 0, st>>>(x, w, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, w_layout, y);
   return 0;
 }
 
-int b2s_conv_wgrad_simt(const float* x, const float* gy, const int32_t* nbr, int64_t n_out, int32_t c_in,
-                        int32_t c_out, int32_t k3, float* gw, cudaStream_t st) {
+int b2s_conv_wgrad_simt(const float* x, const float* gy, const int32_t* nbr, int64_t n_out, const int32_t* n_out_dev,
+                        int32_t c_in, int32_t c_out, int32_t k3, float* gw, cudaStream_t st) {
   cudaMemsetAsync(gw, 0, (size_t)k3 * c_in * c_out * sizeof(float), st);
   if (c_in <= 4 && nbr) {
     const int co_tiles = (c_out + 63) / 64;
@@ -244,7 +253,7 @@ int b2s_conv_wgrad_simt(const float* x, const float* gy, const int32_t* nbr, int
     rows = ceil_div64(rows, SC_WARPS * 32) * (SC_WARPS * 32);
     splits = ceil_div64(n_out, rows);
     dim3 grid((unsigned)k3, (unsigned)co_tiles, (unsigned)splits);
-    wgrad_smallcin_kernel<<<grid, SC_WARPS * 32, 0, st>>>(x, gy, nbr, n_out, c_in, c_out, rows, gw);
+    wgrad_smallcin_kernel<<<grid, SC_WARPS * 32, 0, st>>>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, rows, gw);
     return 0;
   }
   const int ci_tiles = (c_in + BM - 1) / BM, co_tiles = (c_out + BN - 1) / BN;
@@ -258,6 +267,6 @@ int b2s_conv_wgrad_simt(const float* x, const float* gy, const int32_t* nbr, int
   rows = ceil_div64(rows, WG_ROWS) * WG_ROWS;
   splits = ceil_div64(n_out, rows);
   dim3 grid((unsigned)k3, (unsigned)(ci_tiles * co_tiles), (unsigned)splits);
-  wgrad_simt_kernel<<<grid, THREADS, 0, st>>>(x, gy, nbr, n_out, c_in, c_out, co_tiles, rows, gw);
+  wgrad_simt_kernel<<<grid, THREADS, 0, st>>>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, co_tiles, rows, gw);
   return 0;
 }

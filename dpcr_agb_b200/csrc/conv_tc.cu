@@ -89,8 +89,11 @@ struct SmemLayout {
 template <int BN, int STAGES, bool SMALL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
-                          const int* __restrict__ nbr, int64_t n_out, int c_in, int c_out, int k3, int T,
-                          float* __restrict__ y) {
+                          const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
+                          int c_out, int k3, int T, float* __restrict__ y) {
+  const int64_t pitch = n_out;                     // row pitch of the neighbour table (the caller's capacity)
+  n_out = b2s_rows(n_out, n_out_dev);
+  if ((int64_t)blockIdx.x * BM >= n_out) return;   // whole tile beyond the live rows (uniform across the CTA)
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const int row = rsub + 16 * p;
           const int64_t o = m0 + row;
           int i = -1;
-          if (k < k3 && o < n_out) i = nbr ? __ldg(&nbr[(int64_t)k * n_out + o]) : (int)o;
+          if (k < k3 && o < n_out) i = nbr ? __ldg(&nbr[(int64_t)k * pitch + o]) : (int)o;
           const float* src = x + (int64_t)(i >= 0 ? i : 0) * 4;
           cp_async16(a_stage + sw128_offset(row, chunk), src, i >= 0 ? 16u : 0u);
         }
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
           for (int p = 0; p < 8; ++p) {
             const int64_t o = m0 + rsub + 16 * p;
-            idx[p] = o < n_out ? (nbr ? __ldg(&nbr[(int64_t)k * n_out + o]) : (int)o) : -1;
+            idx[p] = o < n_out ? (nbr ? __ldg(&nbr[(int64_t)k * pitch + o]) : (int)o) : -1;
           }
         }
 #pragma unroll
@@ -256,8 +259,8 @@ bool tc_disabled() {
 }
 
 template <int BN, int STAGES, bool SMALL>
-int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, int c_in, int c_out,
-              int k3, int T, float* y, cudaStream_t st) {
+int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
+              int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL>;
   static bool attr_set = false;
@@ -269,7 +272,7 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN));
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, c_in, c_out, k3, T, y);
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y);
   return 0;
 }
 
@@ -295,7 +298,7 @@ int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int
 }
 
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
-                            int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
+                            int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
                             void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   (void)workspace_bytes;
   const bool small = c_in <= 4;
@@ -311,13 +314,13 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   }
   const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
   if (small) {
-    if (bn == 256) return launch_tc<256, 4, true>(xin, img, bias, nbr, n_out, 4, c_out, k3, T, y, st);
-    if (bn == 128) return launch_tc<128, 3, true>(xin, img, bias, nbr, n_out, 4, c_out, k3, T, y, st);
-    return launch_tc<64, 4, true>(xin, img, bias, nbr, n_out, 4, c_out, k3, T, y, st);
+    if (bn == 256) return launch_tc<256, 4, true>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
+    if (bn == 128) return launch_tc<128, 3, true>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
+    return launch_tc<64, 4, true>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
   }
-  if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, c_in, c_out, k3, T, y, st);
-  if (bn == 128) return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, c_in, c_out, k3, T, y, st);
-  return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, c_in, c_out, k3, T, y, st);
+  if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  if (bn == 128) return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
 }
 
 // wgrad on tensor cores: see wgrad_tc.cu

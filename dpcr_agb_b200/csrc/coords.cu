@@ -49,7 +49,9 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int* __restrict__ in, int64_t n,
+                                                                   const int* __restrict__ n_dev,
                                                                    int* __restrict__ block_sums) {
+  n = b2s_rows(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int s = 0;
 #pragma unroll
@@ -77,7 +79,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(int* __re
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out,
-                                                                  int64_t n, const int* __restrict__ block_sums) {
+                                                                  int64_t n, const int* __restrict__ n_dev,
+                                                                  const int* __restrict__ block_sums) {
+  n = b2s_rows(n, n_dev);
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
@@ -98,16 +102,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int* __r
 }
 
 // in-place capable exclusive scan; total (device int) may be null
-int launch_exclusive_scan(const int* in, int* out, int64_t n, int* total_dev, void* ws, cudaStream_t st) {
+int launch_exclusive_scan(const int* in, int* out, int64_t n, const int* n_dev, int* total_dev, void* ws,
+                          cudaStream_t st) {
   if (n <= 0) {
     if (total_dev) cudaMemsetAsync(total_dev, 0, sizeof(int), st);
     return 0;
   }
   int nb = (int)ceil_div64(n, SCAN_TILE);
   int* block_sums = reinterpret_cast<int*>(ws);
-  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, block_sums);
+  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, n, n_dev, block_sums);
   scan_block_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, nb, total_dev);
-  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, block_sums);
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, n_dev, block_sums);
   return 0;
 }
 
@@ -128,8 +133,10 @@ __global__ void init_bounds_kernel(int* bounds) {
 }
 
 // q = rint(pos / size) in fp32 (IEEE divide, round-half-even) -- grid_transform.py:116
-__global__ void __launch_bounds__(256) quantize_points_kernel(const float* __restrict__ pos, int64_t n, float size,
+__global__ void __launch_bounds__(256) quantize_points_kernel(const float* __restrict__ pos, int64_t n,
+                                                              const int* __restrict__ n_dev, float size,
                                                               int* __restrict__ q, int* __restrict__ bounds) {
+  n = b2s_rows(n, n_dev);
   int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
   const int64_t total = n * 3;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -176,8 +183,10 @@ __device__ __forceinline__ int64_t cell_of(const int* __restrict__ q, const int*
 }
 
 __global__ void __launch_bounds__(256) quantize_mark_kernel(const int* __restrict__ q, const int* __restrict__ plot,
-                                                            int64_t n, int num_plots, QBox box,
-                                                            unsigned* __restrict__ bitmap, int* __restrict__ oob) {
+                                                            int64_t n, const int* __restrict__ n_dev, int num_plots,
+                                                            QBox box, unsigned* __restrict__ bitmap,
+                                                            int* __restrict__ oob) {
+  n = b2s_rows(n, n_dev);
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
     int64_t cell = ((unsigned)plot[p] < (unsigned)num_plots) ? cell_of(q, plot, p, box) : -1;
     if (cell < 0) {
@@ -199,9 +208,12 @@ __global__ void quantize_total_kernel(const int* __restrict__ oob, int* __restri
 }
 
 __global__ void __launch_bounds__(256) quantize_rep_kernel(const int* __restrict__ q, const int* __restrict__ plot,
-                                                           const int* __restrict__ order, int64_t n, QBox box,
+                                                           const int* __restrict__ order, int64_t n,
+                                                           const int* __restrict__ n_dev, QBox box,
                                                            const unsigned* __restrict__ bitmap,
-                                                           const int* __restrict__ prefix, int* __restrict__ rep) {
+                                                           const int* __restrict__ prefix, int64_t rep_cap,
+                                                           int* __restrict__ rep) {
+  n = b2s_rows(n, n_dev);
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = order ? order[j] : j;
     int64_t cell = cell_of(q, plot, p, box);
@@ -209,13 +221,15 @@ __global__ void __launch_bounds__(256) quantize_rep_kernel(const int* __restrict
     int64_t w = cell >> 5;
     unsigned bit = (unsigned)(cell & 31);
     int r = prefix[w] + __popc(bitmap[w] & ((1u << bit) - 1u));
-    atomicMax(&rep[r], (int)j);  // last position in the shuffled order wins
+    if (r < rep_cap) atomicMax(&rep[r], (int)j);  // last position in the shuffled order wins
   }
 }
 
 __global__ void __launch_bounds__(256) quantize_emit_kernel(const int* __restrict__ q, const int* __restrict__ plot,
                                                             const int* __restrict__ order, int64_t m,
+                                                            const int* __restrict__ m_dev,
                                                             int* __restrict__ out_coords, int* __restrict__ rep_src) {
+  m = b2s_rows(m, m_dev);
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (int64_t)gridDim.x * blockDim.x) {
     int j = rep_src[r];
     int p = order ? order[j] : j;
@@ -226,7 +240,9 @@ __global__ void __launch_bounds__(256) quantize_emit_kernel(const int* __restric
 }
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ in, const int* __restrict__ idx,
-                                                          int64_t m, int c, float* __restrict__ out) {
+                                                          int64_t m, const int* __restrict__ m_dev, int c,
+                                                          float* __restrict__ out) {
+  m = b2s_rows(m, m_dev);
   const int64_t total = m * c;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = e / c;
@@ -267,13 +283,13 @@ bool quantize_layout(int64_t num_plots, const int32_t* dims, void* ws, QWs* out)
 
 }  // namespace
 
-extern "C" int32_t b2s_quantize_points(const float* pos, int64_t n, float size, int32_t* qcoords, int32_t* bounds,
-                                       b2s_stream_t stream) {
+extern "C" int32_t b2s_quantize_points(const float* pos, int64_t n, const int32_t* n_dev, float size,
+                                       int32_t* qcoords, int32_t* bounds, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && size > 0.f, "n >= 0 and size > 0");
   B2S_CHECK_ARG(bounds && (n == 0 || (pos && qcoords)), "null pointer");
   cudaStream_t st = as_stream(stream);
   init_bounds_kernel<<<1, 32, 0, st>>>(bounds);
-  if (n > 0) quantize_points_kernel<<<grid_for(n * 3, 256), 256, 0, st>>>(pos, n, size, qcoords, bounds);
+  if (n > 0) quantize_points_kernel<<<grid_for(n * 3, 256), 256, 0, st>>>(pos, n, n_dev, size, qcoords, bounds);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -285,7 +301,7 @@ extern "C" int64_t b2s_quantize_workspace_bytes(int64_t num_plots, const int32_t
 }
 
 extern "C" int32_t b2s_quantize_count(const int32_t* qcoords, const int32_t* plot_of_point, int64_t n,
-                                      int32_t num_plots, const int32_t* lo_host, const int32_t* dims_host,
+                                      const int32_t* n_dev, int32_t num_plots, const int32_t* lo_host, const int32_t* dims_host,
                                       void* workspace, int64_t workspace_bytes, int32_t* num_voxels_dev,
                                       b2s_stream_t stream) {
   B2S_CHECK_ARG(lo_host && dims_host && workspace && num_voxels_dev, "null pointer");
@@ -301,17 +317,19 @@ extern "C" int32_t b2s_quantize_count(const int32_t* qcoords, const int32_t* plo
   B2S_CUDA(cudaMemsetAsync(l.bitmap, 0, l.words * 4, st));
   B2S_CUDA(cudaMemsetAsync(l.oob, 0, 4, st));
   if (n > 0)
-    quantize_mark_kernel<<<grid_for(n, 256), 256, 0, st>>>(qcoords, plot_of_point, n, num_plots, box, l.bitmap, l.oob);
+    quantize_mark_kernel<<<grid_for(n, 256), 256, 0, st>>>(qcoords, plot_of_point, n, n_dev, num_plots, box, l.bitmap,
+                                                           l.oob);
   popc_kernel<<<grid_for(l.words, 256), 256, 0, st>>>(l.bitmap, l.words, l.prefix);
-  launch_exclusive_scan(l.prefix, l.prefix, l.words, num_voxels_dev, l.scan_ws, st);
+  launch_exclusive_scan(l.prefix, l.prefix, l.words, nullptr, num_voxels_dev, l.scan_ws, st);
   quantize_total_kernel<<<1, 1, 0, st>>>(l.oob, num_voxels_dev);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_quantize_fill(const int32_t* qcoords, const int32_t* plot_of_point, const int32_t* order,
-                                     int64_t n, int32_t num_plots, const int32_t* lo_host, const int32_t* dims_host,
-                                     void* workspace, int64_t num_voxels, int32_t* out_coords, int32_t* out_src,
+                                     int64_t n, const int32_t* n_dev, int32_t num_plots, const int32_t* lo_host,
+                                     const int32_t* dims_host, void* workspace, int64_t num_voxels,
+                                     const int32_t* num_voxels_dev, int32_t* out_coords, int32_t* out_src,
                                      b2s_stream_t stream) {
   B2S_CHECK_ARG(lo_host && dims_host && workspace, "null pointer");
   B2S_CHECK_ARG(num_voxels >= 0 && num_voxels <= n, "num_voxels out of range");
@@ -322,20 +340,20 @@ extern "C" int32_t b2s_quantize_fill(const int32_t* qcoords, const int32_t* plot
   cudaStream_t st = as_stream(stream);
   QBox box{{lo_host[0], lo_host[1], lo_host[2]}, {dims_host[0], dims_host[1], dims_host[2]}};
   B2S_CUDA(cudaMemsetAsync(out_src, 0xFF, num_voxels * 4, st));  // -1
-  quantize_rep_kernel<<<grid_for(n, 256), 256, 0, st>>>(qcoords, plot_of_point, order, n, box, l.bitmap, l.prefix,
-                                                        out_src);
+  quantize_rep_kernel<<<grid_for(n, 256), 256, 0, st>>>(qcoords, plot_of_point, order, n, n_dev, box, l.bitmap,
+                                                        l.prefix, num_voxels, out_src);
   quantize_emit_kernel<<<grid_for(num_voxels, 256), 256, 0, st>>>(qcoords, plot_of_point, order, num_voxels,
-                                                                   out_coords, out_src);
+                                                                   num_voxels_dev, out_coords, out_src);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-extern "C" int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t m, int32_t c, float* out,
-                                   b2s_stream_t stream) {
+extern "C" int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t m, const int32_t* m_dev, int32_t c,
+                                   float* out, b2s_stream_t stream) {
   B2S_CHECK_ARG(m >= 0 && c > 0, "m >= 0 and c > 0");
   if (m == 0) return B2S_OK;
   B2S_CHECK_ARG(in && idx && out, "null pointer");
-  gather_rows_kernel<<<grid_for(m * c, 256), 256, 0, as_stream(stream)>>>(in, idx, m, c, out);
+  gather_rows_kernel<<<grid_for(m * c, 256), 256, 0, as_stream(stream)>>>(in, idx, m, m_dev, c, out);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -345,10 +363,11 @@ extern "C" int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t 
 // =============================================================================================
 namespace {
 
-__global__ void __launch_bounds__(256) coordmap_insert_kernel(const int4* __restrict__ coords, int64_t n, int tsx,
-                                                              int tsy, int tsz, B2sEntry* __restrict__ table,
-                                                              uint64_t mask, int* __restrict__ slot,
-                                                              int* __restrict__ info) {
+__global__ void __launch_bounds__(256) coordmap_insert_kernel(const int4* __restrict__ coords, int64_t n,
+                                                              const int* __restrict__ n_dev, int tsx, int tsy,
+                                                              int tsz, B2sEntry* __restrict__ table, uint64_t mask,
+                                                              int* __restrict__ slot, int* __restrict__ info) {
+  n = b2s_rows(n, n_dev);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int4 c = coords[i];
     if (c.x < 0 || c.x >= 65535 || abs(c.y) >= B2S_COORD_LIMIT || abs(c.z) >= B2S_COORD_LIMIT ||
@@ -374,7 +393,8 @@ __global__ void __launch_bounds__(256) coordmap_insert_kernel(const int4* __rest
 
 __global__ void __launch_bounds__(256) coordmap_flag_kernel(const B2sEntry* __restrict__ table,
                                                             const int* __restrict__ slot, int64_t n,
-                                                            int* __restrict__ flag) {
+                                                            const int* __restrict__ n_dev, int* __restrict__ flag) {
+  n = b2s_rows(n, n_dev);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int s = slot[i];
     flag[i] = (s >= 0 && table[s].val == (int)i) ? 1 : 0;
@@ -383,25 +403,34 @@ __global__ void __launch_bounds__(256) coordmap_flag_kernel(const B2sEntry* __re
 
 // firsts: emit floored coordinate at their rank and rewrite the table value to that rank.
 // A non-first row i' can never pass the (val == i') test: val is either first(i') < i' or rank <= first.
-__global__ void __launch_bounds__(256) coordmap_emit_kernel(const int4* __restrict__ coords, int64_t n, int tsx,
-                                                            int tsy, int tsz, B2sEntry* __restrict__ table,
+__global__ void __launch_bounds__(256) coordmap_emit_kernel(const int4* __restrict__ coords, int64_t n,
+                                                            const int* __restrict__ n_dev, int tsx, int tsy, int tsz,
+                                                            B2sEntry* __restrict__ table,
                                                             const int* __restrict__ slot,
-                                                            const int* __restrict__ rank, int4* __restrict__ out) {
+                                                            const int* __restrict__ rank, int64_t out_cap,
+                                                            int4* __restrict__ out) {
+  n = b2s_rows(n, n_dev);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int s = slot[i];
     if (s < 0) continue;
     if (table[s].val == (int)i) {
       int r = rank[i];
       int4 c = coords[i];
-      out[r] = make_int4(c.x, b2s_floor_to(c.y, tsx), b2s_floor_to(c.z, tsy), b2s_floor_to(c.w, tsz));
-      table[s].val = r;
+      if (r < out_cap) {
+        out[r] = make_int4(c.x, b2s_floor_to(c.y, tsx), b2s_floor_to(c.z, tsy), b2s_floor_to(c.w, tsz));
+        table[s].val = r;
+      } else {
+        table[s].val = -1;  // beyond the caller's capacity: the key resolves to "no row" (the caller checks info[0])
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(256) coordmap_in2out_kernel(const B2sEntry* __restrict__ table,
                                                               const int* __restrict__ slot, int64_t n,
+                                                              const int* __restrict__ n_dev,
                                                               int* __restrict__ in2out) {
+  n = b2s_rows(n, n_dev);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int s = slot[i];
     in2out[i] = s >= 0 ? table[s].val : -1;
@@ -418,8 +447,8 @@ extern "C" int64_t b2s_hash_capacity(int64_t n) {
   return cap;
 }
 
-extern "C" int32_t b2s_coordmap_insert(const int32_t* coords, int64_t n, const int32_t* ts_host, void* table,
-                                       int64_t capacity, int32_t* slot, int32_t* rank, int32_t* info_dev,
+extern "C" int32_t b2s_coordmap_insert(const int32_t* coords, int64_t n, const int32_t* n_dev,
+                                       const int32_t* ts_host, void* table, int64_t capacity, int32_t* slot, int32_t* rank, int32_t* info_dev,
                                        void* scan_workspace, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && n < INT_MAX, "0 <= n < 2^31");
   B2S_CHECK_ARG(is_pow2(capacity) && capacity >= 2 * n, "capacity must be a power of two >= 2n");
@@ -433,30 +462,33 @@ extern "C" int32_t b2s_coordmap_insert(const int32_t* coords, int64_t n, const i
   B2S_CUDA(cudaMemsetAsync(info_dev + 2, 0xFF, sizeof(int), st));  // max batch id starts at -1
   if (n > 0) {
     B2S_CHECK_ARG(coords && slot && rank, "null pointer");
-    coordmap_insert_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, ts_host[0],
-                                                             ts_host[1], ts_host[2],
+    coordmap_insert_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, n_dev,
+                                                             ts_host[0], ts_host[1], ts_host[2],
                                                              reinterpret_cast<B2sEntry*>(table),
                                                              (uint64_t)capacity - 1, slot, info_dev);
-    coordmap_flag_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const B2sEntry*>(table), slot, n, rank);
-    launch_exclusive_scan(rank, rank, n, info_dev, scan_workspace, st);
+    coordmap_flag_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const B2sEntry*>(table), slot, n, n_dev,
+                                                           rank);
+    launch_exclusive_scan(rank, rank, n, n_dev, info_dev, scan_workspace, st);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-extern "C" int32_t b2s_coordmap_fill(const int32_t* coords, int64_t n, const int32_t* ts_host, void* table,
-                                     int64_t capacity, const int32_t* slot, const int32_t* rank, int32_t* out_coords,
-                                     int32_t* in2out, b2s_stream_t stream) {
+extern "C" int32_t b2s_coordmap_fill(const int32_t* coords, int64_t n, const int32_t* n_dev, const int32_t* ts_host,
+                                     void* table, int64_t capacity, const int32_t* slot, const int32_t* rank,
+                                     int32_t* out_coords, int64_t out_capacity, int32_t* in2out,
+                                     b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && is_pow2(capacity), "bad sizes");
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(coords && table && slot && rank && out_coords && ts_host, "null pointer");
   B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(out_coords) & 15) == 0, "out_coords must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
-  coordmap_emit_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, ts_host[0],
+  coordmap_emit_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, n_dev, ts_host[0],
                                                          ts_host[1], ts_host[2], reinterpret_cast<B2sEntry*>(table),
-                                                         slot, rank, reinterpret_cast<int4*>(out_coords));
+                                                         slot, rank, out_capacity,
+                                                         reinterpret_cast<int4*>(out_coords));
   if (in2out)
-    coordmap_in2out_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const B2sEntry*>(table), slot, n,
+    coordmap_in2out_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const B2sEntry*>(table), slot, n, n_dev,
                                                              in2out);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
@@ -478,10 +510,11 @@ struct KmParams {
 // One thread per query row, blockIdx.y selects a group of kernel offsets.  Writes of nbr[k, q] are
 // coalesced across the warp for every k; the 16-byte coordinate is loaded once per group.
 __global__ void __launch_bounds__(256) kernel_map_kernel(const int4* __restrict__ query, int64_t n,
+                                                         const int* __restrict__ n_dev,
                                                          const B2sEntry* __restrict__ table, uint64_t mask,
                                                          KmParams p, int* __restrict__ nbr) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
+  if (q >= b2s_rows(n, n_dev)) return;
   const int4 c = query[q];
   const int k0 = blockIdx.y * p.group;
   const int k1 = min(k0 + p.group, p.k3);
@@ -535,7 +568,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) pair_fill_kernel(const int* __re
 
 }  // namespace
 
-extern "C" int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, const void* table, int64_t capacity,
+extern "C" int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, const int32_t* n_query_dev,
+                                  const void* table, int64_t capacity,
                                   const int32_t* kernel_size_host, const int32_t* step_host, int32_t sign,
                                   int32_t* nbr, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_query >= 0 && is_pow2(capacity), "bad sizes");
@@ -560,7 +594,7 @@ extern "C" int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, 
   groups = (p.k3 + p.group - 1) / p.group;
   dim3 grid((unsigned)row_blocks, (unsigned)groups);
   kernel_map_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const int4*>(query_coords), n_query,
-                                                         reinterpret_cast<const B2sEntry*>(table),
+                                                         n_query_dev, reinterpret_cast<const B2sEntry*>(table),
                                                          (uint64_t)capacity - 1, p, nbr);
   B2S_LAUNCH_CHECK();
   return B2S_OK;

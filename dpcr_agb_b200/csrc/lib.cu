@@ -30,18 +30,19 @@ extern "C" int32_t b2s_device_check(void) {
 
 // implemented in conv_simt.cu / conv_tc.cu
 int b2s_conv_gather_gemm_simt(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_out,
-                              int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y, cudaStream_t st);
-int b2s_conv_wgrad_simt(const float* x, const float* gy, const int32_t* nbr, int64_t n_out, int32_t c_in,
-                        int32_t c_out, int32_t k3, float* gw, cudaStream_t st);
+                              const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout,
+                              float* y, cudaStream_t st);
+int b2s_conv_wgrad_simt(const float* x, const float* gy, const int32_t* nbr, int64_t n_out, const int32_t* n_out_dev,
+                        int32_t c_in, int32_t c_out, int32_t k3, float* gw, cudaStream_t st);
 bool b2s_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_out);
 int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_in);
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
-                            int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
+                            int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
                             void* workspace, int64_t workspace_bytes, cudaStream_t st);
 bool b2s_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_out, bool has_map);
 int64_t b2s_wgrad_tc_workspace_bytes(int32_t c_in, int64_t n_in);
-int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out, int32_t c_in,
-                      int32_t c_out, int32_t k3, float* gw, void* workspace, cudaStream_t st);
+int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
+                      const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace, cudaStream_t st);
 
 extern "C" int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3) {
   if (c_in <= 0 || c_out <= 0 || k3 <= 0 || n_in < 0 || n_out < 0) return -1;
@@ -51,9 +52,9 @@ extern "C" int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t
 }
 
 extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr,
-                                        int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3,
-                                        int32_t w_layout, float* y, void* workspace, int64_t workspace_bytes,
-                                        int32_t impl, b2s_stream_t stream) {
+                                        int64_t n_in, int64_t n_out, const int32_t* n_out_dev, int32_t c_in,
+                                        int32_t c_out, int32_t k3, int32_t w_layout, float* y, void* workspace,
+                                        int64_t workspace_bytes, int32_t impl, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0, "bad sizes");
   B2S_CHECK_ARG(w_layout >= 0 && w_layout <= 3, "w_layout must be in 0..3");
   B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
@@ -72,18 +73,18 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
     B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) & 15) == 0,
                   "workspace must be 256-byte aligned, x and y 16-byte aligned");
-    if (b2s_conv_gather_gemm_tc(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, y, workspace, workspace_bytes,
-                                st))
+    if (b2s_conv_gather_gemm_tc(x, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout, y, workspace,
+                                workspace_bytes, st))
       return B2S_ECUDA;
   } else {
-    b2s_conv_gather_gemm_simt(x, w, bias, nbr, n_out, c_in, c_out, k3, w_layout, y, st);
+    b2s_conv_gather_gemm_simt(x, w, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, w_layout, y, st);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
-                                  int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace,
+                                  const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace,
                                   int64_t workspace_bytes, int32_t impl, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0 && gw, "bad sizes");
   B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
@@ -103,9 +104,9 @@ extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t
     const int64_t need = b2s_wgrad_tc_workspace_bytes(c_in, n_in);
     B2S_CHECK_ARG(need == 0 || (workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0),
                   "workspace too small (see b2s_conv_workspace_bytes)");
-    if (b2s_conv_wgrad_tc(x, gy, nbr, n_in, n_out, c_in, c_out, k3, gw, workspace, st)) return B2S_ECUDA;
+    if (b2s_conv_wgrad_tc(x, gy, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, gw, workspace, st)) return B2S_ECUDA;
   } else {
-    b2s_conv_wgrad_simt(x, gy, nbr, n_out, c_in, c_out, k3, gw, st);
+    b2s_conv_wgrad_simt(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;

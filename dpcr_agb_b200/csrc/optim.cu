@@ -27,8 +27,12 @@ struct AbHyper {
 
 __global__ void __launch_bounds__(256) adabelief_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ s, int64_t n,
-                                                        AbHyper h, const float* __restrict__ found_inf) {
+                                                        AbHyper h, const float* __restrict__ hyper_dev,
+                                                        const float* __restrict__ found_inf) {
   if (found_inf && *found_inf != 0.f) return;  // GradScaler.step skips the optimiser on inf/nan
+  if (hyper_dev)                               // hyper-parameters live on the device (captured-graph replays)
+    h = AbHyper{hyper_dev[0], hyper_dev[1], hyper_dev[2], hyper_dev[3], hyper_dev[4],
+                hyper_dev[5], hyper_dev[6], hyper_dev[7], hyper_dev[8]};
   const float decay = 1.0f - h.lr * h.wd;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * h.inv_scale;
@@ -62,15 +66,18 @@ extern "C" int32_t b2s_grad_check(const float* grad, int64_t numel, float inv_sc
 }
 
 extern "C" int32_t b2s_adabelief_step(float* param, const float* grad, float* exp_avg, float* exp_avg_var,
-                                      int64_t numel, const float* hyper_host, const float* found_inf_dev,
-                                      b2s_stream_t stream) {
-  B2S_CHECK_ARG(numel >= 0 && hyper_host, "bad arguments");
+                                      int64_t numel, const float* hyper_host, const float* hyper_dev,
+                                      const float* found_inf_dev, b2s_stream_t stream) {
+  B2S_CHECK_ARG(numel >= 0 && ((hyper_host != nullptr) != (hyper_dev != nullptr)),
+                "exactly one of hyper_host / hyper_dev must be given");
   if (numel == 0) return B2S_OK;
   B2S_CHECK_ARG(param && grad && exp_avg && exp_avg_var, "null pointer");
-  AbHyper h{hyper_host[0], hyper_host[1], hyper_host[2], hyper_host[3], hyper_host[4],
-            hyper_host[5], hyper_host[6], hyper_host[7], hyper_host[8]};
+  AbHyper h{};
+  if (hyper_host)
+    h = AbHyper{hyper_host[0], hyper_host[1], hyper_host[2], hyper_host[3], hyper_host[4],
+                hyper_host[5], hyper_host[6], hyper_host[7], hyper_host[8]};
   adabelief_kernel<<<grid_for(numel, 256), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_var, numel, h,
-                                                                       found_inf_dev);
+                                                                       hyper_dev, found_inf_dev);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -1,6 +1,8 @@
 // pointwise.cu -- the bandwidth-bound stages: max pooling (a9), per-plot reductions and broadcasts
 // (a5, a10, a11), batch-norm statistics / apply (a13), GELU (a14), column sums (bias gradient).
-// Every kernel streams fp32 [N, C] rows with coalesced 128-byte warp accesses and is bounded by HBM.
+// Every kernel streams fp32 [N, C] rows: consecutive threads own consecutive 16-byte channel vectors of a row
+// (then the next row), so a warp touches 512 contiguous bytes; per-channel parameters live in registers.
+// All of them are bounded by HBM.  Row counts may live on the device (n_dev, see b200sparse.h "row counts").
 //
 // Reference call sites (R: = /root/reference/torch-points3d/torch_points3d/modules/MinkowskiEngine/):
 //   a9 R:SENet.py:53   a10/a11 R:senet_block.py:43-50, R:common.py:44-48, R:SENet.py:63,117
@@ -19,34 +21,128 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// ---------------------------------------------------------------- vector helpers ------------
+template <int VEC>
+struct V {
+  float v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ V<VEC> ldv(const float* p) {
+  V<VEC> r;
+  if (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x, r.v[1 % VEC] = t.y, r.v[2 % VEC] = t.z, r.v[3 % VEC] = t.w;
+  } else {
+    r.v[0] = *p;
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ V<VEC> ldgv(const float* p) {
+  V<VEC> r;
+  if (VEC == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x, r.v[1 % VEC] = t.y, r.v[2 % VEC] = t.z, r.v[3 % VEC] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* p, const V<VEC>& r) {
+  if (VEC == 4)
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]);
+  else
+    *p = r.v[0];
+}
+template <int VEC>
+__device__ __forceinline__ V<VEC> splat(float s) {
+  V<VEC> r;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) r.v[j] = s;
+  return r;
+}
+// per-channel parameter vector (nullable pointer -> constant)
+template <int VEC>
+__device__ __forceinline__ V<VEC> ldparam(const float* p, int ch, float dflt) {
+  return p ? ldgv<VEC>(p + ch) : splat<VEC>(dflt);
+}
+
+// Thread -> (row lane, channel vector) mapping shared by the row-streaming kernels.
+//   cv = channel vectors per row, tpr = threads per row, rpb = rows per block pass
+struct RowMap {
+  int cv, tpr, rpb, tr, tc;
+  bool active;
+};
+template <int VEC>
+__device__ __forceinline__ RowMap row_map(int c) {
+  RowMap m;
+  m.cv = c / VEC;
+  m.tpr = m.cv < (int)blockDim.x ? m.cv : (int)blockDim.x;
+  m.rpb = (int)blockDim.x / m.tpr;
+  m.tr = (int)threadIdx.x / m.tpr;
+  m.tc = (int)threadIdx.x % m.tpr;
+  m.active = m.tr < m.rpb;
+  return m;
+}
+#define B2S_ROW_LOOP(m, n, r)                                                                       \
+  for (int64_t r = (int64_t)blockIdx.x * (m).rpb + (m).tr; r < (n); r += (int64_t)gridDim.x * (m).rpb)
+
+static inline int rows_grid(int64_t n, int c, int vec) {
+  const int cv = c / vec;
+  const int tpr = cv < PW_THREADS ? cv : PW_THREADS;
+  const int rpb = PW_THREADS / tpr;
+  return grid_for(ceil_div64(n, rpb) * PW_THREADS, PW_THREADS);
+}
+static inline int vec_of(int c, const void* a, const void* b = nullptr, const void* d = nullptr, const void* e = nullptr) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (c % 4 == 0 && al(a) && al(b) && al(d) && al(e)) ? 4 : 1;
+}
+
 // ---------------------------------------------------------------- max pooling ---------------
+template <int VEC>
 __global__ void __launch_bounds__(PW_THREADS) maxpool_fwd_kernel(const float* __restrict__ x,
-                                                                 const int* __restrict__ nbr, int64_t n_out, int c,
-                                                                 int k3, float* __restrict__ y,
-                                                                 int* __restrict__ arg) {
-  const int64_t total = n_out * c;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t o = e / c;
-    const int ch = (int)(e - o * c);
-    float best = -INFINITY;
-    int bi = -1;
-    for (int k = 0; k < k3; ++k) {
-      const int i = __ldg(&nbr[(int64_t)k * n_out + o]);
-      if (i < 0) continue;
-      const float v = __ldg(&x[(int64_t)i * c + ch]);
-      if (bi < 0 || v > best || (v == best && i < bi)) {
-        best = v;
-        bi = i;
+                                                                 const int* __restrict__ nbr, int64_t n_out,
+                                                                 const int* __restrict__ n_dev, int c, int k3,
+                                                                 float* __restrict__ y, int* __restrict__ arg) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_dev);
+  const RowMap m = row_map<VEC>(c);
+  if (!m.active) return;
+  for (int v0 = m.tc; v0 < m.cv; v0 += m.tpr) {
+    const int ch = v0 * VEC;
+    B2S_ROW_LOOP(m, n_out, o) {
+      V<VEC> best = splat<VEC>(-INFINITY);
+      int bi[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) bi[j] = -1;
+      for (int k = 0; k < k3; ++k) {
+        const int i = __ldg(&nbr[(int64_t)k * pitch + o]);
+        if (i < 0) continue;
+        const V<VEC> v = ldgv<VEC>(x + (int64_t)i * c + ch);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          if (bi[j] < 0 || v.v[j] > best.v[j] || (v.v[j] == best.v[j] && i < bi[j])) {
+            best.v[j] = v.v[j];
+            bi[j] = i;
+          }
+        }
       }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (bi[j] < 0) best.v[j] = 0.f;
+        arg[o * c + ch + j] = bi[j];
+      }
+      stv<VEC>(y + o * c + ch, best);
     }
-    y[e] = bi >= 0 ? best : 0.f;
-    arg[e] = bi;
   }
 }
 
 __global__ void __launch_bounds__(PW_THREADS) maxpool_bwd_kernel(const float* __restrict__ gy,
-                                                                 const int* __restrict__ arg, int64_t n_out, int c,
+                                                                 const int* __restrict__ arg, int64_t n_out,
+                                                                 const int* __restrict__ n_dev, int c,
                                                                  float* __restrict__ gx) {
+  n_out = b2s_rows(n_out, n_dev);
   const int64_t total = n_out * c;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int a = arg[e];
@@ -56,7 +152,9 @@ __global__ void __launch_bounds__(PW_THREADS) maxpool_bwd_kernel(const float* __
 
 // ---------------------------------------------------------------- per-plot segments ---------
 __global__ void __launch_bounds__(PW_THREADS) batch_counts_kernel(const int* __restrict__ rb, int stride, int64_t n,
-                                                                  int nb, int* __restrict__ counts) {
+                                                                  const int* __restrict__ n_dev, int nb,
+                                                                  int* __restrict__ counts) {
+  n = b2s_rows(n, n_dev);
   constexpr int CHUNK = 64;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t r0 = t * CHUNK, r1 = min(r0 + CHUNK, n);
@@ -83,7 +181,9 @@ template <bool MUL>
 __global__ void __launch_bounds__(PW_THREADS) segment_sum_kernel(const float* __restrict__ x,
                                                                  const float* __restrict__ x2,
                                                                  const int* __restrict__ rb, int stride, int64_t n,
-                                                                 int c, int nb, float* __restrict__ y) {
+                                                                 const int* __restrict__ n_dev, int c, int nb,
+                                                                 float* __restrict__ y) {
+  n = b2s_rows(n, n_dev);
   const int ch = blockIdx.y * 32 + (threadIdx.x & 31);
   const int ty = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_CTA;
@@ -111,31 +211,57 @@ __global__ void __launch_bounds__(PW_THREADS) scale_rows_kernel(float* __restric
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) y[e] *= scale[e / c];
 }
 
+// out[r, :] = y[batch(r), :] * scale[batch(r)]
+template <int VEC>
 __global__ void __launch_bounds__(PW_THREADS) segment_bcast_kernel(const float* __restrict__ y,
                                                                    const int* __restrict__ rb, int stride, int64_t n,
-                                                                   int c, const float* __restrict__ scale,
+                                                                   const int* __restrict__ n_dev, int c,
+                                                                   const float* __restrict__ scale,
                                                                    float* __restrict__ out) {
-  const int64_t total = n * c;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = e / c;
-    const int ch = (int)(e - r * c);
-    const int b = __ldg(&rb[r * stride]);
-    float v = __ldg(&y[(int64_t)b * c + ch]);
-    if (scale) v *= __ldg(&scale[b]);
-    out[e] = v;
+  n = b2s_rows(n, n_dev);
+  const RowMap m = row_map<VEC>(c);
+  if (!m.active) return;
+  for (int v0 = m.tc; v0 < m.cv; v0 += m.tpr) {
+    const int ch = v0 * VEC;
+    B2S_ROW_LOOP(m, n, r) {
+      const int b = __ldg(&rb[r * stride]);
+      V<VEC> v = ldgv<VEC>(y + (int64_t)b * c + ch);
+      if (scale) {
+        const float s = __ldg(&scale[b]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v.v[j] *= s;
+      }
+      stv<VEC>(out + r * c + ch, v);
+    }
   }
 }
 
+// out[r, :] = x[r, :] * y[batch(r), :]      (y_c == 1: per-plot scalar)
+template <int VEC>
 __global__ void __launch_bounds__(PW_THREADS) bcast_mul_kernel(const float* __restrict__ x,
                                                                const float* __restrict__ y,
                                                                const int* __restrict__ rb, int stride, int64_t n,
-                                                               int c, int y_c, float* __restrict__ out) {
-  const int64_t total = n * c;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = e / c;
-    const int ch = (int)(e - r * c);
-    const int b = __ldg(&rb[r * stride]);
-    out[e] = x[e] * __ldg(&y[(int64_t)b * y_c + (y_c == 1 ? 0 : ch)]);
+                                                               const int* __restrict__ n_dev, int c, int y_c,
+                                                               float* __restrict__ out) {
+  n = b2s_rows(n, n_dev);
+  const RowMap m = row_map<VEC>(c);
+  if (!m.active) return;
+  for (int v0 = m.tc; v0 < m.cv; v0 += m.tpr) {
+    const int ch = v0 * VEC;
+    B2S_ROW_LOOP(m, n, r) {
+      const int b = __ldg(&rb[r * stride]);
+      V<VEC> v = ldv<VEC>(x + r * c + ch);
+      if (y_c == 1) {
+        const float s = __ldg(&y[b]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v.v[j] *= s;
+      } else {
+        const V<VEC> g = ldgv<VEC>(y + (int64_t)b * c + ch);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v.v[j] *= g.v[j];
+      }
+      stv<VEC>(out + r * c + ch, v);
+    }
   }
 }
 
@@ -149,11 +275,14 @@ __global__ void __launch_bounds__(PW_THREADS) colreduce_kernel(const float* __re
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ invstd,
                                                                const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, int64_t n, int c,
-                                                               int act, ACC* __restrict__ ws) {
+                                                               const float* __restrict__ beta, int64_t n,
+                                                               const int* __restrict__ n_dev, int c, int act,
+                                                               ACC* __restrict__ ws) {
+  n = b2s_rows(n, n_dev);
   const int ch = blockIdx.y * 32 + (threadIdx.x & 31);
   const int ty = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_CTA;
+  if (r0 >= n) return;
   const int64_t r1 = min(r0 + ROWS_PER_CTA, n);
   __shared__ float sm[2][8][33];
   float a0 = 0.f, a1 = 0.f;
@@ -195,19 +324,22 @@ __global__ void __launch_bounds__(PW_THREADS) colreduce_kernel(const float* __re
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ ws, int64_t n, int c, float eps, float momentum,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ mean, float* __restrict__ invstd) {
+__global__ void bn_finalize_kernel(const double* __restrict__ ws, int64_t n, const int* __restrict__ n_dev, int c,
+                                   float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ mean,
+                                   float* __restrict__ invstd) {
+  n = b2s_rows(n, n_dev);
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
-  const double m = ws[ch] / (double)n;
-  double var = ws[c + ch] / (double)n - m * m;
+  const double dn = n > 0 ? (double)n : 1.0;
+  const double m = ws[ch] / dn;
+  double var = ws[c + ch] / dn - m * m;
   if (var < 0.0) var = 0.0;
   mean[ch] = (float)m;
   invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
   if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
   if (running_var) {
-    const double unb = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    const double unb = n > 1 ? var * dn / (dn - 1.0) : var;
     running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unb;
   }
 }
@@ -217,61 +349,98 @@ __global__ void double_to_float_kernel(const double* __restrict__ in, float* __r
   if (i < m) out[i] = (float)in[i];
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __restrict__ x,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ invstd,
                                                               const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, int64_t n, int c,
-                                                              int act, float* __restrict__ y) {
-  const int64_t total = n * c;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(e % c);
-    float v = (x[e] - __ldg(&mean[ch])) * __ldg(&invstd[ch]);
-    v = v * (gamma ? __ldg(&gamma[ch]) : 1.f) + (beta ? __ldg(&beta[ch]) : 0.f);
-    y[e] = act == 1 ? gelu_f(v) : v;
+                                                              const float* __restrict__ beta, int64_t n,
+                                                              const int* __restrict__ n_dev, int c, int act,
+                                                              float* __restrict__ y) {
+  n = b2s_rows(n, n_dev);
+  const RowMap m = row_map<VEC>(c);
+  if (!m.active) return;
+  for (int v0 = m.tc; v0 < m.cv; v0 += m.tpr) {
+    const int ch = v0 * VEC;
+    const V<VEC> mu = ldgv<VEC>(mean + ch), is = ldgv<VEC>(invstd + ch);
+    const V<VEC> ga = ldparam<VEC>(gamma, ch, 1.f), be = ldparam<VEC>(beta, ch, 0.f);
+    B2S_ROW_LOOP(m, n, r) {
+      V<VEC> v = ldv<VEC>(x + r * c + ch);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float t = (v.v[j] - mu.v[j]) * is.v[j];
+        t = t * ga.v[j] + be.v[j];
+        v.v[j] = act == 1 ? gelu_f(t) : t;
+      }
+      stv<VEC>(y + r * c + ch, v);
+    }
   }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-    const float* __restrict__ sums, int64_t n, int c, int act, int training, float* __restrict__ gx) {
-  const int64_t total = n * c;
-  const float inv_n = 1.f / (float)n;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(e % c);
-    const float is = __ldg(&invstd[ch]);
-    const float ga = gamma ? __ldg(&gamma[ch]) : 1.f;
-    const float xh = (x[e] - __ldg(&mean[ch])) * is;
-    float g = gy[e];
-    if (act == 1) g *= gelu_grad_f(xh * ga + (beta ? __ldg(&beta[ch]) : 0.f));
-    if (training) g = g - __ldg(&sums[ch]) * inv_n - xh * __ldg(&sums[c + ch]) * inv_n;
-    gx[e] = g * ga * is;
+    const float* __restrict__ sums, int64_t n, const int* __restrict__ n_dev, int c, int act, int training,
+    float* __restrict__ gx) {
+  n = b2s_rows(n, n_dev);
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+  const RowMap m = row_map<VEC>(c);
+  if (!m.active) return;
+  for (int v0 = m.tc; v0 < m.cv; v0 += m.tpr) {
+    const int ch = v0 * VEC;
+    const V<VEC> mu = ldgv<VEC>(mean + ch), is = ldgv<VEC>(invstd + ch);
+    const V<VEC> ga = ldparam<VEC>(gamma, ch, 1.f), be = ldparam<VEC>(beta, ch, 0.f);
+    V<VEC> s0 = splat<VEC>(0.f), s1 = splat<VEC>(0.f);
+    if (training) {
+      s0 = ldgv<VEC>(sums + ch);
+      s1 = ldgv<VEC>(sums + c + ch);
+    }
+    B2S_ROW_LOOP(m, n, r) {
+      const V<VEC> xv = ldv<VEC>(x + r * c + ch);
+      V<VEC> g = ldv<VEC>(gy + r * c + ch);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
+        float t = g.v[j];
+        if (act == 1) t *= gelu_grad_f(xh * ga.v[j] + be.v[j]);
+        if (training) t = t - s0.v[j] * inv_n - xh * s1.v[j] * inv_n;
+        g.v[j] = t * ga.v[j] * is.v[j];
+      }
+      stv<VEC>(gx + r * c + ch, g);
+    }
   }
 }
 
-__global__ void __launch_bounds__(PW_THREADS) gelu_fwd_kernel(const float* __restrict__ x, int64_t numel,
-                                                              float* __restrict__ y) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel; e += (int64_t)gridDim.x * blockDim.x)
-    y[e] = gelu_f(x[e]);
-}
-
-__global__ void __launch_bounds__(PW_THREADS) gelu_bwd_kernel(const float* __restrict__ gy,
-                                                              const float* __restrict__ x, int64_t numel,
-                                                              float* __restrict__ gx) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < numel; e += (int64_t)gridDim.x * blockDim.x)
-    gx[e] = gy[e] * gelu_grad_f(x[e]);
-}
-
-// s = a + b (kept for the backward), y = gelu(s): the residual join of every block (senet_block.py:93-94)
-__global__ void __launch_bounds__(PW_THREADS) add_gelu_fwd_kernel(const float4* __restrict__ a,
-                                                                  const float4* __restrict__ b, int64_t n4,
-                                                                  float4* __restrict__ s, float4* __restrict__ y) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
-    const float4 av = a[e], bv = b[e];
-    const float4 sv = make_float4(av.x + bv.x, av.y + bv.y, av.z + bv.z, av.w + bv.w);
-    s[e] = sv;
-    y[e] = make_float4(gelu_f(sv.x), gelu_f(sv.y), gelu_f(sv.z), gelu_f(sv.w));
+// flat elementwise kernels (numel = rows * c)
+template <int VEC, int OP>  // OP 0: y = gelu(x)   1: gx = gy * gelu'(x)   2: s = a + b, y = gelu(s)
+__global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          int64_t n, const int* __restrict__ n_dev, int c,
+                                                          float* __restrict__ o0, float* __restrict__ o1) {
+  n = b2s_rows(n, n_dev);
+  const int64_t total = n * c / VEC;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const V<VEC> av = ldv<VEC>(a + e * VEC);
+    V<VEC> r0, r1;
+    if (OP == 0) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) r0.v[j] = gelu_f(av.v[j]);
+      stv<VEC>(o0 + e * VEC, r0);
+    } else if (OP == 1) {
+      const V<VEC> bv = ldv<VEC>(b + e * VEC);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) r0.v[j] = av.v[j] * gelu_grad_f(bv.v[j]);
+      stv<VEC>(o0 + e * VEC, r0);
+    } else {
+      const V<VEC> bv = ldv<VEC>(b + e * VEC);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        r0.v[j] = av.v[j] + bv.v[j];
+        r1.v[j] = gelu_f(r0.v[j]);
+      }
+      stv<VEC>(o0 + e * VEC, r0);
+      stv<VEC>(o1 + e * VEC, r1);
+    }
   }
 }
 
@@ -280,19 +449,22 @@ dim3 colgrid(int64_t n, int c) { return dim3((unsigned)ceil_div64(n, ROWS_PER_CT
 }  // namespace
 
 // ================================================================= C ABI ======================
-extern "C" int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_out, int32_t c, int32_t k3, float* y,
-                                   int32_t* arg, b2s_stream_t stream) {
+extern "C" int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_out, const int32_t* n_out_dev,
+                                   int32_t c, int32_t k3, float* y, int32_t* arg, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_out >= 0 && c > 0 && k3 > 0, "bad sizes");
   if (n_out == 0) return B2S_OK;
   B2S_CHECK_ARG(x && nbr && y && arg, "null pointer");
-  maxpool_fwd_kernel<<<grid_for(n_out * c, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(x, nbr, n_out, c, k3, y,
-                                                                                           arg);
+  cudaStream_t st = as_stream(stream);
+  if (vec_of(c, x, y) == 4)
+    maxpool_fwd_kernel<4><<<rows_grid(n_out, c, 4), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg);
+  else
+    maxpool_fwd_kernel<1><<<rows_grid(n_out, c, 1), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-extern "C" int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t n_in, int64_t n_out, int32_t c,
-                                   float* gx, b2s_stream_t stream) {
+extern "C" int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t n_in, int64_t n_out,
+                                   const int32_t* n_out_dev, int32_t c, float* gx, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c > 0, "bad sizes");
   cudaStream_t st = as_stream(stream);
   if (n_in > 0) {
@@ -301,67 +473,79 @@ extern "C" int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t 
   }
   if (n_out == 0) return B2S_OK;
   B2S_CHECK_ARG(gy && arg, "null pointer");
-  maxpool_bwd_kernel<<<grid_for(n_out * c, PW_THREADS), PW_THREADS, 0, st>>>(gy, arg, n_out, c, gx);
+  maxpool_bwd_kernel<<<grid_for(n_out * c, PW_THREADS), PW_THREADS, 0, st>>>(gy, arg, n_out, n_out_dev, c, gx);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_batch_counts(const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
-                                    int32_t num_batches, int32_t* counts, b2s_stream_t stream) {
+                                    const int32_t* n_dev, int32_t num_batches, int32_t* counts,
+                                    b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && num_batches > 0 && counts && row_batch_stride > 0, "bad arguments");
   cudaStream_t st = as_stream(stream);
   B2S_CUDA(cudaMemsetAsync(counts, 0, num_batches * sizeof(int), st));
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(row_batch, "null pointer");
   batch_counts_kernel<<<(unsigned)ceil_div64(ceil_div64(n, 64), PW_THREADS), PW_THREADS, 0, st>>>(
-      row_batch, row_batch_stride, n, num_batches, counts);
+      row_batch, row_batch_stride, n, n_dev, num_batches, counts);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_segment_sum(const float* x, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
-                                   int32_t c, int32_t num_batches, const float* scale, float* y,
-                                   b2s_stream_t stream) {
+                                   const int32_t* n_dev, int32_t c, int32_t num_batches, const float* scale,
+                                   float* y, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && num_batches > 0 && y && row_batch_stride > 0, "bad arguments");
   cudaStream_t st = as_stream(stream);
   B2S_CUDA(cudaMemsetAsync(y, 0, (size_t)num_batches * c * sizeof(float), st));
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(x && row_batch, "null pointer");
-  segment_sum_kernel<false><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, nullptr, row_batch, row_batch_stride, n, c,
-                                                                  num_batches, y);
+  segment_sum_kernel<false><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, nullptr, row_batch, row_batch_stride, n, n_dev,
+                                                                  c, num_batches, y);
   if (scale) scale_rows_kernel<<<grid_for((int64_t)num_batches * c, PW_THREADS), PW_THREADS, 0, st>>>(y, scale, num_batches, c);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_segment_bcast(const float* y, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
-                                     int32_t c, const float* scale, float* x_out, b2s_stream_t stream) {
+                                     const int32_t* n_dev, int32_t c, const float* scale, float* x_out,
+                                     b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && row_batch_stride > 0, "bad arguments");
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(y && row_batch && x_out, "null pointer");
-  segment_bcast_kernel<<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(y, row_batch,
-                                                                                         row_batch_stride, n, c,
-                                                                                         scale, x_out);
+  cudaStream_t st = as_stream(stream);
+  if (vec_of(c, y, x_out) == 4)
+    segment_bcast_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(y, row_batch, row_batch_stride, n, n_dev, c,
+                                                                       scale, x_out);
+  else
+    segment_bcast_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(y, row_batch, row_batch_stride, n, n_dev, c,
+                                                                       scale, x_out);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
+static void launch_bcast_mul(const float* x, const float* y, const int32_t* rb, int32_t stride, int64_t n,
+                             const int32_t* n_dev, int32_t c, int32_t y_c, float* out, cudaStream_t st) {
+  if (vec_of(c, x, out, y_c == 1 ? nullptr : y) == 4)
+    bcast_mul_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, y, rb, stride, n, n_dev, c, y_c, out);
+  else
+    bcast_mul_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(x, y, rb, stride, n, n_dev, c, y_c, out);
+}
+
 extern "C" int32_t b2s_bcast_mul_fwd(const float* x, const float* y, const int32_t* row_batch,
-                                     int32_t row_batch_stride, int64_t n, int32_t c, int32_t y_c, float* out,
-                                     b2s_stream_t stream) {
+                                     int32_t row_batch_stride, int64_t n, const int32_t* n_dev, int32_t c,
+                                     int32_t y_c, float* out, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && (y_c == c || y_c == 1) && row_batch_stride > 0, "bad arguments");
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(x && y && row_batch && out, "null pointer");
-  bcast_mul_kernel<<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(x, y, row_batch,
-                                                                                     row_batch_stride, n, c, y_c,
-                                                                                     out);
+  launch_bcast_mul(x, y, row_batch, row_batch_stride, n, n_dev, c, y_c, out, as_stream(stream));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float* y, const int32_t* row_batch,
-                                     int32_t row_batch_stride, int64_t n, int32_t c, int32_t num_batches, float* gx,
-                                     float* gy, b2s_stream_t stream) {
+                                     int32_t row_batch_stride, int64_t n, const int32_t* n_dev, int32_t c,
+                                     int32_t num_batches, float* gx, float* gy, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && num_batches > 0 && row_batch_stride > 0, "bad arguments");
   cudaStream_t st = as_stream(stream);
   if (gy) B2S_CUDA(cudaMemsetAsync(gy, 0, (size_t)num_batches * c * sizeof(float), st));
@@ -369,109 +553,128 @@ extern "C" int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float
   B2S_CHECK_ARG(g && row_batch, "null pointer");
   if (gx) {
     B2S_CHECK_ARG(y, "null pointer");
-    bcast_mul_kernel<<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, st>>>(g, y, row_batch, row_batch_stride, n, c, c,
-                                                                         gx);
+    launch_bcast_mul(g, y, row_batch, row_batch_stride, n, n_dev, c, c, gx, st);
   }
   if (gy) {
     B2S_CHECK_ARG(x, "null pointer");
-    segment_sum_kernel<true><<<colgrid(n, c), PW_THREADS, 0, st>>>(g, x, row_batch, row_batch_stride, n, c,
+    segment_sum_kernel<true><<<colgrid(n, c), PW_THREADS, 0, st>>>(g, x, row_batch, row_batch_stride, n, n_dev, c,
                                                                    num_batches, gy);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-extern "C" int32_t b2s_colsum(const float* x, int64_t n, int32_t c, float* out, b2s_stream_t stream) {
+extern "C" int32_t b2s_colsum(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* out,
+                              b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && out, "bad arguments");
   cudaStream_t st = as_stream(stream);
   B2S_CUDA(cudaMemsetAsync(out, 0, c * sizeof(float), st));
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(x, "null pointer");
   colreduce_kernel<0, float><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr, n,
-                                                                   c, 0, out);
+                                                                   n_dev, c, 0, out);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-extern "C" int32_t b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
-                                float* running_var, double* stats_ws, float* mean, float* invstd,
-                                b2s_stream_t stream) {
+extern "C" int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float eps,
+                                float momentum, float* running_mean, float* running_var, double* stats_ws,
+                                float* mean, float* invstd, b2s_stream_t stream) {
   B2S_CHECK_ARG(n > 0 && c > 0, "n > 0 and c > 0");
   B2S_CHECK_ARG(x && stats_ws && mean && invstd, "null pointer");
   cudaStream_t st = as_stream(stream);
   B2S_CUDA(cudaMemsetAsync(stats_ws, 0, 2 * (size_t)c * sizeof(double), st));
   colreduce_kernel<1, double><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                    n, c, 0, stats_ws);
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(stats_ws, n, c, eps, momentum, running_mean, running_var, mean,
-                                                      invstd);
+                                                                    n, n_dev, c, 0, stats_ws);
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(stats_ws, n, n_dev, c, eps, momentum, running_mean,
+                                                      running_var, mean, invstd);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma,
-                                const float* beta, int64_t n, int32_t c, int32_t act, float* y,
+                                const float* beta, int64_t n, const int32_t* n_dev, int32_t c, int32_t act, float* y,
                                 b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && (act == 0 || act == 1), "bad arguments");
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(x && mean && invstd && y, "null pointer");
-  bn_apply_kernel<<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(x, mean, invstd, gamma, beta, n,
-                                                                                    c, act, y);
+  cudaStream_t st = as_stream(stream);
+  if (vec_of(c, x, y, mean, invstd) == 4 && vec_of(c, gamma, beta) == 4)
+    bn_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y);
+  else
+    bn_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const float* mean, const float* invstd,
-                                     const float* gamma, const float* beta, int64_t n, int32_t c, int32_t act,
-                                     double* stats_ws, float* sums, b2s_stream_t stream) {
+                                     const float* gamma, const float* beta, int64_t n, const int32_t* n_dev,
+                                     int32_t c, int32_t act, double* stats_ws, float* sums, b2s_stream_t stream) {
   B2S_CHECK_ARG(n > 0 && c > 0 && (act == 0 || act == 1), "bad arguments");
   B2S_CHECK_ARG(gy && x && mean && invstd && stats_ws && sums, "null pointer");
   cudaStream_t st = as_stream(stream);
   B2S_CUDA(cudaMemsetAsync(stats_ws, 0, 2 * (size_t)c * sizeof(double), st));
-  colreduce_kernel<2, double><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, gy, mean, invstd, gamma, beta, n, c, act,
-                                                                    stats_ws);
+  colreduce_kernel<2, double><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, gy, mean, invstd, gamma, beta, n, n_dev, c,
+                                                                    act, stats_ws);
   double_to_float_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(stats_ws, sums, 2 * c);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd,
-                                    const float* gamma, const float* beta, const float* sums, int64_t n, int32_t c,
-                                    int32_t act, int32_t training, float* gx, b2s_stream_t stream) {
+                                    const float* gamma, const float* beta, const float* sums, int64_t n,
+                                    const int32_t* n_dev, int32_t c, int32_t act, int32_t training, float* gx,
+                                    b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && (act == 0 || act == 1), "bad arguments");
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(gy && x && mean && invstd && gx && (sums || !training), "null pointer");
-  bn_bwd_apply_kernel<<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(
-      gy, x, mean, invstd, gamma, beta, sums, n, c, act, training, gx);
+  cudaStream_t st = as_stream(stream);
+  if (vec_of(c, gy, x, gx, mean) == 4 && vec_of(c, invstd, gamma, beta, sums) == 4)
+    bn_bwd_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(gy, x, mean, invstd, gamma, beta, sums, n,
+                                                                      n_dev, c, act, training, gx);
+  else
+    bn_bwd_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(gy, x, mean, invstd, gamma, beta, sums, n,
+                                                                      n_dev, c, act, training, gx);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-extern "C" int32_t b2s_gelu_fwd(const float* x, int64_t numel, float* y, b2s_stream_t stream) {
-  B2S_CHECK_ARG(numel >= 0, "numel >= 0");
-  if (numel == 0) return B2S_OK;
+template <int OP>
+static int32_t launch_flat(const float* a, const float* b, int64_t n, const int32_t* n_dev, int32_t c, float* o0,
+                           float* o1, cudaStream_t st) {
+  if (vec_of(c, a, b, o0, o1) == 4)
+    flat_kernel<4, OP><<<grid_for(n * c / 4, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1);
+  else
+    flat_kernel<1, OP><<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1);
+  return 0;
+}
+
+extern "C" int32_t b2s_gelu_fwd(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y,
+                                b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0, "n >= 0 and c > 0");
+  if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(x && y, "null pointer");
-  gelu_fwd_kernel<<<grid_for(numel, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(x, numel, y);
+  launch_flat<0>(x, nullptr, n, n_dev, c, y, nullptr, as_stream(stream));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-extern "C" int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t numel, float* sum, float* y,
-                                    b2s_stream_t stream) {
-  B2S_CHECK_ARG(numel >= 0 && numel % 4 == 0, "numel must be a non-negative multiple of 4");
-  if (numel == 0) return B2S_OK;
+extern "C" int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t n, const int32_t* n_dev, int32_t c,
+                                    float* sum, float* y, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0, "n >= 0 and c > 0");
+  if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(a && b && sum && y, "null pointer");
-  add_gelu_fwd_kernel<<<grid_for(numel / 4, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), numel / 4,
-      reinterpret_cast<float4*>(sum), reinterpret_cast<float4*>(y));
+  launch_flat<2>(a, b, n, n_dev, c, sum, y, as_stream(stream));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
-extern "C" int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t numel, float* gx, b2s_stream_t stream) {
-  B2S_CHECK_ARG(numel >= 0, "numel >= 0");
-  if (numel == 0) return B2S_OK;
+extern "C" int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t n, const int32_t* n_dev, int32_t c,
+                                float* gx, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0, "n >= 0 and c > 0");
+  if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(gy && x && gx, "null pointer");
-  gelu_bwd_kernel<<<grid_for(numel, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(gy, x, numel, gx);
+  launch_flat<1>(gy, x, n, n_dev, c, gx, nullptr, as_stream(stream));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -56,8 +56,10 @@ __device__ __forceinline__ uint32_t mn_offset(int row, int chunk) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
     wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy, const int* __restrict__ nbr,
-                    int64_t n_out, int c_in, int c_out, int ci_tiles, int co_tiles, int64_t rows_per_split,
-                    int use_atomic, float* __restrict__ gw) {
+                    int64_t n_out, const int* __restrict__ n_out_dev, int c_in, int c_out, int ci_tiles, int co_tiles,
+                    int64_t rows_per_split, int use_atomic, float* __restrict__ gw) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
   using L = WgSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         const int row = p * 4 + warp;
         const int64_t o = r0 + row;
         int i = -1;
-        if (o < r_end) i = nbr ? __ldg(&nbr[(int64_t)k * n_out + o]) : (int)o;
+        if (o < r_end) i = nbr ? __ldg(&nbr[(int64_t)k * pitch + o]) : (int)o;
         const uint32_t nbytes = i >= 0 ? 16u : 0u;
         const int64_t xi = i >= 0 ? i : 0, oo = i >= 0 ? o : 0;
         if (lane < a_chunks) cp_async16(a_stage + mn_offset(row, lane), x + xi * c_in + ci0 + lane * 4, nbytes);
@@ -222,8 +224,10 @@ struct WgSmallSmem {
 template <int STAGES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
     wgrad_small_tc_kernel(const float4* __restrict__ x4, const float* __restrict__ gy, const int* __restrict__ nbr,
-                          int64_t n_out, int c_in, int c_out, int k3, int co_tiles, int64_t rows_per_split,
-                          float* __restrict__ gw) {
+                          int64_t n_out, const int* __restrict__ n_out_dev, int c_in, int c_out, int k3, int co_tiles,
+                          int64_t rows_per_split, float* __restrict__ gw) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
   using L = WgSmallSmem<STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -285,8 +289,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
         const int64_t oo = live ? o : 0;
         if (lane < a_chunks) cp_async16(a_stage + mn_offset(row, lane), gy + oo * c_out + co0 + lane * 4, live ? 16u : 0u);
         int ia = -1, ib = -1;
-        if (live && kA < k3) ia = __ldg(&nbr[(int64_t)kA * n_out + o]);
-        if (live && kB < k3) ib = __ldg(&nbr[(int64_t)kB * n_out + o]);
+        if (live && kA < k3) ia = __ldg(&nbr[(int64_t)kA * pitch + o]);
+        if (live && kB < k3) ib = __ldg(&nbr[(int64_t)kB * pitch + o]);
         cp_async16(b_stage + mn_offset(row, lane), x4 + (ia >= 0 ? ia : 0), ia >= 0 ? 16u : 0u);
         cp_async16(b_stage + mn_offset(row, lane + 32), x4 + (ib >= 0 ? ib : 0), ib >= 0 ? 16u : 0u);
       }
@@ -360,8 +364,8 @@ __global__ void __launch_bounds__(256) wg_pad_rows4_kernel(const float* __restri
   }
 }
 
-int launch_wgrad_small(const float* x, const float* gy, const int* nbr, int64_t n_in, int64_t n_out, int c_in, int c_out,
-                       int k3, float* gw, void* workspace, cudaStream_t st) {
+int launch_wgrad_small(const float* x, const float* gy, const int* nbr, int64_t n_in, int64_t n_out, const int* n_out_dev,
+                       int c_in, int c_out, int k3, float* gw, void* workspace, cudaStream_t st) {
   constexpr int STAGES = 4;
   using L = WgSmallSmem<STAGES>;
   auto kern = wgrad_small_tc_kernel<STAGES>;
@@ -387,7 +391,7 @@ int launch_wgrad_small(const float* x, const float* gy, const int* nbr, int64_t 
   splits = ceil_div64(n_out, rows);
   cudaMemsetAsync(gw, 0, (size_t)k3 * c_in * c_out * sizeof(float), st);
   dim3 grid((unsigned)base, (unsigned)splits);
-  kern<<<grid, WG_THREADS, L::DYN_BYTES, st>>>(x4, gy, nbr, n_out, c_in, c_out, k3, co_tiles, rows, gw);
+  kern<<<grid, WG_THREADS, L::DYN_BYTES, st>>>(x4, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, co_tiles, rows, gw);
   return 0;
 }
 
@@ -402,8 +406,8 @@ bool wgrad_tc_disabled() {
 }
 
 template <int BN, int STAGES>
-int launch_wgrad(const float* x, const float* gy, const int* nbr, int64_t n_out, int c_in, int c_out, int k3, float* gw,
-                 cudaStream_t st) {
+int launch_wgrad(const float* x, const float* gy, const int* nbr, int64_t n_out, const int* n_out_dev, int c_in, int c_out,
+                 int k3, float* gw, cudaStream_t st) {
   using L = WgSmem<BN, STAGES>;
   auto kern = wgrad_tc_kernel<BN, STAGES>;
   static bool attr_set = false;
@@ -428,7 +432,8 @@ int launch_wgrad(const float* x, const float* gy, const int* nbr, int64_t n_out,
   const int use_atomic = splits > 1 ? 1 : 0;
   if (use_atomic) cudaMemsetAsync(gw, 0, (size_t)k3 * c_in * c_out * sizeof(float), st);
   dim3 grid((unsigned)base, (unsigned)splits);
-  kern<<<grid, WG_THREADS, L::DYN_BYTES, st>>>(x, gy, nbr, n_out, c_in, c_out, ci_tiles, co_tiles, rows, use_atomic, gw);
+  kern<<<grid, WG_THREADS, L::DYN_BYTES, st>>>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, ci_tiles, co_tiles, rows,
+                                               use_atomic, gw);
   return 0;
 }
 
@@ -443,11 +448,12 @@ bool b2s_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_o
 
 int64_t b2s_wgrad_tc_workspace_bytes(int32_t c_in, int64_t n_in) { return c_in <= 4 ? ((n_in * 16 + 255) & ~(int64_t)255) : 0; }
 
-int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out, int32_t c_in,
-                      int32_t c_out, int32_t k3, float* gw, void* workspace, cudaStream_t st) {
-  if (c_in <= 4) return launch_wgrad_small(x, gy, nbr, n_in, n_out, c_in, c_out, k3, gw, workspace, st);
+int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
+                      const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace,
+                      cudaStream_t st) {
+  if (c_in <= 4) return launch_wgrad_small(x, gy, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, gw, workspace, st);
   const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
-  if (bn == 256) return launch_wgrad<256, 4>(x, gy, nbr, n_out, c_in, c_out, k3, gw, st);
-  if (bn == 128) return launch_wgrad<128, 3>(x, gy, nbr, n_out, c_in, c_out, k3, gw, st);
-  return launch_wgrad<64, 4>(x, gy, nbr, n_out, c_in, c_out, k3, gw, st);
+  if (bn == 256) return launch_wgrad<256, 4>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
+  if (bn == 128) return launch_wgrad<128, 3>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
+  return launch_wgrad<64, 4>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
 }

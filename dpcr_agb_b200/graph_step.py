@@ -1,0 +1,183 @@
+"""One MSENet training step as ONE CUDA graph.
+
+The eager path (``train.Trainer.step``) issues ~350 C-ABI calls per step from Python and synchronises with the
+host once per coordinate map (its row count decides the next allocation), so on a B200 the host, not the GPU,
+sets the step time.  Here every coordinate map lives at a fixed row CAPACITY, its live row count stays in device
+memory (``include/b200sparse.h`` "row counts"), and the whole step -- voxel quantisation -> coordinate hash ->
+strided / kernel maps -> forward -> loss -> backward -> [gradient all-reduce] -> AdaBelief -- is captured once
+with ``torch.cuda.graph`` and replayed per batch.  Per replay the host only (1) copies the raw points into the
+static input buffers, (2) uploads 16 floats of optimiser hyper-parameters and the per-plot drop-path draws,
+(3) launches the graph.  Nothing is cached across steps: every replay rebuilds every coordinate structure from
+the new points.
+
+Reference call sites: the step is ``BaseModel.optimize_parameters`` (torch_points3d/models/base_model.py:230-256)
+fed by ``MinkowskiBaselineModel.set_input`` (models/instance/minkowski.py:67-80) and the ``GridSampling3D``
+transform (core/data_transform/grid_transform.py:112-128).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+from . import train as T
+from .msenet import DropPath
+from .quantize import GridSampling3D
+
+
+def plan_capacities(gs: GridSampling3D, ME, model, batches, num_plots, bounds, margin=0.12, align=128):
+    """Row capacities per tensor stride for :class:`GraphStep`: the largest row count seen at every level over
+    the sample ``batches`` (dicts with ``pos``/``batch``/``feats``/``perm`` CUDA tensors), plus ``margin``, rounded
+    up to ``align``.  Runs the dynamic (exact-size) path without gradients; a few host syncs, done once."""
+    seen = {}
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        for d in batches:
+            vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d.get("perm"), num_plots=num_plots,
+                     bounds=bounds)
+            x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"])
+            model(x)
+            for key, m in x.coordinate_manager.maps.items():
+                ts = key.tensor_stride[0]
+                if ts > 0:
+                    seen[ts] = max(seen.get(ts, 0), m.n)
+    model.train(was_training)
+    return {ts: max(align, -(-int(n * (1.0 + margin)) // align) * align) for ts, n in seen.items()}
+
+
+class GraphStep:
+    """Captured training step.  ``load(host_batch)`` + ``step()`` per batch; ``verify()`` (one host read) checks
+    that no capacity was exceeded by the steps since the last call."""
+
+    def __init__(self, trainer: T.Trainer, gs: GridSampling3D, num_plots, n_points, bounds, capacities, feat_dim=3,
+                 target_dim=2, capture_collective=True):
+        self.tr, self.gs = trainer, gs
+        self.B, self.n_points, self.bounds = int(num_plots), int(n_points), bounds
+        self.capacities = dict(capacities)
+        dev = trainer.opt.flat_param.device
+        self.dev = dev
+        self.inp = {
+            "pos": torch.zeros((n_points, 3), dtype=torch.float32, device=dev),
+            "feats": torch.zeros((n_points, feat_dim), dtype=torch.float32, device=dev),
+            "batch": torch.zeros(n_points, dtype=torch.int32, device=dev),
+            "perm": torch.arange(n_points, dtype=torch.int32, device=dev),
+            "target": torch.zeros((num_plots, target_dim), dtype=torch.float32, device=dev),
+        }
+        self.n_points_dev = torch.full((1,), n_points, dtype=torch.int32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.drops = [m for m in trainer.model.modules() if isinstance(m, DropPath)]
+        nd = max(len(self.drops), 1)
+        self.drop_dev = torch.ones((nd, self.B, 1), dtype=torch.float32, device=dev)
+        self.drop_pinned = torch.ones((nd, self.B, 1), dtype=torch.float32).pin_memory()
+        for i, m in enumerate(self.drops):
+            m.static_mask = self.drop_dev[i]
+        self.capture_collective = capture_collective or trainer.world == 1
+        self.graph = None
+        self.graph_tail = None
+        self.status = None          # int32 device tensor: live row counts / flags recorded during capture
+        self.status_meta = []
+        self.launches_per_step = 0  # C-ABI calls recorded into the graph (== kernels-of-ours launches, lower bound)
+
+    # ------------------------------------------------------------------ the step body (captured)
+    def _forward_backward(self):
+        tr, ME = self.tr, self.tr.ME
+        vox = self.gs(self.inp["pos"], self.inp["batch"], tensors=(self.inp["feats"],), order=self.inp["perm"],
+                      num_plots=self.B, bounds=self.bounds, capacity=self.capacities[1],
+                      n_points_dev=self.n_points_dev)
+        tr.opt.zero_grad()
+        x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"], num_rows=vox["num_rows"],
+                            capacities=self.capacities, num_batches=self.B)
+        pred = tr.model(x)
+        loss = T.reg_loss(pred, self.inp["target"], tr.center, tr.scale)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+        cm = x.coordinate_manager
+        self.status_meta = [(what, cap) for what, cap, _ in cm.checks]
+        status = torch.cat([t.reshape(-1)[:1] for _, _, t in cm.checks])
+        if self.status is None:
+            self.status = torch.zeros_like(status)
+        # running maximum over replays since the last verify()
+        torch.maximum(self.status, status, out=self.status)
+
+    def _tail(self):
+        T.allreduce_mean_(self.tr.opt.flat_grad, self.tr.world)
+        self.tr.opt.step_from_device()
+
+    def _body(self):
+        self._forward_backward()
+        if self.capture_collective:
+            self._tail()
+
+    # ------------------------------------------------------------------ capture / replay
+    def capture(self, warmup=2):
+        """Warm up on a side stream (kernel attributes, allocator, cuBLAS handles), then capture."""
+        tr = self.tr
+        tr.model.train()
+        tr.opt.upload_hyper()                     # valid hyper-parameters for the warm-up steps
+        tr.opt.step_count -= 1
+        snapshot = [t.clone() for t in (tr.opt.flat_param, tr.opt.exp_avg, tr.opt.exp_avg_var)]
+        buffers = [(b, b.clone()) for b in tr.model.buffers()]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._forward_backward()
+                self._tail()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        # the warm-up steps must not count as training: restore parameters, optimiser state and BN buffers
+        for dst, src in zip((tr.opt.flat_param, tr.opt.exp_avg, tr.opt.exp_avg_var), snapshot):
+            dst.copy_(src)
+        for b, saved in buffers:
+            b.copy_(saved)
+        self.status.zero_()
+        calls0 = L.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches_per_step = L.launch_count - calls0
+        if not self.capture_collective:
+            self.graph_tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_tail):
+                self.tr.opt.step_from_device()
+        return self
+
+    def load(self, host_batch, non_blocking=True):
+        """Copy one collated batch (pinned host tensors or device tensors) into the static input buffers."""
+        for k, dst in self.inp.items():
+            src = host_batch[k]
+            assert src.shape == dst.shape, f"{k}: {tuple(src.shape)} does not match the captured shape {tuple(dst.shape)}"
+            dst.copy_(src, non_blocking=non_blocking)
+
+    def step(self):
+        """Replay the captured step on the data currently in the input buffers; returns the on-device loss."""
+        tr = self.tr
+        tr.num_batches += 1
+        tr.opt.lr = tr.sched.lr_at(tr.num_batches / tr.batches_per_epoch)
+        tr.opt.upload_hyper()
+        if self.drops:
+            for i, m in enumerate(self.drops):
+                vals = m.draw(self.B) if tr.model.training else [1.0] * self.B
+                self.drop_pinned[i, :, 0] = torch.tensor(vals)
+            self.drop_dev.copy_(self.drop_pinned, non_blocking=True)
+        self.graph.replay()
+        if not self.capture_collective:
+            T.allreduce_mean_(tr.opt.flat_grad, tr.world)
+            self.graph_tail.replay()
+        return self.loss
+
+    def verify(self):
+        """One host read: raises if any replay since the last call exceeded a row capacity or left the packed
+        coordinate range; returns {description: largest value seen}."""
+        vals = self.status.tolist()
+        self.status.zero_()
+        out = {}
+        for (what, cap), v in zip(self.status_meta, vals):
+            out[what] = v
+            if cap == 0:
+                if v != 0:
+                    raise L.B2SError(f"{what} raised on the device (B2S_EOVERFLOW)")
+            elif v > cap:
+                raise L.B2SError(f"{what}: {v} exceeds the planned capacity {cap}; re-plan with larger capacities")
+        return out

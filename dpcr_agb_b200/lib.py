@@ -21,38 +21,39 @@ SIGNATURES = {
     "b2s_last_error": (ctypes.c_char_p, []),
     "b2s_version": (_i32, []),
     "b2s_device_check": (_i32, []),
-    "b2s_quantize_points": (_i32, [_vp, _i64, _f32, _vp, _vp, _vp]),
+    "b2s_quantize_points": (_i32, [_vp, _i64, _vp, _f32, _vp, _vp, _vp]),
     "b2s_quantize_workspace_bytes": (_i64, [_i64, _vp]),
-    "b2s_quantize_count": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "b2s_quantize_fill": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "b2s_gather_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "b2s_quantize_count": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "b2s_quantize_fill": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "b2s_gather_rows": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_hash_capacity": (_i64, [_i64]),
     "b2s_scan_workspace_bytes": (_i64, [_i64]),
-    "b2s_coordmap_insert": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "b2s_coordmap_fill": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "b2s_kernel_map": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
+    "b2s_coordmap_insert": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "b2s_coordmap_fill": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "b2s_kernel_map": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     "b2s_kernel_map_pair_counts": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "b2s_kernel_map_pairs_fill": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b2s_conv_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32]),
-    "b2s_conv_gather_gemm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp]),
-    "b2s_conv_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp]),
-    "b2s_colsum": (_i32, [_vp, _i64, _i32, _vp, _vp]),
-    "b2s_maxpool_fwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "b2s_maxpool_bwd": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
-    "b2s_batch_counts": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp]),
-    "b2s_segment_sum": (_i32, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "b2s_segment_bcast": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
-    "b2s_bcast_mul_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp]),
-    "b2s_bcast_mul_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "b2s_bn_stats": (_i32, [_vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "b2s_bn_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
-    "b2s_bn_bwd_reduce": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "b2s_bn_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
-    "b2s_gelu_fwd": (_i32, [_vp, _i64, _vp, _vp]),
-    "b2s_gelu_bwd": (_i32, [_vp, _vp, _i64, _vp, _vp]),
-    "b2s_add_gelu_fwd": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "b2s_conv_gather_gemm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32,
+                                    _vp]),
+    "b2s_conv_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "b2s_colsum": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
+    "b2s_maxpool_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2s_maxpool_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp]),
+    "b2s_batch_counts": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
+    "b2s_segment_sum": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2s_segment_bcast": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "b2s_bcast_mul_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "b2s_bcast_mul_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2s_bn_stats": (_i32, [_vp, _i64, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2s_bn_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "b2s_bn_bwd_reduce": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2s_bn_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "b2s_gelu_fwd": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
+    "b2s_gelu_bwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp]),
+    "b2s_add_gelu_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "b2s_grad_check": (_i32, [_vp, _i64, _f32, _vp, _vp]),
-    "b2s_adabelief_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "b2s_adabelief_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -161,7 +162,7 @@ def call(name: str, *args):
     if _profile is not None and (_profile_names is None or name in _profile_names):
         key = name
         if name == "b2s_conv_gather_gemm":            # w_layout bit 0 set == dgrad
-            key = name + (":dgrad" if (args[9] & 1) else ":fwd")
+            key = name + (":dgrad" if (args[10] & 1) else ":fwd")
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         rc = fn(*conv, stream())

@@ -47,6 +47,15 @@ class DropPath(nn.Module):
         self.drop_prob, self.scale_by_keep = drop_prob, scale_by_keep
         self._ME = [ME]                      # list: keep the namespace out of nn.Module registration
         self.mul = ME.MinkowskiBroadcastMultiplication()
+        # captured-graph mode (dpcr_agb_b200.graph_step): a persistent [B,1] device tensor that the host refills
+        # with draw() before every replay, instead of a fresh tensor per call
+        self.static_mask = None
+
+    def draw(self, nb):
+        """The per-plot keep/scale values of one forward call (python ``random``, the reference's RNG)."""
+        keep = 1.0 - self.drop_prob
+        scale = 1.0 / keep if (keep > 0.0 and self.scale_by_keep) else 1.0
+        return [scale if random.uniform(0, 1) > self.drop_prob else 0.0 for _ in range(nb)]
 
     def forward(self, x):
         if not self.training:
@@ -54,10 +63,10 @@ class DropPath(nn.Module):
         ME = self._ME[0]
         cm = x.coordinate_manager
         nb = cm.num_batches if isinstance(cm.num_batches, int) else cm.num_batches()
-        keep = 1.0 - self.drop_prob
-        scale = 1.0 / keep if (keep > 0.0 and self.scale_by_keep) else 1.0
-        vals = [scale if random.uniform(0, 1) > self.drop_prob else 0.0 for _ in range(nb)]
-        mask = torch.tensor(vals, dtype=x.F.dtype).view(nb, 1).to(x.F.device, non_blocking=True)
+        if self.static_mask is not None:
+            mask = self.static_mask
+        else:
+            mask = torch.tensor(self.draw(nb), dtype=x.F.dtype).view(nb, 1).to(x.F.device, non_blocking=True)
         glob = ME.SparseTensor(mask, coordinate_map_key=cm.origin(x.coordinate_map_key), coordinate_manager=cm)
         return self.mul(x, glob)
 

@@ -26,7 +26,8 @@ class GridSampling3D:
         self._quantize_coords = quantize_coords
         self._mode = mode
 
-    def __call__(self, pos, batch=None, tensors=(), order=None, num_plots=None, bounds=None):
+    def __call__(self, pos, batch=None, tensors=(), order=None, num_plots=None, bounds=None, capacity=None,
+                 n_points_dev=None):
         """Quantise a collated batch.
 
         pos      float32 [n,3] CUDA, positions of all plots concatenated
@@ -37,7 +38,12 @@ class GridSampling3D:
         bounds   optional ((lo_x,lo_y,lo_z),(hi_x,hi_y,hi_z)) of the integer grid; when omitted it is
                  measured on the device (one extra host sync)
 
-        Returns dict(coords=int32 [M,4] (plot,x,y,z), src=int32 [M], pos=[M,3], tensors=[...]).
+        capacity optional fixed number of output rows (STATIC mode, needs ``bounds`` and ``num_plots``): outputs
+                 are allocated at ``capacity`` rows, the voxel count stays on the device (``num_rows`` int32 [1]) and
+                 the call does not synchronise -- the form a captured CUDA graph replays.
+        n_points_dev optional int32 [1] device count of live points when ``pos`` is padded to a fixed size
+
+        Returns dict(coords=int32 [M,4] (plot,x,y,z), src=int32 [M], pos=[M,3], tensors=[...], num_rows).
         """
         assert pos.is_cuda and pos.dtype == torch.float32 and pos.dim() == 2 and pos.shape[1] == 3
         pos = pos.contiguous()
@@ -54,7 +60,10 @@ class GridSampling3D:
 
         q = torch.empty((n, 3), dtype=torch.int32, device=dev)
         bnd = torch.empty(6, dtype=torch.int32, device=dev)
-        L.call("b2s_quantize_points", pos, n, self._grid_size, q, bnd)
+        L.call("b2s_quantize_points", pos, n, n_points_dev, self._grid_size, q, bnd)
+        static = capacity is not None
+        if static:
+            assert bounds is not None and num_plots is not None, "static mode needs bounds and num_plots"
         if bounds is None:
             b = bnd.tolist()
             lo, hi = b[:3], b[3:]
@@ -67,23 +76,26 @@ class GridSampling3D:
             raise L.B2SError(f"voxel box {dims} x {num_plots} plots is too large (B2S_EOVERFLOW)")
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         m_dev = torch.empty(1, dtype=torch.int32, device=dev)
-        L.call("b2s_quantize_count", q, batch, n, num_plots, lo_h, dims_h, ws, ws_bytes, m_dev)
-        m = int(m_dev.item())                                   # host sync: output size
-        if m < 0:
-            raise L.B2SError("a point falls outside the supplied voxel bounds")
+        L.call("b2s_quantize_count", q, batch, n, n_points_dev, num_plots, lo_h, dims_h, ws, ws_bytes, m_dev)
+        if static:
+            m, m_arg = int(capacity), m_dev                     # no sync: the count is read on the device
+        else:
+            m, m_arg = int(m_dev.item()), None                  # host sync: output size
+            if m < 0:
+                raise L.B2SError("a point falls outside the supplied voxel bounds")
         coords = torch.empty((m, 4), dtype=torch.int32, device=dev)
         src = torch.empty(m, dtype=torch.int32, device=dev)
-        L.call("b2s_quantize_fill", q, batch, order, n, num_plots, lo_h, dims_h, ws, m, coords, src)
+        L.call("b2s_quantize_fill", q, batch, order, n, n_points_dev, num_plots, lo_h, dims_h, ws, m, m_arg, coords, src)
 
         def gather(t):
             t = t.contiguous()
             t2 = t.view(n, -1).float()
             out = torch.empty((m, t2.shape[1]), dtype=torch.float32, device=dev)
-            L.call("b2s_gather_rows", t2, src, m, t2.shape[1], out)
+            L.call("b2s_gather_rows", t2, src, m, m_arg, t2.shape[1], out)
             return out
 
         return {"coords": coords, "src": src, "pos": gather(pos), "tensors": [gather(t) for t in tensors],
-                "grid_size": self._grid_size}
+                "grid_size": self._grid_size, "num_rows": m_dev}
 
     def __repr__(self):
         return "{}(grid_size={}, quantize_coords={}, mode={})".format(

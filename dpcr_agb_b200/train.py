@@ -54,6 +54,9 @@ class FlatAdaBelief:
         self.lr, self.betas, self.eps, self.weight_decay, self.grad_clip = lr, betas, eps, weight_decay, grad_clip
         self.step_count = 0
         self.found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
+        # device copy of the hyper-parameter block (captured-graph replays read it; see graph_step.py)
+        self.hyper_dev = torch.zeros(16, dtype=torch.float32, device=dev)
+        self.hyper_pinned = torch.zeros(16, dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -71,18 +74,34 @@ class FlatAdaBelief:
             step_size = 1.0 / (1 - beta1 ** step)
         return sma, step_size
 
-    def step(self, inv_scale=1.0, check_inf=False):
-        self.step_count += 1
+    def hyper_values(self, inv_scale=1.0):
+        """The 16-float hyper-parameter block of ``b2s_adabelief_step`` for the CURRENT step count."""
         b1, b2 = self.betas
         sma, step_size = self.rectified_step(self.step_count, b1, b2)
+        return [self.lr, b1, b2, self.eps, self.weight_decay, step_size, 1.0 if sma >= 5 else 0.0, inv_scale,
+                self.grad_clip, 0, 0, 0, 0, 0, 0, 0]
+
+    def step(self, inv_scale=1.0, check_inf=False):
+        self.step_count += 1
         found = None
         if check_inf:
             L.call("b2s_grad_check", self.flat_grad, self.numel, float(inv_scale), self.found_inf)
             found = self.found_inf
-        hyper = L.host_f32(self.lr, b1, b2, self.eps, self.weight_decay, step_size, 1.0 if sma >= 5 else 0.0,
-                           inv_scale, self.grad_clip, 0, 0, 0, 0, 0, 0, 0)
+        hyper = L.host_f32(*self.hyper_values(inv_scale))
         L.call("b2s_adabelief_step", self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_var, self.numel,
-               hyper, found)
+               hyper, None, found)
+
+    def upload_hyper(self, inv_scale=1.0):
+        """Advance the step count and copy this step's hyper-parameters to the device (stream-ordered); the
+        captured graph's ``step_from_device`` launch reads them."""
+        self.step_count += 1
+        self.hyper_pinned.copy_(torch.tensor(self.hyper_values(inv_scale), dtype=torch.float32))
+        self.hyper_dev.copy_(self.hyper_pinned, non_blocking=True)
+
+    def step_from_device(self):
+        """AdaBelief update with the hyper-parameters read from ``hyper_dev`` (capturable)."""
+        L.call("b2s_adabelief_step", self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_var, self.numel,
+               None, self.hyper_dev, None)
 
 
 class CosineAnnealingWarmRestarts:

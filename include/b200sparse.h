@@ -18,6 +18,12 @@
  *   - a kernel map is a neighbour table nbr int32 [K3, N_out]: nbr[k*N_out + o] = in-row i with
  *     coords_in[i] == coords_out[o] + delta_k, or -1.  k = ix + K*iy + K*K*iz (x fastest).
  *   - features are fp32 row-major [N, C].
+ *   - row counts: every function that takes a row count (n, n_out, n_query, m ...) also takes a device pointer
+ *     `const int32_t* <name>_dev` right after it.  NULL: the host value is exact.  Non-NULL: the host value is the
+ *     CAPACITY of the arrays (pitch of neighbour tables, launch bound) and the kernels read the actual count from
+ *     device memory, clamped to [0, capacity].  With device counts no launch shape depends on the data, so a whole
+ *     training step (quantise -> maps -> forward -> backward -> optimiser) is captured once into a CUDA graph and
+ *     replayed without any host synchronisation (dpcr_agb_b200/graph_step.py).
  */
 #ifndef B200SPARSE_H_
 #define B200SPARSE_H_
@@ -61,17 +67,20 @@ B2S_API int32_t b2s_device_check(void);
  *                       identity): consecutive_cluster's last-write-wins (:121).  Writes
  *                       out_coords int32 [M,4] (plot, x, y, z) and out_src int32 [M] (original index).
  */
-B2S_API int32_t b2s_quantize_points(const float* pos, int64_t n, float size, int32_t* qcoords, int32_t* bounds,
-                            b2s_stream_t stream);
+B2S_API int32_t b2s_quantize_points(const float* pos, int64_t n, const int32_t* n_dev, float size, int32_t* qcoords,
+                                    int32_t* bounds, b2s_stream_t stream);
 B2S_API int64_t b2s_quantize_workspace_bytes(int64_t num_plots, const int32_t* dims_host);
-B2S_API int32_t b2s_quantize_count(const int32_t* qcoords, const int32_t* plot_of_point, int64_t n, int32_t num_plots,
-                           const int32_t* lo_host, const int32_t* dims_host, void* workspace,
-                           int64_t workspace_bytes, int32_t* num_voxels_dev, b2s_stream_t stream);
+B2S_API int32_t b2s_quantize_count(const int32_t* qcoords, const int32_t* plot_of_point, int64_t n, const int32_t* n_dev,
+                                   int32_t num_plots, const int32_t* lo_host, const int32_t* dims_host, void* workspace,
+                                   int64_t workspace_bytes, int32_t* num_voxels_dev, b2s_stream_t stream);
 B2S_API int32_t b2s_quantize_fill(const int32_t* qcoords, const int32_t* plot_of_point, const int32_t* order, int64_t n,
-                          int32_t num_plots, const int32_t* lo_host, const int32_t* dims_host, void* workspace,
-                          int64_t num_voxels, int32_t* out_coords, int32_t* out_src, b2s_stream_t stream);
+                                  const int32_t* n_dev, int32_t num_plots, const int32_t* lo_host,
+                                  const int32_t* dims_host, void* workspace, int64_t num_voxels,
+                                  const int32_t* num_voxels_dev, int32_t* out_coords, int32_t* out_src,
+                                  b2s_stream_t stream);
 /* out[r, :] = in[idx[r], :]  -- the per-point tensors gathered at the representative (:64-66). */
-B2S_API int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t m, int32_t c, float* out, b2s_stream_t stream);
+B2S_API int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t m, const int32_t* m_dev, int32_t c,
+                                float* out, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- (a2,a3) coordinate maps ----
  * R:models/instance/minkowski.py:74 (ME.SparseTensor -> hash build) and every stride-2 op
@@ -87,12 +96,14 @@ B2S_API int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t m, 
  */
 B2S_API int64_t b2s_hash_capacity(int64_t n);
 B2S_API int64_t b2s_scan_workspace_bytes(int64_t n);
-B2S_API int32_t b2s_coordmap_insert(const int32_t* coords, int64_t n, const int32_t* ts_host, void* table, int64_t capacity,
-                            int32_t* slot, int32_t* rank, int32_t* info_dev, void* scan_workspace,
-                            b2s_stream_t stream);
-B2S_API int32_t b2s_coordmap_fill(const int32_t* coords, int64_t n, const int32_t* ts_host, void* table, int64_t capacity,
-                          const int32_t* slot, const int32_t* rank, int32_t* out_coords, int32_t* in2out,
-                          b2s_stream_t stream);
+B2S_API int32_t b2s_coordmap_insert(const int32_t* coords, int64_t n, const int32_t* n_dev, const int32_t* ts_host,
+                                    void* table, int64_t capacity, int32_t* slot, int32_t* rank, int32_t* info_dev,
+                                    void* scan_workspace, b2s_stream_t stream);
+/* out_capacity = rows allocated at out_coords; unique keys ranked beyond it are dropped (their table value becomes
+ * -1) -- the caller compares info_dev[0] with its capacity afterwards. */
+B2S_API int32_t b2s_coordmap_fill(const int32_t* coords, int64_t n, const int32_t* n_dev, const int32_t* ts_host,
+                                  void* table, int64_t capacity, const int32_t* slot, const int32_t* rank,
+                                  int32_t* out_coords, int64_t out_capacity, int32_t* in2out, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- (a4) kernel maps -----------
  * Implicit in every MinkowskiConvolution / MinkowskiMaxPooling call (same call sites).
@@ -102,9 +113,9 @@ B2S_API int32_t b2s_coordmap_fill(const int32_t* coords, int64_t n, const int32_
  * table of the OUT map gives the transposed map (dgrad of strided convs, ConvolutionTranspose).
  * pair_counts / pairs_fill derive MinkowskiEngine's pair-list form (per offset, sorted by out row).
  */
-B2S_API int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, const void* table, int64_t capacity,
-                       const int32_t* kernel_size_host, const int32_t* step_host, int32_t sign, int32_t* nbr,
-                       b2s_stream_t stream);
+B2S_API int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, const int32_t* n_query_dev,
+                               const void* table, int64_t capacity, const int32_t* kernel_size_host,
+                               const int32_t* step_host, int32_t sign, int32_t* nbr, b2s_stream_t stream);
 B2S_API int32_t b2s_kernel_map_pair_counts(const int32_t* nbr, int32_t k3, int64_t n_query, int32_t* counts,
                                    b2s_stream_t stream);
 B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_t n_query, const int64_t* offsets,
@@ -124,38 +135,42 @@ B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_
  */
 B2S_API int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3);
 B2S_API int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
-                             int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
-                             void* workspace, int64_t workspace_bytes, int32_t impl, b2s_stream_t stream);
+                                     int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3,
+                                     int32_t w_layout, float* y, void* workspace, int64_t workspace_bytes,
+                                     int32_t impl, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
-                       int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace,
-                       int64_t workspace_bytes, int32_t impl, b2s_stream_t stream);
-B2S_API int32_t b2s_colsum(const float* x, int64_t n, int32_t c, float* out, b2s_stream_t stream);
+                               const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw,
+                               void* workspace, int64_t workspace_bytes, int32_t impl, b2s_stream_t stream);
+B2S_API int32_t b2s_colsum(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* out, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- (a9) max pooling -----------
  * R:modules/MinkowskiEngine/SENet.py:53.  y[o,c] = max_k x[nbr[k,o],c]; arg[o,c] = winning in-row
  * (lowest row on ties, -1 if the out row has no neighbour -> y = 0).  bwd: gx[arg] += gy.
  */
-B2S_API int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_out, int32_t c, int32_t k3, float* y,
-                        int32_t* arg, b2s_stream_t stream);
-B2S_API int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t n_in, int64_t n_out, int32_t c, float* gx,
-                        b2s_stream_t stream);
+B2S_API int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_out, const int32_t* n_out_dev, int32_t c,
+                                int32_t k3, float* y, int32_t* arg, b2s_stream_t stream);
+B2S_API int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t n_in, int64_t n_out,
+                                const int32_t* n_out_dev, int32_t c, float* gx, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- (a5,a10,a11) per-plot ops --
  * R:modules/MinkowskiEngine/senet_block.py:43-50; common.py:44-48; SENet.py:63,117.
  * row_batch points at the batch id of row 0 and is read with `row_batch_stride` int32s per row (the
  * coords array itself: stride 4).  scale (nullable) is a per-plot factor, e.g. 1/count for average.
  */
-B2S_API int32_t b2s_batch_counts(const int32_t* row_batch, int32_t row_batch_stride, int64_t n, int32_t num_batches,
-                         int32_t* counts, b2s_stream_t stream);
-B2S_API int32_t b2s_segment_sum(const float* x, const int32_t* row_batch, int32_t row_batch_stride, int64_t n, int32_t c,
-                        int32_t num_batches, const float* scale, float* y, b2s_stream_t stream);
-B2S_API int32_t b2s_segment_bcast(const float* y, const int32_t* row_batch, int32_t row_batch_stride, int64_t n, int32_t c,
-                          const float* scale, float* x_out, b2s_stream_t stream);
+B2S_API int32_t b2s_batch_counts(const int32_t* row_batch, int32_t row_batch_stride, int64_t n, const int32_t* n_dev,
+                                 int32_t num_batches, int32_t* counts, b2s_stream_t stream);
+B2S_API int32_t b2s_segment_sum(const float* x, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
+                                const int32_t* n_dev, int32_t c, int32_t num_batches, const float* scale, float* y,
+                                b2s_stream_t stream);
+B2S_API int32_t b2s_segment_bcast(const float* y, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
+                                  const int32_t* n_dev, int32_t c, const float* scale, float* x_out,
+                                  b2s_stream_t stream);
 B2S_API int32_t b2s_bcast_mul_fwd(const float* x, const float* y, const int32_t* row_batch, int32_t row_batch_stride,
-                          int64_t n, int32_t c, int32_t y_c, float* out, b2s_stream_t stream);
+                                  int64_t n, const int32_t* n_dev, int32_t c, int32_t y_c, float* out,
+                                  b2s_stream_t stream);
 B2S_API int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float* y, const int32_t* row_batch,
-                          int32_t row_batch_stride, int64_t n, int32_t c, int32_t num_batches, float* gx, float* gy,
-                          b2s_stream_t stream);
+                                  int32_t row_batch_stride, int64_t n, const int32_t* n_dev, int32_t c,
+                                  int32_t num_batches, float* gx, float* gy, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- (a13,a14,a16) norm / act ---
  * R:modules/MinkowskiEngine/SENet.py:35,51,98; resnet_block.py:51-56,65,73; common.py:41.
@@ -170,31 +185,37 @@ B2S_API int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float* y
  * bn_bwd_apply  : training: gx = gamma*invstd*(gy' - sums0/n - xhat*sums1/n); eval: gx = gamma*invstd*gy'.
  * gelu_fwd/bwd  : exact erf GELU on a flat array.
  */
-B2S_API int32_t b2s_bn_stats(const float* x, int64_t n, int32_t c, float eps, float momentum, float* running_mean,
-                     float* running_var, double* stats_ws, float* mean, float* invstd, b2s_stream_t stream);
+B2S_API int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float eps, float momentum,
+                             float* running_mean, float* running_var, double* stats_ws, float* mean, float* invstd,
+                             b2s_stream_t stream);
 B2S_API int32_t b2s_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                     int64_t n, int32_t c, int32_t act, float* y, b2s_stream_t stream);
+                             int64_t n, const int32_t* n_dev, int32_t c, int32_t act, float* y, b2s_stream_t stream);
 B2S_API int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const float* mean, const float* invstd,
-                          const float* gamma, const float* beta, int64_t n, int32_t c, int32_t act, double* stats_ws,
-                          float* sums, b2s_stream_t stream);
+                                  const float* gamma, const float* beta, int64_t n, const int32_t* n_dev, int32_t c,
+                                  int32_t act, double* stats_ws, float* sums, b2s_stream_t stream);
 B2S_API int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd, const float* gamma,
-                         const float* beta, const float* sums, int64_t n, int32_t c, int32_t act, int32_t training,
-                         float* gx, b2s_stream_t stream);
-B2S_API int32_t b2s_gelu_fwd(const float* x, int64_t numel, float* y, b2s_stream_t stream);
+                                 const float* beta, const float* sums, int64_t n, const int32_t* n_dev, int32_t c,
+                                 int32_t act, int32_t training, float* gx, b2s_stream_t stream);
+/* elementwise over n rows of c floats */
+B2S_API int32_t b2s_gelu_fwd(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y, b2s_stream_t stream);
 /* sum = a + b, y = gelu(sum): the residual join out = act(drop_path(out) + residual); backward = gelu_bwd(gy, sum)
  * for both addends (R:modules/MinkowskiEngine/senet_block.py:93-94, resnet_block.py:72-73). */
-B2S_API int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t numel, float* sum, float* y,
-                                 b2s_stream_t stream);
-B2S_API int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t numel, float* gx, b2s_stream_t stream);
+B2S_API int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t n, const int32_t* n_dev, int32_t c, float* sum,
+                                 float* y, b2s_stream_t stream);
+B2S_API int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* gx,
+                             b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- optimiser ----
  * R:core/optimizer/adabelief.py:90-201 over one flat fp32 parameter buffer, with GradScaler
  * unscale (R:models/base_model.py:241), clip_grad_value_ (:243) and the inf/nan skip fused in.
- * found_inf_dev[0] != 0 -> the step is skipped (GradScaler semantics).  hyper_host: see csrc/optim.cu.
+ * found_inf_dev[0] != 0 -> the step is skipped (GradScaler semantics).  hyper: 16 floats, see csrc/optim.cu; given
+ * either on the host (hyper_host, baked into the launch) or on the device (hyper_dev, read by the kernel -- the
+ * form a captured CUDA graph needs, since the learning rate changes every step).  Exactly one must be non-NULL.
  */
 B2S_API int32_t b2s_grad_check(const float* grad, int64_t numel, float inv_scale, float* found_inf_dev, b2s_stream_t stream);
 B2S_API int32_t b2s_adabelief_step(float* param, const float* grad, float* exp_avg, float* exp_avg_var, int64_t numel,
-                           const float* hyper_host, const float* found_inf_dev, b2s_stream_t stream);
+                                   const float* hyper_host, const float* hyper_dev, const float* found_inf_dev,
+                                   b2s_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ def test_product_path_has_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         ME.SparseTensor(features=torch.zeros(2, 3), coordinates=torch.zeros(2, 4, dtype=torch.int32))
     with pytest.raises(lib.B2SError):
-        lib.call("b2s_gelu_fwd", torch.zeros(4), 4, torch.zeros(4))
+        lib.call("b2s_gelu_fwd", torch.zeros(4), 1, None, 4, torch.zeros(4))
     # nothing of the product imports the oracle
     for mod in list(sys.modules):
         if mod.startswith("dpcr_agb_b200"):

@@ -153,9 +153,9 @@ def test_conv_rejects_bad_arguments(cuda):
     w = torch.zeros((27, 8, 8), device=cuda)
     y = torch.zeros((4, 8), device=cuda)
     with pytest.raises(L.B2SError):   # nbr may be null only for k3 == 1
-        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, 8, 8, 27, 0, y, None, 0, 1)
+        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, None, 8, 8, 27, 0, y, None, 0, 1)
     with pytest.raises(L.B2SError):   # tcgen05 kernel does not cover c_out = 8
-        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, 8, 8, 1, 0, y, None, 0, 2)
+        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, None, 8, 8, 1, 0, y, None, 0, 2)
 
 
 @pytest.mark.parametrize("n,cin,cout,K,strided", [

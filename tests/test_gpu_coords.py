@@ -66,7 +66,7 @@ def test_quantize_rounding_half_even(cuda):
     q_ref = oc.quantize_points(pos, size).astype(np.int32)
     q = torch.empty((len(vals), 3), dtype=torch.int32, device=cuda)
     bnd = torch.empty(6, dtype=torch.int32, device=cuda)
-    L.call("b2s_quantize_points", torch.from_numpy(pos).to(cuda), len(vals), size, q, bnd)
+    L.call("b2s_quantize_points", torch.from_numpy(pos).to(cuda), len(vals), None, size, q, bnd)
     assert np.array_equal(q.cpu().numpy(), q_ref)
     assert bnd.tolist() == [int(q_ref[:, 0].min()), 0, 0, int(q_ref[:, 0].max()), 0, 0]
 

@@ -1,0 +1,114 @@
+"""Captured-graph training step (static capacities, device-side row counts) against the eager step: same batches,
+same initial parameters, same drop-path draws -> same parameters after every step.  Runs through the C ABI."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from dpcr_agb_b200 import MinkowskiEngine as ME
+from dpcr_agb_b200 import graph_step, lib, msenet, train
+from dpcr_agb_b200.quantize import GridSampling3D
+import b2s_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+SIZE = 0.03
+BOUNDS = ((0, 0, 0), (34, 34, 45))
+
+
+def _batches(cuda, num, plots=3, n_points=2500):
+    out = []
+    for i in range(num):
+        b = util.make_points(plots, n_points, cfg=21, first=i * plots)
+        out.append({k: torch.from_numpy(np.ascontiguousarray(v)).to(cuda) for k, v in b.items()})
+    return out
+
+
+def _model(cuda, seed=0, drop_path=0.2):
+    torch.manual_seed(seed)
+    return msenet.build(ME, "SENet14", drop_path=drop_path).to(cuda)
+
+
+def test_graph_step_matches_eager(cuda):
+    plots, n_points = 3, 2500
+    batches = _batches(cuda, 3, plots, n_points)
+    gs = GridSampling3D(SIZE)
+    # eager reference run
+    m1 = _model(cuda)
+    t1 = train.Trainer(m1, ME, lr=1e-3)
+    random.seed(5)
+    losses1 = []
+    for d in batches:
+        vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=plots, bounds=BOUNDS)
+        losses1.append(float(t1.step(vox["coords"], vox["tensors"][0], d["target"])))
+    # captured run
+    m2 = _model(cuda)
+    t2 = train.Trainer(m2, ME, lr=1e-3)
+    caps = graph_step.plan_capacities(gs, ME, m2, batches, plots, BOUNDS)
+    assert sorted(caps) == [1, 2, 4, 8, 16]
+    g = graph_step.GraphStep(t2, gs, plots, plots * n_points, BOUNDS, caps).capture()
+    assert g.launches_per_step > 100
+    random.seed(5)
+    losses2 = []
+    for d in batches:
+        g.load(d)
+        losses2.append(float(g.step()))
+    seen = g.verify()
+    assert all(v <= caps[int(k.split()[-1])] for k, v in seen.items() if k.startswith("rows"))
+    np.testing.assert_allclose(losses2, losses1, rtol=2e-4)
+    util.assert_close(t2.opt.flat_param, t1.opt.flat_param, tol=2e-4, what="parameters after 3 steps")
+    util.assert_close(t2.opt.exp_avg, t1.opt.exp_avg, tol=2e-3, what="AdaBelief first moment")
+    for (n1, b1), (n2, b2) in zip(m1.named_buffers(), m2.named_buffers()):
+        if b1.dtype.is_floating_point:
+            util.assert_close(b2, b1, tol=2e-4, what=f"buffer {n1}")
+        else:
+            assert int(b1) == int(b2), n1
+
+
+def test_graph_step_static_maps_bit_exact(cuda):
+    """The static-capacity coordinate manager produces the same coordinates and neighbour tables as the dynamic one
+    on the live rows."""
+    plots, n_points = 2, 3000
+    d = _batches(cuda, 1, plots, n_points)[0]
+    gs = GridSampling3D(SIZE)
+    dyn = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=plots, bounds=BOUNDS)
+    m = dyn["coords"].shape[0]
+    cap = {1: m + 300, 2: m, 4: m, 8: m, 16: m}
+    sta = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=plots, bounds=BOUNDS,
+             capacity=cap[1])
+    assert int(sta["num_rows"]) == m and sta["coords"].shape[0] == cap[1]
+    assert torch.equal(sta["coords"][:m], dyn["coords"]) and torch.equal(sta["tensors"][0][:m], dyn["tensors"][0])
+    xd = ME.SparseTensor(features=dyn["tensors"][0], coordinates=dyn["coords"])
+    xs = ME.SparseTensor(features=sta["tensors"][0], coordinates=sta["coords"], num_rows=sta["num_rows"],
+                         capacities=cap, num_batches=plots)
+    cd, cs = xd.coordinate_manager, xs.coordinate_manager
+    kd, ks = xd.coordinate_map_key, xs.coordinate_map_key
+    for _ in range(3):
+        kd2, ks2 = cd.stride(kd, 2), cs.stride(ks, 2)
+        n2 = cd.maps[kd2].n
+        assert int(cs.maps[ks2].n_dev) == n2
+        assert torch.equal(cs.coords(ks2)[:n2], cd.coords(kd2))
+        for (a, b, K) in ((kd, kd2, 3), (kd2, kd2, 3), (kd, kd2, 1)):
+            sa, sb = (ks if a is kd else ks2), (ks if b is kd else ks2)
+            md, ms = cd.kernel_map(a, b, K), cs.kernel_map(sa, sb, K)
+            assert torch.equal(ms.nbr[:, :md.n_out], md.nbr)
+            if a != b:
+                assert torch.equal(ms.inv[:, :md.n_in], md.inv)
+        kd, ks = kd2, ks2
+    cs.verify()
+
+
+def test_graph_step_capacity_overflow_is_detected(cuda):
+    plots, n_points = 2, 3000
+    d = _batches(cuda, 1, plots, n_points)[0]
+    gs = GridSampling3D(SIZE)
+    m = gs(d["pos"], d["batch"], num_plots=plots, bounds=BOUNDS)["coords"].shape[0]
+    cap = {1: m, 2: 128, 4: 128, 8: 128, 16: 128}          # far too small below the first level
+    model = _model(cuda, drop_path=0.0)
+    tr = train.Trainer(model, ME, lr=1e-3)
+    g = graph_step.GraphStep(tr, gs, plots, plots * n_points, BOUNDS, cap).capture()
+    g.load(d)
+    g.step()
+    with pytest.raises(lib.B2SError):
+        g.verify()
