@@ -286,177 +286,6 @@ def run_b200(args):
     breakdown = {k: {"calls_per_step": n / bsteps, "ms_per_step": t / bsteps} for k, (n, t) in lib.profile_stop().items()}
 
     if rank != 0:
-        return
-    sample = max(1, args.cpu_sample_plots)
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    cb = cpu_arm(args, steps, warmup, sample)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference MinkowskiEngine (CPU build, env_cpu.yml) is an un-vendored pip dependency and cannot "
-                    "be built offline; this arm is the oracle port of its algorithm on the host cores"}
-    print(json.dumps(line), flush=True)
-
-
-# ------------------------------------------------------------------------------------------------
-# clocks
-# ------------------------------------------------------------------------------------------------
-class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, device_index):
-        self.path = tempfile.mktemp(prefix="b2s_clocks_", suffix=".csv")
-        self.proc = None
-        try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(device_index)], stdout=self.f,
-                                         stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in open(self.path):
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-                power.append(float(parts[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        try:
-            os.unlink(self.path)
-        except OSError:
-            pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "power_w_max": float(max(power)), "samples": len(sm)}
-
-
-# ------------------------------------------------------------------------------------------------
-# B200 arm
-# ------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch.distributed as dist
-
-    from dpcr_agb_b200 import MinkowskiEngine as ME
-    from dpcr_agb_b200 import graph_step, lib, msenet, plots, train
-    from dpcr_agb_b200.MinkowskiEngine import functional as Fn
-    from dpcr_agb_b200.quantize import GridSampling3D
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib.load()
-    B = args.plots_per_gpu
-
-    torch.manual_seed(0)
-    model = msenet.build(ME, args.model, drop_path=0.01).to(dev)
-    trainer = train.Trainer(model, ME)
-    trainer.broadcast_parameters()
-    gs = GridSampling3D(GRID)
-
-    # ---- synthetic input: NUM_DISTINCT_BATCHES different batches per rank, cycled (pinned host + device copies)
-    nb = min(NUM_DISTINCT_BATCHES, args.steps + args.warmup)
-    host, devb = [], []
-    for i in range(nb):
-        b = plots.synth_batch(2, (rank * nb + i) * B, B, n_points=POINTS_PER_PLOT)
-        h = {k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in ("pos", "feats", "batch", "perm", "target")}
-        host.append(h)
-        devb.append({k: v.to(dev) for k, v in h.items()})
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
-
-    def step_from_device(d):
-        vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=B, bounds=BOUNDS)
-        return trainer.step(vox["coords"], vox["tensors"][0], d["target"])
-
-    def step_from_host(h):
-        for k, v in h.items():
-            staging[k].copy_(v, non_blocking=True)
-        loss = step_from_device(staging)
-        return float(loss)                                         # device -> host read of the step's result
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, items, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        calls0 = lib.launch_count
-        e0.record()
-        for i in range(steps):
-            fn(items[i % len(items)])
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # max over ranks, timed on the device
-        return float(ms.item()), lib.launch_count - calls0
-
-    # ---- algorithmic work per step (untimed statistics pass over every distinct batch)
-    Fn.WORK_STATS = {}
-    for d in devb:
-        step_from_device(d)
-    torch.cuda.synchronize()
-    work = {k: {kk: vv / len(devb) for kk, vv in v.items()} for k, v in Fn.WORK_STATS.items()}
-    Fn.WORK_STATS = None
-
-    # ---- warm-up
-    for i in range(args.warmup):
-        step_from_device(devb[i % nb])
-    barrier()
-
-    # ---- timed region 1: inputs resident in HBM; CUDA events around the conv entry points only
-    clocks = ClockSampler(local)
-    lib.profile_start(["b2s_conv_gather_gemm", "b2s_conv_wgrad"])
-    ms_total, calls = timed(step_from_device, devb, args.steps)
-    prof = lib.profile_stop()
-    clk = clocks.stop()
-    ms_step = ms_total / args.steps
-    value = world * B / (ms_step * 1e-3)
-
-    # ---- timed region 2: end to end from pinned host buffers
-    for i in range(min(2, args.warmup)):
-        step_from_host(host[i % nb])
-    ms_e2e, _ = timed(step_from_host, host, args.steps)
-    e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
-
-    # ---- full per-entry-point breakdown (separate short pass, every C-ABI call wrapped in events)
-    lib.profile_start(None)
-    bsteps = min(3, args.steps)
-    ms_b, _ = timed(step_from_device, devb, bsteps)
-    breakdown = {k: {"calls_per_step": n / bsteps, "ms_per_step": t / bsteps} for k, (n, t) in lib.profile_stop().items()}
-
-    if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return

@@ -32,7 +32,7 @@ pytestmark = pytest.mark.gpu
 #     the benchmark runs -- where the coarse maps hold hundreds of rows (test_full_size_training_parity).
 E2E_OUT_TOL = {("tc", False): 1e-3, ("tc", True): 1e-2, ("simt", False): 1e-3, ("simt", True): 1e-3}
 E2E_GRAD_TOL = {("tc", False): 2e-3, ("tc", True): 1e-1, ("simt", False): 1e-3, ("simt", True): 1e-3}
-E2E_BUF_TOL = {"tc": 5e-3, "simt": 1e-3}
+E2E_BUF_TOL = {"tc": 1e-2, "simt": 1e-3}
 # absolute slack of the gradient check as a fraction of the largest gradient of the whole model (scalar bias
 # gradients are sums with heavy cancellation)
 E2E_GRAD_ABS = {("tc", False): 2e-5, ("tc", True): 2e-3, ("simt", False): 2e-5, ("simt", True): 2e-5}
