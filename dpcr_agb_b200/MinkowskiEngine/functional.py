@@ -39,30 +39,45 @@ _fwd = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _bwd = custom_bwd(device_type="cuda")
 
 
-def _ws(n_in, n_out, c_in, c_out, k3, device):
-    nbytes = L.query("b2s_conv_workspace_bytes", n_in, n_out, c_in, c_out, k3)
+def round_tf32(x, n_dev=None):
+    """TF32 round-to-nearest copy of a feature matrix (C ABI ``b2s_round_tf32``): the operand form the tensor-core
+    kernels consume.  An operand used by several passes is rounded once and passed with ``prerounded=True``."""
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    if x.numel():
+        L.call("b2s_round_tf32", x, x.shape[0], n_dev, x.numel() // x.shape[0], y)
+    return y
+
+
+def _ws(n_in, n_out, c_in, c_out, k3, device, prerounded=False):
+    nbytes = L.query("b2s_conv_workspace_bytes", n_in, n_out, c_in, c_out, k3, 1 if prerounded else 0)
     if nbytes < 0:
         raise L.B2SError("b2s_conv_workspace_bytes rejected the shape")
     return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device), nbytes
 
 
-def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None, n_out_dev=None):
+def _tc(impl):
+    return (CONV_IMPL if impl is None else impl) != 1
+
+
+def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None, n_out_dev=None,
+                prerounded=False):
     """y[o] = bias + sum_k x[nbr[k,o]] @ B_k  (C ABI ``b2s_conv_gather_gemm``).  ``n_out_dev``: device row count
-    (then ``n_out`` is the capacity / pitch of ``nbr``)."""
+    (then ``n_out`` is the capacity / pitch of ``nbr``).  ``prerounded``: x is already TF32-representable."""
     y = torch.empty((n_out, c_out), dtype=torch.float32, device=x.device)
     _account("dgrad" if (w_layout & 1) else "fwd", nbr, n_out, c_in, c_out, k3, n_out_dev)
-    ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device)
-    L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout, y, ws, nbytes,
-           CONV_IMPL if impl is None else impl)
+    ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device, prerounded)
+    L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3,
+           w_layout | (4 if prerounded else 0), y, ws, nbytes, CONV_IMPL if impl is None else impl)
     return y
 
 
-def wgrad(x, gy, nbr, n_in, n_out, c_in, c_out, k3, impl=None, n_out_dev=None):
+def wgrad(x, gy, nbr, n_in, n_out, c_in, c_out, k3, impl=None, n_out_dev=None, prerounded=False):
     gw = torch.empty((k3, c_in, c_out), dtype=torch.float32, device=x.device)
     _account("wgrad", nbr, n_out, c_in, c_out, k3, n_out_dev)
-    ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device) if c_in <= 4 else (None, 0)
+    ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device, prerounded)
     L.call("b2s_conv_wgrad", x, gy, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, gw, ws, nbytes,
-           CONV_IMPL if impl is None else impl)
+           CONV_IMPL if impl is None else impl, 1 if prerounded else 0)
     return gw
 
 
@@ -87,7 +102,13 @@ class ConvolutionFunction(torch.autograd.Function):
             nd_in, nd_out = kmap.n_in_dev, kmap.n_out_dev
         assert feats.shape == (n_in, c_in), f"feature shape {tuple(feats.shape)} does not match the map ({n_in},{c_in})"
         b = bias.contiguous().view(-1) if bias is not None else None
-        out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0, n_out_dev=nd_out)
+        # the tensor-core kernels consume TF32 operands: x is rounded once here and the rounded copy is what is
+        # saved for wgrad (c_in <= 4: the stem pads + rounds inside the library)
+        pre = _tc(None) and c_in > 4
+        if pre:
+            feats = round_tf32(feats, nd_in)
+        out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0, n_out_dev=nd_out, prerounded=pre)
+        ctx.pre = pre
         ctx.kmap = kmap
         ctx.nd = (nd_in, nd_out)
         ctx.dims = (n_in, n_out, c_in, c_out, k3)
@@ -104,16 +125,23 @@ class ConvolutionFunction(torch.autograd.Function):
         gy = gy.contiguous()
         nd_in, nd_out = ctx.nd
         gx = gw = gb = None
+        gyr, pre_gy = gy, False
+        if _tc(None) and c_out > 4:           # grad_out feeds dgrad and wgrad: round it once
+            gyr, pre_gy = round_tf32(gy, nd_out), True
         if ctx.needs_input_grad[0]:
             if kmap is None:
-                gx = gather_gemm(gy, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1, n_out_dev=nd_in)
+                gx = gather_gemm(gyr, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1, n_out_dev=nd_in,
+                                 prerounded=pre_gy)
             elif kmap.symmetric:      # transposed map == same table with the kernel index reversed
-                gx = gather_gemm(gy, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2, n_out_dev=nd_in)
+                gx = gather_gemm(gyr, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2, n_out_dev=nd_in,
+                                 prerounded=pre_gy)
             else:
-                gx = gather_gemm(gy, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1, n_out_dev=nd_in)
+                gx = gather_gemm(gyr, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1, n_out_dev=nd_in,
+                                 prerounded=pre_gy)
         if ctx.needs_input_grad[1]:
-            gw = wgrad(feats, gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out, k3,
-                       n_out_dev=nd_out).view(kernel.shape)
+            both = pre_gy and (ctx.pre or c_in <= 4)      # feats is the rounded copy saved by forward
+            gw = wgrad(feats, gyr if both else gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out, k3,
+                       n_out_dev=nd_out, prerounded=both).view(kernel.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = torch.empty((1, c_out), dtype=torch.float32, device=gy.device)
             L.call("b2s_colsum", gy, n_out, nd_out, c_out, gb)

@@ -135,11 +135,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int p = 0; p < 8; ++p) idx[p] = -1;
 
     auto publish = [&](int it_done) {  // all of this thread's LDGSTS for it_done have landed
-      if (!SMALL) {                    // round the chunks this thread gathered to tf32 (SMALL: x4 is pre-rounded)
-        const uint32_t st = a_base + (it_done % STAGES) * A_STAGE_BYTES;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) round_chunk_tf32(st + sw128_offset(rsub + 16 * p, chunk));
-      }
       fence_proxy_async();
       mbar_arrive(full_bar(it_done % STAGES));
     };

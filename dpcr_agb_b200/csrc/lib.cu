@@ -44,10 +44,24 @@ int64_t b2s_wgrad_tc_workspace_bytes(int32_t c_in, int64_t n_in);
 int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
                       const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace, cudaStream_t st);
 
-extern "C" int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3) {
+void b2s_launch_round_tf32(const float* in, int64_t n, const int32_t* n_dev, int32_t c, float* out, cudaStream_t st);
+
+static inline int64_t al256(int64_t b) { return (b + 255) & ~(int64_t)255; }
+// bytes of the internally rounded operand copies (0 when the caller pre-rounds; c_in <= 4 is rounded while padding)
+static int64_t round_copy_fwd(int64_t n_in, int32_t c_in, int32_t pre) { return (pre || c_in <= 4) ? 0 : al256(n_in * c_in * 4); }
+static int64_t round_copy_wg_x(int64_t n_in, int32_t c_in, int32_t pre) { return (pre || c_in <= 4) ? 0 : al256(n_in * c_in * 4); }
+static int64_t round_copy_wg_gy(int64_t n_out, int32_t c_out, int32_t pre) { return pre ? 0 : al256(n_out * c_out * 4); }
+
+extern "C" int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3,
+                                            int32_t prerounded) {
   if (c_in <= 0 || c_out <= 0 || k3 <= 0 || n_in < 0 || n_out < 0) return -1;
-  int64_t fwd = b2s_conv_tc_supported(c_in, c_out, k3, n_out) ? b2s_conv_tc_workspace_bytes(c_in, c_out, k3, n_in) : 0;
-  int64_t wg = b2s_wgrad_tc_supported(c_in, c_out, k3, n_out, true) ? b2s_wgrad_tc_workspace_bytes(c_in, n_in) : 0;
+  int64_t fwd = b2s_conv_tc_supported(c_in, c_out, k3, n_out)
+                    ? al256(b2s_conv_tc_workspace_bytes(c_in, c_out, k3, n_in)) + round_copy_fwd(n_in, c_in, prerounded)
+                    : 0;
+  int64_t wg = b2s_wgrad_tc_supported(c_in, c_out, k3, n_out, true)
+                   ? al256(b2s_wgrad_tc_workspace_bytes(c_in, n_in)) + round_copy_wg_x(n_in, c_in, prerounded) +
+                         round_copy_wg_gy(n_out, c_out, prerounded)
+                   : 0;
   return fwd > wg ? fwd : wg;
 }
 
@@ -56,7 +70,7 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
                                         int32_t c_out, int32_t k3, int32_t w_layout, float* y, void* workspace,
                                         int64_t workspace_bytes, int32_t impl, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0, "bad sizes");
-  B2S_CHECK_ARG(w_layout >= 0 && w_layout <= 3, "w_layout must be in 0..3");
+  B2S_CHECK_ARG(w_layout >= 0 && w_layout <= 7, "w_layout must be in 0..7");
   B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
   B2S_CHECK_ARG(nbr || (k3 == 1 && n_in == n_out), "nbr may be null only for the identity map (k3 == 1)");
   if (n_out == 0) return B2S_OK;
@@ -68,24 +82,33 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
     return B2S_EINVAL;
   }
   if (impl == 2 || (impl == 0 && tc_ok)) {
-    B2S_CHECK_ARG(workspace && workspace_bytes >= b2s_conv_tc_workspace_bytes(c_in, c_out, k3, n_in),
+    const int pre = (w_layout & 4) ? 1 : 0;
+    const int64_t tc_bytes = al256(b2s_conv_tc_workspace_bytes(c_in, c_out, k3, n_in));
+    B2S_CHECK_ARG(workspace && workspace_bytes >= tc_bytes + round_copy_fwd(n_in, c_in, pre),
                   "workspace too small (see b2s_conv_workspace_bytes)");
     B2S_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(y) & 15) == 0,
                   "workspace must be 256-byte aligned, x and y 16-byte aligned");
-    if (b2s_conv_gather_gemm_tc(x, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout, y, workspace,
+    const float* xin = x;
+    if (!pre && c_in > 4) {   // tcgen05 truncates fp32 operands: round the gathered operand to nearest first
+      float* xr = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + tc_bytes);
+      b2s_launch_round_tf32(x, n_in, nullptr, c_in, xr, st);
+      xin = xr;
+    }
+    if (b2s_conv_gather_gemm_tc(xin, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout & 3, y, workspace,
                                 workspace_bytes, st))
       return B2S_ECUDA;
   } else {
-    b2s_conv_gather_gemm_simt(x, w, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, w_layout, y, st);
+    b2s_conv_gather_gemm_simt(x, w, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, w_layout & 3, y, st);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
-                                  const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw, void* workspace,
-                                  int64_t workspace_bytes, int32_t impl, b2s_stream_t stream) {
+                                  const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw,
+                                  void* workspace, int64_t workspace_bytes, int32_t impl, int32_t flags,
+                                  b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0 && gw, "bad sizes");
   B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
   B2S_CHECK_ARG(nbr || (k3 == 1 && n_in == n_out), "nbr may be null only for the identity map (k3 == 1)");
@@ -101,10 +124,23 @@ extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t
     return B2S_EINVAL;
   }
   if (impl == 2 || (impl == 0 && tc_ok)) {
-    const int64_t need = b2s_wgrad_tc_workspace_bytes(c_in, n_in);
-    B2S_CHECK_ARG(need == 0 || (workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0),
-                  "workspace too small (see b2s_conv_workspace_bytes)");
-    if (b2s_conv_wgrad_tc(x, gy, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, gw, workspace, st)) return B2S_ECUDA;
+    const int pre = flags & 1;
+    const int64_t own = al256(b2s_wgrad_tc_workspace_bytes(c_in, n_in));
+    const int64_t need = own + round_copy_wg_x(n_in, c_in, pre) + round_copy_wg_gy(n_out, c_out, pre);
+    B2S_CHECK_ARG(need == 0 || (workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0),
+                  "workspace too small or not 256-byte aligned (see b2s_conv_workspace_bytes)");
+    const float *xin = x, *gin = gy;
+    if (!pre) {
+      char* wsp = reinterpret_cast<char*>(workspace) + own;
+      if (c_in > 4) {
+        b2s_launch_round_tf32(x, n_in, nullptr, c_in, reinterpret_cast<float*>(wsp), st);
+        xin = reinterpret_cast<const float*>(wsp);
+        wsp += round_copy_wg_x(n_in, c_in, pre);
+      }
+      b2s_launch_round_tf32(gy, n_out, n_out_dev, c_out, reinterpret_cast<float*>(wsp), st);
+      gin = reinterpret_cast<const float*>(wsp);
+    }
+    if (b2s_conv_wgrad_tc(xin, gin, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, gw, workspace, st)) return B2S_ECUDA;
   } else {
     b2s_conv_wgrad_simt(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
   }

@@ -8,6 +8,7 @@
 //   a9 R:SENet.py:53   a10/a11 R:senet_block.py:43-50, R:common.py:44-48, R:SENet.py:63,117
 //   a13 R:SENet.py:35,51,98 + R:resnet_block.py:51-55   a14 R:common.py:41
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <math.h>
 
 namespace {
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
 }
 
 // flat elementwise kernels (numel = rows * c)
-template <int VEC, int OP>  // OP 0: y = gelu(x)   1: gx = gy * gelu'(x)   2: s = a + b, y = gelu(s)
+template <int VEC, int OP>  // OP 0: y = gelu(x)   1: gx = gy * gelu'(x)   2: s = a + b, y = gelu(s)   3: y = tf32(x)
 __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                           int64_t n, const int* __restrict__ n_dev, int c,
                                                           float* __restrict__ o0, float* __restrict__ o1) {
@@ -425,6 +426,10 @@ __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restric
     if (OP == 0) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) r0.v[j] = gelu_f(av.v[j]);
+      stv<VEC>(o0 + e * VEC, r0);
+    } else if (OP == 3) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) r0.v[j] = __uint_as_float(tc::rna_tf32(__float_as_uint(av.v[j])));
       stv<VEC>(o0 + e * VEC, r0);
     } else if (OP == 1) {
       const V<VEC> bv = ldv<VEC>(b + e * VEC);
@@ -647,6 +652,21 @@ static int32_t launch_flat(const float* a, const float* b, int64_t n, const int3
   else
     flat_kernel<1, OP><<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1);
   return 0;
+}
+
+// internal: rounding pass used by the convolution entry points when the caller did not pre-round
+void b2s_launch_round_tf32(const float* in, int64_t n, const int32_t* n_dev, int32_t c, float* out, cudaStream_t st) {
+  launch_flat<3>(in, nullptr, n, n_dev, c, out, nullptr, st);
+}
+
+extern "C" int32_t b2s_round_tf32(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y,
+                                  b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0, "n >= 0 and c > 0");
+  if (n == 0) return B2S_OK;
+  B2S_CHECK_ARG(x && y, "null pointer");
+  launch_flat<3>(x, nullptr, n, n_dev, c, y, nullptr, as_stream(stream));
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
 }
 
 extern "C" int32_t b2s_gelu_fwd(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y,

@@ -2,15 +2,22 @@
 //
 //   gw[k, ci, co] = sum over out rows o of  x[nbr[k, o], ci] * gy[o, co]
 //
-// As a GEMM per kernel offset k: D[M = ci, N = co] with the reduction (UMMA "K") running over OUT ROWS.
-// Both operands are gathered feature rows, i.e. M/N-contiguous ("MN-major") in shared memory, which for
-// 32-bit elements requires the SWIZZLE_128B_BASE32B layout (see tc_ptx.cuh):
-//   A stage [128 ci x 32 rows]: block j = ci/32 at j*4096, inside it row r at r*128 (atoms of 4 rows),
-//   B stage [BN  co x 32 rows]: same shape with j = co/32,
-//   the four 32-byte units of every 128-byte row XOR-ed with (r & 3).  One tcgen05.mma (M=128, N=BN, K=8)
-//   consumes 8 rows (two atoms); descriptors carry LBO = 4096 (next 32 channels), SBO = 512 (next 4 rows).
-// Rows without a neighbour at offset k are zero-filled by LDGSTS (no global read for either operand).
-// The out rows are split across CTAs (grid.y); partial tiles are combined with vector fp32 reductions.
+// As a GEMM: D[M = (kernel offset, ci), N = co] with the reduction (UMMA "K") running over OUT ROWS.  Both operands
+// are feature rows, i.e. M/N-contiguous ("MN-major") in shared memory, which for 32-bit elements requires the
+// SWIZZLE_128B_BASE32B layout (see tc_ptx.cuh).
+//
+// One CTA owns a GROUP of KG kernel offsets x one slice of ci (CB blocks of 32 channels) x one tile of BN output
+// channels x one range of out rows.  Per pipeline stage of R = 16 out rows it stages
+//   B: the gy rows ONCE                                 [BN/32 blocks][16 rows][128 B]
+//   A: for every offset of the group the gathered x rows [KG*CB blocks][16 rows][128 B]  (zero-filled where nbr = -1)
+// and issues, per M tile of 128 (= 4 consecutive A blocks: 4/CB offsets x CB*32 channels), 2 x tcgen05.mma
+// (M=128, N=BN, K=8 rows) into that tile's own TMEM accumulator (columns t*BN ...).  Sharing the gy rows between
+// the offsets of a group is what this layout buys: the 64->64 layers read gy 2x instead of 27x and fill all 128
+// lanes of the tensor core with two offsets x 64 channels.
+// Producers: 8 warps, 8 lanes per (block, row) item = one 128-byte LDGSTS run; the neighbour indices of the NEXT
+// stage are prefetched into registers while the current stage's copies are in flight.
+// Operands must already be TF32-representable (b2s_round_tf32): tcgen05 kind::tf32 truncates.
+// Row ranges are split across CTAs (grid.y); partial tiles are combined with vector fp32 reductions.
 //
 // Reference call site: autograd of MinkowskiConvolution (R:models/base_model.py:262 -> loss.backward()).
 #include "common.cuh"
@@ -21,8 +28,8 @@ namespace {
 
 using namespace tc;
 
-constexpr int WG_BM = 128;        // input channels per CTA == UMMA M
-constexpr int WG_ROWS = 32;       // out rows per pipeline stage (4 MMAs of K = 8 rows)
+constexpr int WG_BM = 128;        // UMMA M
+constexpr int WG_ROWS = 32;       // (small-c_in kernel) out rows per pipeline stage
 constexpr int WG_A_STAGE = WG_BM * WG_ROWS * 4;   // 16 KB
 constexpr int WG_PRODUCERS = 128;
 constexpr int WG_THREADS = 160;
@@ -30,16 +37,6 @@ constexpr int WG_LAG = 2;
 constexpr uint32_t ATOM_BYTES = 1024;             // 8 rows x 128 B consumed per MMA (two 4-row swizzle atoms)
 constexpr uint32_t SBO_BYTES = 512;               // next 4-row atom along the reduction
 constexpr uint32_t LBO_BYTES = WG_ROWS * 128;     // next 32-channel block
-
-template <int BN, int STAGES>
-struct WgSmem {
-  static constexpr int B_STAGE = BN * WG_ROWS * 4;
-  static constexpr int A_OFF = 0;
-  static constexpr int B_OFF = STAGES * WG_A_STAGE;
-  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 2) * 8;
-  static constexpr int DYN_BYTES = TOTAL + 1024;
-};
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -53,94 +50,148 @@ __device__ __forceinline__ uint32_t mn_offset(int row, int chunk) {
   return (uint32_t)j * LBO_BYTES + (uint32_t)row * 128u + (uint32_t)(((unit << 1) | (c & 1)) << 4);
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(WG_THREADS, 1)
-    wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ gy, const int* __restrict__ nbr,
-                    int64_t n_out, const int* __restrict__ n_out_dev, int c_in, int c_out, int ci_tiles, int co_tiles,
-                    int64_t rows_per_split, int use_atomic, float* __restrict__ gw) {
+// ---------------------------------------------------------------------------------------------
+// general kernel: offset groups sharing the gy rows
+// ---------------------------------------------------------------------------------------------
+constexpr int G_R = 16;                         // out rows per stage (2 MMAs of K = 8 rows per M tile)
+constexpr int G_BLOCK = G_R * 128;              // bytes of one 32-channel block of a stage
+constexpr int G_PRODUCERS = 256;                // warps 0..7
+constexpr int G_THREADS = 288;                  // + warp 8 = MMA issuer
+constexpr int G_MAX_STAGES = 8;
+constexpr int G_MAX_ROUNDS = 16;                // A items per thread per stage (<= 32 blocks x 16 rows / 32)
+constexpr int G_LAG = 2;
+
+__device__ __forceinline__ uint32_t g_offset(int row, int c8) {  // chunk c8 (0..7) of a block-local row
+  const int unit = (c8 >> 1) ^ (row & 3);
+  return (uint32_t)row * 128u + (uint32_t)(((unit << 1) | (c8 & 1)) << 4);
+}
+
+struct G2Params {
+  int c_in, c_out, k3;
+  int KG, CB;          // offsets per group, 32-channel blocks per offset inside this CTA's ci slice
+  int MT;              // M tiles of 128 = ceil(KG*CB / 4)
+  int ci_tiles, co_tiles, groups;
+  int stages;
+  int use_atomic;
+  int64_t rows_per_split;
+};
+
+template <int BN, int TCOLS>
+__global__ void __launch_bounds__(G_THREADS, 1)
+    wgrad_group_kernel(const float* __restrict__ x, const float* __restrict__ gy, const int* __restrict__ nbr,
+                       int64_t n_out, const int* __restrict__ n_out_dev, G2Params p, float* __restrict__ gw) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
-  using L = WgSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t a_base = base + L::A_OFF, b_base = base + L::B_OFF, bar_base = base + L::BAR_OFF;
+  const int NBP = p.MT * 4;                                   // A blocks per stage incl. zero padding
+  const uint32_t a_stage_bytes = (uint32_t)NBP * G_BLOCK, b_stage_bytes = (uint32_t)(BN / 32) * G_BLOCK;
+  const uint32_t stage_bytes = a_stage_bytes + b_stage_bytes;
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + 8 * (2 * STAGES + 1));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (G_MAX_STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * G_MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * G_MAX_STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + (size_t)p.stages * stage_bytes + 8 * (2 * G_MAX_STAGES + 1));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int t = blockIdx.x;
-  const int cot = t % co_tiles;
-  t /= co_tiles;
-  const int cit = t % ci_tiles;
-  const int k = t / ci_tiles;
-  const int ci0 = cit * WG_BM, co0 = cot * BN;
-  const int ci_valid = min(WG_BM, c_in - ci0);
-  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
-  const int64_t r_end = min(r_begin + rows_per_split, n_out);
-  const int T = (int)((r_end - r_begin + WG_ROWS - 1) / WG_ROWS);
+  const int cot = t % p.co_tiles;
+  t /= p.co_tiles;
+  const int cit = t % p.ci_tiles;
+  const int grp = t / p.ci_tiles;
+  const int k0 = grp * p.KG;
+  const int ci0 = cit * p.CB * 32, co0 = cot * BN;
+  const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_split;
+  const int64_t r_end = min(r_begin + p.rows_per_split, n_out);
+  const int T = (int)((r_end - r_begin + G_R - 1) / G_R);
   if (T <= 0) return;  // uniform across the CTA
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), WG_PRODUCERS);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), G_PRODUCERS);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<BN>(tmem_slot);
+  if (warp == 8) tmem_alloc<TCOLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_ptr;
 
-  if (warp < 4) {
-    const int a_chunks = ci_valid >> 2;  // 16-byte chunks of the A row piece (multiple of 8)
-    auto publish = [&](int it_done) {    // round this thread's own chunks of stage it_done to tf32, then hand over
-      const uint32_t a_st = a_base + (it_done % STAGES) * WG_A_STAGE, b_st = b_base + (it_done % STAGES) * L::B_STAGE;
+  if (warp < 8) {
+    // ===================== producers =====================
+    // item = (block b, row r) = one 128-byte run; 8 lanes per item, 32 items per round of the 256 producers.
+    // With 16 rows per block, item j*32 + slot is block 2j + h, row r with h = slot >> 4, r = slot & 15: the row and
+    // the swizzled destination are per-thread constants and everything else is linear in the round j.
+    const int l8 = tid & 7;
+    const int slot = tid >> 3;
+    const int h = slot >> 4, r = slot & (G_R - 1);
+    const int a_rounds = NBP >> 1;                  // NBP blocks, two per round (NBP is a multiple of 4)
+    constexpr int B_ROUNDS = BN / 64;
+    const int cb_mask = p.CB - 1, cb_shift = 31 - __clz(p.CB);   // CB is a power of two
+    const uint32_t dst0 = (uint32_t)h * G_BLOCK + g_offset(r, l8);
+    unsigned valid = 0;                              // bit j: round j addresses a real (offset, channel block)
 #pragma unroll
-      for (int p = 0; p < WG_ROWS / 4; ++p) {
-        const int row = p * 4 + warp;
-        if (lane < a_chunks) round_chunk_tf32(a_st + mn_offset(row, lane));
+    for (int j = 0; j < G_MAX_ROUNDS; ++j) {
+      const int bb = 2 * j + h, kk = bb >> cb_shift;
+      if (j < a_rounds && kk < p.KG && k0 + kk < p.k3 && ci0 + (bb & cb_mask) * 32 < p.c_in) valid |= 1u << j;
+    }
+    const int* nbr_r = nbr ? nbr + r : nullptr;
+    const float* x_l = x + ci0 + l8 * 4;
+    const float* gy_l = gy + co0 + h * 32 + l8 * 4;
+    int idx[G_MAX_ROUNDS];
+
+    auto load_idx = [&](int it) {        // neighbour rows of stage `it` for this thread's A items
+      const int64_t r0 = r_begin + (int64_t)it * G_R;
+      const bool live = r0 + r < r_end;
 #pragma unroll
-        for (int q = 0; q < (BN + 127) / 128; ++q) {
-          const int chunk = q * 32 + lane;
-          if (chunk < BN / 4) round_chunk_tf32(b_st + mn_offset(row, chunk));
+      for (int j = 0; j < G_MAX_ROUNDS; ++j) {
+        int v = -1;
+        if (((valid >> j) & 1u) && live) {
+          const int k = k0 + ((2 * j + h) >> cb_shift);
+          v = nbr_r ? __ldg(nbr_r + (int64_t)k * pitch + r0) : (int)(r0 + r);
+        }
+        idx[j] = v;
+      }
+    };
+    auto publish = [&](int it_done) {
+      fence_proxy_async();
+      mbar_arrive(full_bar(it_done % p.stages));
+    };
+
+    load_idx(0);
+    for (int it = 0; it < T; ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const uint32_t a_dst = base + (uint32_t)s * stage_bytes + dst0, b_dst = a_dst + a_stage_bytes;
+      const int64_t o = r_begin + (int64_t)it * G_R + r;
+#pragma unroll
+      for (int j = 0; j < G_MAX_ROUNDS; ++j) {
+        if (j < a_rounds) {
+          const int i = idx[j];
+          const float* src = x_l + (int64_t)(i >= 0 ? i : 0) * p.c_in + ((2 * j + h) & cb_mask) * 32;
+          cp_async16(a_dst + (uint32_t)j * (2 * G_BLOCK), src, i >= 0 ? 16u : 0u);
         }
       }
-      fence_proxy_async();
-      mbar_arrive(full_bar(it_done % STAGES));
-    };
-    for (int it = 0; it < T; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      const uint32_t a_stage = a_base + s * WG_A_STAGE, b_stage = b_base + s * L::B_STAGE;
-      const int64_t r0 = r_begin + (int64_t)it * WG_ROWS;
+      {
+        const bool live = o < r_end;
+        const float* src = gy_l + (live ? o : 0) * p.c_out;
 #pragma unroll
-      for (int p = 0; p < WG_ROWS / 4; ++p) {
-        const int row = p * 4 + warp;
-        const int64_t o = r0 + row;
-        int i = -1;
-        if (o < r_end) i = nbr ? __ldg(&nbr[(int64_t)k * pitch + o]) : (int)o;
-        const uint32_t nbytes = i >= 0 ? 16u : 0u;
-        const int64_t xi = i >= 0 ? i : 0, oo = i >= 0 ? o : 0;
-        if (lane < a_chunks) cp_async16(a_stage + mn_offset(row, lane), x + xi * c_in + ci0 + lane * 4, nbytes);
-#pragma unroll
-        for (int q = 0; q < (BN + 127) / 128; ++q) {
-          const int chunk = q * 32 + lane;
-          if (chunk < BN / 4) cp_async16(b_stage + mn_offset(row, chunk), gy + oo * c_out + co0 + chunk * 4, nbytes);
-        }
+        for (int j = 0; j < B_ROUNDS; ++j)
+          cp_async16(b_dst + (uint32_t)j * (2 * G_BLOCK), src + j * 64, live ? 16u : 0u);
       }
       cp_async_commit();
-      if (it >= WG_LAG) {
-        cp_async_wait<WG_LAG>();
-        publish(it - WG_LAG);
+      if (it + 1 < T) load_idx(it + 1);   // overlaps with the copies in flight
+      if (it >= G_LAG) {
+        cp_async_wait<G_LAG>();
+        publish(it - G_LAG);
       }
     }
     if (T >= 2) {
@@ -150,44 +201,56 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     cp_async_wait<0>();
     publish(T - 1);
 
-    // ---- epilogue: thread = one input channel (TMEM lane), 32 output channels per tcgen05.ld
+    // ===================== epilogue: TMEM lane = (block 4t + q, channel lane), 32 columns per tcgen05.ld
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int ci = warp * 32 + lane;
-    const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
-    float* dst_row = gw + ((int64_t)k * c_in + ci0 + ci) * c_out + co0;
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may read
+    const uint32_t t_lane = tmem_d + ((uint32_t)(q * 32) << 16);
+    for (int mt = (warp >> 2); mt < p.MT; mt += 2) {   // warps 0-3 take even M tiles, warps 4-7 odd ones
+      const int b = mt * 4 + q;
+      const int kk = b / p.CB, cb = b % p.CB;
+      const int k = k0 + kk;
+      const int ci = ci0 + cb * 32 + lane;
+      const bool ok = kk < p.KG && k < p.k3 && ci < p.c_in;
+      float* dst_row = gw + ((int64_t)k * p.c_in + ci) * p.c_out + co0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (ci < ci_valid) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + (uint32_t)(mt * BN + c0), v);
+        tmem_ld_wait();
+        if (ok) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (use_atomic)
-            red_add_v4(dst_row + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                       __uint_as_float(v[j + 3]));
-          else
-            *reinterpret_cast<float4*>(dst_row + c0 + j) =
-                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                            __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 4) {
+            if (p.use_atomic)
+              red_add_v4(dst_row + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                         __uint_as_float(v[j + 3]));
+            else
+              *reinterpret_cast<float4*>(dst_row + c0 + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                              __uint_as_float(v[j + 3]));
+          }
         }
       }
     }
     tc_fence_before();
   } else {
+    // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_tf32(WG_BM, BN, 1, 1);  // both operands MN-major
     for (int it = 0; it < T; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      const int s = it % p.stages;
+      const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       if (lane == 0) {
+        const uint32_t a_stage = base + (uint32_t)s * stage_bytes, b_stage = a_stage + a_stage_bytes;
+        for (int mt = 0; mt < p.MT; ++mt) {
 #pragma unroll
-        for (int g = 0; g < WG_ROWS / 8; ++g) {
-          const uint64_t a_desc = smem_desc_sw128_base32(a_base + s * WG_A_STAGE + g * ATOM_BYTES, LBO_BYTES, SBO_BYTES);
-          const uint64_t b_desc = smem_desc_sw128_base32(b_base + s * L::B_STAGE + g * ATOM_BYTES, LBO_BYTES, SBO_BYTES);
-          mma_tf32(tmem_d, a_desc, b_desc, IDESC, (it | g) ? 1u : 0u);
+          for (int g = 0; g < G_R / 8; ++g) {
+            const uint64_t a_desc =
+                smem_desc_sw128_base32(a_stage + (uint32_t)mt * 4 * G_BLOCK + g * ATOM_BYTES, G_BLOCK, SBO_BYTES);
+            const uint64_t b_desc = smem_desc_sw128_base32(b_stage + g * ATOM_BYTES, G_BLOCK, SBO_BYTES);
+            mma_tf32(tmem_d + (uint32_t)(mt * BN), a_desc, b_desc, IDESC, (it | g) ? 1u : 0u);
+          }
         }
         mma_commit(empty_bar(s));
       }
@@ -197,10 +260,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_d);
+    tmem_dealloc<TCOLS>(tmem_d);
   }
 }
 
@@ -266,11 +329,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
   if (warp < 4) {
     const int a_chunks = co_valid >> 2;
-    auto publish = [&](int it_done) {    // gy chunks are rounded here; x4 was rounded by the padding kernel
-      const uint32_t a_st = a_base + (it_done % STAGES) * WG_A_STAGE;
-#pragma unroll
-      for (int p = 0; p < WG_ROWS / 4; ++p)
-        if (lane < a_chunks) round_chunk_tf32(a_st + mn_offset(p * 4 + warp, lane));
+    auto publish = [&](int it_done) {
       fence_proxy_async();
       mbar_arrive(full_bar(it_done % STAGES));
     };
@@ -405,35 +464,44 @@ bool wgrad_tc_disabled() {
   return v == 1;
 }
 
-template <int BN, int STAGES>
-int launch_wgrad(const float* x, const float* gy, const int* nbr, int64_t n_out, const int* n_out_dev, int c_in, int c_out,
-                 int k3, float* gw, cudaStream_t st) {
-  using L = WgSmem<BN, STAGES>;
-  auto kern = wgrad_tc_kernel<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
-      b2s_set_error("wgrad_tc: cannot opt in to %d bytes of shared memory", L::DYN_BYTES);
+template <int BN, int TCOLS>
+int launch_group(const float* x, const float* gy, const int* nbr, int64_t n_out, const int* n_out_dev, G2Params p,
+                 float* gw, cudaStream_t st) {
+  auto kern = wgrad_group_kernel<BN, TCOLS>;
+  const int stage_bytes = (p.MT * 4 + BN / 32) * G_BLOCK;
+  int stages = (222 * 1024) / stage_bytes;
+  if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
+  if (stages <= G_LAG) {   // the producers run G_LAG stages ahead of their own hand-over
+    b2s_set_error("wgrad_tc: stage of %d bytes does not fit %d times in shared memory", stage_bytes, G_LAG + 1);
+    return -1;
+  }
+  p.stages = stages;
+  // >= 114 KB keeps one CTA per SM (each CTA may hold all 512 TMEM columns)
+  int dyn = stages * stage_bytes + (2 * G_MAX_STAGES + 2) * 8 + 1024;
+  if (dyn < 116 * 1024) dyn = 116 * 1024;
+  static int attr_set = 0;
+  if (attr_set < dyn) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      b2s_set_error("wgrad_tc: cannot opt in to 227 KB of shared memory");
       return -1;
     }
-    attr_set = true;
+    attr_set = 227 * 1024;
   }
-  const int ci_tiles = (c_in + WG_BM - 1) / WG_BM, co_tiles = c_out / BN;
-  const int64_t base = (int64_t)k3 * ci_tiles * co_tiles;
-  // aim at ~3 waves of 148 SMs; every split gets at least 8 stages of rows
-  int64_t splits = (3LL * B2S_NUM_SMS + base - 1) / base;
-  const int64_t max_splits = ceil_div64(n_out, 8 * WG_ROWS);
+  const int64_t base = (int64_t)p.groups * p.ci_tiles * p.co_tiles;
+  // two waves of 148 single-CTA SMs; every split gets at least 16 stages of rows
+  int64_t splits = (2LL * B2S_NUM_SMS + base - 1) / base;
+  const int64_t max_splits = ceil_div64(n_out, 16 * G_R);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
   int64_t rows = ceil_div64(n_out, splits);
-  rows = ceil_div64(rows, WG_ROWS) * WG_ROWS;
+  rows = ceil_div64(rows, G_R) * G_R;
   splits = ceil_div64(n_out, rows);
-  const int use_atomic = splits > 1 ? 1 : 0;
-  if (use_atomic) cudaMemsetAsync(gw, 0, (size_t)k3 * c_in * c_out * sizeof(float), st);
+  p.rows_per_split = rows;
+  p.use_atomic = splits > 1 ? 1 : 0;
+  if (p.use_atomic) cudaMemsetAsync(gw, 0, (size_t)p.k3 * p.c_in * p.c_out * sizeof(float), st);
   dim3 grid((unsigned)base, (unsigned)splits);
-  kern<<<grid, WG_THREADS, L::DYN_BYTES, st>>>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, ci_tiles, co_tiles, rows,
-                                               use_atomic, gw);
+  kern<<<grid, G_THREADS, dyn, st>>>(x, gy, nbr, n_out, n_out_dev, p, gw);
   return 0;
 }
 
@@ -443,7 +511,8 @@ bool b2s_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_o
   (void)k3;
   if (wgrad_tc_disabled() || n_out <= 0) return false;
   if (c_in <= 4) return has_map && c_out % 32 == 0;
-  return c_in % 32 == 0 && c_out % 64 == 0;
+  const int blocks = c_in / 32;   // the group kernel slices ci into power-of-two runs of 32-channel blocks (<= 8)
+  return c_in % 32 == 0 && c_out % 64 == 0 && (blocks >= 8 || (blocks & (blocks - 1)) == 0);
 }
 
 int64_t b2s_wgrad_tc_workspace_bytes(int32_t c_in, int64_t n_in) { return c_in <= 4 ? ((n_in * 16 + 255) & ~(int64_t)255) : 0; }
@@ -453,7 +522,28 @@ int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64
                       cudaStream_t st) {
   if (c_in <= 4) return launch_wgrad_small(x, gy, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, gw, workspace, st);
   const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
-  if (bn == 256) return launch_wgrad<256, 4>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
-  if (bn == 128) return launch_wgrad<128, 3>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
-  return launch_wgrad<64, 4>(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
+  G2Params p{};
+  p.c_in = c_in, p.c_out = c_out, p.k3 = k3;
+  const int blocks_in = c_in / 32;
+  p.CB = blocks_in < 8 ? blocks_in : 8;                  // ci slice of at most 256 channels per CTA
+  p.ci_tiles = (blocks_in + p.CB - 1) / p.CB;
+  p.co_tiles = c_out / bn;
+  const int mt_max = 512 / bn;                           // TMEM columns
+  int kg = (mt_max * 4) / p.CB;
+  if (kg < 1) kg = 1;
+  if (kg > k3) kg = k3;
+  p.groups = (k3 + kg - 1) / kg;
+  kg = (k3 + p.groups - 1) / p.groups;                   // even out the groups (27 -> 14 + 13, 7+7+7+6 ...)
+  p.KG = kg;
+  p.MT = (kg * p.CB + 3) / 4;
+  const int cols = p.MT * bn;
+  if (bn == 256) return cols <= 256 ? launch_group<256, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+                                    : launch_group<256, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
+  if (bn == 128) return cols <= 128 ? launch_group<128, 128>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+                       : cols <= 256 ? launch_group<128, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+                                     : launch_group<128, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
+  return cols <= 64 ? launch_group<64, 64>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+       : cols <= 128 ? launch_group<64, 128>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+       : cols <= 256 ? launch_group<64, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+                     : launch_group<64, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
 }

@@ -33,10 +33,11 @@ SIGNATURES = {
     "b2s_kernel_map": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     "b2s_kernel_map_pair_counts": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "b2s_kernel_map_pairs_fill": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
-    "b2s_conv_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32]),
+    "b2s_conv_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),
+    "b2s_round_tf32": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_conv_gather_gemm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32,
                                     _vp]),
-    "b2s_conv_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "b2s_conv_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
     "b2s_colsum": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_maxpool_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2s_maxpool_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp]),

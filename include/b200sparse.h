@@ -128,19 +128,30 @@ B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_
  *     w_layout bit 0 set  : w is [K3, c_out, c_in]  (dgrad: x = grad_out, nbr = transposed map, w = kernel)
  *     w_layout bit 1 set  : B_k is taken from w[K3-1-k] -- for point-symmetric maps (stride 1, odd K) the
  *                           transposed table is the forward table with k reversed, so dgrad reuses nbr.
+ *     w_layout bit 2 set  : x is already TF32-representable (see b2s_round_tf32) -- skip the internal rounding pass.
  *     k3 == 1 and nbr == NULL means the identity map (the K=1, stride=1 `use_mm` case).
  *     impl: 0 = auto, 1 = SIMT fp32 reference kernel, 2 = tcgen05 kind::tf32 kernel.
- * b2s_conv_wgrad       : gw[k] = sum_o x[nbr[k,o],:]^T gy[o,:]   (gw fp32 [K3, c_in, c_out])
+ * b2s_conv_wgrad       : gw[k] = sum_o x[nbr[k,o],:]^T gy[o,:]   (gw fp32 [K3, c_in, c_out]);
+ *                        flags bit 0: x and gy are already TF32-representable.
  * b2s_colsum           : out[c] = sum_rows x[r,c]                (bias gradient)
+ * b2s_round_tf32       : y = x rounded to TF32 (10-bit mantissa, round-to-nearest, ties away: cvt.rna.tf32.f32).
+ *                        The tensor-core kernels compute with TF32 operands and fp32 accumulation, and tcgen05 itself
+ *                        TRUNCATES fp32 operands; an operand that is consumed by several passes (x by forward and
+ *                        wgrad, grad_out by dgrad and wgrad) is rounded once by the caller and flagged pre-rounded,
+ *                        otherwise the entry points round internally into `workspace`.
+ * b2s_conv_workspace_bytes: prerounded != 0 sizes the workspace for calls that set the pre-rounded flags.
  */
-B2S_API int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3);
+B2S_API int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3,
+                                         int32_t prerounded);
+B2S_API int32_t b2s_round_tf32(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                                      int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3,
                                      int32_t w_layout, float* y, void* workspace, int64_t workspace_bytes,
                                      int32_t impl, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
                                const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw,
-                               void* workspace, int64_t workspace_bytes, int32_t impl, b2s_stream_t stream);
+                               void* workspace, int64_t workspace_bytes, int32_t impl, int32_t flags,
+                               b2s_stream_t stream);
 B2S_API int32_t b2s_colsum(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* out, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- (a9) max pooling -----------

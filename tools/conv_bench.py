@@ -65,18 +65,19 @@ for name, its, ots, K, cin, cout in layers:
            "fill": pairs / (km.n_out * km.k3), "kernel_map_ms": t_map,
            "kernel_map_GBps": (16 * km.n_out + 4 * km.k3 * km.n_out) / t_map / 1e6}
     if cin:
-        xf = torch.randn(km.n_in, cin, device=dev)
-        w = torch.randn(km.k3, cin, cout, device=dev) * 0.02
-        gy = torch.randn(km.n_out, cout, device=dev)
+        xf = Fn.round_tf32(torch.randn(km.n_in, cin, device=dev))          # operands pre-rounded, as the autograd
+        w = torch.randn(km.k3, cin, cout, device=dev) * 0.02                # Function hands them to the kernels
+        gy = Fn.round_tf32(torch.randn(km.n_out, cout, device=dev))
+        pre = cin > 4
         flops = 2.0 * pairs * cin * cout
-        t = timeit(lambda: Fn.gather_gemm(xf, w, None, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, 0))
+        t = timeit(lambda: Fn.gather_gemm(xf, w, None, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, 0, prerounded=pre))
         row.update(fwd_ms=t, fwd_tflops=flops / t / 1e9)
         if cin >= 32:
             tbl = km.nbr if km.symmetric else km.inv
             lay = 3 if km.symmetric else 1
-            t = timeit(lambda: Fn.gather_gemm(gy, w, None, tbl, km.n_out, km.n_in, cout, cin, km.k3, lay))
+            t = timeit(lambda: Fn.gather_gemm(gy, w, None, tbl, km.n_out, km.n_in, cout, cin, km.k3, lay, prerounded=True))
             row.update(dgrad_ms=t, dgrad_tflops=flops / t / 1e9)
-        t = timeit(lambda: Fn.wgrad(xf, gy, km.nbr, km.n_in, km.n_out, cin, cout, km.k3))
+        t = timeit(lambda: Fn.wgrad(xf, gy, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, prerounded=True))
         row.update(wgrad_ms=t, wgrad_tflops=flops / t / 1e9)
     out.append(row)
     print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in row.items()})
