@@ -204,7 +204,7 @@ def run_b200(args):
 
     def eager_step(d):
         vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=B, bounds=BOUNDS)
-        return trainer.step(vox["coords"], vox["tensors"][0], d["target"])
+        return trainer.step(vox["coords"], vox["tensors"][0], d["target"], dense_index=vox["index"])
 
     def barrier():
         if world > 1:

@@ -19,6 +19,9 @@ import torch
 from dpcr_agb_b200 import lib as L
 
 
+USE_DENSE_INDEX = True   # tests flip this to compare the occupancy-index kernel map with the hash one
+
+
 def _triple(v):
     if isinstance(v, torch.Tensor):
         v = v.tolist()
@@ -59,7 +62,7 @@ class CoordinateMapKey:
 class CoordMap:
     """One coordinate map: rows ``int32 [N,4]`` (batch,x,y,z) + its open-addressing hash table."""
 
-    __slots__ = ("coords", "table", "capacity", "n", "n_dev", "info", "_inv_counts", "_counts_host")
+    __slots__ = ("coords", "table", "capacity", "n", "n_dev", "info", "dense", "_inv_counts", "_counts_host")
 
     def __init__(self, coords, table, capacity, n_dev=None, info=None):
         self.coords = coords
@@ -68,6 +71,8 @@ class CoordMap:
         self.n = coords.shape[0]          # rows allocated: the exact count (dynamic) or the capacity (static)
         self.n_dev = n_dev                # int32 [1] device tensor with the live row count, or None
         self.info = info                  # int32 [4] device tensor of b2s_coordmap_insert (static mode checks)
+        self.dense = None                 # (workspace, lo, dims, num_plots): the quantiser's occupancy index, if the
+        #                                   rows of this map are exactly the quantiser's output rows
         self._inv_counts = None
         self._counts_host = None
 
@@ -130,7 +135,8 @@ class CoordinateManager:
             raise L.B2SError(f"no row capacity planned for tensor stride {ts} (have {sorted(self.capacities)})")
         return int(self.capacities[ts])
 
-    def insert_static(self, coords: torch.Tensor, n_dev: torch.Tensor, tensor_stride=(1, 1, 1), tag=""):
+    def insert_static(self, coords: torch.Tensor, n_dev: torch.Tensor, tensor_stride=(1, 1, 1), tag="",
+                      dense_index=None):
         """STATIC mode: register ``coords`` int32 [capacity, 4] whose first ``n_dev[0]`` rows are live, unique and
         batch-sorted (the quantiser's output contract) -- hash build only, no host sync."""
         assert self.static and coords.dtype == torch.int32 and coords.is_contiguous() and coords.shape[1] == 4
@@ -146,6 +152,7 @@ class CoordinateManager:
                scan_ws)
         key = CoordinateMapKey(tensor_stride, tag)
         self.maps[key] = CoordMap(coords, table, hcap, n_dev=n_dev, info=info)   # unique rows: table values == rows
+        self.maps[key].dense = dense_index
         self.device = dev
         self.checks.append((f"rows at tensor stride {key.tensor_stride[0]}", cap_rows, n_dev))
         self.checks.append(("coordinate range flag", 0, info[1:2]))
@@ -176,8 +183,9 @@ class CoordinateManager:
         L.call("b2s_coordmap_fill", coords, n, None, ts, table, cap, slot, rank, out, n_unique, in2out)
         return CoordMap(out, table, cap), (in2out[:n] if want_in2out else None), n_unique
 
-    def insert(self, coords: torch.Tensor, tensor_stride=(1, 1, 1), tag=""):
-        """Create the map of a new SparseTensor.  Returns (key, unique_index or None)."""
+    def insert(self, coords: torch.Tensor, tensor_stride=(1, 1, 1), tag="", dense_index=None):
+        """Create the map of a new SparseTensor.  Returns (key, unique_index or None).  ``dense_index``: the
+        ``"index"`` entry of the GridSampling3D output these coordinates came from (optional accelerator)."""
         coords = coords.to(torch.int32).contiguous()
         assert coords.dim() == 2 and coords.shape[1] == 4, "coordinates must be [N, 1+3] (batch first)"
         key = CoordinateMapKey(tensor_stride, tag)
@@ -185,6 +193,8 @@ class CoordinateManager:
         self.maps[key] = cmap
         self.device = coords.device
         unique_index = None
+        if in2out is None:
+            cmap.dense = dense_index                            # rows are the quantiser's rows, unchanged
         if in2out is not None:                                  # duplicates: keep the first occurrence
             n = coords.shape[0]
             first = torch.full((n_unique,), n, dtype=torch.int64, device=coords.device)
@@ -235,6 +245,11 @@ class CoordinateManager:
         n = query_map.n
         k3 = kernel_size[0] * kernel_size[1] * kernel_size[2]
         nbr = torch.empty((k3, n), dtype=torch.int32, device=query_map.coords.device)
+        if table_map.dense is not None and USE_DENSE_INDEX:
+            ws, lo, dims, num_plots = table_map.dense
+            L.call("b2s_kernel_map_dense", query_map.coords, n, query_map.n_dev, ws, num_plots, L.host_i32(*lo),
+                   L.host_i32(*dims), L.host_i32(*kernel_size), L.host_i32(*step), sign, nbr)
+            return nbr
         L.call("b2s_kernel_map", query_map.coords, n, query_map.n_dev, table_map.table, table_map.capacity,
                L.host_i32(*kernel_size), L.host_i32(*step), sign, nbr)
         return nbr

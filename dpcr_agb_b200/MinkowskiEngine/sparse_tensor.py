@@ -16,10 +16,12 @@ class SparseTensor:
     def __init__(self, features, coordinates=None, tensor_stride=1, coordinate_map_key=None,
                  coordinate_manager=None, quantization_mode=None, allocator_type=None,
                  minkowski_algorithm=None, requires_grad=None, device=None, num_rows=None, capacities=None,
-                 num_batches=None):
+                 num_batches=None, dense_index=None):
         """Beyond the MinkowskiEngine signature: ``num_rows`` (int32 [1] device tensor), ``capacities`` and
         ``num_batches`` create the tensor in STATIC mode -- ``features`` / ``coordinates`` are allocated at a fixed
-        capacity, only the first ``num_rows[0]`` rows are live (unique, batch-sorted), and nothing synchronises."""
+        capacity, only the first ``num_rows[0]`` rows are live (unique, batch-sorted), and nothing synchronises.
+        ``dense_index``: the ``"index"`` entry of the ``GridSampling3D`` output the coordinates came from; kernel maps
+        that look rows up in this tensor's map then use the occupancy index instead of hash probes."""
         assert isinstance(features, torch.Tensor), "features must be a torch.Tensor"
         if device is not None:
             features = features.to(device, non_blocking=True)
@@ -27,7 +29,8 @@ class SparseTensor:
             assert coordinates is not None and capacities is not None and num_batches is not None
             coordinate_manager = CoordinateManager(D=3, device=features.device, capacities=capacities,
                                                    num_batches=num_batches)
-            coordinate_map_key = coordinate_manager.insert_static(coordinates, num_rows, _triple(tensor_stride))
+            coordinate_map_key = coordinate_manager.insert_static(coordinates, num_rows, _triple(tensor_stride),
+                                                                  dense_index=dense_index)
         elif coordinate_manager is None:
             assert coordinates is not None, "either coordinates or (coordinate_map_key, coordinate_manager)"
             coordinates = coordinates.to(features.device, non_blocking=True)
@@ -35,7 +38,8 @@ class SparseTensor:
                 raise RuntimeError("dpcr_agb_b200.MinkowskiEngine runs on CUDA (B200) only: pass device='cuda' -- "
                                    "there is no CPU path")
             coordinate_manager = CoordinateManager(D=coordinates.shape[1] - 1, device=features.device)
-            coordinate_map_key, unique_index = coordinate_manager.insert(coordinates, _triple(tensor_stride))
+            coordinate_map_key, unique_index = coordinate_manager.insert(coordinates, _triple(tensor_stride),
+                                                                         dense_index=dense_index)
             if unique_index is not None:
                 features = features[unique_index]
         else:

@@ -15,6 +15,7 @@
 // Reference call sites: R:modules/MinkowskiEngine/SENet.py:49-52,94-97; resnet_block.py:48-54,95-107.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cuda.h>
 #include <stdlib.h>
 
 namespace {
@@ -26,7 +27,6 @@ constexpr int BK = 32;             // fp32 per K step == one 128-byte swizzle ro
 constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int PRODUCERS = 128;     // warps 0..3 gather A and run the epilogue; warp 4 issues MMA
 constexpr int TC_THREADS = 160;
-constexpr int LAG = 2;             // a producer publishes stage (it - LAG) after issuing stage it
 
 // ---------------------------------------------------------------------------------------------
 // weight image: img[it][n][32] (128 bytes per n, 16-byte chunks XOR-swizzled by n & 7)
@@ -86,11 +86,12 @@ struct SmemLayout {
   static constexpr int DYN_BYTES = TOTAL + 1024;                   // slack for manual 1024-byte alignment
 };
 
-template <int BN, int STAGES, bool SMALL>
+// LAG: a producer hands over stage (it - LAG) after issuing the copies of stage it (LAG + 1 stages of copies in flight)
+template <int BN, int STAGES, bool SMALL, int LAG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
-                          int c_out, int k3, int T, float* __restrict__ y) {
+                          int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y) {
   const int64_t pitch = n_out;                     // row pitch of the neighbour table (the caller's capacity)
   n_out = b2s_rows(n_out, n_out_dev);
   if ((int64_t)blockIdx.x * BM >= n_out) return;   // whole tile beyond the live rows (uniform across the CTA)
@@ -110,6 +111,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
+  // split-K: blockIdx.z owns iterations [it0, it0 + T) of the (offset x channel-chunk) loop; partial tiles are
+  // combined with fp32 vector reductions into a zero-initialised y (small maps: too few row tiles to fill 148 SMs)
+  const int it0 = blockIdx.z * it_per_split;
+  const int T = min(it_per_split, T_total - it0);
+  if (T <= 0) return;
+  const bool split = gridDim.z > 1;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -130,66 +137,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int chunk = tid & 7;   // 16-byte chunk inside the 128-byte row
     const int rsub = tid >> 3;   // rows rsub + 16 p
     const int kc = SMALL ? 1 : c_in / BK;
-    int idx[8];
+    // Neighbour indices are fetched TWO index groups ahead of their use (a group = one kernel offset; in SMALL mode
+    // one stage = 8 offsets), so the gather never waits on the dependent nbr -> row-address load chain.
+    int idx[8], idx1[8], idx2[8];
+    const int* nbr_t = nbr ? nbr + m0 + rsub : nullptr;          // this thread's rows: + 16 p
+    auto load_group = [&](int g, int (&dst)[8]) {                 // g: offset index (general) / stage index (SMALL)
+      const int k = SMALL ? g * 8 + chunk : g;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) idx[p] = -1;
+      for (int p = 0; p < 8; ++p) {
+        const int64_t o = m0 + rsub + 16 * p;
+        int v = -1;
+        if (k < k3 && o < n_out) v = nbr_t ? __ldg(nbr_t + (int64_t)k * pitch + 16 * p) : (int)o;
+        dst[p] = v;
+      }
+    };
+    const int g0 = SMALL ? it0 : it0 / kc;                        // it0 is a multiple of kc
+    load_group(g0, idx);
+    load_group(g0 + 1, idx1);
+    load_group(g0 + 2, idx2);
 
-    auto publish = [&](int it_done) {  // all of this thread's LDGSTS for it_done have landed
+    auto publish = [&](int s_done) {  // all of this thread's LDGSTS for that stage have landed
       fence_proxy_async();
-      mbar_arrive(full_bar(it_done % STAGES));
+      mbar_arrive(full_bar(s_done));
     };
 
+    int s = 0, cc = 0, g = g0;
+    uint32_t ph = 0;
+    int s_pub = 0;                    // stage to hand over next (LAG iterations behind)
     for (int it = 0; it < T; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(empty_bar(s), ph ^ 1u);
+      const int git = it0 + it;     // iteration index in the whole (offset x channel-chunk) loop
       if (tid == 0) {
         mbar_arrive_expect_tx(full_bar(s), L::B_STAGE_BYTES);
-        bulk_g2s(b_base + s * L::B_STAGE_BYTES, wimg + ((int64_t)it * c_out + n0) * BK, L::B_STAGE_BYTES,
+        bulk_g2s(b_base + s * L::B_STAGE_BYTES, wimg + ((int64_t)git * c_out + n0) * BK, L::B_STAGE_BYTES,
                  full_bar(s));
       }
       const uint32_t a_stage = a_base + s * A_STAGE_BYTES;
-      if (SMALL) {
-        const int k = it * 8 + chunk;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int row = rsub + 16 * p;
-          const int64_t o = m0 + row;
-          int i = -1;
-          if (k < k3 && o < n_out) i = nbr ? __ldg(&nbr[(int64_t)k * pitch + o]) : (int)o;
-          const float* src = x + (int64_t)(i >= 0 ? i : 0) * 4;
-          cp_async16(a_stage + sw128_offset(row, chunk), src, i >= 0 ? 16u : 0u);
-        }
-      } else {
-        const int k = it / kc, cc = it - k * kc;
-        if (cc == 0) {
-#pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            const int64_t o = m0 + rsub + 16 * p;
-            idx[p] = o < n_out ? (nbr ? __ldg(&nbr[(int64_t)k * pitch + o]) : (int)o) : -1;
-          }
-        }
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int row = rsub + 16 * p;
-          const int i = idx[p];
-          const float* src = x + (int64_t)(i >= 0 ? i : 0) * c_in + cc * BK + chunk * 4;
-          cp_async16(a_stage + sw128_offset(row, chunk), src, i >= 0 ? 16u : 0u);
-        }
+      for (int p = 0; p < 8; ++p) {
+        const int row = rsub + 16 * p;
+        const int i = idx[p];
+        const float* src = SMALL ? x + (int64_t)(i >= 0 ? i : 0) * 4
+                                 : x + (int64_t)(i >= 0 ? i : 0) * c_in + cc * BK + chunk * 4;
+        cp_async16(a_stage + sw128_offset(row, chunk), src, i >= 0 ? 16u : 0u);
       }
       cp_async_commit();
+      if (++cc == kc) {             // next index group: rotate the prefetch ring, fetch group g + 3
+        cc = 0;
+        ++g;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          idx[p] = idx1[p];
+          idx1[p] = idx2[p];
+        }
+        load_group(g + 2, idx2);
+      }
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
       if (it >= LAG) {
         cp_async_wait<LAG>();
-        publish(it - LAG);
+        publish(s_pub);
+        if (++s_pub == STAGES) s_pub = 0;
       }
     }
-    // drain the last LAG stages
-    if (T >= 2) {
-      cp_async_wait<1>();
-      publish(T - 2);
-    }
+    // drain the last min(LAG, T) stages
     cp_async_wait<0>();
-    publish(T - 1);
+    for (int r = T < LAG ? T : LAG; r > 0; --r) {
+      publish(s_pub);
+      if (++s_pub == STAGES) s_pub = 0;
+    }
 
     // ===================== epilogue: TMEM -> registers -> y =====================
     mbar_wait(accum_bar, 0);
@@ -203,14 +221,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tmem_ld_wait();
       if (o < n_out) {
         float* dst = y + o * c_out + n0 + c0;
+        const bool add_bias = bias && it0 == 0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 r;
-          r.x = __uint_as_float(v[j]) + (bias ? __ldg(&bias[n0 + c0 + j]) : 0.f);
-          r.y = __uint_as_float(v[j + 1]) + (bias ? __ldg(&bias[n0 + c0 + j + 1]) : 0.f);
-          r.z = __uint_as_float(v[j + 2]) + (bias ? __ldg(&bias[n0 + c0 + j + 2]) : 0.f);
-          r.w = __uint_as_float(v[j + 3]) + (bias ? __ldg(&bias[n0 + c0 + j + 3]) : 0.f);
-          *reinterpret_cast<float4*>(dst + j) = r;
+          r.x = __uint_as_float(v[j]) + (add_bias ? __ldg(&bias[n0 + c0 + j]) : 0.f);
+          r.y = __uint_as_float(v[j + 1]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 1]) : 0.f);
+          r.z = __uint_as_float(v[j + 2]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 2]) : 0.f);
+          r.w = __uint_as_float(v[j + 3]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 3]) : 0.f);
+          if (split)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(r.x), "f"(r.y), "f"(r.z),
+                         "f"(r.w)
+                         : "memory");
+          else
+            *reinterpret_cast<float4*>(dst + j) = r;
         }
       }
     }
@@ -218,9 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else {
     // ===================== MMA issuer: warp 4 stays converged, lane 0 issues =====================
     constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < T; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
       if (lane == 0) {
@@ -232,6 +256,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         mma_commit(empty_bar(s));
       }
       __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
     if (lane == 0) mma_commit(accum_bar);
     __syncwarp();
@@ -244,6 +272,234 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TMA variant of the general (c_in % 32 == 0) kernel: the A rows are gathered by the TMA unit
+// (cp.async.bulk.tensor ... tile::gather4, 128B swizzle) instead of 16-byte LDGSTS -- the LSU path saturates at
+// ~27 B/clk/SM (4 tag look-ups + 4-5 shared-memory wavefronts per 512-byte warp instruction, zero-fills included),
+// which capped the tensor pipe at ~20-37 %.  One producer warp: lane j owns rows 4j..4j+3 of the tile and issues one
+// gather4 per stage; rows without a neighbour use an out-of-range row index and are zero-filled by the hardware.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    gather_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmx, const float* __restrict__ wimg,
+                           const float* __restrict__ bias, const int* __restrict__ nbr, int64_t n_out,
+                           const int* __restrict__ n_out_dev, int oob_row, int c_in, int c_out, int k3, int T_total,
+                           int it_per_split, float* __restrict__ y) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
+  if ((int64_t)blockIdx.x * BM >= n_out) return;
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base + L::A_OFF, b_base = base + L::B_OFF;
+  const uint32_t bar_base = base + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + 8 * (2 * STAGES + 1));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int it0 = blockIdx.z * it_per_split;
+  const int T = min(it_per_split, T_total - it0);
+  if (T <= 0) return;
+  const bool split = gridDim.z > 1;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmx);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);    // one arrive.expect_tx; the TMA and bulk copies complete the bytes
+      mbar_init(empty_bar(s), 1);   // one tcgen05.commit
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== producer warp: lane j gathers rows 4j .. 4j+3 =====================
+    const int kc = c_in / BK;
+    const int64_t r0 = m0 + 4 * lane;
+    const int* nbr_t = nbr ? nbr + r0 : nullptr;
+    auto load_group = [&](int k, int (&dst)[4]) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        int v = -1;
+        if (k < k3 && r0 + p < n_out) v = nbr_t ? __ldg(nbr_t + (int64_t)k * pitch + p) : (int)(r0 + p);
+        dst[p] = v >= 0 ? v : oob_row;
+      }
+    };
+    int idx[4], idx1[4], idx2[4];
+    int g = it0 / kc;
+    load_group(g, idx);
+    load_group(g + 1, idx1);
+    load_group(g + 2, idx2);
+    int s = 0, cc = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < T; ++it) {
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full_bar(s), A_STAGE_BYTES + L::B_STAGE_BYTES);
+        bulk_g2s(b_base + s * L::B_STAGE_BYTES, wimg + ((int64_t)(it0 + it) * c_out + n0) * BK, L::B_STAGE_BYTES,
+                 full_bar(s));
+      }
+      __syncwarp();
+      tma_gather4(a_base + s * A_STAGE_BYTES + lane * 512, &tmx, cc * BK, idx[0], idx[1], idx[2], idx[3], full_bar(s));
+      if (++cc == kc) {
+        cc = 0;
+        ++g;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          idx[p] = idx1[p];
+          idx1[p] = idx2[p];
+        }
+        load_group(g + 2, idx2);
+      }
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+  }
+  if (warp < 4) {
+    // ===================== epilogue: TMEM -> registers -> y =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int64_t o = m0 + warp * 32 + lane;
+    const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (o < n_out) {
+        float* dst = y + o * c_out + n0 + c0;
+        const bool add_bias = bias && it0 == 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 r;
+          r.x = __uint_as_float(v[j]) + (add_bias ? __ldg(&bias[n0 + c0 + j]) : 0.f);
+          r.y = __uint_as_float(v[j + 1]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 1]) : 0.f);
+          r.z = __uint_as_float(v[j + 2]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 2]) : 0.f);
+          r.w = __uint_as_float(v[j + 3]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 3]) : 0.f);
+          if (split)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(r.x), "f"(r.y), "f"(r.z),
+                         "f"(r.w)
+                         : "memory");
+          else
+            *reinterpret_cast<float4*>(dst + j) = r;
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < T; ++it) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t a_desc = smem_desc_sw128(a_base + s * A_STAGE_BYTES, 16, 1024);
+        const uint64_t b_desc = smem_desc_sw128(b_base + s * L::B_STAGE_BYTES, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk)
+          mma_tf32(tmem_d, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC, (it | kk) ? 1u : 0u);
+        mma_commit(empty_bar(s));
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+    if (lane == 0) mma_commit(accum_bar);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_d);
+  }
+}
+
+// 2-D tensor map over a row-major fp32 matrix [rows, cols] with box {BK columns, 1 row} and 128-byte swizzle
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+bool make_row_map(CUtensorMap* m, const float* base, int64_t rows, int cols) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES>
+int launch_tma(const float* x, int64_t n_in, const float* wimg, const float* bias, const int* nbr, int64_t n_out,
+               const int* n_out_dev, int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = gather_gemm_tma_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
+      b2s_set_error("conv_tc: cannot opt in to %d bytes of shared memory", L::DYN_BYTES);
+      return -1;
+    }
+    attr_set = true;
+  }
+  CUtensorMap tmx;
+  if (!make_row_map(&tmx, x, n_in, c_in)) {
+    b2s_set_error("conv_tc: cuTensorMapEncodeTiled failed for a [%lld, %d] fp32 matrix", (long long)n_in, c_in);
+    return -1;
+  }
+  const int64_t ctas = ceil_div64(n_out, BM) * (c_out / BN);
+  const int kc = c_in / BK;
+  int splits = 1;
+  if (ctas < B2S_NUM_SMS) {
+    splits = (int)((B2S_NUM_SMS + ctas - 1) / ctas);
+    const int max_splits = T / 16 > 0 ? T / 16 : 1;
+    if (splits > max_splits) splits = max_splits;
+  }
+  int per = (T + splits - 1) / splits;
+  per = ((per + kc - 1) / kc) * kc;
+  splits = (T + per - 1) / per;
+  if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
+  dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(tmx, wimg, bias, nbr, n_out, n_out_dev, (int)n_in, c_in, c_out, k3, T, per,
+                                              y);
+  return 0;
+}
+
 bool tc_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -253,11 +509,12 @@ bool tc_disabled() {
   return v == 1;
 }
 
-template <int BN, int STAGES, bool SMALL>
+template <int BN, int STAGES, bool SMALL, int LAG = 2>
 int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
-  auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL>;
+  static_assert(LAG < STAGES, "producers run LAG stages ahead of their hand-over");
+  auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL, LAG>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
@@ -266,8 +523,20 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
     }
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN));
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y);
+  const int64_t ctas = ceil_div64(n_out, BM) * (c_out / BN);
+  const int kc = SMALL ? 1 : c_in / BK;
+  int splits = 1;
+  if (ctas < B2S_NUM_SMS) {                      // too few output tiles for 148 SMs: split the K loop
+    splits = (int)((B2S_NUM_SMS + ctas - 1) / ctas);
+    const int max_splits = T / 16 > 0 ? T / 16 : 1;                 // >= 16 stages per split
+    if (splits > max_splits) splits = max_splits;
+  }
+  int per = (T + splits - 1) / splits;
+  per = ((per + kc - 1) / kc) * kc;
+  splits = (T + per - 1) / per;
+  if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
+  dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y);
   return 0;
 }
 
@@ -313,8 +582,28 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
     if (bn == 128) return launch_tc<128, 3, true>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
     return launch_tc<64, 4, true>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
   }
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("B2S_TC_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  if (variant >= 10 && n_in > 0) {   // TMA row gather (variant 10: default stages; 11: deeper)
+    if (bn == 256) return launch_tma<256, 4>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    if (bn == 128) return variant == 11 ? launch_tma<128, 6>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st)
+                                        : launch_tma<128, 3>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    return variant == 11 ? launch_tma<64, 8>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st)
+                         : launch_tma<64, 4>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  }
   if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
-  if (bn == 128) return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  if (bn == 128) {
+    if (variant == 1) return launch_tc<128, 3, false, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    if (variant == 2) return launch_tc<128, 6, false, 4>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    if (variant == 3) return launch_tc<128, 6, false, 5>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  }
+  if (variant == 1) return launch_tc<64, 3, false, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  if (variant == 2) return launch_tc<64, 4, false, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  if (variant == 3) return launch_tc<64, 8, false, 6>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
 }
 

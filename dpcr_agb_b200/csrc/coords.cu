@@ -536,6 +536,47 @@ __global__ void __launch_bounds__(256) kernel_map_kernel(const int4* __restrict_
   }
 }
 
+// Kernel map through the quantiser's occupancy index instead of the hash: the rows of a quantised map are sorted by
+// cell (plot, z, y, x), so  row(cell) = prefix[cell >> 5] + popc(bitmap[cell >> 5] & below(cell & 31)).  The index of
+// a full batch is ~5 MB (L2 / L1 resident) and the x-neighbours of x-consecutive rows share words, which turns the
+// 343 random 16-byte hash probes per row of the k7 stem map into L1 hits.  Same output as kernel_map_kernel, bit for bit.
+__global__ void __launch_bounds__(256) kernel_map_dense_kernel(const int4* __restrict__ query, int64_t n,
+                                                               const int* __restrict__ n_dev,
+                                                               const unsigned* __restrict__ bitmap,
+                                                               const int* __restrict__ prefix, QBox box,
+                                                               int num_plots, KmParams p, int* __restrict__ nbr) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= b2s_rows(n, n_dev)) return;
+  const int4 c = query[q];
+  const int k0 = blockIdx.y * p.group;
+  const int k1 = min(k0 + p.group, p.k3);
+  const int hx = (p.K[0] & 1) ? p.K[0] / 2 : 0, hy = (p.K[1] & 1) ? p.K[1] / 2 : 0, hz = (p.K[2] & 1) ? p.K[2] / 2 : 0;
+  int ix = k0 % p.K[0], iy = (k0 / p.K[0]) % p.K[1], iz = k0 / (p.K[0] * p.K[1]);
+  const bool plot_ok = (unsigned)c.x < (unsigned)num_plots;
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    const int x = c.y + p.sign * (ix - hx) * p.step[0] - box.lo[0];
+    const int y = c.z + p.sign * (iy - hy) * p.step[1] - box.lo[1];
+    const int z = c.w + p.sign * (iz - hz) * p.step[2] - box.lo[2];
+    int row = -1;
+    if (plot_ok && (unsigned)x < (unsigned)box.dim[0] && (unsigned)y < (unsigned)box.dim[1] &&
+        (unsigned)z < (unsigned)box.dim[2]) {
+      const int64_t cell = (((int64_t)c.x * box.dim[2] + z) * box.dim[1] + y) * box.dim[0] + x;
+      const unsigned w = __ldg(&bitmap[cell >> 5]);
+      const unsigned bit = (unsigned)(cell & 31);
+      if ((w >> bit) & 1u) row = __ldg(&prefix[cell >> 5]) + __popc(w & ((1u << bit) - 1u));
+    }
+    nbr[(int64_t)k * n + q] = row;
+    if (++ix == p.K[0]) {
+      ix = 0;
+      if (++iy == p.K[1]) {
+        iy = 0;
+        ++iz;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) pair_count_kernel(const int* __restrict__ nbr, int64_t n,
                                                          int* __restrict__ counts) {
   const int k = blockIdx.y;
@@ -596,6 +637,39 @@ extern "C" int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, 
   kernel_map_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const int4*>(query_coords), n_query,
                                                          n_query_dev, reinterpret_cast<const B2sEntry*>(table),
                                                          (uint64_t)capacity - 1, p, nbr);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_kernel_map_dense(const int32_t* query_coords, int64_t n_query, const int32_t* n_query_dev,
+                                        const void* quantize_workspace, int32_t num_plots, const int32_t* lo_host,
+                                        const int32_t* dims_host, const int32_t* kernel_size_host,
+                                        const int32_t* step_host, int32_t sign, int32_t* nbr, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n_query >= 0 && kernel_size_host && step_host && quantize_workspace && lo_host && dims_host,
+                "bad arguments");
+  B2S_CHECK_ARG(sign == 1 || sign == -1, "sign must be +1 or -1");
+  QWs l;
+  B2S_CHECK_ARG(quantize_layout(num_plots, dims_host, const_cast<void*>(quantize_workspace), &l), "bad voxel box");
+  KmParams p;
+  for (int d = 0; d < 3; ++d) {
+    B2S_CHECK_ARG(kernel_size_host[d] >= 1 && kernel_size_host[d] <= 15 && step_host[d] >= 1, "kernel size 1..15");
+    p.K[d] = kernel_size_host[d];
+    p.step[d] = step_host[d];
+  }
+  p.sign = sign;
+  p.k3 = p.K[0] * p.K[1] * p.K[2];
+  if (n_query == 0) return B2S_OK;
+  B2S_CHECK_ARG(query_coords && nbr, "null pointer");
+  int64_t row_blocks = ceil_div64(n_query, 256);
+  int groups = 1;
+  while (row_blocks * groups < 2 * B2S_NUM_SMS * 8 && groups < p.k3) ++groups;
+  p.group = (p.k3 + groups - 1) / groups;
+  groups = (p.k3 + p.group - 1) / p.group;
+  QBox box{{lo_host[0], lo_host[1], lo_host[2]}, {dims_host[0], dims_host[1], dims_host[2]}};
+  dim3 grid((unsigned)row_blocks, (unsigned)groups);
+  kernel_map_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const int4*>(query_coords), n_query,
+                                                               n_query_dev, l.bitmap, l.prefix, box, num_plots, p,
+                                                               nbr);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -73,6 +73,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
+// TMA row gather: 4 rows (row indices r0..r3, any order, out-of-range rows are zero-filled) x one box of columns
+// starting at `col` of a 2-D tensor map whose box is {box_cols, 1}, written as 4 consecutive rows at `dst` with the
+// map's shared-memory swizzle applied; bytes complete on the mbarrier (SASS: UTMALDG ... gather4).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const void* tmap, int col, int r0, int r1, int r2, int r3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::1 "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 ------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_slot) {  // whole warp

@@ -36,7 +36,7 @@ def plan_capacities(gs: GridSampling3D, ME, model, batches, num_plots, bounds, m
         for d in batches:
             vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d.get("perm"), num_plots=num_plots,
                      bounds=bounds)
-            x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"])
+            x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"], dense_index=vox["index"])
             model(x)
             for key, m in x.coordinate_manager.maps.items():
                 ts = key.tensor_stride[0]
@@ -87,7 +87,7 @@ class GraphStep:
                       n_points_dev=self.n_points_dev)
         tr.opt.zero_grad()
         x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"], num_rows=vox["num_rows"],
-                            capacities=self.capacities, num_batches=self.B)
+                            capacities=self.capacities, num_batches=self.B, dense_index=vox["index"])
         pred = tr.model(x)
         loss = T.reg_loss(pred, self.inp["target"], tr.center, tr.scale)
         loss.backward()

@@ -31,6 +31,7 @@ SIGNATURES = {
     "b2s_coordmap_insert": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "b2s_coordmap_fill": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "b2s_kernel_map": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
+    "b2s_kernel_map_dense": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b2s_kernel_map_pair_counts": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "b2s_kernel_map_pairs_fill": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b2s_conv_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),

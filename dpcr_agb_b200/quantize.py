@@ -95,7 +95,10 @@ class GridSampling3D:
             return out
 
         return {"coords": coords, "src": src, "pos": gather(pos), "tensors": [gather(t) for t in tensors],
-                "grid_size": self._grid_size, "num_rows": m_dev}
+                "grid_size": self._grid_size, "num_rows": m_dev,
+                # the occupancy bitmap + popcount prefix of this batch: rank(cell) == output row, so the coordinate
+                # manager can resolve neighbours of THIS map without hash probes (b2s_kernel_map_dense)
+                "index": (ws, tuple(lo), tuple(dims), int(num_plots))}
 
     def __repr__(self):
         return "{}(grid_size={}, quantize_coords={}, mode={})".format(

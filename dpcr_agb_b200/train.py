@@ -166,12 +166,14 @@ class Trainer:
         if self.world > 1:
             dist.broadcast(self.opt.flat_param, src=0)
 
-    def step(self, coords, feats, target):
-        """coords int32 [N,4] (plot,x,y,z), feats fp32 [N,3], target fp32 [B,2] -- all on this rank's GPU.
+    def step(self, coords, feats, target, dense_index=None):
+        """coords int32 [N,4] (plot,x,y,z), feats fp32 [N,3], target fp32 [B,2] -- all on this rank's GPU;
+        ``dense_index``: the quantiser's ``"index"`` entry when ``coords`` are its unmodified output rows.
         Returns the (detached, on-device) loss."""
         self.model.train()
         self.opt.zero_grad()
-        x = self.ME.SparseTensor(features=feats, coordinates=coords)
+        kw = {"dense_index": dense_index} if dense_index is not None else {}
+        x = self.ME.SparseTensor(features=feats, coordinates=coords, **kw)
         pred = self.model(x)
         loss = reg_loss(pred, target, self.center, self.scale)
         loss.backward()

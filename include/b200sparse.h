@@ -116,6 +116,13 @@ B2S_API int32_t b2s_coordmap_fill(const int32_t* coords, int64_t n, const int32_
 B2S_API int32_t b2s_kernel_map(const int32_t* query_coords, int64_t n_query, const int32_t* n_query_dev,
                                const void* table, int64_t capacity, const int32_t* kernel_size_host,
                                const int32_t* step_host, int32_t sign, int32_t* nbr, b2s_stream_t stream);
+/* Same table through the quantiser's occupancy index (the `workspace` of b2s_quantize_count/_fill with the same
+ * num_plots / lo / dims) instead of the hash: valid when the rows of the looked-up map ARE the quantiser's output rows
+ * (unique, sorted by (plot, z, y, x)); row = prefix popcount rank.  Bit-identical to b2s_kernel_map. */
+B2S_API int32_t b2s_kernel_map_dense(const int32_t* query_coords, int64_t n_query, const int32_t* n_query_dev,
+                                     const void* quantize_workspace, int32_t num_plots, const int32_t* lo_host,
+                                     const int32_t* dims_host, const int32_t* kernel_size_host,
+                                     const int32_t* step_host, int32_t sign, int32_t* nbr, b2s_stream_t stream);
 B2S_API int32_t b2s_kernel_map_pair_counts(const int32_t* nbr, int32_t k3, int64_t n_query, int32_t* counts,
                                    b2s_stream_t stream);
 B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_t n_query, const int64_t* offsets,

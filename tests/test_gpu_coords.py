@@ -173,3 +173,28 @@ def test_kernel_map_even_kernel_and_dilation(cuda):
         km = cm.kernel_map(key, key, K, dil)
         ref = oc.kernel_map_table(c, c, K, (dil,) * 3)
         assert np.array_equal(km.nbr.cpu().numpy(), ref)
+
+
+def test_kernel_map_dense_index_equals_hash(cuda):
+    """Kernel maps resolved through the quantiser's occupancy index (bitmap + popcount rank) are bit-identical to
+    the hash-probed ones: k7 stride-1 (the stem), k3 stride-2 (max pool), and the transposed table."""
+    from dpcr_agb_b200.MinkowskiEngine import coordinate_manager as CM
+    batch = util.make_points(3, 6000, cfg=31)
+    gs = GridSampling3D(0.02)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(cuda) for k, v in batch.items()}
+    vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=3)
+    tables = {}
+    for dense in (True, False):
+        CM.USE_DENSE_INDEX = dense
+        try:
+            cm = CM.CoordinateManager(D=3, device=cuda)
+            k1, _ = cm.insert(vox["coords"], dense_index=vox["index"])
+            k2 = cm.stride(k1, 2)
+            km7 = cm.kernel_map(k1, k1, 7)
+            kmp = cm.kernel_map(k1, k2, 3)
+            tables[dense] = (km7.nbr.clone(), kmp.nbr.clone(), kmp.inv.clone())
+        finally:
+            CM.USE_DENSE_INDEX = True
+    for a, b in zip(tables[True], tables[False]):
+        assert torch.equal(a, b)
+    assert (tables[True][0] >= 0).sum() > vox["coords"].shape[0]       # not trivially empty

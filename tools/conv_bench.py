@@ -36,7 +36,8 @@ res = {}
 res["quantize_ms"] = timeit(lambda: gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=B,
                                        bounds=((0, 0, 0), (80, 80, 100))))
 vox = gs(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=B, bounds=((0, 0, 0), (80, 80, 100)))
-x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"])
+x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"],
+                    dense_index=None if os.environ.get("NO_DENSE") else vox["index"])
 cm = x.coordinate_manager
 keys = {1: x.coordinate_map_key}
 for ts in (2, 4, 8, 16):
