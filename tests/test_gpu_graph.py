@@ -56,10 +56,11 @@ def test_graph_step_matches_eager(cuda):
         losses2.append(float(g.step()))
     seen = g.verify()
     assert all(v <= caps[int(k.split()[-1])] for k, v in seen.items() if k.startswith("rows"))
-    # the first step sees identical parameters (only the order of fp32 atomics differs); later steps inherit that
-    # noise through the optimiser, amplified by training-mode batch norm on these small plots
-    np.testing.assert_allclose(losses2[:1], losses1[:1], rtol=2e-5)
-    np.testing.assert_allclose(losses2, losses1, rtol=2e-3)
+    # the first step sees identical parameters; only the fp32 summation order differs (atomics, and split-K / row
+    # split counts that follow the capacity instead of the exact row count), amplified by training-mode batch norm
+    # on these small plots; later steps inherit that noise through the optimiser
+    np.testing.assert_allclose(losses2[:1], losses1[:1], rtol=1e-3)
+    np.testing.assert_allclose(losses2, losses1, rtol=3e-3)
     util.assert_close(t2.opt.flat_param, t1.opt.flat_param, tol=1e-3, what="parameters after 3 steps")
     util.assert_close(t2.opt.exp_avg, t1.opt.exp_avg, tol=2e-2, what="AdaBelief first moment")
     for (n1, b1), (n2, b2) in zip(m1.named_buffers(), m2.named_buffers()):
