@@ -98,6 +98,28 @@ class KernelMap:
             self._inv = cm._probe(cm.maps[self.in_key], cm.maps[self.out_key], self.kernel_size, self.step, -1)
         return self._inv
 
+    @property
+    def parity_plan(self):
+        """(perm, bounds) of ``b2s_parity_plan`` for the fine (input) rows of a stride-2 map, or None when the map is
+        not a stride-2 map with kernel sizes 1 or 3 (dgrad then takes the dense transposed table)."""
+        if getattr(self, "_plan", None) is None:
+            cm = self.manager
+            tin, tout = self.in_key.tensor_stride, self.out_key.tensor_stride
+            ok = all(o == 2 * i for i, o in zip(tin, tout)) and all(k in (1, 3) for k in self.kernel_size) \
+                and all(s == t for s, t in zip(self.step, tin))
+            if not ok:
+                self._plan = False
+            else:
+                imap = cm.maps[self.in_key]
+                rows = L.query("b2s_parity_plan_rows", imap.n)
+                dev = imap.coords.device
+                perm = torch.empty(rows, dtype=torch.int32, device=dev)
+                bounds = torch.empty(9, dtype=torch.int32, device=dev)
+                scratch = torch.empty(16, dtype=torch.int32, device=dev)
+                L.call("b2s_parity_plan", imap.coords, imap.n, imap.n_dev, L.host_i32(*tout), perm, bounds, scratch)
+                self._plan = (perm, bounds)
+        return self._plan or None
+
     def pairs(self):
         """MinkowskiEngine's pair-list form: (in_idx, out_idx, offsets[K^3+1]); sorted by out row per offset."""
         assert self.n_out_dev is None, "pairs() needs exact row counts (dynamic mode)"

@@ -16,6 +16,8 @@ from dpcr_agb_b200 import lib as L
 # 0 = auto (tcgen05 where the shape qualifies, SIMT otherwise), 1 = force SIMT, 2 = force tcgen05
 CONV_IMPL = int(os.environ.get("B2S_CONV_IMPL", "0"))
 
+USE_PARITY_DGRAD = True   # tests flip this to compare the parity-plan dgrad with the dense transposed-table one
+
 # bench.py sets this to a dict to collect ALGORITHMIC work per conv launch kind (pairs come from the neighbour
 # table: one device reduction + host sync per launch, so only ever enabled in an untimed statistics pass)
 WORK_STATS = None
@@ -54,6 +56,19 @@ def _ws(n_in, n_out, c_in, c_out, k3, device, prerounded=False):
     if nbytes < 0:
         raise L.B2SError("b2s_conv_workspace_bytes rejected the shape")
     return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device), nbytes
+
+
+def dgrad_strided(gy, w, kmap, c_gy, c_x):
+    """gx[i] = sum_k gy[inv[k,i]] @ W[k]^T for a stride-2 map through the parity plan (C ABI
+    ``b2s_conv_dgrad_strided``); ``gy`` must be TF32-rounded."""
+    perm, bounds = kmap.parity_plan
+    gx = torch.empty((kmap.n_in, c_x), dtype=torch.float32, device=gy.device)
+    _account("dgrad", kmap.inv, kmap.n_in, c_gy, c_x, kmap.k3, kmap.n_in_dev)
+    nbytes = L.query("b2s_conv_dgrad_strided_workspace_bytes", c_gy, c_x, kmap.k3)
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=gy.device)
+    L.call("b2s_conv_dgrad_strided", gy, w, kmap.inv, perm, bounds, kmap.n_in, kmap.n_in_dev, c_gy, c_x,
+           L.host_i32(*kmap.kernel_size), gx, ws, nbytes)
+    return gx
 
 
 def _tc(impl):
@@ -135,6 +150,9 @@ class ConvolutionFunction(torch.autograd.Function):
             elif kmap.symmetric:      # transposed map == same table with the kernel index reversed
                 gx = gather_gemm(gyr, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2, n_out_dev=nd_in,
                                  prerounded=pre_gy)
+            elif (USE_PARITY_DGRAD and pre_gy and CONV_IMPL == 0 and c_out % 32 == 0 and c_in % 64 == 0
+                  and kmap.parity_plan is not None):
+                gx = dgrad_strided(gyr, kernel, kmap, c_out, c_in)
             else:
                 gx = gather_gemm(gyr, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1, n_out_dev=nd_in,
                                  prerounded=pre_gy)

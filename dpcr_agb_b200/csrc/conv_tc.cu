@@ -86,15 +86,37 @@ struct SmemLayout {
   static constexpr int DYN_BYTES = TOTAL + 1024;                   // slack for manual 1024-byte alignment
 };
 
+// PERM mode (dgrad of stride-2 convolutions).  In the transposed map of a stride-2 conv a fine row only has partners
+// at the kernel offsets whose parity matches the row's position inside its 2x2x2 cell: 27/8 = 3.4 offsets on average
+// instead of 27, so the dense loop over all offsets gathers ~89 % zero rows.  b2s_parity_plan sorts the fine rows by
+// parity class (tile-aligned); a tile then walks only the offsets of its class (klist) and writes its rows through
+// the permutation.
+struct PermArgs {
+  const int* perm;      // [tiles * 128] output row of every tile row, -1 = padding
+  const int* bounds;    // [9] first tile of every parity class; bounds[8] = number of tiles
+  unsigned char nk[8];  // offsets per class
+  unsigned char klist[8][27];
+};
+
 // LAG: a producer hands over stage (it - LAG) after issuing the copies of stage it (LAG + 1 stages of copies in flight)
-template <int BN, int STAGES, bool SMALL, int LAG>
+template <int BN, int STAGES, bool SMALL, int LAG, bool PERM = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
-                          int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y) {
+                          int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y,
+                          const PermArgs pa) {
   const int64_t pitch = n_out;                     // row pitch of the neighbour table (the caller's capacity)
   n_out = b2s_rows(n_out, n_out_dev);
-  if ((int64_t)blockIdx.x * BM >= n_out) return;   // whole tile beyond the live rows (uniform across the CTA)
+  int cls = 0;
+  if (PERM) {
+    const int tile = blockIdx.x;
+    if (tile >= __ldg(&pa.bounds[8])) return;      // beyond the last class tile (uniform across the CTA)
+    while (cls < 7 && tile >= __ldg(&pa.bounds[cls + 1])) ++cls;
+    T_total = (int)pa.nk[cls] * (c_in / BK);
+    it_per_split = T_total;
+  } else if ((int64_t)blockIdx.x * BM >= n_out) {
+    return;                                        // whole tile beyond the live rows (uniform across the CTA)
+  }
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -115,7 +137,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   // combined with fp32 vector reductions into a zero-initialised y (small maps: too few row tiles to fill 148 SMs)
   const int it0 = blockIdx.z * it_per_split;
   const int T = min(it_per_split, T_total - it0);
-  if (T <= 0) return;
+  if (T <= 0) {
+    if (PERM) {   // a class without any offset (K = 1: rows off the coarse lattice): its rows are zero
+      for (int e = tid; e < BM * (BN / 4); e += TC_THREADS) {
+        const int o = __ldg(&pa.perm[m0 + e / (BN / 4)]);
+        if (o >= 0) reinterpret_cast<float4*>(y + (int64_t)o * c_out + n0)[e % (BN / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    return;
+  }
   const bool split = gridDim.z > 1;
 
   if (tid == 0) {
@@ -141,13 +171,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // one stage = 8 offsets), so the gather never waits on the dependent nbr -> row-address load chain.
     int idx[8], idx1[8], idx2[8];
     const int* nbr_t = nbr ? nbr + m0 + rsub : nullptr;          // this thread's rows: + 16 p
+    int orow[8];                                                  // PERM: output (= table query) row of tile row p
+    if (PERM) {
+#pragma unroll
+      for (int p = 0; p < 8; ++p) orow[p] = __ldg(&pa.perm[m0 + rsub + 16 * p]);
+    }
+    auto kof = [&](int g) -> int {                                // PERM: g-th offset of this tile's parity class
+      return PERM ? (g < (int)pa.nk[cls] ? (int)pa.klist[cls][g] : k3) : g;
+    };
     auto load_group = [&](int g, int (&dst)[8]) {                 // g: offset index (general) / stage index (SMALL)
-      const int k = SMALL ? g * 8 + chunk : g;
+      const int k = SMALL ? g * 8 + chunk : kof(g);
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
-        const int64_t o = m0 + rsub + 16 * p;
         int v = -1;
-        if (k < k3 && o < n_out) v = nbr_t ? __ldg(nbr_t + (int64_t)k * pitch + 16 * p) : (int)o;
+        if (PERM) {
+          if (k < k3 && orow[p] >= 0) v = __ldg(nbr + (int64_t)k * pitch + orow[p]);
+        } else {
+          const int64_t o = m0 + rsub + 16 * p;
+          if (k < k3 && o < n_out) v = nbr_t ? __ldg(nbr_t + (int64_t)k * pitch + 16 * p) : (int)o;
+        }
         dst[p] = v;
       }
     };
@@ -166,7 +208,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     int s_pub = 0;                    // stage to hand over next (LAG iterations behind)
     for (int it = 0; it < T; ++it) {
       mbar_wait(empty_bar(s), ph ^ 1u);
-      const int git = it0 + it;     // iteration index in the whole (offset x channel-chunk) loop
+      // index of this iteration's weight tile in the image: (offset, channel chunk), offset-major
+      const int git = PERM ? kof(g) * kc + cc : it0 + it;
       if (tid == 0) {
         mbar_arrive_expect_tx(full_bar(s), L::B_STAGE_BYTES);
         bulk_g2s(b_base + s * L::B_STAGE_BYTES, wimg + ((int64_t)git * c_out + n0) * BK, L::B_STAGE_BYTES,
@@ -212,14 +255,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===================== epilogue: TMEM -> registers -> y =====================
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int64_t o = m0 + warp * 32 + lane;
+    const int64_t o = PERM ? (int64_t)__ldg(&pa.perm[m0 + warp * 32 + lane]) : m0 + warp * 32 + lane;
+    const bool o_ok = PERM ? o >= 0 : o < n_out;
     const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(t_lane + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (o < n_out) {
+      if (o_ok) {
         float* dst = y + o * c_out + n0 + c0;
         const bool add_bias = bias && it0 == 0;
 #pragma unroll
@@ -500,6 +544,25 @@ int launch_tma(const float* x, int64_t n_in, const float* wimg, const float* bia
   return 0;
 }
 
+
+template <int BN, int STAGES>
+int launch_perm(const float* x, const float* wimg, const int* nbr, int64_t n_out, const int* n_out_dev, int c_in,
+                int c_out, int k3, float* y, const PermArgs& pa, int64_t tiles_cap, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = gather_gemm_tc_kernel<BN, STAGES, false, 2, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
+      b2s_set_error("conv_tc: cannot opt in to %d bytes of shared memory", L::DYN_BYTES);
+      return -1;
+    }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)tiles_cap, (unsigned)(c_out / BN), 1);
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, nullptr, nbr, n_out, n_out_dev, c_in, c_out, k3, 0, 0, y, pa);
+  return 0;
+}
+
 bool tc_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -536,7 +599,8 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
   splits = (T + per - 1) / per;
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y);
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y,
+                                               PermArgs{});
   return 0;
 }
 
@@ -605,6 +669,43 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   if (variant == 2) return launch_tc<64, 4, false, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   if (variant == 3) return launch_tc<64, 8, false, 6>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+}
+
+
+// dgrad of a stride-2 convolution through the parity plan (see PermArgs).  x = rounded grad_out [n_coarse, c_in],
+// nbr = transposed table [k3, n_fine], y = grad_in [n_fine, c_out]; w_layout as in b2s_conv_gather_gemm.
+int b2s_conv_dgrad_perm_tc(const float* x, const float* w, const int32_t* nbr, int64_t n_fine, const int32_t* n_fine_dev,
+                           int32_t c_in, int32_t c_out, const int32_t* ksize, int32_t w_layout, const int32_t* perm,
+                           const int32_t* bounds, float* y, void* workspace, cudaStream_t st) {
+  const int k3 = ksize[0] * ksize[1] * ksize[2];
+  const int T = iterations(c_in, k3);
+  float* img = reinterpret_cast<float*>(workspace);
+  prep_weights_kernel<<<grid_for((int64_t)T * c_out * BK, 256), 256, 0, st>>>(w, c_in, c_out, k3, w_layout, 0, T, img);
+  PermArgs pa{};
+  pa.perm = perm;
+  pa.bounds = bounds;
+  // class bit d set <=> the fine coordinate is OFF the coarse lattice in dimension d; the partner offsets are those
+  // whose centred index has the same parity as the position inside the cell
+  for (int c = 0; c < 8; ++c) {
+    int n = 0;
+    for (int iz = 0; iz < ksize[2]; ++iz)
+      for (int iy = 0; iy < ksize[1]; ++iy)
+        for (int ix = 0; ix < ksize[0]; ++ix) {
+          const int i3[3] = {ix, iy, iz};
+          bool ok = true;
+          for (int d = 0; d < 3; ++d) {
+            const int centred = (ksize[d] & 1) ? i3[d] - ksize[d] / 2 : i3[d];
+            if ((abs(centred) & 1) != ((c >> d) & 1)) ok = false;
+          }
+          if (ok) pa.klist[c][n++] = (unsigned char)(ix + ksize[0] * (iy + ksize[1] * iz));
+        }
+    pa.nk[c] = (unsigned char)n;
+  }
+  const int64_t tiles_cap = ceil_div64(n_fine, BM) + 8;
+  const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
+  if (bn == 256) return launch_perm<256, 4>(x, img, nbr, n_fine, n_fine_dev, c_in, c_out, k3, y, pa, tiles_cap, st);
+  if (bn == 128) return launch_perm<128, 3>(x, img, nbr, n_fine, n_fine_dev, c_in, c_out, k3, y, pa, tiles_cap, st);
+  return launch_perm<64, 4>(x, img, nbr, n_fine, n_fine_dev, c_in, c_out, k3, y, pa, tiles_cap, st);
 }
 
 // wgrad on tensor cores: see wgrad_tc.cu

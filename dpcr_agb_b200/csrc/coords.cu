@@ -674,6 +674,93 @@ extern "C" int32_t b2s_kernel_map_dense(const int32_t* query_coords, int64_t n_q
   return B2S_OK;
 }
 
+// =============================================================================================
+// parity plan: fine rows of a stride-2 map sorted by their position inside the 2x2x2 coarse cell
+// =============================================================================================
+namespace {
+
+__device__ __forceinline__ int parity_class(const int4 c, int tx, int ty, int tz) {
+  // bit d set <=> the coordinate is off the coarse lattice (not a multiple of the coarse tensor stride)
+  return ((c.y - b2s_floor_to(c.y, tx)) != 0 ? 1 : 0) | ((c.z - b2s_floor_to(c.z, ty)) != 0 ? 2 : 0) |
+         ((c.w - b2s_floor_to(c.w, tz)) != 0 ? 4 : 0);
+}
+
+__global__ void __launch_bounds__(256) parity_count_kernel(const int4* __restrict__ coords, int64_t n,
+                                                           const int* __restrict__ n_dev, int tx, int ty, int tz,
+                                                           int* __restrict__ counts) {
+  n = b2s_rows(n, n_dev);
+  __shared__ int h[8];
+  if (threadIdx.x < 8) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&h[parity_class(coords[i], tx, ty, tz)], 1);
+  __syncthreads();
+  if (threadIdx.x < 8 && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+
+// bounds[c] = first tile of class c (tiles of 128 rows), bounds[8] = number of tiles; cursor[c] = first slot of class c
+__global__ void parity_bounds_kernel(const int* __restrict__ counts, int* __restrict__ bounds, int* __restrict__ cursor) {
+  if (threadIdx.x == 0) {
+    int tile = 0;
+    for (int c = 0; c < 8; ++c) {
+      bounds[c] = tile;
+      cursor[c] = tile * 128;
+      tile += (counts[c] + 127) / 128;
+    }
+    bounds[8] = tile;
+  }
+}
+
+__global__ void __launch_bounds__(256) parity_scatter_kernel(const int4* __restrict__ coords, int64_t n,
+                                                             const int* __restrict__ n_dev, int tx, int ty, int tz,
+                                                             int* __restrict__ cursor, int* __restrict__ perm) {
+  n = b2s_rows(n, n_dev);
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
+    const int cls = i < n ? parity_class(coords[i], tx, ty, tz) : -1;
+    // warp-aggregated slot claim: one atomic per (warp, class)
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+      if (m == 0) continue;
+      const int leader = __ffs(m) - 1;
+      int basev = 0;
+      if ((int)lane == leader) basev = atomicAdd(&cursor[c], __popc(m));
+      basev = __shfl_sync(0xffffffffu, basev, leader);
+      if (cls == c) perm[basev + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t b2s_parity_plan_rows(int64_t n) { return (ceil_div64(n > 0 ? n : 1, 128) + 8) * 128; }
+
+extern "C" int32_t b2s_parity_plan(const int32_t* coords, int64_t n, const int32_t* n_dev, const int32_t* ts_coarse_host,
+                                   int32_t* perm, int32_t* bounds, int32_t* scratch16, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && ts_coarse_host && perm && bounds && scratch16, "bad arguments");
+  B2S_CHECK_ARG(ts_coarse_host[0] > 0 && ts_coarse_host[1] > 0 && ts_coarse_host[2] > 0, "tensor stride must be positive");
+  cudaStream_t st = as_stream(stream);
+  int* counts = scratch16;        // [8]
+  int* cursor = scratch16 + 8;    // [8]
+  B2S_CUDA(cudaMemsetAsync(scratch16, 0, 16 * sizeof(int), st));
+  B2S_CUDA(cudaMemsetAsync(perm, 0xFF, b2s_parity_plan_rows(n) * sizeof(int), st));   // -1 = padding
+  if (n > 0) {
+    B2S_CHECK_ARG(coords, "null pointer");
+    parity_count_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, n_dev,
+                                                             ts_coarse_host[0], ts_coarse_host[1], ts_coarse_host[2],
+                                                             counts);
+  }
+  parity_bounds_kernel<<<1, 32, 0, st>>>(counts, bounds, cursor);
+  if (n > 0)
+    parity_scatter_kernel<<<grid_for(n, 256, 4), 256, 0, st>>>(reinterpret_cast<const int4*>(coords), n, n_dev,
+                                                               ts_coarse_host[0], ts_coarse_host[1], ts_coarse_host[2],
+                                                               cursor, perm);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 extern "C" int32_t b2s_kernel_map_pair_counts(const int32_t* nbr, int32_t k3, int64_t n_query, int32_t* counts,
                                               b2s_stream_t stream) {
   B2S_CHECK_ARG(k3 > 0 && n_query >= 0 && counts, "bad arguments");

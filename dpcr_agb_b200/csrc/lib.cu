@@ -105,6 +105,36 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
   return B2S_OK;
 }
 
+int b2s_conv_dgrad_perm_tc(const float* x, const float* w, const int32_t* nbr, int64_t n_fine, const int32_t* n_fine_dev,
+                           int32_t c_in, int32_t c_out, const int32_t* ksize, int32_t w_layout, const int32_t* perm,
+                           const int32_t* bounds, float* y, void* workspace, cudaStream_t st);
+int64_t b2s_conv_tc_image_bytes(int32_t c_in, int32_t c_out, int32_t k3);
+
+extern "C" int64_t b2s_conv_dgrad_strided_workspace_bytes(int32_t c_gy, int32_t c_x, int32_t k3) {
+  if (c_gy <= 0 || c_x <= 0 || k3 <= 0) return -1;
+  return al256(b2s_conv_tc_image_bytes(c_gy, c_x, k3));
+}
+
+extern "C" int32_t b2s_conv_dgrad_strided(const float* gy, const float* w, const int32_t* inv_nbr, const int32_t* perm,
+                                          const int32_t* bounds, int64_t n_fine, const int32_t* n_fine_dev,
+                                          int32_t c_gy, int32_t c_x, const int32_t* kernel_size_host, float* gx,
+                                          void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n_fine >= 0 && c_gy > 0 && c_x > 0 && kernel_size_host, "bad sizes");
+  const int k3 = kernel_size_host[0] * kernel_size_host[1] * kernel_size_host[2];
+  B2S_CHECK_ARG(k3 >= 1 && k3 <= 27, "kernel volume must be 1..27");
+  B2S_CHECK_ARG(c_gy % 32 == 0 && c_x % 64 == 0, "tcgen05 path: c_gy % 32 == 0 and c_x % 64 == 0");
+  if (n_fine == 0) return B2S_OK;
+  B2S_CHECK_ARG(gy && w && inv_nbr && perm && bounds && gx, "null pointer");
+  B2S_CHECK_ARG(workspace && workspace_bytes >= b2s_conv_dgrad_strided_workspace_bytes(c_gy, c_x, k3) &&
+                    (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                "workspace too small or misaligned");
+  if (b2s_conv_dgrad_perm_tc(gy, w, inv_nbr, n_fine, n_fine_dev, c_gy, c_x, kernel_size_host, 1, perm, bounds, gx,
+                             workspace, as_stream(stream)))
+    return B2S_ECUDA;
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
                                   const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw,
                                   void* workspace, int64_t workspace_bytes, int32_t impl, int32_t flags,

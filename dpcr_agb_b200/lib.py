@@ -39,6 +39,10 @@ SIGNATURES = {
     "b2s_conv_gather_gemm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32,
                                     _vp]),
     "b2s_conv_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "b2s_parity_plan_rows": (_i64, [_i64]),
+    "b2s_parity_plan": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2s_conv_dgrad_strided_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "b2s_conv_dgrad_strided": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "b2s_colsum": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_maxpool_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2s_maxpool_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp]),

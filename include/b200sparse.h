@@ -159,6 +159,22 @@ B2S_API int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* n
                                const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw,
                                void* workspace, int64_t workspace_bytes, int32_t impl, int32_t flags,
                                b2s_stream_t stream);
+/* dgrad of a STRIDE-2 convolution (gx[i] = sum_k gy[inv[k,i]] W[k]^T) without gathering zero rows.  In the
+ * transposed map a fine row has partners only at the offsets whose parity matches its position inside the 2x2x2 coarse
+ * cell (27/8 offsets on average).  b2s_parity_plan sorts the fine rows of `coords` by that position into tile-aligned
+ * classes: perm int32 [b2s_parity_plan_rows(n)] (out row of every tile row, -1 = padding), bounds int32 [9] (first
+ * 128-row tile of every class, [8] = number of tiles), scratch16 = 16 ints.  b2s_conv_dgrad_strided then walks, per
+ * tile, only the offsets of its class.  gy must be TF32-representable (b2s_round_tf32); w is the forward kernel
+ * [K3, c_x, c_gy]; inv_nbr is the transposed table [K3, n_fine] (b2s_kernel_map with sign = -1).  Same result as
+ * b2s_conv_gather_gemm with w_layout = 1 on inv_nbr. */
+B2S_API int64_t b2s_parity_plan_rows(int64_t n);
+B2S_API int32_t b2s_parity_plan(const int32_t* coords, int64_t n, const int32_t* n_dev, const int32_t* ts_coarse_host,
+                                int32_t* perm, int32_t* bounds, int32_t* scratch16, b2s_stream_t stream);
+B2S_API int64_t b2s_conv_dgrad_strided_workspace_bytes(int32_t c_gy, int32_t c_x, int32_t k3);
+B2S_API int32_t b2s_conv_dgrad_strided(const float* gy, const float* w, const int32_t* inv_nbr, const int32_t* perm,
+                                       const int32_t* bounds, int64_t n_fine, const int32_t* n_fine_dev, int32_t c_gy,
+                                       int32_t c_x, const int32_t* kernel_size_host, float* gx, void* workspace,
+                                       int64_t workspace_bytes, b2s_stream_t stream);
 B2S_API int32_t b2s_colsum(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* out, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- (a9) max pooling -----------

@@ -192,3 +192,31 @@ def test_wgrad_tcgen05_null_map(cuda):
     gy = rng.standard_normal((n, cout)).astype(np.float32)
     got = Fn.wgrad(torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda), None, n, n, cin, cout, 1, impl=TC)
     util.assert_close(got[0], torch.from_numpy(x).double().T @ torch.from_numpy(gy).double(), what="wgrad use_mm")
+
+
+def test_parity_plan_and_strided_dgrad(cuda):
+    """b2s_parity_plan covers every fine row exactly once in tile-aligned parity classes, and the parity-plan dgrad
+    equals the dense transposed-table dgrad (same products, different zero rows skipped)."""
+    from dpcr_agb_b200.MinkowskiEngine.coordinate_manager import CoordinateManager
+    rng = np.random.default_rng(21)
+    c = util.random_coords(rng, 5000, nb=3, extent=14)
+    cm = CoordinateManager(D=3, device=cuda)
+    key, _ = cm.insert(torch.from_numpy(c).to(cuda))
+    out_key = cm.stride(key, 2)
+    for K, cin, cout in ((3, 64, 128), (1, 64, 128), (3, 128, 256)):
+        km = cm.kernel_map(key, out_key, K)
+        perm, bounds = km.parity_plan
+        p = perm.cpu().numpy()
+        b = bounds.cpu().numpy()
+        live = p[p >= 0]
+        assert np.array_equal(np.sort(live), np.arange(c.shape[0]))              # a permutation of the fine rows
+        assert b[8] * 128 <= p.shape[0] and np.all(p[b[8] * 128:] == -1)
+        cls = (c[:, 1] & 1) | ((c[:, 2] & 1) << 1) | ((c[:, 3] & 1) << 2)
+        for k in range(8):
+            rows = p[b[k] * 128:b[k + 1] * 128]
+            assert np.all(cls[rows[rows >= 0]] == k)
+        gy = Fn.round_tf32(torch.from_numpy(rng.standard_normal((km.n_out, cout)).astype(np.float32)).to(cuda))
+        w = torch.from_numpy((rng.standard_normal((K ** 3, cin, cout)) * 0.05).astype(np.float32)).to(cuda)
+        dense = Fn.gather_gemm(gy, w, None, km.inv, km.n_out, km.n_in, cout, cin, km.k3, 1, impl=TC, prerounded=True)
+        sparse = Fn.dgrad_strided(gy, w, km, cout, cin)
+        util.assert_close(sparse, dense, tol=2e-5, what=f"parity dgrad K={K}")   # fp32 summation order only

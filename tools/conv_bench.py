@@ -78,6 +78,9 @@ for name, its, ots, K, cin, cout in layers:
             lay = 3 if km.symmetric else 1
             t = timeit(lambda: Fn.gather_gemm(gy, w, None, tbl, km.n_out, km.n_in, cout, cin, km.k3, lay, prerounded=True))
             row.update(dgrad_ms=t, dgrad_tflops=flops / t / 1e9)
+            if not km.symmetric and km.parity_plan is not None:
+                t = timeit(lambda: Fn.dgrad_strided(gy, w, km, cout, cin))
+                row.update(dgrad_parity_ms=t, dgrad_parity_tflops=flops / t / 1e9)
         t = timeit(lambda: Fn.wgrad(xf, gy, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, prerounded=True))
         row.update(wgrad_ms=t, wgrad_tflops=flops / t / 1e9)
     out.append(row)

@@ -2,5 +2,4 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout -k 10 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_coords.py -m gpu -q -p no:cacheprovider -x 2>&1 | tail -15
-echo "=== conv bench ==="; timeout -k 10 600 python tools/conv_bench.py 2>&1 | tail -12 | cut -c1-520
+timeout -k 10 600 python tools/conv_bench.py 2>&1 | grep -E "s2" | sed -E "s/'n_in.*'fill': [0-9.]+, 'kernel_map_ms': [0-9.]+, 'kernel_map_GBps': [0-9.]+, //" | cut -c1-300
