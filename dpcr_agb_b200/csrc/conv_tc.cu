@@ -18,6 +18,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+extern int g_b2s_tc_rot;   // lib.cu (b2s_set_tuning)
+
 namespace {
 
 using namespace tc;
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y,
-                          const PermArgs pa) {
+                          const PermArgs pa, int rot_on) {
   const int64_t pitch = n_out;                     // row pitch of the neighbour table (the caller's capacity)
   n_out = b2s_rows(n_out, n_out_dev);
   int cls = 0;
@@ -176,8 +178,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
       for (int p = 0; p < 8; ++p) orow[p] = __ldg(&pa.perm[m0 + rsub + 16 * p]);
     }
+    // ROT (tuning knob "tc_rot"): every row tile starts its walk over the kernel offsets at a different offset, so
+    // that the CTAs running side by side do not all fetch the same weight tile from the same L2 slices at once
+    const int rot = (!PERM && !SMALL && rot_on && gridDim.z == 1) ? (int)((blockIdx.x * 11u) % (unsigned)k3) : 0;
     auto kof = [&](int g) -> int {                                // PERM: g-th offset of this tile's parity class
-      return PERM ? (g < (int)pa.nk[cls] ? (int)pa.klist[cls][g] : k3) : g;
+      if (PERM) return g < (int)pa.nk[cls] ? (int)pa.klist[cls][g] : k3;
+      const int k = g + rot;
+      return (k >= k3 && g < k3) ? k - k3 : k;
     };
     auto load_group = [&](int g, int (&dst)[8]) {                 // g: offset index (general) / stage index (SMALL)
       const int k = SMALL ? g * 8 + chunk : kof(g);
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int it = 0; it < T; ++it) {
       mbar_wait(empty_bar(s), ph ^ 1u);
       // index of this iteration's weight tile in the image: (offset, channel chunk), offset-major
-      const int git = PERM ? kof(g) * kc + cc : it0 + it;
+      const int git = (PERM || !SMALL) ? kof(g) * kc + cc : it0 + it;
       if (tid == 0) {
         mbar_arrive_expect_tx(full_bar(s), L::B_STAGE_BYTES);
         bulk_g2s(b_base + s * L::B_STAGE_BYTES, wimg + ((int64_t)git * c_out + n0) * BK, L::B_STAGE_BYTES,
@@ -559,7 +566,7 @@ int launch_perm(const float* x, const float* wimg, const int* nbr, int64_t n_out
     attr_set = true;
   }
   dim3 grid((unsigned)tiles_cap, (unsigned)(c_out / BN), 1);
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, nullptr, nbr, n_out, n_out_dev, c_in, c_out, k3, 0, 0, y, pa);
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, nullptr, nbr, n_out, n_out_dev, c_in, c_out, k3, 0, 0, y, pa, 0);
   return 0;
 }
 
@@ -570,6 +577,15 @@ bool tc_disabled() {
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
+}
+
+int tc_rot() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("B2S_TC_ROT");
+    env = e ? atoi(e) : 0;
+  }
+  return g_b2s_tc_rot >= 0 ? g_b2s_tc_rot : env;
 }
 
 template <int BN, int STAGES, bool SMALL, int LAG = 2>
@@ -600,7 +616,7 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
   kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y,
-                                               PermArgs{});
+                                               PermArgs{}, tc_rot());
   return 0;
 }
 

@@ -28,6 +28,22 @@ extern "C" int32_t b2s_device_check(void) {
   return B2S_OK;
 }
 
+// launch-tuning knobs (wgrad_tc.cu / conv_tc.cu read them at every launch)
+int g_b2s_wg_nbp = -1, g_b2s_wg_lag = -1, g_b2s_wg_occ2 = -1, g_b2s_tc_rot = -1;
+
+extern "C" int32_t b2s_set_tuning(const char* key, int32_t value) {
+  B2S_CHECK_ARG(key != nullptr, "key is NULL");
+  if (!strcmp(key, "wg_nbp")) g_b2s_wg_nbp = value;
+  else if (!strcmp(key, "wg_lag")) g_b2s_wg_lag = value;
+  else if (!strcmp(key, "wg_occ2")) g_b2s_wg_occ2 = value;
+  else if (!strcmp(key, "tc_rot")) g_b2s_tc_rot = value;
+  else {
+    b2s_set_error("b2s_set_tuning: unknown key '%s'", key);
+    return B2S_EINVAL;
+  }
+  return B2S_OK;
+}
+
 // implemented in conv_simt.cu / conv_tc.cu
 int b2s_conv_gather_gemm_simt(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_out,
                               const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout,

@@ -24,6 +24,8 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 
+extern int g_b2s_wg_nbp, g_b2s_wg_lag, g_b2s_wg_occ2;   // lib.cu (b2s_set_tuning)
+
 namespace {
 
 using namespace tc;
@@ -58,8 +60,20 @@ constexpr int G_BLOCK = G_R * 128;              // bytes of one 32-channel block
 constexpr int G_PRODUCERS = 256;                // warps 0..7
 constexpr int G_THREADS = 288;                  // + warp 8 = MMA issuer
 constexpr int G_MAX_STAGES = 8;
-constexpr int G_MAX_ROUNDS = 16;                // A items per thread per stage (<= 32 blocks x 16 rows / 32)
-constexpr int G_LAG = 2;
+constexpr int G_MAX_LAG = 6;                    // producers may run up to this many stages ahead of their hand-over
+
+// cp.async.wait_group with a run-time count (uniform across the CTA)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    default: cp_async_wait<6>(); break;
+  }
+}
 
 __device__ __forceinline__ uint32_t g_offset(int row, int c8) {  // chunk c8 (0..7) of a block-local row
   const int unit = (c8 >> 1) ^ (row & 3);
@@ -72,12 +86,15 @@ struct G2Params {
   int MT;              // M tiles of 128 = ceil(KG*CB / 4)
   int ci_tiles, co_tiles, groups;
   int stages;
+  int lag;             // stages a producer keeps in flight behind the one it is issuing (< stages)
   int use_atomic;
   int64_t rows_per_split;
 };
 
-template <int BN, int TCOLS>
-__global__ void __launch_bounds__(G_THREADS, 1)
+// MAXR: A items per thread per stage (>= NBP / 2; 16 covers 32 blocks x 16 rows / 32 items per round);
+// MINB: CTAs per SM the register budget is sized for (2 needs TCOLS <= 256 and <= 113 KB of shared memory)
+template <int BN, int TCOLS, int MAXR, int MINB>
+__global__ void __launch_bounds__(G_THREADS, MINB)
     wgrad_group_kernel(const float* __restrict__ x, const float* __restrict__ gy, const int* __restrict__ nbr,
                        int64_t n_out, const int* __restrict__ n_out_dev, G2Params p, float* __restrict__ gw) {
   const int64_t pitch = n_out;
@@ -138,20 +155,20 @@ __global__ void __launch_bounds__(G_THREADS, 1)
     const uint32_t dst0 = (uint32_t)h * G_BLOCK + g_offset(r, l8);
     unsigned valid = 0;                              // bit j: round j addresses a real (offset, channel block)
 #pragma unroll
-    for (int j = 0; j < G_MAX_ROUNDS; ++j) {
+    for (int j = 0; j < MAXR; ++j) {
       const int bb = 2 * j + h, kk = bb >> cb_shift;
       if (j < a_rounds && kk < p.KG && k0 + kk < p.k3 && ci0 + (bb & cb_mask) * 32 < p.c_in) valid |= 1u << j;
     }
     const int* nbr_r = nbr ? nbr + r : nullptr;
     const float* x_l = x + ci0 + l8 * 4;
     const float* gy_l = gy + co0 + h * 32 + l8 * 4;
-    int idx[G_MAX_ROUNDS];
+    int idx[MAXR];
 
     auto load_idx = [&](int it) {        // neighbour rows of stage `it` for this thread's A items
       const int64_t r0 = r_begin + (int64_t)it * G_R;
       const bool live = r0 + r < r_end;
 #pragma unroll
-      for (int j = 0; j < G_MAX_ROUNDS; ++j) {
+      for (int j = 0; j < MAXR; ++j) {
         int v = -1;
         if (((valid >> j) & 1u) && live) {
           const int k = k0 + ((2 * j + h) >> cb_shift);
@@ -173,7 +190,7 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       const uint32_t a_dst = base + (uint32_t)s * stage_bytes + dst0, b_dst = a_dst + a_stage_bytes;
       const int64_t o = r_begin + (int64_t)it * G_R + r;
 #pragma unroll
-      for (int j = 0; j < G_MAX_ROUNDS; ++j) {
+      for (int j = 0; j < MAXR; ++j) {
         if (j < a_rounds) {
           const int i = idx[j];
           const float* src = x_l + (int64_t)(i >= 0 ? i : 0) * p.c_in + ((2 * j + h) & cb_mask) * 32;
@@ -189,17 +206,15 @@ __global__ void __launch_bounds__(G_THREADS, 1)
       }
       cp_async_commit();
       if (it + 1 < T) load_idx(it + 1);   // overlaps with the copies in flight
-      if (it >= G_LAG) {
-        cp_async_wait<G_LAG>();
-        publish(it - G_LAG);
+      if (it >= p.lag) {
+        cp_async_wait_dyn(p.lag);
+        publish(it - p.lag);
       }
     }
-    if (T >= 2) {
-      cp_async_wait<1>();
-      publish(T - 2);
+    for (int r = T < p.lag ? T : p.lag; r > 0; --r) {   // drain: stage T - r is complete once <= r - 1 groups are pending
+      cp_async_wait_dyn(r - 1);
+      publish(T - r);
     }
-    cp_async_wait<0>();
-    publish(T - 1);
 
     // ===================== epilogue: TMEM lane = (block 4t + q, channel lane), 32 columns per tcgen05.ld
     mbar_wait(accum_bar, 0);
@@ -464,32 +479,60 @@ bool wgrad_tc_disabled() {
   return v == 1;
 }
 
-template <int BN, int TCOLS>
+int wg_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Tuning knobs: nbp_cap = cap on the A blocks a stage holds (smaller stages -> deeper ring), lag = stages a producer
+// keeps in flight (0 = derive from the ring depth), occ2 = 1 sizes the kernel for two CTAs per SM where the
+// accumulators fit 256 TMEM columns.  Environment (B2S_WG_NBP / _LAG / _OCC2) read once; b2s_set_tuning overrides.
+struct WgTuning {
+  int nbp_cap, lag, occ2;
+};
+WgTuning wg_tuning() {
+  static const WgTuning env = {wg_env("B2S_WG_NBP", 16), wg_env("B2S_WG_LAG", 0), wg_env("B2S_WG_OCC2", 0)};
+  WgTuning t = env;
+  if (g_b2s_wg_nbp >= 0) t.nbp_cap = g_b2s_wg_nbp;
+  if (g_b2s_wg_lag >= 0) t.lag = g_b2s_wg_lag;
+  if (g_b2s_wg_occ2 >= 0) t.occ2 = g_b2s_wg_occ2;
+  return t;
+}
+
+template <int BN, int TCOLS, int MAXR, int MINB>
 int launch_group(const float* x, const float* gy, const int* nbr, int64_t n_out, const int* n_out_dev, G2Params p,
                  float* gw, cudaStream_t st) {
-  auto kern = wgrad_group_kernel<BN, TCOLS>;
+  auto kern = wgrad_group_kernel<BN, TCOLS, MAXR, MINB>;
   const int stage_bytes = (p.MT * 4 + BN / 32) * G_BLOCK;
-  int stages = (222 * 1024) / stage_bytes;
+  const int bar_bytes = (2 * G_MAX_STAGES + 2) * 8 + 1024;
+  const int budget = MINB == 2 ? 112 * 1024 : 226 * 1024;   // per-CTA shared memory incl. barriers and alignment slack
+  int stages = (budget - bar_bytes) / stage_bytes;
   if (stages > G_MAX_STAGES) stages = G_MAX_STAGES;
-  if (stages <= G_LAG) {   // the producers run G_LAG stages ahead of their own hand-over
-    b2s_set_error("wgrad_tc: stage of %d bytes does not fit %d times in shared memory", stage_bytes, G_LAG + 1);
+  if (stages < 2) {
+    b2s_set_error("wgrad_tc: stage of %d bytes does not fit twice in shared memory", stage_bytes);
     return -1;
   }
   p.stages = stages;
-  // >= 114 KB keeps one CTA per SM (each CTA may hold all 512 TMEM columns)
-  int dyn = stages * stage_bytes + (2 * G_MAX_STAGES + 2) * 8 + 1024;
-  if (dyn < 116 * 1024) dyn = 116 * 1024;
-  static int attr_set = 0;
-  if (attr_set < dyn) {
+  // default: leave one stage being consumed and one being filled beyond the in-flight ones when the ring allows it
+  int lag = wg_tuning().lag > 0 ? wg_tuning().lag : (stages >= 4 ? stages - 2 : stages - 1);
+  if (lag > stages - 1) lag = stages - 1;
+  if (lag < 1) lag = 1;
+  if (lag > G_MAX_LAG) lag = G_MAX_LAG;
+  p.lag = lag;
+  int dyn = stages * stage_bytes + bar_bytes;
+  // one CTA per SM unless sized for two: a CTA may hold all 512 TMEM columns, a second one would wait for them
+  if (MINB == 1 && dyn < 116 * 1024) dyn = 116 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       b2s_set_error("wgrad_tc: cannot opt in to 227 KB of shared memory");
       return -1;
     }
-    attr_set = 227 * 1024;
+    attr_set = true;
   }
   const int64_t base = (int64_t)p.groups * p.ci_tiles * p.co_tiles;
-  // two waves of 148 single-CTA SMs; every split gets at least 16 stages of rows
-  int64_t splits = (2LL * B2S_NUM_SMS + base - 1) / base;
+  // two waves of the resident CTAs; every split gets at least 16 stages of rows
+  int64_t splits = (2LL * MINB * B2S_NUM_SMS + base - 1) / base;
   const int64_t max_splits = ceil_div64(n_out, 16 * G_R);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -503,6 +546,20 @@ int launch_group(const float* x, const float* gy, const int* nbr, int64_t n_out,
   dim3 grid((unsigned)base, (unsigned)splits);
   kern<<<grid, G_THREADS, dyn, st>>>(x, gy, nbr, n_out, n_out_dev, p, gw);
   return 0;
+}
+
+// picks the kernel instance for a given accumulator width: MAXR 8 when a stage holds <= 16 A blocks, two CTAs per SM
+// when asked for and the accumulators fit half of TMEM
+template <int BN, int TCOLS>
+int launch_group_sel(const float* x, const float* gy, const int* nbr, int64_t n_out, const int* n_out_dev,
+                     const G2Params& p, float* gw, cudaStream_t st) {
+  if (p.MT * 4 <= 16) {
+    if constexpr (TCOLS <= 256) {
+      if (wg_tuning().occ2) return launch_group<BN, TCOLS, 8, 2>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
+    }
+    return launch_group<BN, TCOLS, 8, 1>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
+  }
+  return launch_group<BN, TCOLS, 16, 1>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
 }
 
 }  // namespace
@@ -528,7 +585,9 @@ int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64
   p.CB = blocks_in < 8 ? blocks_in : 8;                  // ci slice of at most 256 channels per CTA
   p.ci_tiles = (blocks_in + p.CB - 1) / p.CB;
   p.co_tiles = c_out / bn;
-  const int mt_max = 512 / bn;                           // TMEM columns
+  int mt_max = 512 / bn;                                 // TMEM columns
+  const int mt_cap = wg_tuning().nbp_cap / 4;            // stage-size cap: NBP = 4 MT A blocks of 2 KB
+  if (mt_cap >= 1 && mt_max > mt_cap) mt_max = mt_cap;
   int kg = (mt_max * 4) / p.CB;
   if (kg < 1) kg = 1;
   if (kg > k3) kg = k3;
@@ -537,13 +596,13 @@ int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64
   p.KG = kg;
   p.MT = (kg * p.CB + 3) / 4;
   const int cols = p.MT * bn;
-  if (bn == 256) return cols <= 256 ? launch_group<256, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
-                                    : launch_group<256, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
-  if (bn == 128) return cols <= 128 ? launch_group<128, 128>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
-                       : cols <= 256 ? launch_group<128, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
-                                     : launch_group<128, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
-  return cols <= 64 ? launch_group<64, 64>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
-       : cols <= 128 ? launch_group<64, 128>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
-       : cols <= 256 ? launch_group<64, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
-                     : launch_group<64, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
+  if (bn == 256) return cols <= 256 ? launch_group_sel<256, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+                                    : launch_group_sel<256, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
+  if (bn == 128) return cols <= 128 ? launch_group_sel<128, 128>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+                       : cols <= 256 ? launch_group_sel<128, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+                                     : launch_group_sel<128, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
+  return cols <= 64 ? launch_group_sel<64, 64>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+       : cols <= 128 ? launch_group_sel<64, 128>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+       : cols <= 256 ? launch_group_sel<64, 256>(x, gy, nbr, n_out, n_out_dev, p, gw, st)
+                     : launch_group_sel<64, 512>(x, gy, nbr, n_out, n_out_dev, p, gw, st);
 }

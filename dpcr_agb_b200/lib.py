@@ -21,6 +21,7 @@ SIGNATURES = {
     "b2s_last_error": (ctypes.c_char_p, []),
     "b2s_version": (_i32, []),
     "b2s_device_check": (_i32, []),
+    "b2s_set_tuning": (_i32, [ctypes.c_char_p, _i32]),
     "b2s_quantize_points": (_i32, [_vp, _i64, _vp, _f32, _vp, _vp, _vp]),
     "b2s_quantize_workspace_bytes": (_i64, [_i64, _vp]),
     "b2s_quantize_count": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
@@ -106,6 +107,13 @@ def load() -> ctypes.CDLL:
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def set_tuning(key: str, value: int) -> None:
+    """Diagnostic knob override (``b2s_set_tuning``); kernel results do not depend on it."""
+    lib = load()
+    if lib.b2s_set_tuning(key.encode(), int(value)) != 0:
+        raise B2SError(lib.b2s_last_error().decode())
 
 
 def ptr(t):

@@ -53,6 +53,11 @@ B2S_API const char* b2s_last_error(void);
 B2S_API int32_t b2s_version(void);
 /* 0 iff the current device is compute capability 10.x (B200); B2S_ECUDA otherwise. */
 B2S_API int32_t b2s_device_check(void);
+/* Diagnostic: overrides one launch-tuning knob of the convolution kernels for this process (results are unaffected,
+ * only tile / pipeline shapes).  Keys: "wg_nbp", "wg_lag", "wg_occ2" (weight-gradient stage size cap in 2 KB blocks,
+ * producer run-ahead in stages, 1 = two CTAs per SM), "tc_rot" (1 = every output tile starts its kernel-offset
+ * loop at a different offset).  B2S_EINVAL for an unknown key.  Not part of the reference-facing surface. */
+B2S_API int32_t b2s_set_tuning(const char* key, int32_t value);
 
 /* ---------------------------------------------------------------- (a1) voxel quantisation ----
  * R:core/data_transform/grid_transform.py:112-128 (GridSampling3D._process, mode="last").
