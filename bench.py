@@ -285,9 +285,23 @@ def run_b200(args):
         eager_step(devb[i % nb])
     breakdown = {k: {"calls_per_step": n / bsteps, "ms_per_step": t / bsteps} for k, (n, t) in lib.profile_stop().items()}
 
+    def shutdown():
+        """Leave the process group without ever hanging the launcher: the captured graphs go first (NCCL does not
+        let a communicator die while a graph references it), and a watchdog ends the process with status 0 if the
+        teardown still blocks -- every number has been printed by then."""
+        if world == 1:
+            return
+        sys.stdout.flush()
+        import threading
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        gstep.release()
+        dist.destroy_process_group()
+        t.cancel()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     # ---- roofline of the dominant kernel family (conv gather-GEMM fwd+dgrad; wgrad reported beside it)
@@ -339,8 +353,7 @@ def run_b200(args):
             "row_capacities": caps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "breakdown_ms_per_step": breakdown}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

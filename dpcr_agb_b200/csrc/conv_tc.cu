@@ -18,7 +18,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-extern int g_b2s_tc_rot;   // lib.cu (b2s_set_tuning)
+extern int g_b2s_tc_rot, g_b2s_tc_ca, g_b2s_tc_occ1;   // lib.cu (b2s_set_tuning)
 
 namespace {
 
@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y,
-                          const PermArgs pa, int rot_on) {
+                          const PermArgs pa, int flags) {
+  const int rot_on = flags & 1;
+  const bool l1 = (flags & 2) != 0;                // gather through L1 (cp.async.ca) instead of L2 only (.cg)
   const int64_t pitch = n_out;                     // row pitch of the neighbour table (the caller's capacity)
   n_out = b2s_rows(n_out, n_out_dev);
   int cls = 0;
@@ -187,7 +189,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       return (k >= k3 && g < k3) ? k - k3 : k;
     };
     auto load_group = [&](int g, int (&dst)[8]) {                 // g: offset index (general) / stage index (SMALL)
-      const int k = SMALL ? g * 8 + chunk : kof(g);
+      if (SMALL) {
+        // thread = tile row, p = the 8 kernel offsets of the stage: a warp reads 32 consecutive entries of one table
+        // row (128 B) and, rows being sorted along x, gathers mostly consecutive feature rows -- instead of 32
+        // scattered 16-byte sectors per instruction when the lanes of a warp walk the offsets of one row
+        const int64_t o = m0 + tid;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const int k = g * 8 + p;
+          dst[p] = (k < k3 && o < n_out) ? (nbr ? __ldg(nbr + (int64_t)k * pitch + o) : (int)o) : -1;
+        }
+        return;
+      }
+      const int k = kof(g);
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         int v = -1;
@@ -225,11 +239,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t a_stage = a_base + s * A_STAGE_BYTES;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
-        const int row = rsub + 16 * p;
+        const int row = SMALL ? tid : rsub + 16 * p;
         const int i = idx[p];
         const float* src = SMALL ? x + (int64_t)(i >= 0 ? i : 0) * 4
                                  : x + (int64_t)(i >= 0 ? i : 0) * c_in + cc * BK + chunk * 4;
-        cp_async16(a_stage + sw128_offset(row, chunk), src, i >= 0 ? 16u : 0u);
+        cp_async16_sel(a_stage + sw128_offset(row, SMALL ? p : chunk), src, i >= 0 ? 16u : 0u, l1);
       }
       cp_async_commit();
       if (++cc == kc) {             // next index group: rotate the prefetch ring, fetch group g + 3
@@ -552,6 +566,14 @@ int launch_tma(const float* x, int64_t n_in, const float* wimg, const float* bia
 }
 
 
+int tc_knob(int global, const char* env_name, int dflt) {
+  if (global >= 0) return global;
+  const char* e = getenv(env_name);
+  return e ? atoi(e) : dflt;
+}
+int tc_ca() { return tc_knob(g_b2s_tc_ca, "B2S_TC_CA", 0); }
+int tc_occ1() { return tc_knob(g_b2s_tc_occ1, "B2S_TC_OCC1", 0); }
+
 template <int BN, int STAGES>
 int launch_perm(const float* x, const float* wimg, const int* nbr, int64_t n_out, const int* n_out_dev, int c_in,
                 int c_out, int k3, float* y, const PermArgs& pa, int64_t tiles_cap, cudaStream_t st) {
@@ -566,7 +588,8 @@ int launch_perm(const float* x, const float* wimg, const int* nbr, int64_t n_out
     attr_set = true;
   }
   dim3 grid((unsigned)tiles_cap, (unsigned)(c_out / BN), 1);
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, nullptr, nbr, n_out, n_out_dev, c_in, c_out, k3, 0, 0, y, pa, 0);
+  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, nullptr, nbr, n_out, n_out_dev, c_in, c_out, k3, 0, 0, y, pa,
+                                               tc_ca() ? 2 : 0);
   return 0;
 }
 
@@ -596,12 +619,16 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
   auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL, LAG>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
-      b2s_set_error("conv_tc: cannot opt in to %d bytes of shared memory", L::DYN_BYTES);
+    constexpr int OPT_IN = L::DYN_BYTES > 116 * 1024 ? L::DYN_BYTES : 116 * 1024;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OPT_IN) != cudaSuccess) {
+      b2s_set_error("conv_tc: cannot opt in to %d bytes of shared memory", OPT_IN);
       return -1;
     }
     attr_set = true;
   }
+  // tc_occ1: ask for more than half of the SM's shared memory so that ONE CTA runs per SM and the rest of the
+  // unified array stays L1 (the .ca gathers live there)
+  const int dyn = (tc_occ1() && L::DYN_BYTES < 116 * 1024) ? 116 * 1024 : L::DYN_BYTES;
   const int64_t ctas = ceil_div64(n_out, BM) * (c_out / BN);
   const int kc = SMALL ? 1 : c_in / BK;
   int splits = 1;
@@ -615,8 +642,8 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
   splits = (T + per - 1) / per;
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
-  kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y,
-                                               PermArgs{}, tc_rot());
+  kern<<<grid, TC_THREADS, dyn, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y, PermArgs{},
+                                      (tc_rot() ? 1 : 0) | (tc_ca() ? 2 : 0));
   return 0;
 }
 

@@ -30,6 +30,8 @@ extern "C" int32_t b2s_device_check(void) {
 
 // launch-tuning knobs (wgrad_tc.cu / conv_tc.cu read them at every launch)
 int g_b2s_wg_nbp = -1, g_b2s_wg_lag = -1, g_b2s_wg_occ2 = -1, g_b2s_tc_rot = -1;
+int g_b2s_tc_ca = -1, g_b2s_tc_occ1 = -1, g_b2s_wg_ca = -1;
+int g_b2s_cr_v4 = -1, g_b2s_cr_cap = -1, g_b2s_cr_unroll = -1;
 
 extern "C" int32_t b2s_set_tuning(const char* key, int32_t value) {
   B2S_CHECK_ARG(key != nullptr, "key is NULL");
@@ -37,6 +39,12 @@ extern "C" int32_t b2s_set_tuning(const char* key, int32_t value) {
   else if (!strcmp(key, "wg_lag")) g_b2s_wg_lag = value;
   else if (!strcmp(key, "wg_occ2")) g_b2s_wg_occ2 = value;
   else if (!strcmp(key, "tc_rot")) g_b2s_tc_rot = value;
+  else if (!strcmp(key, "tc_ca")) g_b2s_tc_ca = value;
+  else if (!strcmp(key, "tc_occ1")) g_b2s_tc_occ1 = value;
+  else if (!strcmp(key, "wg_ca")) g_b2s_wg_ca = value;
+  else if (!strcmp(key, "cr_v4")) g_b2s_cr_v4 = value;
+  else if (!strcmp(key, "cr_cap")) g_b2s_cr_cap = value;
+  else if (!strcmp(key, "cr_unroll")) g_b2s_cr_unroll = value;
   else {
     b2s_set_error("b2s_set_tuning: unknown key '%s'", key);
     return B2S_EINVAL;

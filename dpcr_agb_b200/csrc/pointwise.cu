@@ -11,6 +11,8 @@
 #include "tc_ptx.cuh"
 #include <math.h>
 
+extern int g_b2s_cr_v4, g_b2s_cr_cap, g_b2s_cr_unroll;   // lib.cu (b2s_set_tuning)
+
 namespace {
 
 constexpr int PW_THREADS = 256;
@@ -325,6 +327,97 @@ __global__ void __launch_bounds__(PW_THREADS) colreduce_kernel(const float* __re
   }
 }
 
+// Vectorised form of the same reductions (c % 64 == 0, 16-byte aligned rows).  A 512-thread CTA owns a slab of 64
+// channels (blockIdx.y) and a strided share of the rows (blockIdx.x): 16 threads x float4 per row, 32 row lanes, U
+// independent 16-byte loads in flight per operand and thread (64 KB per SM).  Partial sums are combined across the
+// row lanes by a shared-memory tree and leave the CTA as one atomic per channel.  Same-address fp64 atomics
+// serialise at ~20 ns each in L2 (measured: tools/pw_bench.py), so the launch keeps slabs x row shares at about one
+// CTA per SM: the chain on any accumulator is at most 148 deep (the scalar kernel issues one per 256 rows).
+constexpr int CR_THREADS = 512;
+constexpr int CR_SLAB = 64;                         // channels per CTA
+constexpr int CR_TPR = CR_SLAB / 4;                 // threads per row
+constexpr int CR_RPB = CR_THREADS / CR_TPR;         // row lanes
+template <int MODE, typename ACC, int U>
+__global__ void __launch_bounds__(CR_THREADS, 1) colreduce_v4_kernel(const float* __restrict__ x,
+                                                                     const float* __restrict__ g,
+                                                                     const float* __restrict__ mean,
+                                                                     const float* __restrict__ invstd,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, int64_t n,
+                                                                     const int* __restrict__ n_dev, int c, int act,
+                                                                     ACC* __restrict__ ws) {
+  n = b2s_rows(n, n_dev);
+  __shared__ float4 sm[2][CR_THREADS];
+  const int tc = threadIdx.x % CR_TPR, tr = threadIdx.x / CR_TPR;
+  const int ch = blockIdx.y * CR_SLAB + tc * 4;
+  const int64_t step = (int64_t)gridDim.x * CR_RPB;
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  V<4> mu = splat<4>(0.f), is = splat<4>(1.f), ga = splat<4>(1.f), be = splat<4>(0.f);
+  if (MODE == 2) {
+    mu = ldgv<4>(mean + ch), is = ldgv<4>(invstd + ch);
+    ga = ldparam<4>(gamma, ch, 1.f), be = ldparam<4>(beta, ch, 0.f);
+  }
+  auto accumulate = [&](const V<4>& xv, const V<4>& gv) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v = xv.v[j];
+      if (MODE == 0) {
+        a0[j] += v;
+      } else if (MODE == 1) {
+        a0[j] += v;
+        a1[j] += v * v;
+      } else {
+        const float xh = (v - mu.v[j]) * is.v[j];
+        float gg = gv.v[j];
+        if (act == 1) gg *= gelu_grad_f(xh * ga.v[j] + be.v[j]);
+        a0[j] += gg;
+        a1[j] += gg * xh;
+      }
+    }
+  };
+  int64_t r = (int64_t)blockIdx.x * CR_RPB + tr;
+  for (; r + (U - 1) * step < n; r += U * step) {
+    V<4> xv[U], gv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = ldv<4>(x + (r + u * step) * c + ch);
+    if (MODE == 2) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) gv[u] = ldv<4>(g + (r + u * step) * c + ch);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) accumulate(xv[u], gv[u]);
+  }
+  for (; r < n; r += step) {   // < U rows left
+    const V<4> xv = ldv<4>(x + r * c + ch);
+    V<4> gv = xv;
+    if (MODE == 2) gv = ldv<4>(g + r * c + ch);
+    accumulate(xv, gv);
+  }
+  sm[0][threadIdx.x] = make_float4(a0[0], a0[1], a0[2], a0[3]);
+  if (MODE != 0) sm[1][threadIdx.x] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+  __syncthreads();
+#pragma unroll
+  for (int sft = CR_RPB >> 1; sft > 0; sft >>= 1) {
+    if (tr < sft) {
+      const int o = threadIdx.x + sft * CR_TPR;
+      float4 p = sm[0][threadIdx.x], q = sm[0][o];
+      sm[0][threadIdx.x] = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+      if (MODE != 0) {
+        p = sm[1][threadIdx.x], q = sm[1][o];
+        sm[1][threadIdx.x] = make_float4(p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < CR_SLAB) {       // one atomic per thread: channel blockIdx.y * 64 + threadIdx.x
+    const float* s0 = reinterpret_cast<const float*>(&sm[0][0]);
+    const float* s1 = reinterpret_cast<const float*>(&sm[1][0]);
+    const int cc = blockIdx.y * CR_SLAB + threadIdx.x;
+    atomicAdd(&ws[cc], (ACC)s0[threadIdx.x]);
+    if (MODE != 0) atomicAdd(&ws[c + cc], (ACC)s1[threadIdx.x]);
+  }
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ ws, int64_t n, const int* __restrict__ n_dev, int c,
                                    float eps, float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ mean,
@@ -451,6 +544,28 @@ __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restric
 
 dim3 colgrid(int64_t n, int c) { return dim3((unsigned)ceil_div64(n, ROWS_PER_CTA), (unsigned)((c + 31) / 32)); }
 
+// column reduction launch: the float4 kernel whenever the rows are 16-byte aligned vectors, else the scalar one
+template <int MODE, typename ACC>
+void launch_colreduce(const float* x, const float* g, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, int64_t n, const int* n_dev, int c, int act, ACC* ws, cudaStream_t st) {
+  const int v4 = g_b2s_cr_v4 >= 0 ? g_b2s_cr_v4 : 1;
+  if (v4 && c % CR_SLAB == 0 && vec_of(c, x, g, mean, invstd) == 4 && vec_of(c, gamma, beta) == 4) {
+    // slabs x row shares ~ `cap` (default one) CTA per SM, >= 4 rows per thread
+    const int slabs = c / CR_SLAB;
+    const int64_t ctas = (int64_t)B2S_NUM_SMS * (g_b2s_cr_cap > 0 ? g_b2s_cr_cap : 1);
+    int64_t shares = (ctas + slabs - 1) / slabs;
+    const int64_t max_shares = ceil_div64(n, (int64_t)CR_RPB * 4);
+    if (shares > max_shares) shares = max_shares;
+    if (shares < 1) shares = 1;
+    constexpr int U = MODE == 2 ? 4 : 8;
+    colreduce_v4_kernel<MODE, ACC, U><<<dim3((unsigned)shares, (unsigned)slabs), CR_THREADS, 0, st>>>(
+        x, g, mean, invstd, gamma, beta, n, n_dev, c, act, ws);
+  } else {
+    colreduce_kernel<MODE, ACC><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, g, mean, invstd, gamma, beta, n, n_dev, c, act,
+                                                                      ws);
+  }
+}
+
 }  // namespace
 
 // ================================================================= C ABI ======================
@@ -576,8 +691,7 @@ extern "C" int32_t b2s_colsum(const float* x, int64_t n, const int32_t* n_dev, i
   B2S_CUDA(cudaMemsetAsync(out, 0, c * sizeof(float), st));
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(x, "null pointer");
-  colreduce_kernel<0, float><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr, n,
-                                                                   n_dev, c, 0, out);
+  launch_colreduce<0, float>(x, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c, 0, out, st);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -589,8 +703,7 @@ extern "C" int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev,
   B2S_CHECK_ARG(x && stats_ws && mean && invstd, "null pointer");
   cudaStream_t st = as_stream(stream);
   B2S_CUDA(cudaMemsetAsync(stats_ws, 0, 2 * (size_t)c * sizeof(double), st));
-  colreduce_kernel<1, double><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                    n, n_dev, c, 0, stats_ws);
+  launch_colreduce<1, double>(x, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c, 0, stats_ws, st);
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(stats_ws, n, n_dev, c, eps, momentum, running_mean,
                                                       running_var, mean, invstd);
   B2S_LAUNCH_CHECK();
@@ -619,8 +732,7 @@ extern "C" int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const floa
   B2S_CHECK_ARG(gy && x && mean && invstd && stats_ws && sums, "null pointer");
   cudaStream_t st = as_stream(stream);
   B2S_CUDA(cudaMemsetAsync(stats_ws, 0, 2 * (size_t)c * sizeof(double), st));
-  colreduce_kernel<2, double><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, gy, mean, invstd, gamma, beta, n, n_dev, c,
-                                                                    act, stats_ws);
+  launch_colreduce<2, double>(x, gy, mean, invstd, gamma, beta, n, n_dev, c, act, stats_ws, st);
   double_to_float_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(stats_ws, sums, 2 * c);
   B2S_LAUNCH_CHECK();
   return B2S_OK;

@@ -42,6 +42,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// same copy, allocating the line in L1 as well: gathers of neighbouring kernel offsets touch the same feature rows
+// again within a few pipeline stages, and an L1 hit takes that re-read off the L2 fabric
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_sel(uint32_t dst, const void* src, uint32_t src_bytes, bool l1) {
+  if (l1) cp_async16_ca(dst, src, src_bytes);
+  else cp_async16(dst, src, src_bytes);
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

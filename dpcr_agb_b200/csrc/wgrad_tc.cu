@@ -24,7 +24,7 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 
-extern int g_b2s_wg_nbp, g_b2s_wg_lag, g_b2s_wg_occ2;   // lib.cu (b2s_set_tuning)
+extern int g_b2s_wg_nbp, g_b2s_wg_lag, g_b2s_wg_occ2, g_b2s_wg_ca;   // lib.cu (b2s_set_tuning)
 
 namespace {
 
@@ -88,6 +88,7 @@ struct G2Params {
   int stages;
   int lag;             // stages a producer keeps in flight behind the one it is issuing (< stages)
   int use_atomic;
+  int l1;              // 1: gather the x rows through L1 (offsets of a group re-read the same rows within a stage)
   int64_t rows_per_split;
 };
 
@@ -163,8 +164,10 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
     const float* x_l = x + ci0 + l8 * 4;
     const float* gy_l = gy + co0 + h * 32 + l8 * 4;
     int idx[MAXR];
+    const bool l1 = p.l1 != 0;
 
-    auto load_idx = [&](int it) {        // neighbour rows of stage `it` for this thread's A items
+    int idx_n[MAXR];                     // neighbour rows of the stage after next (two-deep index prefetch)
+    auto load_idx = [&](int it, int (&dst)[MAXR]) {   // neighbour rows of stage `it` for this thread's A items
       const int64_t r0 = r_begin + (int64_t)it * G_R;
       const bool live = r0 + r < r_end;
 #pragma unroll
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
           const int k = k0 + ((2 * j + h) >> cb_shift);
           v = nbr_r ? __ldg(nbr_r + (int64_t)k * pitch + r0) : (int)(r0 + r);
         }
-        idx[j] = v;
+        dst[j] = v;
       }
     };
     auto publish = [&](int it_done) {
@@ -182,7 +185,8 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
       mbar_arrive(full_bar(it_done % p.stages));
     };
 
-    load_idx(0);
+    load_idx(0, idx);
+    load_idx(1, idx_n);                  // beyond the range: all -1, no loads
     for (int it = 0; it < T; ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
         if (j < a_rounds) {
           const int i = idx[j];
           const float* src = x_l + (int64_t)(i >= 0 ? i : 0) * p.c_in + ((2 * j + h) & cb_mask) * 32;
-          cp_async16(a_dst + (uint32_t)j * (2 * G_BLOCK), src, i >= 0 ? 16u : 0u);
+          cp_async16_sel(a_dst + (uint32_t)j * (2 * G_BLOCK), src, i >= 0 ? 16u : 0u, l1);
         }
       }
       {
@@ -205,7 +209,11 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
           cp_async16(b_dst + (uint32_t)j * (2 * G_BLOCK), src + j * 64, live ? 16u : 0u);
       }
       cp_async_commit();
-      if (it + 1 < T) load_idx(it + 1);   // overlaps with the copies in flight
+      // rotate the index ring; the loads for stage it + 2 overlap with two stages of copies (the neighbour table is
+      // streamed from HBM: one stage of run-ahead left the gather waiting on it every other stage)
+#pragma unroll
+      for (int j = 0; j < MAXR; ++j) idx[j] = idx_n[j];
+      load_idx(it + 2, idx_n);
       if (it >= p.lag) {
         cp_async_wait_dyn(p.lag);
         publish(it - p.lag);
@@ -303,7 +311,8 @@ template <int STAGES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
     wgrad_small_tc_kernel(const float4* __restrict__ x4, const float* __restrict__ gy, const int* __restrict__ nbr,
                           int64_t n_out, const int* __restrict__ n_out_dev, int c_in, int c_out, int k3, int co_tiles,
-                          int64_t rows_per_split, float* __restrict__ gw) {
+                          int64_t rows_per_split, int l1_on, float* __restrict__ gw) {
+  const bool l1 = l1_on != 0;
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
   using L = WgSmallSmem<STAGES>;
@@ -348,27 +357,45 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       fence_proxy_async();
       mbar_arrive(full_bar(it_done % STAGES));
     };
-    const int kA = k0 + lane, kB = k0 + 32 + lane;       // the two kernel offsets this lane gathers
+    // B gather mapping: lane = stage row, this warp owns the 16 kernel offsets k0 + 16 warp + p.  A warp then reads 32
+    // consecutive entries of one neighbour-table row (128 B) and -- rows being sorted along x -- mostly consecutive
+    // 16-byte feature rows, instead of 32 scattered sectors per instruction with lanes walking the offsets of one row.
+    constexpr int NK = 16;
+    const int kw = k0 + warp * NK;
+    // neighbour rows are fetched two stages ahead of their gather (the table streams from HBM)
+    int ia[NK], ia_n[NK];
+    auto load_nbr = [&](int it, int (&da)[NK]) {
+      const int64_t o = r_begin + (int64_t)it * WG_ROWS + lane;
+      const bool live = o < r_end;
+#pragma unroll
+      for (int p = 0; p < NK; ++p) da[p] = (live && kw + p < k3) ? __ldg(&nbr[(int64_t)(kw + p) * pitch + o]) : -1;
+    };
+    load_nbr(0, ia);
+    load_nbr(1, ia_n);
     for (int it = 0; it < T; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(empty_bar(s), ph ^ 1u);
       const uint32_t a_stage = a_base + s * WG_A_STAGE, b_stage = b_base + s * SM_B_STAGE;
       const int64_t r0 = r_begin + (int64_t)it * WG_ROWS;
+      if (lane < a_chunks) {
 #pragma unroll
-      for (int p = 0; p < WG_ROWS / 4; ++p) {
-        const int row = p * 4 + warp;
-        const int64_t o = r0 + row;
-        const bool live = o < r_end;
-        const int64_t oo = live ? o : 0;
-        if (lane < a_chunks) cp_async16(a_stage + mn_offset(row, lane), gy + oo * c_out + co0 + lane * 4, live ? 16u : 0u);
-        int ia = -1, ib = -1;
-        if (live && kA < k3) ia = __ldg(&nbr[(int64_t)kA * pitch + o]);
-        if (live && kB < k3) ib = __ldg(&nbr[(int64_t)kB * pitch + o]);
-        cp_async16(b_stage + mn_offset(row, lane), x4 + (ia >= 0 ? ia : 0), ia >= 0 ? 16u : 0u);
-        cp_async16(b_stage + mn_offset(row, lane + 32), x4 + (ib >= 0 ? ib : 0), ib >= 0 ? 16u : 0u);
+        for (int p = 0; p < WG_ROWS / 4; ++p) {
+          const int row = p * 4 + warp;
+          const int64_t o = r0 + row;
+          const bool live = o < r_end;
+          cp_async16(a_stage + mn_offset(row, lane), gy + (live ? o : 0) * c_out + co0 + lane * 4, live ? 16u : 0u);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < NK; ++p) {
+        const int v = ia[p];
+        cp_async16_sel(b_stage + mn_offset(lane, warp * NK + p), x4 + (v >= 0 ? v : 0), v >= 0 ? 16u : 0u, l1);
       }
       cp_async_commit();
+#pragma unroll
+      for (int p = 0; p < NK; ++p) ia[p] = ia_n[p];
+      load_nbr(it + 2, ia_n);
       if (it >= WG_LAG) {
         cp_async_wait<WG_LAG>();
         publish(it - WG_LAG);
@@ -429,6 +456,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   }
 }
 
+int wg_ca_knob();
+
 __global__ void __launch_bounds__(256) wg_pad_rows4_kernel(const float* __restrict__ x, int64_t n, int c,
                                                            float4* __restrict__ x4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -465,7 +494,8 @@ int launch_wgrad_small(const float* x, const float* gy, const int* nbr, int64_t 
   splits = ceil_div64(n_out, rows);
   cudaMemsetAsync(gw, 0, (size_t)k3 * c_in * c_out * sizeof(float), st);
   dim3 grid((unsigned)base, (unsigned)splits);
-  kern<<<grid, WG_THREADS, L::DYN_BYTES, st>>>(x4, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, co_tiles, rows, gw);
+  kern<<<grid, WG_THREADS, L::DYN_BYTES, st>>>(x4, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, co_tiles, rows,
+                                               wg_ca_knob(), gw);
   return 0;
 }
 
@@ -488,16 +518,20 @@ int wg_env(const char* name, int dflt) {
 // keeps in flight (0 = derive from the ring depth), occ2 = 1 sizes the kernel for two CTAs per SM where the
 // accumulators fit 256 TMEM columns.  Environment (B2S_WG_NBP / _LAG / _OCC2) read once; b2s_set_tuning overrides.
 struct WgTuning {
-  int nbp_cap, lag, occ2;
+  int nbp_cap, lag, occ2, ca;
 };
 WgTuning wg_tuning() {
-  static const WgTuning env = {wg_env("B2S_WG_NBP", 16), wg_env("B2S_WG_LAG", 0), wg_env("B2S_WG_OCC2", 0)};
+  static const WgTuning env = {wg_env("B2S_WG_NBP", 16), wg_env("B2S_WG_LAG", 2), wg_env("B2S_WG_OCC2", 1),
+                               wg_env("B2S_WG_CA", 0)};
   WgTuning t = env;
   if (g_b2s_wg_nbp >= 0) t.nbp_cap = g_b2s_wg_nbp;
   if (g_b2s_wg_lag >= 0) t.lag = g_b2s_wg_lag;
   if (g_b2s_wg_occ2 >= 0) t.occ2 = g_b2s_wg_occ2;
+  if (g_b2s_wg_ca >= 0) t.ca = g_b2s_wg_ca;
   return t;
 }
+
+int wg_ca_knob() { return wg_tuning().ca; }
 
 template <int BN, int TCOLS, int MAXR, int MINB>
 int launch_group(const float* x, const float* gy, const int* nbr, int64_t n_out, const int* n_out_dev, G2Params p,
@@ -513,6 +547,7 @@ int launch_group(const float* x, const float* gy, const int* nbr, int64_t n_out,
     return -1;
   }
   p.stages = stages;
+  p.l1 = wg_tuning().ca;
   // default: leave one stage being consumed and one being filled beyond the in-flight ones when the ring allows it
   int lag = wg_tuning().lag > 0 ? wg_tuning().lag : (stages >= 4 ? stages - 2 : stages - 1);
   if (lag > stages - 1) lag = stages - 1;

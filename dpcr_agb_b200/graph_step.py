@@ -167,6 +167,17 @@ class GraphStep:
             self.graph_tail.replay()
         return self.loss
 
+    def release(self):
+        """Destroy the captured graphs.  With the gradient all-reduce captured, NCCL keeps the communicator alive
+        until every graph that references it is gone: ``dist.destroy_process_group()`` blocks (measured: forever)
+        unless this runs first."""
+        torch.cuda.synchronize()
+        self.graph = None
+        self.graph_tail = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
     def verify(self):
         """One host read: raises if any replay since the last call exceeded a row capacity or left the packed
         coordinate range; returns {description: largest value seen}."""

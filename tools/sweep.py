@@ -41,31 +41,42 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-layers = [("L1 64->64 ts2", 2, 2, 3, 64, 64), ("L2 s2 64->128", 2, 4, 3, 64, 128), ("L2 128->128 ts4", 4, 4, 3, 128, 128),
+layers = [("stem k7 3->64 ts1", 1, 1, 7, 3, 64), ("L1 64->64 ts2", 2, 2, 3, 64, 64), ("L2 s2 64->128", 2, 4, 3, 64, 128), ("L2 128->128 ts4", 4, 4, 3, 128, 128),
           ("L3 s2 128->256", 4, 8, 3, 128, 256), ("L3 256->256 ts8", 8, 8, 3, 256, 256),
           ("L4 s2 256->512", 8, 16, 3, 256, 512), ("L4 512->512 ts16", 16, 16, 3, 512, 512)]
 # calls per training step of each shape (MSENet14): weights the per-layer times into one figure
-calls = {"L1 64->64 ts2": 4, "L2 s2 64->128": 1, "L2 128->128 ts4": 3, "L3 s2 128->256": 1, "L3 256->256 ts8": 3,
+calls = {"stem k7 3->64 ts1": 1, "L1 64->64 ts2": 4, "L2 s2 64->128": 1, "L2 128->128 ts4": 3, "L3 s2 128->256": 1, "L3 256->256 ts8": 3,
          "L4 s2 256->512": 1, "L4 512->512 ts16": 3}
 prep = []
 for name, its, ots, K, cin, cout in layers:
     km = cm.kernel_map(keys[its], keys[ots], K)
-    xf = Fn.round_tf32(torch.randn(km.n_in, cin, device=dev))
+    xf = torch.randn(km.n_in, cin, device=dev)
+    if cin > 4:
+        xf = Fn.round_tf32(xf)
     w = torch.randn(km.k3, cin, cout, device=dev) * 0.02
     gy = Fn.round_tf32(torch.randn(km.n_out, cout, device=dev))
     prep.append((name, km, xf, w, gy, cin, cout))
 
+
+ALL_KEYS = ("wg_nbp", "wg_lag", "wg_occ2", "wg_ca", "tc_rot", "tc_ca", "tc_occ1")
+
+
+def apply(cfg):
+    for k in ALL_KEYS:
+        lib.set_tuning(k, cfg.get(k, -1))
+
+
 res = {"wgrad": [], "fwd": []}
 ref = {}
-wg_cfgs = [(32, 2, 0)] + [c for c in itertools.product((16, 8), (0, 2, 3, 4, 5), (0, 1))]
-for nbp, lag, occ2 in wg_cfgs:
-    lib.set_tuning("wg_nbp", nbp)
-    lib.set_tuning("wg_lag", lag)
-    lib.set_tuning("wg_occ2", occ2)
-    row = {"nbp": nbp, "lag": lag, "occ2": occ2, "ms": {}, "err": {}}
+wg_cfgs = [dict(wg_ca=ca, wg_occ2=o2, wg_nbp=nbp) for ca in (0, 1) for o2 in (1, 0) for nbp in (16, 32)]
+if os.environ.get("SWEEP_WG"):
+    wg_cfgs = json.loads(os.environ["SWEEP_WG"])
+for cfg in wg_cfgs:
+    apply(cfg)
+    row = {"cfg": cfg, "ms": {}, "err": {}}
     tot = 0.0
     for name, km, xf, w, gy, cin, cout in prep:
-        f = lambda: Fn.wgrad(xf, gy, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, prerounded=True)
+        f = lambda: Fn.wgrad(xf, gy, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, prerounded=cin > 4)
         g = f()
         if name not in ref:
             ref[name] = g
@@ -78,18 +89,18 @@ for nbp, lag, occ2 in wg_cfgs:
     del row["err"]
     res["wgrad"].append(row)
     print("wgrad", row, flush=True)
-lib.set_tuning("wg_nbp", -1)
-lib.set_tuning("wg_lag", -1)
-lib.set_tuning("wg_occ2", -1)
 
 ref = {}
-for rot in (0, 1, 0, 1):
-    lib.set_tuning("tc_rot", rot)
-    row = {"rot": rot, "fwd_ms": {}, "dgrad_ms": {}}
+tc_cfgs = [dict(tc_ca=ca, tc_occ1=o1) for ca in (0, 1) for o1 in (0, 1)]
+if os.environ.get("SWEEP_TC"):
+    tc_cfgs = json.loads(os.environ["SWEEP_TC"])
+for cfg in tc_cfgs:
+    apply(cfg)
+    row = {"cfg": cfg, "fwd_ms": {}, "dgrad_ms": {}}
     tot = 0.0
     err = 0.0
     for name, km, xf, w, gy, cin, cout in prep:
-        f = lambda: Fn.gather_gemm(xf, w, None, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, 0, prerounded=True)
+        f = lambda: Fn.gather_gemm(xf, w, None, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, 0, prerounded=cin > 4)
         y = f()
         if name not in ref:
             ref[name] = y
@@ -97,7 +108,7 @@ for rot in (0, 1, 0, 1):
         t = timeit(f)
         row["fwd_ms"][name] = round(t, 4)
         tot += calls[name] * t
-        if km.symmetric:
+        if km.symmetric and cin > 4:
             f2 = lambda: Fn.gather_gemm(gy, w, None, km.nbr, km.n_out, km.n_in, cout, cin, km.k3, 3, prerounded=True)
             t2 = timeit(f2)
             row["dgrad_ms"][name] = round(t2, 4)
@@ -106,6 +117,6 @@ for rot in (0, 1, 0, 1):
     row["max_err"] = err
     res["fwd"].append(row)
     print("fwd", row, flush=True)
-lib.set_tuning("tc_rot", -1)
+apply({})
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/sweep.json", "w"), indent=1)
