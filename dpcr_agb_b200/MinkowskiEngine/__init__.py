@@ -24,6 +24,18 @@ __version__ = "0.5.4+b200"
 B200_FUSED_OPS = True
 
 
-def fused_add_gelu(x, y):
+def fused_add_gelu(x, y, tf32_out=0):
+    """``tf32_out``: 1 = also emit the TF32 operand twin for the convolutions that consume the result, 2 = the result
+    is consumed by convolutions only and is written TF32-rounded (dpcr_agb_b200.msenet decides per block)."""
     assert x._same_map(y), "fused_add_gelu needs both tensors on the same coordinate map"
-    return x._wrap(MinkowskiFunctional.AddGELUFunction.apply(x.F, y.F, x.n_dev))
+    Fn = MinkowskiFunctional
+    if not Fn.twins_on() or x.F.shape[1] <= 4:
+        tf32_out = 0
+    if tf32_out == 1:
+        out, out_r = Fn.AddGELUFunction.apply(x.F, y.F, x.n_dev, 1)
+        Fn.attach_twin(out, out_r)
+    else:
+        out = Fn.AddGELUFunction.apply(x.F, y.F, x.n_dev, tf32_out)
+        if tf32_out == 2:
+            Fn.mark_rounded(out)
+    return x._wrap(out)

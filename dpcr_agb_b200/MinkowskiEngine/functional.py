@@ -51,6 +51,40 @@ def round_tf32(x, n_dev=None):
     return y
 
 
+# ---- TF32 twins -------------------------------------------------------------------------------------------------
+# A producer whose result feeds a convolution can write the TF32-rounded operand itself (C ABI: the `*_tf32` output of
+# b2s_maxpool_fwd / b2s_bn_apply / b2s_bn_bwd_apply / b2s_add_gelu_fwd).  The twin travels as a Python attribute of the
+# plain tensor, stamped with that tensor's version counter; a convolution that finds a valid twin skips its own
+# b2s_round_tf32 pass.  A tensor that IS the rounded result (no plain copy was written) is marked ``_b2s_is_tf32``.
+# Nothing depends on the attribute surviving: without it the convolution rounds as before.
+TWINS = True
+
+
+def twins_on():
+    return TWINS and CONV_IMPL != 1
+
+
+def attach_twin(y, yr):
+    y._b2s_tf32 = (yr, y._version)
+    return y
+
+
+def mark_rounded(y):
+    y._b2s_is_tf32 = y._version
+    return y
+
+
+def rounded_operand(x, n_dev=None):
+    """The TF32 operand form of ``x``: ``x`` itself if it was produced rounded, its twin if one is attached, else a
+    fresh b2s_round_tf32 copy."""
+    if getattr(x, "_b2s_is_tf32", None) == x._version:
+        return x
+    tw = getattr(x, "_b2s_tf32", None)
+    if tw is not None and tw[1] == x._version and tw[0].shape == x.shape:
+        return tw[0]
+    return round_tf32(x, n_dev)
+
+
 def _ws(n_in, n_out, c_in, c_out, k3, device, prerounded=False):
     nbytes = L.query("b2s_conv_workspace_bytes", n_in, n_out, c_in, c_out, k3, 1 if prerounded else 0)
     if nbytes < 0:
@@ -121,7 +155,7 @@ class ConvolutionFunction(torch.autograd.Function):
         # saved for wgrad (c_in <= 4: the stem pads + rounds inside the library)
         pre = _tc(None) and c_in > 4
         if pre:
-            feats = round_tf32(feats, nd_in)
+            feats = rounded_operand(feats, nd_in)
         out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0, n_out_dev=nd_out, prerounded=pre)
         ctx.pre = pre
         ctx.kmap = kmap
@@ -142,7 +176,7 @@ class ConvolutionFunction(torch.autograd.Function):
         gx = gw = gb = None
         gyr, pre_gy = gy, False
         if _tc(None) and c_out > 4:           # grad_out feeds dgrad and wgrad: round it once
-            gyr, pre_gy = round_tf32(gy, nd_out), True
+            gyr, pre_gy = rounded_operand(gy, nd_out), True
         if ctx.needs_input_grad[0]:
             if kmap is None:
                 gx = gather_gemm(gyr, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1, n_out_dev=nd_in,
@@ -171,25 +205,29 @@ class MaxPoolFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, feats, kmap):
+    def forward(ctx, feats, kmap, twin=False):
         feats = feats.contiguous()
         c = feats.shape[1]
         y = torch.empty((kmap.n_out, c), dtype=torch.float32, device=feats.device)
         arg = torch.empty((kmap.n_out, c), dtype=torch.int32, device=feats.device)
-        L.call("b2s_maxpool_fwd", feats, kmap.nbr, kmap.n_out, kmap.n_out_dev, c, kmap.k3, y, arg)
+        yr = torch.empty_like(y) if twin else None
+        L.call("b2s_maxpool_fwd", feats, kmap.nbr, kmap.n_out, kmap.n_out_dev, c, kmap.k3, y, arg, yr)
         ctx.save_for_backward(arg)
         ctx.nd_out = kmap.n_out_dev
         ctx.dims = (kmap.n_in, kmap.n_out, c)
+        if twin:
+            ctx.mark_non_differentiable(yr)
+            return y, yr
         return y
 
     @staticmethod
     @_bwd
-    def backward(ctx, gy):
+    def backward(ctx, gy, *unused):
         (arg,) = ctx.saved_tensors
         n_in, n_out, c = ctx.dims
         gx = torch.empty((n_in, c), dtype=torch.float32, device=gy.device)
         L.call("b2s_maxpool_bwd", gy.contiguous(), arg, n_in, n_out, ctx.nd_out, c, gx)
-        return gx, None
+        return gx, None, None
 
 
 class GlobalPoolFunction(torch.autograd.Function):
@@ -251,7 +289,9 @@ class BatchNormFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act, n_dev=None):
+    def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act, n_dev=None,
+                tf32_only=False):
+        """``tf32_only``: the result is written TF32-rounded and nothing else (its only consumer is a convolution)."""
         x = x.contiguous()
         n, c = x.shape
         dev = x.device
@@ -265,7 +305,10 @@ class BatchNormFunction(torch.autograd.Function):
             mean = running_mean
             invstd = torch.rsqrt(running_var + eps)
         y = torch.empty_like(x)
-        L.call("b2s_bn_apply", x, mean, invstd, weight, bias, n, n_dev, c, act, y)
+        if tf32_only:
+            L.call("b2s_bn_apply", x, mean, invstd, weight, bias, n, n_dev, c, act, None, y)
+        else:
+            L.call("b2s_bn_apply", x, mean, invstd, weight, bias, n, n_dev, c, act, y, None)
         ctx.save_for_backward(x, mean, invstd, weight, bias)
         ctx.training, ctx.act, ctx.nd = training, act, n_dev
         return y
@@ -283,11 +326,16 @@ class BatchNormFunction(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
+            # the input gradient of a batch norm is the output gradient of the convolution in front of it: write
+            # the TF32 operand for its dgrad / wgrad alongside
+            gxr = torch.empty_like(x) if (twins_on() and c > 4) else None
             L.call("b2s_bn_bwd_apply", gy, x, mean, invstd, weight, bias, sums, n, ctx.nd, c, ctx.act,
-                   1 if ctx.training else 0, gx)
+                   1 if ctx.training else 0, gx, gxr)
+            if gxr is not None:
+                attach_twin(gx, gxr)
         gw = sums[c:].clone() if (weight is not None and ctx.needs_input_grad[1]) else None
         gb = sums[:c].clone() if (bias is not None and ctx.needs_input_grad[2]) else None
-        return gx, gw, gb, None, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None, None
 
 
 class GELUFunction(torch.autograd.Function):
@@ -320,20 +368,30 @@ class AddGELUFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, a, b, n_dev=None):
+    def forward(ctx, a, b, n_dev=None, tf32_out=0):
+        """``tf32_out``: 0 plain result; 1 plain result + TF32 twin (returned second); 2 TF32-rounded result only."""
         a, b = a.contiguous(), b.contiguous()
         s, y = torch.empty_like(a), torch.empty_like(a)
         n = a.shape[0]
-        L.call("b2s_add_gelu_fwd", a, b, n, n_dev, a.numel() // max(n, 1), s, y)
+        c = a.numel() // max(n, 1)
         ctx.save_for_backward(s)
         ctx.nd = n_dev
+        if tf32_out == 1:
+            yr = torch.empty_like(a)
+            L.call("b2s_add_gelu_fwd", a, b, n, n_dev, c, s, y, yr)
+            ctx.mark_non_differentiable(yr)
+            return y, yr
+        if tf32_out == 2:
+            L.call("b2s_add_gelu_fwd", a, b, n, n_dev, c, s, None, y)
+        else:
+            L.call("b2s_add_gelu_fwd", a, b, n, n_dev, c, s, y, None)
         return y
 
     @staticmethod
     @_bwd
-    def backward(ctx, gy):
+    def backward(ctx, gy, *unused):
         (s,) = ctx.saved_tensors
         g = torch.empty_like(s)
         n = s.shape[0]
         L.call("b2s_gelu_bwd", gy.contiguous(), s, n, ctx.nd, s.numel() // max(n, 1), g)
-        return g, g, None
+        return g, g, None, None

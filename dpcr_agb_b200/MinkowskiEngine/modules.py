@@ -159,7 +159,11 @@ class MinkowskiMaxPooling(MinkowskiModuleBase):
         cm = input.coordinate_manager
         out_key = _out_key(input, self.stride)
         kmap = cm.kernel_map(input.coordinate_map_key, out_key, self.kernel_size, self.dilation)
-        out = Fn.MaxPoolFunction.apply(input.F, kmap)
+        if Fn.twins_on() and input.F.shape[1] > 4:      # the pooled rows feed a convolution: TF32 operand alongside
+            out, out_r = Fn.MaxPoolFunction.apply(input.F, kmap, True)
+            Fn.attach_twin(out, out_r)
+        else:
+            out = Fn.MaxPoolFunction.apply(input.F, kmap)
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
 
     def __repr__(self):
@@ -263,8 +267,11 @@ class MinkowskiBatchNorm(nn.Module):
         self.bn = nn.BatchNorm1d(num_features, eps=eps, momentum=momentum, affine=affine,
                                  track_running_stats=track_running_stats)
 
-    def forward(self, input: SparseTensor, act: int = 0):
+    def forward(self, input: SparseTensor, act: int = 0, tf32_only: bool = False):
+        """``act=1`` fuses the exact GELU; ``tf32_only`` (product-path extension, used by dpcr_agb_b200.msenet when
+        the only consumer is a convolution) writes the result already rounded to the TF32 operand form."""
         bn = self.bn
+        tf32_only = bool(tf32_only and Fn.twins_on() and input.F.shape[1] > 4)
         use_batch_stats = bn.training or bn.running_mean is None
         momentum = bn.momentum
         if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -276,7 +283,9 @@ class MinkowskiBatchNorm(nn.Module):
                                          bn.running_mean if (update or not use_batch_stats) else None,
                                          bn.running_var if (update or not use_batch_stats) else None,
                                          use_batch_stats, 0.0 if momentum is None else momentum, bn.eps, act,
-                                         input.n_dev)
+                                         input.n_dev, tf32_only)
+        if tf32_only:
+            Fn.mark_rounded(out)
         return input._wrap(out)
 
     def __repr__(self):

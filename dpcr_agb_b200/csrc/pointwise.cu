@@ -65,6 +65,16 @@ __device__ __forceinline__ V<VEC> splat(float s) {
   for (int j = 0; j < VEC; ++j) r.v[j] = s;
   return r;
 }
+// TF32 round-to-nearest copy of a vector: the operand form of the tensor-core convolutions.  Producers whose output
+// feeds a convolution write it alongside (or instead of) the plain result, which takes the separate b2s_round_tf32
+// pass -- one more read and write of the tensor, one more launch -- off the step.
+template <int VEC>
+__device__ __forceinline__ V<VEC> tf32v(const V<VEC>& a) {
+  V<VEC> r;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) r.v[j] = __uint_as_float(tc::rna_tf32(__float_as_uint(a.v[j])));
+  return r;
+}
 // per-channel parameter vector (nullable pointer -> constant)
 template <int VEC>
 __device__ __forceinline__ V<VEC> ldparam(const float* p, int ch, float dflt) {
@@ -107,7 +117,8 @@ template <int VEC>
 __global__ void __launch_bounds__(PW_THREADS) maxpool_fwd_kernel(const float* __restrict__ x,
                                                                  const int* __restrict__ nbr, int64_t n_out,
                                                                  const int* __restrict__ n_dev, int c, int k3,
-                                                                 float* __restrict__ y, int* __restrict__ arg) {
+                                                                 float* __restrict__ y, int* __restrict__ arg,
+                                                                 float* __restrict__ y_tf32) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_dev);
   const RowMap m = row_map<VEC>(c);
@@ -137,6 +148,7 @@ __global__ void __launch_bounds__(PW_THREADS) maxpool_fwd_kernel(const float* __
         arg[o * c + ch + j] = bi[j];
       }
       stv<VEC>(y + o * c + ch, best);
+      if (y_tf32) stv<VEC>(y_tf32 + o * c + ch, tf32v<VEC>(best));
     }
   }
 }
@@ -450,7 +462,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __res
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int64_t n,
                                                               const int* __restrict__ n_dev, int c, int act,
-                                                              float* __restrict__ y) {
+                                                              float* __restrict__ y, float* __restrict__ y_tf32) {
   n = b2s_rows(n, n_dev);
   const RowMap m = row_map<VEC>(c);
   if (!m.active) return;
@@ -466,7 +478,8 @@ __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __res
         t = t * ga.v[j] + be.v[j];
         v.v[j] = act == 1 ? gelu_f(t) : t;
       }
-      stv<VEC>(y + r * c + ch, v);
+      if (y) stv<VEC>(y + r * c + ch, v);
+      if (y_tf32) stv<VEC>(y_tf32 + r * c + ch, tf32v<VEC>(v));
     }
   }
 }
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ sums, int64_t n, const int* __restrict__ n_dev, int c, int act, int training,
-    float* __restrict__ gx) {
+    float* __restrict__ gx, float* __restrict__ gx_tf32) {
   n = b2s_rows(n, n_dev);
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
   const RowMap m = row_map<VEC>(c);
@@ -502,6 +515,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
         g.v[j] = t * ga.v[j] * is.v[j];
       }
       stv<VEC>(gx + r * c + ch, g);
+      if (gx_tf32) stv<VEC>(gx_tf32 + r * c + ch, tf32v<VEC>(g));
     }
   }
 }
@@ -510,7 +524,8 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
 template <int VEC, int OP>  // OP 0: y = gelu(x)   1: gx = gy * gelu'(x)   2: s = a + b, y = gelu(s)   3: y = tf32(x)
 __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                           int64_t n, const int* __restrict__ n_dev, int c,
-                                                          float* __restrict__ o0, float* __restrict__ o1) {
+                                                          float* __restrict__ o0, float* __restrict__ o1,
+                                                          float* __restrict__ o2) {
   n = b2s_rows(n, n_dev);
   const int64_t total = n * c / VEC;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -537,7 +552,8 @@ __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restric
         r1.v[j] = gelu_f(r0.v[j]);
       }
       stv<VEC>(o0 + e * VEC, r0);
-      stv<VEC>(o1 + e * VEC, r1);
+      if (o1) stv<VEC>(o1 + e * VEC, r1);
+      if (o2) stv<VEC>(o2 + e * VEC, tf32v<VEC>(r1));
     }
   }
 }
@@ -570,15 +586,18 @@ void launch_colreduce(const float* x, const float* g, const float* mean, const f
 
 // ================================================================= C ABI ======================
 extern "C" int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_out, const int32_t* n_out_dev,
-                                   int32_t c, int32_t k3, float* y, int32_t* arg, b2s_stream_t stream) {
+                                   int32_t c, int32_t k3, float* y, int32_t* arg, float* y_tf32,
+                                   b2s_stream_t stream) {
   B2S_CHECK_ARG(n_out >= 0 && c > 0 && k3 > 0, "bad sizes");
   if (n_out == 0) return B2S_OK;
   B2S_CHECK_ARG(x && nbr && y && arg, "null pointer");
   cudaStream_t st = as_stream(stream);
-  if (vec_of(c, x, y) == 4)
-    maxpool_fwd_kernel<4><<<rows_grid(n_out, c, 4), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg);
+  if (vec_of(c, x, y, y_tf32) == 4)
+    maxpool_fwd_kernel<4><<<rows_grid(n_out, c, 4), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg,
+                                                                         y_tf32);
   else
-    maxpool_fwd_kernel<1><<<rows_grid(n_out, c, 1), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg);
+    maxpool_fwd_kernel<1><<<rows_grid(n_out, c, 1), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg,
+                                                                         y_tf32);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -712,15 +731,17 @@ extern "C" int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev,
 
 extern "C" int32_t b2s_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma,
                                 const float* beta, int64_t n, const int32_t* n_dev, int32_t c, int32_t act, float* y,
-                                b2s_stream_t stream) {
+                                float* y_tf32, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && (act == 0 || act == 1), "bad arguments");
   if (n == 0) return B2S_OK;
-  B2S_CHECK_ARG(x && mean && invstd && y, "null pointer");
+  B2S_CHECK_ARG(x && mean && invstd && (y || y_tf32), "null pointer");
   cudaStream_t st = as_stream(stream);
-  if (vec_of(c, x, y, mean, invstd) == 4 && vec_of(c, gamma, beta) == 4)
-    bn_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y);
+  if (vec_of(c, x, y, mean, invstd) == 4 && vec_of(c, gamma, beta, y_tf32) == 4)
+    bn_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
+                                                                  y_tf32);
   else
-    bn_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y);
+    bn_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
+                                                                  y_tf32);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -741,28 +762,28 @@ extern "C" int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const floa
 extern "C" int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd,
                                     const float* gamma, const float* beta, const float* sums, int64_t n,
                                     const int32_t* n_dev, int32_t c, int32_t act, int32_t training, float* gx,
-                                    b2s_stream_t stream) {
+                                    float* gx_tf32, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && (act == 0 || act == 1), "bad arguments");
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(gy && x && mean && invstd && gx && (sums || !training), "null pointer");
   cudaStream_t st = as_stream(stream);
-  if (vec_of(c, gy, x, gx, mean) == 4 && vec_of(c, invstd, gamma, beta, sums) == 4)
+  if (vec_of(c, gy, x, gx, mean) == 4 && vec_of(c, invstd, gamma, beta, sums) == 4 && vec_of(c, gx_tf32) == 4)
     bn_bwd_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(gy, x, mean, invstd, gamma, beta, sums, n,
-                                                                      n_dev, c, act, training, gx);
+                                                                      n_dev, c, act, training, gx, gx_tf32);
   else
     bn_bwd_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(gy, x, mean, invstd, gamma, beta, sums, n,
-                                                                      n_dev, c, act, training, gx);
+                                                                      n_dev, c, act, training, gx, gx_tf32);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
 
 template <int OP>
 static int32_t launch_flat(const float* a, const float* b, int64_t n, const int32_t* n_dev, int32_t c, float* o0,
-                           float* o1, cudaStream_t st) {
-  if (vec_of(c, a, b, o0, o1) == 4)
-    flat_kernel<4, OP><<<grid_for(n * c / 4, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1);
+                           float* o1, cudaStream_t st, float* o2 = nullptr) {
+  if (vec_of(c, a, b, o0, o1) == 4 && vec_of(c, o2) == 4)
+    flat_kernel<4, OP><<<grid_for(n * c / 4, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1, o2);
   else
-    flat_kernel<1, OP><<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1);
+    flat_kernel<1, OP><<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1, o2);
   return 0;
 }
 
@@ -792,11 +813,11 @@ extern "C" int32_t b2s_gelu_fwd(const float* x, int64_t n, const int32_t* n_dev,
 }
 
 extern "C" int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t n, const int32_t* n_dev, int32_t c,
-                                    float* sum, float* y, b2s_stream_t stream) {
+                                    float* sum, float* y, float* y_tf32, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0, "n >= 0 and c > 0");
   if (n == 0) return B2S_OK;
-  B2S_CHECK_ARG(a && b && sum && y, "null pointer");
-  launch_flat<2>(a, b, n, n_dev, c, sum, y, as_stream(stream));
+  B2S_CHECK_ARG(a && b && sum && (y || y_tf32), "null pointer");
+  launch_flat<2>(a, b, n, n_dev, c, sum, y, as_stream(stream), y_tf32);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

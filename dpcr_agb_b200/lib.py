@@ -45,7 +45,7 @@ SIGNATURES = {
     "b2s_conv_dgrad_strided_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "b2s_conv_dgrad_strided": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "b2s_colsum": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
-    "b2s_maxpool_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2s_maxpool_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b2s_maxpool_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp]),
     "b2s_batch_counts": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "b2s_segment_sum": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
@@ -53,12 +53,12 @@ SIGNATURES = {
     "b2s_bcast_mul_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp]),
     "b2s_bcast_mul_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2s_bn_stats": (_i32, [_vp, _i64, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "b2s_bn_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "b2s_bn_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2s_bn_bwd_reduce": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "b2s_bn_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "b2s_bn_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b2s_gelu_fwd": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_gelu_bwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp]),
-    "b2s_add_gelu_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp]),
+    "b2s_add_gelu_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "b2s_grad_check": (_i32, [_vp, _i64, _f32, _vp, _vp]),
     "b2s_adabelief_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
 }

@@ -109,6 +109,9 @@ class SEResidualBlock(nn.Module):
         super().__init__()
         self._fuse = fuse and _is_gelu(ME, act)
         self._add_act = [ME.fused_add_gelu] if self._fuse else None
+        # who consumes this block's output (set by MSENet): 0 = something that needs the plain values, 1 = convolutions
+        # and an identity residual (plain result + TF32 operand twin), 2 = convolutions only (written TF32-rounded)
+        self.out_tf32 = 0
         self.expansion = 4 if bottleneck else 1
         if bottleneck:
             spec = [(inplanes, planes, 1, 1), (planes, planes, 3, stride), (planes, planes * 4, 1, 1)]
@@ -129,12 +132,13 @@ class SEResidualBlock(nn.Module):
         for i in range(1, self.num_convs + 1):
             conv, norm = getattr(self, f"conv{i}"), getattr(self, f"norm{i}")
             if i < self.num_convs:
-                out = norm(conv(out), act=1) if self._fuse else self.relu(norm(conv(out)))
+                # fused: batch norm + GELU in one kernel, written as the TF32 operand of the next convolution
+                out = norm(conv(out), act=1, tf32_only=True) if self._fuse else self.relu(norm(conv(out)))
             else:
                 out = norm(conv(out))
         out = self.se(out)
         if self._fuse:
-            return self._add_act[0](self.drop_path(out), self.downsample(x))
+            return self._add_act[0](self.drop_path(out), self.downsample(x), self.out_tf32)
         out = self.drop_path(out) + self.downsample(x)
         return self.relu(out)
 
@@ -180,6 +184,9 @@ class MSENet(nn.Module):
                 self.inplanes = planes * expansion
             stages.append(nn.Sequential(*blocks))
         self.blocks = nn.ModuleList(stages)
+        res_blocks = [b for st in stages[1:] for b in st]
+        for blk, nxt in zip(res_blocks, res_blocks[1:]):
+            blk.out_tf32 = 1 if isinstance(nxt.downsample, nn.Identity) else 2
         self.glob_avg = getattr(ME, POOL_NAMES[global_pool])()
         if dropout > 0:
             self.glob_avg = nn.Sequential(self.glob_avg, ME.MinkowskiDropout(dropout))

@@ -187,7 +187,7 @@ B2S_API int32_t b2s_colsum(const float* x, int64_t n, const int32_t* n_dev, int3
  * (lowest row on ties, -1 if the out row has no neighbour -> y = 0).  bwd: gx[arg] += gy.
  */
 B2S_API int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_out, const int32_t* n_out_dev, int32_t c,
-                                int32_t k3, float* y, int32_t* arg, b2s_stream_t stream);
+                                int32_t k3, float* y, int32_t* arg, float* y_tf32, b2s_stream_t stream);
 B2S_API int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t n_in, int64_t n_out,
                                 const int32_t* n_out_dev, int32_t c, float* gx, b2s_stream_t stream);
 
@@ -223,24 +223,29 @@ B2S_API int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float* y
  *                 these are also grad_beta and grad_gamma.
  * bn_bwd_apply  : training: gx = gamma*invstd*(gy' - sums0/n - xhat*sums1/n); eval: gx = gamma*invstd*gy'.
  * gelu_fwd/bwd  : exact erf GELU on a flat array.
+ * TF32 twins     : maxpool_fwd, bn_apply, bn_bwd_apply and add_gelu_fwd take a nullable `*_tf32` output that receives
+ *                 the result rounded to TF32 (round-to-nearest), i.e. the operand form b2s_round_tf32 would produce
+ *                 for the convolution that consumes it -- the separate rounding pass disappears.  Where the plain
+ *                 result has no other consumer (bn_apply, add_gelu_fwd) `y` may be NULL and only the twin is written.
  */
 B2S_API int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float eps, float momentum,
                              float* running_mean, float* running_var, double* stats_ws, float* mean, float* invstd,
                              b2s_stream_t stream);
 B2S_API int32_t b2s_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                             int64_t n, const int32_t* n_dev, int32_t c, int32_t act, float* y, b2s_stream_t stream);
+                             int64_t n, const int32_t* n_dev, int32_t c, int32_t act, float* y, float* y_tf32,
+                             b2s_stream_t stream);
 B2S_API int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const float* mean, const float* invstd,
                                   const float* gamma, const float* beta, int64_t n, const int32_t* n_dev, int32_t c,
                                   int32_t act, double* stats_ws, float* sums, b2s_stream_t stream);
 B2S_API int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd, const float* gamma,
                                  const float* beta, const float* sums, int64_t n, const int32_t* n_dev, int32_t c,
-                                 int32_t act, int32_t training, float* gx, b2s_stream_t stream);
+                                 int32_t act, int32_t training, float* gx, float* gx_tf32, b2s_stream_t stream);
 /* elementwise over n rows of c floats */
 B2S_API int32_t b2s_gelu_fwd(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y, b2s_stream_t stream);
 /* sum = a + b, y = gelu(sum): the residual join out = act(drop_path(out) + residual); backward = gelu_bwd(gy, sum)
  * for both addends (R:modules/MinkowskiEngine/senet_block.py:93-94, resnet_block.py:72-73). */
 B2S_API int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t n, const int32_t* n_dev, int32_t c, float* sum,
-                                 float* y, b2s_stream_t stream);
+                                 float* y, float* y_tf32, b2s_stream_t stream);
 B2S_API int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* gx,
                              b2s_stream_t stream);
 

@@ -235,3 +235,42 @@ def test_full_size_properties(cuda):
     y2 = conv(ME.SparseTensor(f2, coordinate_map_key=k1, coordinate_manager=cm)).F
     y3 = conv(ME.SparseTensor(2.0 * f1 + f2, coordinate_map_key=k1, coordinate_manager=cm)).F
     util.assert_close(y3, 2.0 * y1 + y2, tol=2e-3, what="linearity")
+
+
+@pytest.mark.parametrize("name", ["SENet14", "SENet50"])
+def test_tf32_twins_match_the_rounding_pass_and_remove_it(cuda, name):
+    """Producers that write the TF32 operand of the next convolution themselves (C ABI ``*_tf32`` outputs) must give
+    the results of the separate b2s_round_tf32 pass -- same rounding, same operands; what is left is the summation
+    order of the split-K / wgrad atomics, 1e-7-level noise, hence eval-mode batch norm and a 1e-5 / 1e-4 bound --
+    while the number of rounding launches drops to the few convolutions whose input has no fused producer."""
+    from dpcr_agb_b200 import lib
+    from dpcr_agb_b200.MinkowskiEngine import functional as Fn
+    batch = util.make_points(2, 2500, cfg=2)
+    c, f, _, _, _ = util.oracle_quantize(batch, 0.04)
+    torch.manual_seed(3)
+    model = msenet.MSENet(ME, name, drop_path=0.0).to(cuda).eval()
+    target = torch.from_numpy(batch["target"]).to(cuda)
+    center, scale = torch.tensor([107.0, 200.0], device=cuda), torch.tensor([103.0, 194.0], device=cuda)
+    runs = {}
+    old = Fn.TWINS
+    try:
+        for twins in (False, True):
+            Fn.TWINS = twins
+            model.zero_grad(set_to_none=True)
+            for b in model.buffers():          # same BN running statistics at the start of both runs
+                if b.dtype.is_floating_point:
+                    b.fill_(0.5)
+            lib.profile_start(["b2s_round_tf32"])
+            y = model(ME.SparseTensor(features=torch.from_numpy(f), coordinates=torch.from_numpy(c), device=cuda))
+            loss = train.reg_loss(y, target, center, scale)
+            loss.backward()
+            rounds = sum(n for n, _ in lib.profile_stop().values())
+            runs[twins] = (y.detach().clone(), [p.grad.detach().clone() for p in model.parameters()], rounds)
+    finally:
+        Fn.TWINS = old
+    util.assert_close(runs[True][0], runs[False][0], tol=1e-5, what="output with / without twins")
+    gmax = max(g.abs().max().item() for g in runs[False][1])
+    for g1, g0 in zip(runs[True][1], runs[False][1]):
+        assert (g1 - g0).abs().max().item() <= 1e-4 * max(g0.abs().max().item(), 1e-3 * gmax)
+    assert runs[True][2] < runs[False][2] // 2, f"rounding launches {runs[False][2]} -> {runs[True][2]}"
+    _report(f"{name}-tf32-twins", rounding_launches_without=runs[False][2], rounding_launches_with=runs[True][2])
