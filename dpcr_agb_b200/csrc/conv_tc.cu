@@ -215,9 +215,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     };
     const int g0 = SMALL ? it0 : it0 / kc;                        // it0 is a multiple of kc
-    load_group(g0, idx);
-    load_group(g0 + 1, idx1);
-    load_group(g0 + 2, idx2);
 
     auto publish = [&](int s_done) {  // all of this thread's LDGSTS for that stage have landed
       fence_proxy_async();
@@ -227,7 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     int s = 0, cc = 0, g = g0;
     uint32_t ph = 0;
     int s_pub = 0;                    // stage to hand over next (LAG iterations behind)
-    for (int it = 0; it < T; ++it) {
+    auto issue_stage = [&](int it, const int (&cur)[8]) {   // wait for the slot, start the B copy and the A gathers
       mbar_wait(empty_bar(s), ph ^ 1u);
       // index of this iteration's weight tile in the image: (offset, channel chunk), offset-major
       const int git = (PERM || !SMALL) ? kof(g) * kc + cc : it0 + it;
@@ -240,22 +237,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         const int row = SMALL ? tid : rsub + 16 * p;
-        const int i = idx[p];
+        const int i = cur[p];
         const float* src = SMALL ? x + (int64_t)(i >= 0 ? i : 0) * 4
                                  : x + (int64_t)(i >= 0 ? i : 0) * c_in + cc * BK + chunk * 4;
         cp_async16_sel(a_stage + sw128_offset(row, SMALL ? p : chunk), src, i >= 0 ? 16u : 0u, l1);
       }
       cp_async_commit();
-      if (++cc == kc) {             // next index group: rotate the prefetch ring, fetch group g + 3
-        cc = 0;
-        ++g;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          idx[p] = idx1[p];
-          idx1[p] = idx2[p];
-        }
-        load_group(g + 2, idx2);
-      }
+    };
+    auto finish_stage = [&](int it) {                        // advance the ring, hand over stage it - LAG
       if (++s == STAGES) {
         s = 0;
         ph ^= 1u;
@@ -264,6 +253,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         cp_async_wait<LAG>();
         publish(s_pub);
         if (++s_pub == STAGES) s_pub = 0;
+      }
+    };
+
+    if (SMALL) {
+      // one index group per stage: three register sets used round-robin (loop unrolled by three), so that a set is
+      // loaded two stages before its gathers WITHOUT being copied in between -- a register move out of a set whose
+      // loads are in flight waits for them, which held the k7 stem to one stage per memory latency
+      int r0[8], r1[8], r2[8];
+      load_group(g0, r0);
+      load_group(g0 + 1, r1);
+      for (int it = 0; it < T; it += 3) {
+        issue_stage(it, r0);
+        load_group(g0 + it + 2, r2);
+        finish_stage(it);
+        if (it + 1 < T) {
+          issue_stage(it + 1, r1);
+          load_group(g0 + it + 3, r0);
+          finish_stage(it + 1);
+        }
+        if (it + 2 < T) {
+          issue_stage(it + 2, r2);
+          load_group(g0 + it + 4, r1);
+          finish_stage(it + 2);
+        }
+      }
+    } else {
+      // same move-free scheme per index group (= kernel offset, kc stages each): the set of group g is refilled with
+      // group g + 3 as soon as the group's last stage has been issued
+      load_group(g0, idx);
+      load_group(g0 + 1, idx1);
+      load_group(g0 + 2, idx2);
+      int it = 0;
+      auto run_group = [&](const int (&cur)[8]) {
+        for (cc = 0; cc < kc && it < T; ++cc, ++it) {
+          issue_stage(it, cur);
+          finish_stage(it);
+        }
+        ++g;
+      };
+      while (it < T) {
+        run_group(idx);
+        load_group(g + 2, idx);
+        if (it < T) {
+          run_group(idx1);
+          load_group(g + 2, idx1);
+        }
+        if (it < T) {
+          run_group(idx2);
+          load_group(g + 2, idx2);
+        }
       }
     }
     // drain the last min(LAG, T) stages

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
     int idx[MAXR];
     const bool l1 = p.l1 != 0;
 
-    int idx_n[MAXR];                     // neighbour rows of the stage after next (two-deep index prefetch)
+    int idx_n[MAXR], idx_nn[MAXR];       // neighbour rows of the next two stages (two-deep index prefetch)
     auto load_idx = [&](int it, int (&dst)[MAXR]) {   // neighbour rows of stage `it` for this thread's A items
       const int64_t r0 = r_begin + (int64_t)it * G_R;
       const bool live = r0 + r < r_end;
@@ -185,9 +185,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
       mbar_arrive(full_bar(it_done % p.stages));
     };
 
-    load_idx(0, idx);
-    load_idx(1, idx_n);                  // beyond the range: all -1, no loads
-    for (int it = 0; it < T; ++it) {
+    auto stage = [&](int it, const int (&cur)[MAXR], int (&fill)[MAXR]) {
       const int s = it % p.stages;
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       mbar_wait(empty_bar(s), ph ^ 1u);
@@ -196,7 +194,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
 #pragma unroll
       for (int j = 0; j < MAXR; ++j) {
         if (j < a_rounds) {
-          const int i = idx[j];
+          const int i = cur[j];
           const float* src = x_l + (int64_t)(i >= 0 ? i : 0) * p.c_in + ((2 * j + h) & cb_mask) * 32;
           cp_async16_sel(a_dst + (uint32_t)j * (2 * G_BLOCK), src, i >= 0 ? 16u : 0u, l1);
         }
@@ -209,15 +207,20 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
           cp_async16(b_dst + (uint32_t)j * (2 * G_BLOCK), src + j * 64, live ? 16u : 0u);
       }
       cp_async_commit();
-      // rotate the index ring; the loads for stage it + 2 overlap with two stages of copies (the neighbour table is
-      // streamed from HBM: one stage of run-ahead left the gather waiting on it every other stage)
-#pragma unroll
-      for (int j = 0; j < MAXR; ++j) idx[j] = idx_n[j];
-      load_idx(it + 2, idx_n);
+      load_idx(it + 2, fill);             // overlaps with two stages of copies (the table streams from HBM)
       if (it >= p.lag) {
         cp_async_wait_dyn(p.lag);
         publish(it - p.lag);
       }
+    };
+    // three index sets used round-robin (loop unrolled by three): no register moves out of a set whose loads are in
+    // flight -- such a move waits for the loads and cuts the run-ahead to one stage
+    load_idx(0, idx);
+    load_idx(1, idx_n);
+    for (int it = 0; it < T; it += 3) {
+      stage(it, idx, idx_nn);
+      if (it + 1 < T) stage(it + 1, idx_n, idx);
+      if (it + 2 < T) stage(it + 2, idx_nn, idx_n);
     }
     for (int r = T < p.lag ? T : p.lag; r > 0; --r) {   // drain: stage T - r is complete once <= r - 1 groups are pending
       cp_async_wait_dyn(r - 1);
@@ -363,16 +366,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     constexpr int NK = 16;
     const int kw = k0 + warp * NK;
     // neighbour rows are fetched two stages ahead of their gather (the table streams from HBM)
-    int ia[NK], ia_n[NK];
     auto load_nbr = [&](int it, int (&da)[NK]) {
       const int64_t o = r_begin + (int64_t)it * WG_ROWS + lane;
       const bool live = o < r_end;
 #pragma unroll
       for (int p = 0; p < NK; ++p) da[p] = (live && kw + p < k3) ? __ldg(&nbr[(int64_t)(kw + p) * pitch + o]) : -1;
     };
-    load_nbr(0, ia);
-    load_nbr(1, ia_n);
-    for (int it = 0; it < T; ++it) {
+    auto stage = [&](int it, const int (&cur)[NK], int (&fill)[NK]) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(empty_bar(s), ph ^ 1u);
@@ -389,17 +389,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       }
 #pragma unroll
       for (int p = 0; p < NK; ++p) {
-        const int v = ia[p];
+        const int v = cur[p];
         cp_async16_sel(b_stage + mn_offset(lane, warp * NK + p), x4 + (v >= 0 ? v : 0), v >= 0 ? 16u : 0u, l1);
       }
       cp_async_commit();
-#pragma unroll
-      for (int p = 0; p < NK; ++p) ia[p] = ia_n[p];
-      load_nbr(it + 2, ia_n);
+      load_nbr(it + 2, fill);
       if (it >= WG_LAG) {
         cp_async_wait<WG_LAG>();
         publish(it - WG_LAG);
       }
+    };
+    // three index sets used round-robin (loop unrolled by three): a set is loaded two stages before its gathers and
+    // never copied in between -- a register move out of a set whose loads are in flight waits for them, which held
+    // this kernel to one stage per memory latency
+    int ia[NK], ia_n[NK], ia_nn[NK];
+    load_nbr(0, ia);
+    load_nbr(1, ia_n);
+    for (int it = 0; it < T; it += 3) {
+      stage(it, ia, ia_nn);
+      if (it + 1 < T) stage(it + 1, ia_n, ia);
+      if (it + 2 < T) stage(it + 2, ia_nn, ia_n);
     }
     if (T >= 2) {
       cp_async_wait<1>();
