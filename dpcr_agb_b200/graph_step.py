@@ -90,7 +90,8 @@ class GraphStep:
                             capacities=self.capacities, num_batches=self.B, dense_index=vox["index"])
         pred = tr.model(x)
         loss = T.reg_loss(pred, self.inp["target"], tr.center, tr.scale)
-        loss.backward()
+        with tr.direct_grads():
+            loss.backward()
         self.loss.copy_(loss.detach())
         cm = x.coordinate_manager
         self.status_meta = [(what, cap) for what, cap, _ in cm.checks]

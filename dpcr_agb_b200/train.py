@@ -162,6 +162,13 @@ class Trainer:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.num_batches = 0
 
+    def direct_grads(self):
+        fn = getattr(self.ME, "MinkowskiFunctional", None)
+        if fn is not None and hasattr(fn, "direct_param_grads"):
+            return fn.direct_param_grads()
+        import contextlib
+        return contextlib.nullcontext()
+
     def broadcast_parameters(self):
         if self.world > 1:
             dist.broadcast(self.opt.flat_param, src=0)
@@ -176,7 +183,8 @@ class Trainer:
         x = self.ME.SparseTensor(features=feats, coordinates=coords, **kw)
         pred = self.model(x)
         loss = reg_loss(pred, target, self.center, self.scale)
-        loss.backward()
+        with self.direct_grads():            # .grad = views of the flat buffer zeroed above: kernels write in place
+            loss.backward()
         allreduce_mean_(self.opt.flat_grad, self.world)   # == DDP's all-reduce with a single bucket
         self.num_batches += 1
         self.opt.lr = self.sched.lr_at(self.num_batches / self.batches_per_epoch)
