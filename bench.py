@@ -328,9 +328,24 @@ def run_b200(args):
     gg_flops = work.get("fwd", {"flops": 0})["flops"] + work.get("dgrad", {"flops": 0})["flops"]
     gg_launch = per_kind["fwd"]["launches_per_step"] + per_kind["dgrad"]["launches_per_step"]
     achieved = (gg_flops / 1e12) / (gg_ms * 1e-3) if gg_ms > 0 else 0.0
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, weighted by the
+    # launches per step of the captured instances); null when the capture file is absent
+    traffic, traffic_note = None, None
+    try:
+        tr_ = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        inst = tr_["instances"]
+        n_l = sum(i["launches_per_step"] for i in inst)
+        traffic = sum(i["dram_bytes"] * i["launches_per_step"] for i in inst) / n_l
+        traffic_note = (f"bytes per launch, mean over {n_l} of the {int(gg_launch)} launches per step "
+                        f"({'; '.join(i['instance'] for i in inst)}); {tr_['source']}")
+    except Exception:
+        pass
     roofline = {"kernel": "gather_gemm_tc_kernel (b2s_conv_gather_gemm: conv forward + dgrad, tcgen05 kind::tf32)",
                 "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak if tf32_peak else None, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / tf32_peak if tf32_peak else None, "traffic": traffic, "traffic_note": traffic_note,
+                "algorithmic_bytes_per_launch": (work.get("fwd", {"bytes": 0})["bytes"]
+                                                 + work.get("dgrad", {"bytes": 0})["bytes"]) / gg_launch if gg_launch else None,
+                "peak_source": peak_src,
                 "avg_launch_ms": gg_ms / gg_launch if gg_launch else None, "launches_per_step": gg_launch,
                 "algorithmic_gflop_per_launch": gg_flops / 1e9 / gg_launch if gg_launch else None,
                 "share_of_step": gg_ms / ms_step if ms_step else None,
