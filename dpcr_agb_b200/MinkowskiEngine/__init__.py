@@ -39,3 +39,24 @@ def fused_add_gelu(x, y, tf32_out=0):
         if tf32_out == 2:
             Fn.mark_rounded(out)
     return x._wrap(out)
+
+
+def fused_se_tail(u, res, fc1, fc2, keep=None, tf32_out=0):
+    """``gelu(u * (sigmoid(fc2(gelu(fc1(mean_plot(u))))) * keep[plot]) + res)`` -- squeeze-excite gate, drop-path
+    scale, residual join and activation of an SE block as one op (``MinkowskiFunctional.SETailFunction``).
+    ``fc1`` / ``fc2``: the block's ``MinkowskiLinear`` modules; ``keep``: [B,1] drop-path scale or None."""
+    assert u._same_map(res), "fused_se_tail needs both tensors on the same coordinate map"
+    Fn = MinkowskiFunctional
+    cm, key = u.coordinate_manager, u.coordinate_map_key
+    if not Fn.twins_on() or u.F.shape[1] <= 4:
+        tf32_out = 0
+    args = (u.F, res.F, fc1.linear.weight, fc1.linear.bias, fc2.linear.weight, fc2.linear.bias, keep, cm.coords(key),
+            cm.num_batches, cm.inv_counts(key), u.n_dev, tf32_out)
+    if tf32_out == 1:
+        out, out_r = Fn.SETailFunction.apply(*args)
+        Fn.attach_twin(out, out_r)
+    else:
+        out = Fn.SETailFunction.apply(*args)
+        if tf32_out == 2:
+            Fn.mark_rounded(out)
+    return u._wrap(out)

@@ -437,3 +437,66 @@ class AddGELUFunction(torch.autograd.Function):
         n = s.shape[0]
         L.call("b2s_gelu_bwd", gy.contiguous(), s, n, ctx.nd, s.numel() // max(n, 1), g)
         return g, g, None, None
+
+
+class SETailFunction(torch.autograd.Function):
+    """The tail of an SE residual block as one op (senet_block.py:33-50 SELayer, :83-94 drop path + residual + act):
+    ``y = gelu(u * (sigmoid(fc2(gelu(fc1(mean_plot(u))))) * keep[plot]) + res)``.  Forward = per-plot mean, one MLP
+    launch for all plots, one gated add+GELU pass over the rows; backward = one pass over the rows (residual
+    gradient, gated gradient, per-plot product sums), one MLP launch pair, one broadcast add of the pooled branch."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, u, res, w1, b1, w2, b2, keep, coords, num_batches, inv_counts, n_dev=None, tf32_out=0):
+        u, res = u.contiguous(), res.contiguous()
+        n, c = u.shape
+        h = w1.shape[0]
+        dev = u.device
+        w1c, w2c = w1.contiguous(), w2.contiguous()
+        keep = keep.contiguous().view(-1) if keep is not None else None
+        pooled = torch.empty((num_batches, c), dtype=torch.float32, device=dev)
+        L.call("b2s_segment_sum", u, coords, 4, n, n_dev, c, num_batches, inv_counts, pooled)
+        h_pre = torch.empty((num_batches, h), dtype=torch.float32, device=dev)
+        gate, gate_eff = torch.empty_like(pooled), torch.empty_like(pooled)
+        L.call("b2s_se_gate_fwd", pooled, w1c, b1, w2c, b2, keep, num_batches, c, h, h_pre, gate, gate_eff)
+        s, y = torch.empty_like(u), torch.empty_like(u)
+        yr = torch.empty_like(u) if tf32_out == 1 else None
+        if tf32_out == 2:
+            L.call("b2s_gated_add_gelu_fwd", u, gate_eff, res, coords, 4, n, n_dev, c, s, None, y)
+        else:
+            L.call("b2s_gated_add_gelu_fwd", u, gate_eff, res, coords, 4, n, n_dev, c, s, y, yr)
+        ctx.save_for_backward(u, s, pooled, h_pre, gate, gate_eff, w1c, w2c, keep, inv_counts)
+        ctx.coords, ctx.nb, ctx.nd = coords, num_batches, n_dev
+        ctx.params = (w1, b1, w2, b2)
+        if yr is not None:
+            ctx.mark_non_differentiable(yr)
+            return y, yr
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy, *unused):
+        u, s, pooled, h_pre, gate, gate_eff, w1c, w2c, keep, inv_counts = ctx.saved_tensors
+        n, c = u.shape
+        h, nb, dev = w1c.shape[0], ctx.nb, u.device
+        g_res, g_u = torch.empty_like(u), torch.empty_like(u)
+        g_ge = torch.empty((nb, c), dtype=torch.float32, device=dev)
+        L.call("b2s_gated_add_gelu_bwd", gy.contiguous(), s, u, gate_eff, ctx.coords, 4, n, ctx.nd, c, nb, g_res, g_u,
+               g_ge)
+        w1, b1, w2, b2 = ctx.params
+        outs = []
+        for prm in (w1, b1, w2, b2):
+            if prm is None:
+                outs.append(None)
+            elif _direct(prm):
+                outs.append(prm.grad)
+            else:
+                outs.append(torch.empty_like(prm, memory_format=torch.contiguous_format))
+        gz2 = torch.empty((nb, c), dtype=torch.float32, device=dev)
+        ghp = torch.empty((nb, h), dtype=torch.float32, device=dev)
+        g_pooled = torch.empty((nb, c), dtype=torch.float32, device=dev)
+        L.call("b2s_se_gate_bwd", g_ge, keep, gate, h_pre, pooled, w1c, w2c, inv_counts, nb, c, h, gz2, ghp, g_pooled,
+               outs[0], outs[1], outs[2], outs[3])
+        L.call("b2s_bcast_add_", g_u, g_pooled, ctx.coords, 4, n, ctx.nd, c)
+        grads = [None if (prm is None or _direct(prm)) else o for prm, o in zip((w1, b1, w2, b2), outs)]
+        return (g_u, g_res, grads[0], grads[1], grads[2], grads[3], None, None, None, None, None, None)

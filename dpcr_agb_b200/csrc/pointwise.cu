@@ -558,6 +558,226 @@ __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------- fused SE block tail ---------
+// The tail of every SE residual block (R:senet_block.py:33-50,83-94):
+//     y = act( drop_path( u * sigmoid(fc2(act(fc1(mean_plot(u))))) ) + residual )
+// as three kernels forward (per-plot mean = segment_sum; the excitation MLP of ALL plots in one launch; gate x
+// drop-path scale x residual add x GELU in one pass over the rows) and three backward -- instead of ~14 launches
+// forward and ~20 backward with 21 passes over the [N, C] tensors.  Same arithmetic in the same order per element
+// (u * (gate * keep) + res); the MLP sums are fp32 FMAs over <= 2048 terms.
+
+// one CTA per plot: h_pre = W1 p + b1, h = gelu(h_pre), gate = sigmoid(W2 h + b2), gate_eff = gate * keep[b]
+__global__ void __launch_bounds__(256) se_gate_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, const float* __restrict__ w2,
+                                                          const float* __restrict__ b2, const float* __restrict__ keep,
+                                                          int c, int h, float* __restrict__ h_pre,
+                                                          float* __restrict__ gate, float* __restrict__ gate_eff) {
+  extern __shared__ float se_sm[];
+  float* p = se_sm;          // [c]
+  float* hh = se_sm + c;     // [h]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < c; i += blockDim.x) p[i] = pooled[(int64_t)b * c + i];
+  __syncthreads();
+  for (int j = warp; j < h; j += (int)(blockDim.x >> 5)) {
+    float acc = 0.f;
+    for (int i = lane; i < c; i += 32) acc = fmaf(__ldg(&w1[(int64_t)j * c + i]), p[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float hp = acc + (b1 ? b1[j] : 0.f);
+      h_pre[(int64_t)b * h + j] = hp;
+      hh[j] = gelu_f(hp);
+    }
+  }
+  __syncthreads();
+  const float kp = keep ? keep[b] : 1.f;
+  for (int i = tid; i < c; i += blockDim.x) {
+    float z = b2 ? b2[i] : 0.f;
+    for (int j = 0; j < h; ++j) z = fmaf(__ldg(&w2[(int64_t)i * h + j]), hh[j], z);
+    const float g = 1.f / (1.f + expf(-z));
+    gate[(int64_t)b * c + i] = g;
+    gate_eff[(int64_t)b * c + i] = g * kp;
+  }
+}
+
+// one CTA per plot: back through keep, sigmoid, fc2, GELU, fc1 and the per-plot mean
+__global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restrict__ g_gate_eff,
+                                                          const float* __restrict__ keep, const float* __restrict__ gate,
+                                                          const float* __restrict__ h_pre, const float* __restrict__ w1,
+                                                          const float* __restrict__ w2, const float* __restrict__ inv_count,
+                                                          int c, int h, float* __restrict__ gz2,
+                                                          float* __restrict__ gh_pre, float* __restrict__ g_pooled) {
+  extern __shared__ float se_sm[];
+  float* z = se_sm;          // [c]  gradient at the sigmoid input
+  float* hp = se_sm + c;     // [h]  gradient at the GELU input
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float kp = keep ? keep[b] : 1.f;
+  for (int i = tid; i < c; i += blockDim.x) {
+    const float g = gate[(int64_t)b * c + i];
+    const float v = g_gate_eff[(int64_t)b * c + i] * kp * g * (1.f - g);
+    z[i] = v;
+    gz2[(int64_t)b * c + i] = v;
+  }
+  __syncthreads();
+  for (int j = warp; j < h; j += (int)(blockDim.x >> 5)) {
+    float acc = 0.f;
+    for (int i = lane; i < c; i += 32) acc = fmaf(z[i], __ldg(&w2[(int64_t)i * h + j]), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float v = acc * gelu_grad_f(h_pre[(int64_t)b * h + j]);
+      hp[j] = v;
+      gh_pre[(int64_t)b * h + j] = v;
+    }
+  }
+  __syncthreads();
+  const float ic = inv_count ? inv_count[b] : 1.f;
+  for (int i = tid; i < c; i += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < h; ++j) acc = fmaf(hp[j], __ldg(&w1[(int64_t)j * c + i]), acc);
+    g_pooled[(int64_t)b * c + i] = acc * ic;
+  }
+}
+
+// parameter gradients of the two linears: sums over the plots
+__global__ void __launch_bounds__(256) se_param_grad_kernel(const float* __restrict__ gz2,
+                                                            const float* __restrict__ gh_pre,
+                                                            const float* __restrict__ h_pre,
+                                                            const float* __restrict__ pooled, int nb, int c, int h,
+                                                            float* __restrict__ gw1, float* __restrict__ gb1,
+                                                            float* __restrict__ gw2, float* __restrict__ gb2) {
+  const int hc = h * c;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 2 * hc + h + c; e += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    if (e < hc) {                         // gw1[j, i] = sum_b gh_pre[b, j] * pooled[b, i]
+      const int j = e / c, i = e % c;
+      for (int b = 0; b < nb; ++b) acc = fmaf(gh_pre[b * h + j], pooled[(int64_t)b * c + i], acc);
+      gw1[e] = acc;
+    } else if (e < 2 * hc) {              // gw2[i, j] = sum_b gz2[b, i] * gelu(h_pre[b, j])
+      const int f = e - hc, i = f / h, j = f % h;
+      for (int b = 0; b < nb; ++b) acc = fmaf(gz2[(int64_t)b * c + i], gelu_f(h_pre[b * h + j]), acc);
+      gw2[f] = acc;
+    } else if (e < 2 * hc + h) {
+      const int j = e - 2 * hc;
+      for (int b = 0; b < nb; ++b) acc += gh_pre[b * h + j];
+      if (gb1) gb1[j] = acc;
+    } else {
+      const int i = e - 2 * hc - h;
+      for (int b = 0; b < nb; ++b) acc += gz2[(int64_t)b * c + i];
+      if (gb2) gb2[i] = acc;
+    }
+  }
+}
+
+// s = u * gate_eff[plot] + res ; y = gelu(s)   (y and / or its TF32 twin)
+template <int VEC>
+__global__ void __launch_bounds__(PW_THREADS) gated_add_gelu_fwd_kernel(
+    const float* __restrict__ u, const float* __restrict__ gate_eff, const float* __restrict__ res,
+    const int* __restrict__ rb, int stride, int64_t n, const int* __restrict__ n_dev, int c, float* __restrict__ s,
+    float* __restrict__ y, float* __restrict__ y_tf32) {
+  n = b2s_rows(n, n_dev);
+  const RowMap m = row_map<VEC>(c);
+  if (!m.active) return;
+  for (int v0 = m.tc; v0 < m.cv; v0 += m.tpr) {
+    const int ch = v0 * VEC;
+    B2S_ROW_LOOP(m, n, r) {
+      const int b = __ldg(&rb[r * stride]);
+      const V<VEC> g = ldgv<VEC>(gate_eff + (int64_t)b * c + ch);
+      const V<VEC> uv = ldv<VEC>(u + r * c + ch), rv = ldv<VEC>(res + r * c + ch);
+      V<VEC> sv, yv;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        sv.v[j] = uv.v[j] * g.v[j] + rv.v[j];
+        yv.v[j] = gelu_f(sv.v[j]);
+      }
+      stv<VEC>(s + r * c + ch, sv);
+      if (y) stv<VEC>(y + r * c + ch, yv);
+      if (y_tf32) stv<VEC>(y_tf32 + r * c + ch, tf32v<VEC>(yv));
+    }
+  }
+}
+
+// g_s = gy * gelu'(s) (gradient of the residual), g_u = g_s * gate_eff[plot], g_gate[plot] += g_s * u.
+// CTA = 64-channel slab (blockIdx.y) x CONTIGUOUS row chunk (blockIdx.x), so that a thread's rows (chunk rows
+// tr, tr + 32, ...) stay within one plot almost always: the per-plot product sum lives in registers and is flushed
+// with one fp32 atomic per channel when the plot changes and at the end.
+__global__ void __launch_bounds__(CR_THREADS, 1) gated_add_gelu_bwd_kernel(
+    const float* __restrict__ gy, const float* __restrict__ s, const float* __restrict__ u,
+    const float* __restrict__ gate_eff, const int* __restrict__ rb, int stride, int64_t n,
+    const int* __restrict__ n_dev, int c, int nb, int64_t rows_per_cta, float* __restrict__ g_s,
+    float* __restrict__ g_u, float* __restrict__ g_gate) {
+  n = b2s_rows(n, n_dev);
+  const int tc = threadIdx.x % CR_TPR, tr = threadIdx.x / CR_TPR;
+  const int ch = blockIdx.y * CR_SLAB + tc * 4;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(r0 + rows_per_cta, n);
+  int cur = -1;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  V<4> g = splat<4>(0.f);
+  auto flush = [&]() {
+    if (cur >= 0 && cur < nb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&g_gate[(int64_t)cur * c + ch + j], acc[j]);
+    }
+  };
+  constexpr int U = 2;
+  for (int64_t r = r0 + tr; r < r1; r += U * CR_RPB) {
+    V<4> gv[U], sv[U], uv[U];
+    int bb[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int64_t rr = r + q * CR_RPB;
+      const bool ok = rr < r1;
+      bb[q] = ok ? __ldg(&rb[rr * stride]) : -1;
+      gv[q] = ok ? ldv<4>(gy + rr * c + ch) : splat<4>(0.f);
+      sv[q] = ok ? ldv<4>(s + rr * c + ch) : splat<4>(0.f);
+      uv[q] = ok ? ldv<4>(u + rr * c + ch) : splat<4>(0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int64_t rr = r + q * CR_RPB;
+      if (rr >= r1) break;
+      if (bb[q] != cur) {
+        flush();
+        cur = bb[q];
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        g = (cur >= 0 && cur < nb) ? ldgv<4>(gate_eff + (int64_t)cur * c + ch) : splat<4>(0.f);
+      }
+      V<4> gs, gu;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        gs.v[j] = gv[q].v[j] * gelu_grad_f(sv[q].v[j]);
+        gu.v[j] = gs.v[j] * g.v[j];
+        acc[j] = fmaf(gs.v[j], uv[q].v[j], acc[j]);
+      }
+      stv<4>(g_s + rr * c + ch, gs);
+      stv<4>(g_u + rr * c + ch, gu);
+    }
+  }
+  flush();
+}
+
+// x[r, :] += y[plot(r), :]
+template <int VEC>
+__global__ void __launch_bounds__(PW_THREADS) bcast_add_kernel(float* __restrict__ x, const float* __restrict__ y,
+                                                               const int* __restrict__ rb, int stride, int64_t n,
+                                                               const int* __restrict__ n_dev, int c) {
+  n = b2s_rows(n, n_dev);
+  const RowMap m = row_map<VEC>(c);
+  if (!m.active) return;
+  for (int v0 = m.tc; v0 < m.cv; v0 += m.tpr) {
+    const int ch = v0 * VEC;
+    B2S_ROW_LOOP(m, n, r) {
+      const int b = __ldg(&rb[r * stride]);
+      const V<VEC> a = ldgv<VEC>(y + (int64_t)b * c + ch);
+      V<VEC> v = ldv<VEC>(x + r * c + ch);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v.v[j] += a.v[j];
+      stv<VEC>(x + r * c + ch, v);
+    }
+  }
+}
+
 dim3 colgrid(int64_t n, int c) { return dim3((unsigned)ceil_div64(n, ROWS_PER_CTA), (unsigned)((c + 31) / 32)); }
 
 // column reduction launch: the float4 kernel whenever the rows are 16-byte aligned vectors, else the scalar one
@@ -828,6 +1048,93 @@ extern "C" int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t n, cons
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(gy && x && gx, "null pointer");
   launch_flat<1>(gy, x, n, n_dev, c, gx, nullptr, as_stream(stream));
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+// ---------------------------------------------------------------- fused SE block tail (C ABI) ---
+extern "C" int32_t b2s_se_gate_fwd(const float* pooled, const float* w1, const float* b1, const float* w2,
+                                   const float* b2, const float* keep, int32_t num_batches, int32_t c, int32_t h,
+                                   float* h_pre, float* gate, float* gate_eff, b2s_stream_t stream) {
+  B2S_CHECK_ARG(num_batches > 0 && c > 0 && h > 0 && (c + h) * sizeof(float) <= 48 * 1024, "bad sizes");
+  B2S_CHECK_ARG(pooled && w1 && w2 && h_pre && gate && gate_eff, "null pointer");
+  se_gate_fwd_kernel<<<num_batches, 256, (c + h) * sizeof(float), as_stream(stream)>>>(pooled, w1, b1, w2, b2, keep, c, h,
+                                                                                       h_pre, gate, gate_eff);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_se_gate_bwd(const float* g_gate_eff, const float* keep, const float* gate, const float* h_pre,
+                                   const float* pooled, const float* w1, const float* w2, const float* inv_count,
+                                   int32_t num_batches, int32_t c, int32_t h, float* gz2, float* gh_pre,
+                                   float* g_pooled, float* gw1, float* gb1, float* gw2, float* gb2,
+                                   b2s_stream_t stream) {
+  B2S_CHECK_ARG(num_batches > 0 && c > 0 && h > 0 && (c + h) * sizeof(float) <= 48 * 1024, "bad sizes");
+  B2S_CHECK_ARG(g_gate_eff && gate && h_pre && pooled && w1 && w2 && gz2 && gh_pre && g_pooled && gw1 && gw2,
+                "null pointer");
+  cudaStream_t st = as_stream(stream);
+  se_gate_bwd_kernel<<<num_batches, 256, (c + h) * sizeof(float), st>>>(g_gate_eff, keep, gate, h_pre, w1, w2, inv_count,
+                                                                        c, h, gz2, gh_pre, g_pooled);
+  se_param_grad_kernel<<<grid_for(2 * (int64_t)h * c + h + c, 256), 256, 0, st>>>(gz2, gh_pre, h_pre, pooled,
+                                                                                 num_batches, c, h, gw1, gb1, gw2, gb2);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_gated_add_gelu_fwd(const float* u, const float* gate_eff, const float* res,
+                                          const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
+                                          const int32_t* n_dev, int32_t c, float* sum, float* y, float* y_tf32,
+                                          b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0 && row_batch_stride > 0, "bad arguments");
+  if (n == 0) return B2S_OK;
+  B2S_CHECK_ARG(u && gate_eff && res && row_batch && sum && (y || y_tf32), "null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (vec_of(c, u, res, sum, gate_eff) == 4 && vec_of(c, y, y_tf32) == 4)
+    gated_add_gelu_fwd_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(u, gate_eff, res, row_batch,
+                                                                            row_batch_stride, n, n_dev, c, sum, y, y_tf32);
+  else
+    gated_add_gelu_fwd_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(u, gate_eff, res, row_batch,
+                                                                            row_batch_stride, n, n_dev, c, sum, y, y_tf32);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_gated_add_gelu_bwd(const float* gy, const float* sum, const float* u, const float* gate_eff,
+                                          const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
+                                          const int32_t* n_dev, int32_t c, int32_t num_batches, float* g_res,
+                                          float* g_u, float* g_gate_eff, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0 && c % CR_SLAB == 0 && num_batches > 0 && row_batch_stride > 0,
+                "c must be a multiple of 64");
+  B2S_CHECK_ARG(g_gate_eff, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  B2S_CUDA(cudaMemsetAsync(g_gate_eff, 0, (size_t)num_batches * c * sizeof(float), st));
+  if (n == 0) return B2S_OK;
+  B2S_CHECK_ARG(gy && sum && u && gate_eff && row_batch && g_res && g_u, "null pointer");
+  B2S_CHECK_ARG(vec_of(c, gy, sum, u, gate_eff) == 4 && vec_of(c, g_res, g_u, g_gate_eff) == 4, "16-byte aligned rows");
+  const int slabs = c / CR_SLAB;
+  int64_t chunks = (2LL * B2S_NUM_SMS + slabs - 1) / slabs;       // ~two CTAs per SM over all slabs
+  const int64_t max_chunks = ceil_div64(n, (int64_t)CR_RPB * 4);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int64_t rows = ceil_div64(n, chunks);
+  rows = ceil_div64(rows, CR_RPB) * CR_RPB;
+  chunks = ceil_div64(n, rows);
+  gated_add_gelu_bwd_kernel<<<dim3((unsigned)chunks, (unsigned)slabs), CR_THREADS, 0, st>>>(
+      gy, sum, u, gate_eff, row_batch, row_batch_stride, n, n_dev, c, num_batches, rows, g_res, g_u, g_gate_eff);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_bcast_add_(float* x, const float* y, const int32_t* row_batch, int32_t row_batch_stride,
+                                  int64_t n, const int32_t* n_dev, int32_t c, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0 && row_batch_stride > 0, "bad arguments");
+  if (n == 0) return B2S_OK;
+  B2S_CHECK_ARG(x && y && row_batch, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (vec_of(c, x, y) == 4)
+    bcast_add_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, y, row_batch, row_batch_stride, n, n_dev, c);
+  else
+    bcast_add_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(x, y, row_batch, row_batch_stride, n, n_dev, c);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -58,6 +58,12 @@ SIGNATURES = {
     "b2s_bn_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b2s_gelu_fwd": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_gelu_bwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp]),
+    "b2s_se_gate_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "b2s_se_gate_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                               _vp, _vp]),
+    "b2s_gated_add_gelu_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "b2s_gated_add_gelu_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "b2s_bcast_add_": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _vp]),
     "b2s_add_gelu_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "b2s_grad_check": (_i32, [_vp, _i64, _f32, _vp, _vp]),
     "b2s_adabelief_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -57,16 +57,22 @@ class DropPath(nn.Module):
         scale = 1.0 / keep if (keep > 0.0 and self.scale_by_keep) else 1.0
         return [scale if random.uniform(0, 1) > self.drop_prob else 0.0 for _ in range(nb)]
 
-    def forward(self, x):
+    def mask(self, x):
+        """[B,1] keep/scale tensor of this forward call on the device, or None in eval mode."""
         if not self.training:
-            return x
-        ME = self._ME[0]
+            return None
         cm = x.coordinate_manager
         nb = cm.num_batches if isinstance(cm.num_batches, int) else cm.num_batches()
         if self.static_mask is not None:
-            mask = self.static_mask
-        else:
-            mask = torch.tensor(self.draw(nb), dtype=x.F.dtype).view(nb, 1).to(x.F.device, non_blocking=True)
+            return self.static_mask
+        return torch.tensor(self.draw(nb), dtype=x.F.dtype).view(nb, 1).to(x.F.device, non_blocking=True)
+
+    def forward(self, x):
+        mask = self.mask(x)
+        if mask is None:
+            return x
+        ME = self._ME[0]
+        cm = x.coordinate_manager
         glob = ME.SparseTensor(mask, coordinate_map_key=cm.origin(x.coordinate_map_key), coordinate_manager=cm)
         return self.mul(x, glob)
 
@@ -109,6 +115,10 @@ class SEResidualBlock(nn.Module):
         super().__init__()
         self._fuse = fuse and _is_gelu(ME, act)
         self._add_act = [ME.fused_add_gelu] if self._fuse else None
+        # squeeze-excite gate + drop path + residual add + GELU as one op where the namespace has it and the channel
+        # count suits its kernels
+        self._se_tail = [ME.fused_se_tail] if (self._fuse and hasattr(ME, "fused_se_tail")
+                                               and (planes * (4 if bottleneck else 1)) % 64 == 0) else None
         # who consumes this block's output (set by MSENet): 0 = something that needs the plain values, 1 = convolutions
         # and an identity residual (plain result + TF32 operand twin), 2 = convolutions only (written TF32-rounded)
         self.out_tf32 = 0
@@ -136,6 +146,9 @@ class SEResidualBlock(nn.Module):
                 out = norm(conv(out), act=1, tf32_only=True) if self._fuse else self.relu(norm(conv(out)))
             else:
                 out = norm(conv(out))
+        if self._se_tail is not None:
+            keep = self.drop_path.mask(out) if isinstance(self.drop_path, DropPath) else None
+            return self._se_tail[0](out, self.downsample(x), self.se.fc[0], self.se.fc[2], keep, self.out_tf32)
         out = self.se(out)
         if self._fuse:
             return self._add_act[0](self.drop_path(out), self.downsample(x), self.out_tf32)

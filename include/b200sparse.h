@@ -249,6 +249,37 @@ B2S_API int32_t b2s_add_gelu_fwd(const float* a, const float* b, int64_t n, cons
 B2S_API int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* gx,
                              b2s_stream_t stream);
 
+/* ---------------------------------------------------------------- fused SE block tail --------
+ * R:modules/MinkowskiEngine/senet_block.py:33-50 (SELayer) + :83-94 (drop path, residual add, activation):
+ *     y = gelu( u * (sigmoid(W2 gelu(W1 mean_plot(u) + b1) + b2) * keep[plot]) + res )
+ * se_gate_fwd        : the excitation MLP of all plots in one launch; pooled [B,c] (per-plot mean of u, from
+ *                      b2s_segment_sum), W1 [h,c], W2 [c,h] (nn.Linear layout), keep [B] = drop-path scale or NULL;
+ *                      writes h_pre [B,h], gate [B,c], gate_eff = gate * keep [B,c].
+ * gated_add_gelu_fwd : sum = u * gate_eff[plot] + res, y = gelu(sum); y and / or its TF32 twin (see above).
+ * gated_add_gelu_bwd : g_res = gy * gelu'(sum), g_u = g_res * gate_eff[plot], g_gate_eff[plot] = sum_rows g_res * u
+ *                      (c % 64 == 0).
+ * se_gate_bwd        : back through keep, sigmoid, W2, GELU, W1 and the mean: g_pooled [B,c] (already scaled by
+ *                      inv_count[plot]), gradients of W1, b1, W2, b2 (written, not accumulated); gz2 [B,c] and
+ *                      gh_pre [B,h] are caller-provided scratch.
+ * bcast_add_         : x[r,:] += y[plot(r),:] in place (adds the pooled branch's gradient to g_u).
+ */
+B2S_API int32_t b2s_se_gate_fwd(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
+                                const float* keep, int32_t num_batches, int32_t c, int32_t h, float* h_pre, float* gate,
+                                float* gate_eff, b2s_stream_t stream);
+B2S_API int32_t b2s_se_gate_bwd(const float* g_gate_eff, const float* keep, const float* gate, const float* h_pre,
+                                const float* pooled, const float* w1, const float* w2, const float* inv_count,
+                                int32_t num_batches, int32_t c, int32_t h, float* gz2, float* gh_pre, float* g_pooled,
+                                float* gw1, float* gb1, float* gw2, float* gb2, b2s_stream_t stream);
+B2S_API int32_t b2s_gated_add_gelu_fwd(const float* u, const float* gate_eff, const float* res, const int32_t* row_batch,
+                                       int32_t row_batch_stride, int64_t n, const int32_t* n_dev, int32_t c, float* sum,
+                                       float* y, float* y_tf32, b2s_stream_t stream);
+B2S_API int32_t b2s_gated_add_gelu_bwd(const float* gy, const float* sum, const float* u, const float* gate_eff,
+                                       const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
+                                       const int32_t* n_dev, int32_t c, int32_t num_batches, float* g_res, float* g_u,
+                                       float* g_gate_eff, b2s_stream_t stream);
+B2S_API int32_t b2s_bcast_add_(float* x, const float* y, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
+                               const int32_t* n_dev, int32_t c, b2s_stream_t stream);
+
 /* ---------------------------------------------------------------- optimiser ----
  * R:core/optimizer/adabelief.py:90-201 over one flat fp32 parameter buffer, with GradScaler
  * unscale (R:models/base_model.py:241), clip_grad_value_ (:243) and the inf/nan skip fused in.

@@ -275,3 +275,41 @@ def test_tf32_twins_match_the_rounding_pass_and_remove_it(cuda, name):
         assert (g1 - g0).abs().max().item() <= 1e-3 * g0.abs().max().item() + 1e-5 * gmax
     assert runs[True][2] < runs[False][2] // 2, f"rounding launches {runs[False][2]} -> {runs[True][2]}"
     _report(f"{name}-tf32-twins", rounding_launches_without=runs[False][2], rounding_launches_with=runs[True][2])
+
+
+@pytest.mark.parametrize("name", ["SENet14", "SENet50"])
+def test_fused_se_tail_matches_the_unfused_chain(cuda, name):
+    """``ME.fused_se_tail`` (per-plot mean, excitation MLP, gate x drop-path scale, residual add, GELU and their
+    backward as six kernels) against the same block tail composed of the individual ME ops: outputs and every
+    gradient, batch norm in eval mode (so that only summation order differs), drop path active."""
+    batch = util.make_points(3, 2500, cfg=2)
+    c, f, _, _, _ = util.oracle_quantize(batch, 0.04)
+    torch.manual_seed(5)
+    model = msenet.MSENet(ME, name, drop_path=0.3).to(cuda).eval()
+    blocks = [b for st in model.blocks[1:] for b in st]
+    assert all(b._se_tail is not None for b in blocks)
+    for b in blocks:
+        b.drop_path.train()
+    target = torch.from_numpy(batch["target"]).to(cuda)
+    center, scale = torch.tensor([107.0, 200.0], device=cuda), torch.tensor([103.0, 194.0], device=cuda)
+    tails = [b._se_tail for b in blocks]
+    runs = {}
+    try:
+        for fused in (False, True):
+            for b, t in zip(blocks, tails):
+                b._se_tail = t if fused else None
+            model.zero_grad(set_to_none=True)
+            random.seed(23)
+            y = model(ME.SparseTensor(features=torch.from_numpy(f), coordinates=torch.from_numpy(c), device=cuda))
+            train.reg_loss(y, target, center, scale).backward()
+            runs[fused] = (y.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters()})
+    finally:
+        for b, t in zip(blocks, tails):
+            b._se_tail = t
+    # u * (gate * keep) instead of (u * gate) * keep: one-ulp differences, which the TF32 rounding of the next
+    # convolution's operands turns into occasional 5e-4 flips of single operands -> 1e-5 .. 1e-4 downstream
+    util.assert_close(runs[True][0], runs[False][0], tol=2e-4, what="output, fused vs unfused SE tail")
+    gmax = max(g.abs().max().item() for g in runs[False][1].values())
+    for n, g0 in runs[False][1].items():
+        err = (runs[True][1][n] - g0).abs().max().item()
+        assert err <= 2e-3 * g0.abs().max().item() + 1e-4 * gmax, f"{n}: {err:.3e}"
