@@ -493,7 +493,7 @@ class SETailFunction(torch.autograd.Function):
             else:
                 outs.append(torch.empty_like(prm, memory_format=torch.contiguous_format))
         gz2 = torch.empty((nb, c), dtype=torch.float32, device=dev)
-        ghp = torch.empty((nb, h), dtype=torch.float32, device=dev)
+        ghp = torch.empty((2, nb, h), dtype=torch.float32, device=dev)
         g_pooled = torch.empty((nb, c), dtype=torch.float32, device=dev)
         L.call("b2s_se_gate_bwd", g_ge, keep, gate, h_pre, pooled, w1c, w2c, inv_counts, nb, c, h, gz2, ghp, g_pooled,
                outs[0], outs[1], outs[2], outs[3])

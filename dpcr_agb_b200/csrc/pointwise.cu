@@ -566,7 +566,9 @@ __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restric
 // forward and ~20 backward with 21 passes over the [N, C] tensors.  Same arithmetic in the same order per element
 // (u * (gate * keep) + res); the MLP sums are fp32 FMAs over <= 2048 terms.
 
-// one CTA per plot: h_pre = W1 p + b1, h = gelu(h_pre), gate = sigmoid(W2 h + b2), gate_eff = gate * keep[b]
+// CTA = (plot, chunk of SE_CHUNK gate channels): h_pre = W1 p + b1 and h = gelu(h_pre) are recomputed per chunk (h * c
+// MACs, nothing), gate = sigmoid(W2 h + b2), gate_eff = gate * keep[b] for the chunk's channels
+constexpr int SE_CHUNK = 128;
 __global__ void __launch_bounds__(256) se_gate_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ w1,
                                                           const float* __restrict__ b1, const float* __restrict__ w2,
                                                           const float* __restrict__ b2, const float* __restrict__ keep,
@@ -585,38 +587,48 @@ __global__ void __launch_bounds__(256) se_gate_fwd_kernel(const float* __restric
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
       const float hp = acc + (b1 ? b1[j] : 0.f);
-      h_pre[(int64_t)b * h + j] = hp;
+      if (blockIdx.y == 0) h_pre[(int64_t)b * h + j] = hp;
       hh[j] = gelu_f(hp);
     }
   }
   __syncthreads();
   const float kp = keep ? keep[b] : 1.f;
-  for (int i = tid; i < c; i += blockDim.x) {
-    float z = b2 ? b2[i] : 0.f;
-    for (int j = 0; j < h; ++j) z = fmaf(__ldg(&w2[(int64_t)i * h + j]), hh[j], z);
-    const float g = 1.f / (1.f + expf(-z));
-    gate[(int64_t)b * c + i] = g;
-    gate_eff[(int64_t)b * c + i] = g * kp;
+  // a warp per gate channel: lanes stride the hidden units (W2 row = h contiguous floats)
+  const int i1 = min(c, (int)(blockIdx.y + 1) * SE_CHUNK);
+  for (int i = blockIdx.y * SE_CHUNK + warp; i < i1; i += (int)(blockDim.x >> 5)) {
+    float acc = 0.f;
+    for (int j = lane; j < h; j += 32) acc = fmaf(__ldg(&w2[(int64_t)i * h + j]), hh[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float z = acc + (b2 ? b2[i] : 0.f);
+      const float g = 1.f / (1.f + expf(-z));
+      gate[(int64_t)b * c + i] = g;
+      gate_eff[(int64_t)b * c + i] = g * kp;
+    }
   }
 }
 
-// one CTA per plot: back through keep, sigmoid, fc2, GELU, fc1 and the per-plot mean
+// CTA = (plot, chunk of SE_CHUNK channels): back through keep, sigmoid, fc2, GELU (recomputed per chunk), then the
+// chunk's slice of fc1^T and the per-plot mean.  Chunk 0 also stores gz2, gh_pre and h = gelu(h_pre) for the
+// parameter-gradient kernel (gh_pre: [2, B, h] scratch, second half = h).
 __global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restrict__ g_gate_eff,
                                                           const float* __restrict__ keep, const float* __restrict__ gate,
                                                           const float* __restrict__ h_pre, const float* __restrict__ w1,
                                                           const float* __restrict__ w2, const float* __restrict__ inv_count,
-                                                          int c, int h, float* __restrict__ gz2,
+                                                          int nb, int c, int h, float* __restrict__ gz2,
                                                           float* __restrict__ gh_pre, float* __restrict__ g_pooled) {
   extern __shared__ float se_sm[];
   float* z = se_sm;          // [c]  gradient at the sigmoid input
   float* hp = se_sm + c;     // [h]  gradient at the GELU input
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool first = blockIdx.y == 0;
   const float kp = keep ? keep[b] : 1.f;
   for (int i = tid; i < c; i += blockDim.x) {
     const float g = gate[(int64_t)b * c + i];
     const float v = g_gate_eff[(int64_t)b * c + i] * kp * g * (1.f - g);
     z[i] = v;
-    gz2[(int64_t)b * c + i] = v;
+    if (first) gz2[(int64_t)b * c + i] = v;
   }
   __syncthreads();
   for (int j = warp; j < h; j += (int)(blockDim.x >> 5)) {
@@ -625,24 +637,29 @@ __global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restric
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
-      const float v = acc * gelu_grad_f(h_pre[(int64_t)b * h + j]);
+      const float pre = h_pre[(int64_t)b * h + j];
+      const float v = acc * gelu_grad_f(pre);
       hp[j] = v;
-      gh_pre[(int64_t)b * h + j] = v;
+      if (first) {
+        gh_pre[(int64_t)b * h + j] = v;
+        gh_pre[((int64_t)nb + b) * h + j] = gelu_f(pre);
+      }
     }
   }
   __syncthreads();
   const float ic = inv_count ? inv_count[b] : 1.f;
-  for (int i = tid; i < c; i += blockDim.x) {
+  const int i1 = min(c, (int)(blockIdx.y + 1) * SE_CHUNK);
+  for (int i = blockIdx.y * SE_CHUNK + tid; i < i1; i += blockDim.x) {
     float acc = 0.f;
     for (int j = 0; j < h; ++j) acc = fmaf(hp[j], __ldg(&w1[(int64_t)j * c + i]), acc);
     g_pooled[(int64_t)b * c + i] = acc * ic;
   }
 }
 
-// parameter gradients of the two linears: sums over the plots
+// parameter gradients of the two linears: sums over the plots (h_act = gelu(h_pre), stored by se_gate_bwd_kernel)
 __global__ void __launch_bounds__(256) se_param_grad_kernel(const float* __restrict__ gz2,
                                                             const float* __restrict__ gh_pre,
-                                                            const float* __restrict__ h_pre,
+                                                            const float* __restrict__ h_act,
                                                             const float* __restrict__ pooled, int nb, int c, int h,
                                                             float* __restrict__ gw1, float* __restrict__ gb1,
                                                             float* __restrict__ gw2, float* __restrict__ gb2) {
@@ -653,9 +670,9 @@ __global__ void __launch_bounds__(256) se_param_grad_kernel(const float* __restr
       const int j = e / c, i = e % c;
       for (int b = 0; b < nb; ++b) acc = fmaf(gh_pre[b * h + j], pooled[(int64_t)b * c + i], acc);
       gw1[e] = acc;
-    } else if (e < 2 * hc) {              // gw2[i, j] = sum_b gz2[b, i] * gelu(h_pre[b, j])
+    } else if (e < 2 * hc) {              // gw2[i, j] = sum_b gz2[b, i] * h[b, j]
       const int f = e - hc, i = f / h, j = f % h;
-      for (int b = 0; b < nb; ++b) acc = fmaf(gz2[(int64_t)b * c + i], gelu_f(h_pre[b * h + j]), acc);
+      for (int b = 0; b < nb; ++b) acc = fmaf(gz2[(int64_t)b * c + i], h_act[b * h + j], acc);
       gw2[f] = acc;
     } else if (e < 2 * hc + h) {
       const int j = e - 2 * hc;
@@ -752,6 +769,55 @@ __global__ void __launch_bounds__(CR_THREADS, 1) gated_add_gelu_bwd_kernel(
       }
       stv<4>(g_s + rr * c + ch, gs);
       stv<4>(g_u + rr * c + ch, gu);
+    }
+  }
+  flush();
+}
+
+// float4 form of segment_sum (c % 64 == 0): CTA = 64-channel slab x CONTIGUOUS row chunk, a thread's rows (chunk rows
+// tr, tr + 32, ...) almost always belong to one plot, whose partial sum stays in registers and leaves as one fp32
+// atomic per channel (times the per-plot scale, e.g. 1 / rows for the mean) when the plot changes and at the end.
+__global__ void __launch_bounds__(CR_THREADS, 1) segment_sum_v4_kernel(const float* __restrict__ x,
+                                                                       const int* __restrict__ rb, int stride,
+                                                                       int64_t n, const int* __restrict__ n_dev, int c,
+                                                                       int nb, int64_t rows_per_cta,
+                                                                       const float* __restrict__ scale,
+                                                                       float* __restrict__ y) {
+  n = b2s_rows(n, n_dev);
+  const int tc = threadIdx.x % CR_TPR, tr = threadIdx.x / CR_TPR;
+  const int ch = blockIdx.y * CR_SLAB + tc * 4;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(r0 + rows_per_cta, n);
+  int cur = -1;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  auto flush = [&]() {
+    if (cur >= 0 && cur < nb) {
+      const float sc = scale ? __ldg(&scale[cur]) : 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&y[(int64_t)cur * c + ch + j], acc[j] * sc);
+    }
+  };
+  constexpr int U = 4;
+  for (int64_t r = r0 + tr; r < r1; r += U * CR_RPB) {
+    V<4> xv[U];
+    int bb[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int64_t rr = r + q * CR_RPB;
+      const bool ok = rr < r1;
+      bb[q] = ok ? __ldg(&rb[rr * stride]) : -1;
+      xv[q] = ok ? ldv<4>(x + rr * c + ch) : splat<4>(0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      if (r + q * CR_RPB >= r1) break;
+      if (bb[q] != cur) {
+        flush();
+        cur = bb[q];
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += xv[q].v[j];
     }
   }
   flush();
@@ -859,6 +925,20 @@ extern "C" int32_t b2s_segment_sum(const float* x, const int32_t* row_batch, int
   B2S_CUDA(cudaMemsetAsync(y, 0, (size_t)num_batches * c * sizeof(float), st));
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(x && row_batch, "null pointer");
+  if (c % CR_SLAB == 0 && vec_of(c, x, y) == 4) {
+    const int slabs = c / CR_SLAB;
+    int64_t chunks = (2LL * B2S_NUM_SMS + slabs - 1) / slabs;
+    const int64_t max_chunks = ceil_div64(n, (int64_t)CR_RPB * 4);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int64_t rows = ceil_div64(n, chunks);
+    rows = ceil_div64(rows, CR_RPB) * CR_RPB;
+    chunks = ceil_div64(n, rows);
+    segment_sum_v4_kernel<<<dim3((unsigned)chunks, (unsigned)slabs), CR_THREADS, 0, st>>>(
+        x, row_batch, row_batch_stride, n, n_dev, c, num_batches, rows, scale, y);
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+  }
   segment_sum_kernel<false><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, nullptr, row_batch, row_batch_stride, n, n_dev,
                                                                   c, num_batches, y);
   if (scale) scale_rows_kernel<<<grid_for((int64_t)num_batches * c, PW_THREADS), PW_THREADS, 0, st>>>(y, scale, num_batches, c);
@@ -1058,8 +1138,8 @@ extern "C" int32_t b2s_se_gate_fwd(const float* pooled, const float* w1, const f
                                    float* h_pre, float* gate, float* gate_eff, b2s_stream_t stream) {
   B2S_CHECK_ARG(num_batches > 0 && c > 0 && h > 0 && (c + h) * sizeof(float) <= 48 * 1024, "bad sizes");
   B2S_CHECK_ARG(pooled && w1 && w2 && h_pre && gate && gate_eff, "null pointer");
-  se_gate_fwd_kernel<<<num_batches, 256, (c + h) * sizeof(float), as_stream(stream)>>>(pooled, w1, b1, w2, b2, keep, c, h,
-                                                                                       h_pre, gate, gate_eff);
+  se_gate_fwd_kernel<<<dim3(num_batches, (c + SE_CHUNK - 1) / SE_CHUNK), 256, (c + h) * sizeof(float),
+                       as_stream(stream)>>>(pooled, w1, b1, w2, b2, keep, c, h, h_pre, gate, gate_eff);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -1073,10 +1153,10 @@ extern "C" int32_t b2s_se_gate_bwd(const float* g_gate_eff, const float* keep, c
   B2S_CHECK_ARG(g_gate_eff && gate && h_pre && pooled && w1 && w2 && gz2 && gh_pre && g_pooled && gw1 && gw2,
                 "null pointer");
   cudaStream_t st = as_stream(stream);
-  se_gate_bwd_kernel<<<num_batches, 256, (c + h) * sizeof(float), st>>>(g_gate_eff, keep, gate, h_pre, w1, w2, inv_count,
-                                                                        c, h, gz2, gh_pre, g_pooled);
-  se_param_grad_kernel<<<grid_for(2 * (int64_t)h * c + h + c, 256), 256, 0, st>>>(gz2, gh_pre, h_pre, pooled,
-                                                                                 num_batches, c, h, gw1, gb1, gw2, gb2);
+  se_gate_bwd_kernel<<<dim3(num_batches, (c + SE_CHUNK - 1) / SE_CHUNK), 256, (c + h) * sizeof(float), st>>>(
+      g_gate_eff, keep, gate, h_pre, w1, w2, inv_count, num_batches, c, h, gz2, gh_pre, g_pooled);
+  se_param_grad_kernel<<<grid_for(2 * (int64_t)h * c + h + c, 256), 256, 0, st>>>(
+      gz2, gh_pre, gh_pre + (int64_t)num_batches * h, pooled, num_batches, c, h, gw1, gb1, gw2, gb2);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -260,7 +260,7 @@ B2S_API int32_t b2s_gelu_bwd(const float* gy, const float* x, int64_t n, const i
  *                      (c % 64 == 0).
  * se_gate_bwd        : back through keep, sigmoid, W2, GELU, W1 and the mean: g_pooled [B,c] (already scaled by
  *                      inv_count[plot]), gradients of W1, b1, W2, b2 (written, not accumulated); gz2 [B,c] and
- *                      gh_pre [B,h] are caller-provided scratch.
+ *                      gh_pre [2,B,h] are caller-provided scratch.
  * bcast_add_         : x[r,:] += y[plot(r),:] in place (adds the pooled branch's gradient to g_u).
  */
 B2S_API int32_t b2s_se_gate_fwd(const float* pooled, const float* w1, const float* b1, const float* w2, const float* b2,
