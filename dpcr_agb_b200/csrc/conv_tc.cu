@@ -69,6 +69,30 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
   }
 }
 
+// Same image for the forward layout (w[k][ci][co], co contiguous) through a shared-memory transpose: the kernel above
+// reads that layout with ci fastest across threads -- one 32-byte sector per element.  Block = (iteration, 32 output
+// channels): rows of 32 co are read coalesced, 128-byte image rows are written coalesced.
+__global__ void __launch_bounds__(256) prep_weights_t_kernel(const float* __restrict__ w, int c_in, int c_out, int k3,
+                                                             int w_layout, float* __restrict__ img) {
+  __shared__ float t[32][33];
+  const int it = blockIdx.x, n0 = blockIdx.y * 32, kc = c_in / BK;
+  const int k = it / kc, ci0 = (it % kc) * BK;
+  const int kw = (w_layout & 2) ? k3 - 1 - k : k;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) t[r][tx] = w[((int64_t)kw * c_in + ci0 + r) * c_out + n0 + tx];
+  __syncthreads();
+#pragma unroll
+  for (int y = ty; y < 32; y += 8) {
+    const int n = n0 + y;
+    const int chunk = (tx >> 2) ^ (n & 7);
+    const int kk = chunk * 4 + (tx & 3);
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t[kk][y]));
+    img[((int64_t)it * c_out + n) * BK + tx] = __uint_as_float(r);
+  }
+}
+
 __global__ void __launch_bounds__(256) pad_rows4_kernel(const float* __restrict__ x, int64_t n, int c,
                                                         float4* __restrict__ x4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -707,6 +731,15 @@ int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int
   return b2s_conv_tc_image_bytes(c_in, c_out, k3) + (c_in <= 4 ? align256(n_in * 16) : 0);
 }
 
+static void launch_prep_weights(const float* w, int c_in, int c_out, int k3, int w_layout, bool small, int T, float* img,
+                                cudaStream_t st) {
+  if (!small && !(w_layout & 1) && c_in % BK == 0 && c_out % 32 == 0)
+    prep_weights_t_kernel<<<dim3((unsigned)T, (unsigned)(c_out / 32)), 256, 0, st>>>(w, c_in, c_out, k3, w_layout, img);
+  else
+    prep_weights_kernel<<<grid_for((int64_t)T * c_out * BK, 256), 256, 0, st>>>(w, c_in, c_out, k3, w_layout,
+                                                                               small ? 1 : 0, T, img);
+}
+
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                             int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
                             void* workspace, int64_t workspace_bytes, cudaStream_t st) {
@@ -714,8 +747,7 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   const bool small = c_in <= 4;
   const int T = iterations(c_in, k3);
   float* img = reinterpret_cast<float*>(workspace);
-  prep_weights_kernel<<<grid_for((int64_t)T * c_out * BK, 256), 256, 0, st>>>(w, c_in, c_out, k3, w_layout, small ? 1 : 0,
-                                                                             T, img);
+  launch_prep_weights(w, c_in, c_out, k3, w_layout, small, T, img, st);
   const float* xin = x;
   if (small) {
     float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + b2s_conv_tc_image_bytes(c_in, c_out, k3));
@@ -762,7 +794,7 @@ int b2s_conv_dgrad_perm_tc(const float* x, const float* w, const int32_t* nbr, i
   const int k3 = ksize[0] * ksize[1] * ksize[2];
   const int T = iterations(c_in, k3);
   float* img = reinterpret_cast<float*>(workspace);
-  prep_weights_kernel<<<grid_for((int64_t)T * c_out * BK, 256), 256, 0, st>>>(w, c_in, c_out, k3, w_layout, 0, T, img);
+  launch_prep_weights(w, c_in, c_out, k3, w_layout, false, T, img, st);
   PermArgs pa{};
   pa.perm = perm;
   pa.bounds = bounds;

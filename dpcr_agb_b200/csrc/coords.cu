@@ -553,6 +553,56 @@ __global__ void __launch_bounds__(256) kernel_map_dense_kernel(const int4* __res
   const int hx = (p.K[0] & 1) ? p.K[0] / 2 : 0, hy = (p.K[1] & 1) ? p.K[1] / 2 : 0, hz = (p.K[2] & 1) ? p.K[2] / 2 : 0;
   int ix = k0 % p.K[0], iy = (k0 / p.K[0]) % p.K[1], iz = k0 / (p.K[0] * p.K[1]);
   const bool plot_ok = (unsigned)c.x < (unsigned)num_plots;
+  if (p.step[0] == 1) {
+    // x-lines: the K[0] cells of one (iy, iz) line are consecutive bits of the occupancy bitmap (at most two words), so
+    // the words and their ranks are loaded once per line -- 2-4 loads instead of 2 K[0] -- and every offset of the line
+    // is a popcount.  With sign = -1 the line is walked downwards; the bits are the same.
+    int wi0 = 0;
+    int64_t cellbase = 0;
+    unsigned w0 = 0, w1 = 0;
+    int p0 = 0, p1 = 0;
+    bool line_ok = false;
+    for (int k = k0; k < k1; ++k) {
+      if (k == k0 || ix == 0) {
+        const int y = c.z + p.sign * (iy - hy) * p.step[1] - box.lo[1];
+        const int z = c.w + p.sign * (iz - hz) * p.step[2] - box.lo[2];
+        line_ok = plot_ok && (unsigned)y < (unsigned)box.dim[1] && (unsigned)z < (unsigned)box.dim[2];
+        if (line_ok) {
+          const int xlo = c.y - box.lo[0] - (p.sign > 0 ? hx : (p.K[0] - 1 - hx));   // smallest x of the line
+          const int xa = max(xlo, 0), xb = min(xlo + p.K[0] - 1, box.dim[0] - 1);
+          cellbase = (((int64_t)c.x * box.dim[2] + z) * box.dim[1] + y) * box.dim[0];
+          line_ok = xa <= xb;
+          if (line_ok) {
+            wi0 = (int)((cellbase + xa) >> 5);
+            w0 = __ldg(&bitmap[wi0]);
+            p0 = __ldg(&prefix[wi0]);
+            if ((int)((cellbase + xb) >> 5) != wi0) {
+              w1 = __ldg(&bitmap[wi0 + 1]);
+              p1 = __ldg(&prefix[wi0 + 1]);
+            }
+          }
+        }
+      }
+      int row = -1;
+      const int x = c.y + p.sign * (ix - hx) - box.lo[0];
+      if (line_ok && (unsigned)x < (unsigned)box.dim[0]) {
+        const int64_t cell = cellbase + x;
+        const bool first = (int)(cell >> 5) == wi0;
+        const unsigned w = first ? w0 : w1;
+        const unsigned bit = (unsigned)(cell & 31);
+        if ((w >> bit) & 1u) row = (first ? p0 : p1) + __popc(w & ((1u << bit) - 1u));
+      }
+      nbr[(int64_t)k * n + q] = row;
+      if (++ix == p.K[0]) {
+        ix = 0;
+        if (++iy == p.K[1]) {
+          iy = 0;
+          ++iz;
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll 4
   for (int k = k0; k < k1; ++k) {
     const int x = c.y + p.sign * (ix - hx) * p.step[0] - box.lo[0];
