@@ -18,7 +18,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-extern int g_b2s_tc_rot, g_b2s_tc_ca, g_b2s_tc_occ1;   // lib.cu (b2s_set_tuning)
+extern int g_b2s_tc_rot, g_b2s_tc_ca, g_b2s_tc_occ1, g_b2s_tc_m256;   // lib.cu (b2s_set_tuning)
 
 namespace {
 
@@ -402,6 +402,216 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
 
 // ---------------------------------------------------------------------------------------------
+// M = 256 variant of the general kernel (c_in % 32 == 0, no split-K, no permutation): TWO 128-row accumulator tiles
+// per CTA share every weight stage, so the weight image -- half of the L2->SM traffic of the 64- and 128-channel
+// layers, whose conv kernels run at 60-80 % of the L2 fabric ceiling -- is fetched once per 256 output rows instead
+// of once per 128.  8 producer warps (tile half = warp / 4), warp 8 issues 2 x 4 MMAs per stage; one CTA per SM with
+// the same bytes in flight as two CTAs of the M = 128 kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int TC2_THREADS = 288;
+template <int BN, int STAGES>
+struct SmemLayout2 {
+  static constexpr int A_STAGE = 2 * A_STAGE_BYTES;
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = STAGES * A_STAGE;
+  static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 2) * 8;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+template <int BN, int STAGES, int LAG>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+    gather_gemm_tc2_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
+                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
+                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
+  if ((int64_t)blockIdx.x * (2 * BM) >= n_out) return;
+  // split-K as in the M = 128 kernel: blockIdx.z owns iterations [it0, it0 + T), partial tiles are combined with
+  // fp32 vector reductions into a zero-initialised y
+  const int it0 = blockIdx.z * it_per_split;       // a multiple of c_in / 32
+  const int T = min(it_per_split, T_total - it0);
+  if (T <= 0) return;
+  const bool split = gridDim.z > 1;
+  using L = SmemLayout2<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t a_base = base + L::A_OFF, b_base = base + L::B_OFF;
+  const uint32_t bar_base = base + L::BAR_OFF;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + 8 * (2 * STAGES + 1));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * (2 * BM);
+  const int n0 = blockIdx.y * BN;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2 * PRODUCERS + 1);   // 256 gather arrivals + 1 arrive.expect_tx for the B bulk copy
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp < 8) {
+    const int half = tid >> 7, t = tid & 127;
+    const int chunk = t & 7, rsub = t >> 3;
+    const int kc = c_in / BK;
+    const int64_t mh = m0 + half * BM;
+    const int* nbr_t = nbr ? nbr + mh + rsub : nullptr;
+    int idx[8], idx1[8], idx2[8];
+    auto load_group = [&](int g, int (&dst)[8]) {
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int64_t o = mh + rsub + 16 * p;
+        int v = -1;
+        if (g < k3 && o < n_out) v = nbr_t ? __ldg(nbr_t + (int64_t)g * pitch + 16 * p) : (int)o;
+        dst[p] = v;
+      }
+    };
+    auto publish = [&](int s_done) {
+      fence_proxy_async();
+      mbar_arrive(full_bar(s_done));
+    };
+    const int g0 = it0 / kc;
+    int s = 0, cc = 0, g = g0, s_pub = 0;
+    uint32_t ph = 0;
+    auto issue_stage = [&](const int (&cur)[8]) {
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (tid == 0) {
+        mbar_arrive_expect_tx(full_bar(s), L::B_STAGE_BYTES);
+        bulk_g2s(b_base + s * L::B_STAGE_BYTES, wimg + ((int64_t)(g * kc + cc) * c_out + n0) * BK, L::B_STAGE_BYTES,
+                 full_bar(s));
+      }
+      const uint32_t a_stage = a_base + s * L::A_STAGE + half * A_STAGE_BYTES;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int i = cur[p];
+        cp_async16(a_stage + sw128_offset(rsub + 16 * p, chunk),
+                   x + (int64_t)(i >= 0 ? i : 0) * c_in + cc * BK + chunk * 4, i >= 0 ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+    auto finish_stage = [&](int it) {
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+      if (it >= LAG) {
+        cp_async_wait<LAG>();
+        publish(s_pub);
+        if (++s_pub == STAGES) s_pub = 0;
+      }
+    };
+    load_group(g0, idx);
+    load_group(g0 + 1, idx1);
+    load_group(g0 + 2, idx2);
+    int it = 0;
+    auto run_group = [&](const int (&cur)[8]) {
+      for (cc = 0; cc < kc && it < T; ++cc, ++it) {
+        issue_stage(cur);
+        finish_stage(it);
+      }
+      ++g;
+    };
+    while (it < T) {
+      run_group(idx);
+      load_group(g + 2, idx);
+      if (it < T) {
+        run_group(idx1);
+        load_group(g + 2, idx1);
+      }
+      if (it < T) {
+        run_group(idx2);
+        load_group(g + 2, idx2);
+      }
+    }
+    cp_async_wait<0>();
+    for (int r = T < LAG ? T : LAG; r > 0; --r) {
+      publish(s_pub);
+      if (++s_pub == STAGES) s_pub = 0;
+    }
+
+    // epilogue: warps 0-3 read tile 0, warps 4-7 tile 1; a warp may touch TMEM lanes 32 (warp % 4) ...
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int64_t o = mh + q * 32 + lane;
+    const uint32_t t_lane = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BN);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (o < n_out) {
+        float* dst = y + o * c_out + n0 + c0;
+        const bool add_bias = bias && it0 == 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 r;
+          r.x = __uint_as_float(v[j]) + (add_bias ? __ldg(&bias[n0 + c0 + j]) : 0.f);
+          r.y = __uint_as_float(v[j + 1]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 1]) : 0.f);
+          r.z = __uint_as_float(v[j + 2]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 2]) : 0.f);
+          r.w = __uint_as_float(v[j + 3]) + (add_bias ? __ldg(&bias[n0 + c0 + j + 3]) : 0.f);
+          if (split)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(r.x), "f"(r.y), "f"(r.z),
+                         "f"(r.w)
+                         : "memory");
+          else
+            *reinterpret_cast<float4*>(dst + j) = r;
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < T; ++it) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t b_desc = smem_desc_sw128(b_base + s * L::B_STAGE_BYTES, 16, 1024);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint64_t a_desc = smem_desc_sw128(a_base + s * L::A_STAGE + mt * A_STAGE_BYTES, 16, 1024);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk)
+            mma_tf32(tmem_d + (uint32_t)(mt * BN), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC,
+                     (it | kk) ? 1u : 0u);
+        }
+        mma_commit(empty_bar(s));
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+    if (lane == 0) mma_commit(accum_bar);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_d);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // TMA variant of the general (c_in % 32 == 0) kernel: the A rows are gathered by the TMA unit
 // (cp.async.bulk.tensor ... tile::gather4, 128B swizzle) instead of 16-byte LDGSTS -- the LSU path saturates at
 // ~27 B/clk/SM (4 tag look-ups + 4-5 shared-memory wavefronts per 512-byte warp instruction, zero-fills included),
@@ -674,6 +884,39 @@ int tc_rot() {
   return g_b2s_tc_rot >= 0 ? g_b2s_tc_rot : env;
 }
 
+template <int BN, int STAGES, int LAG>
+int launch_tc2(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
+               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
+  using L = SmemLayout2<BN, STAGES>;
+  static_assert(LAG < STAGES, "producers run LAG stages ahead of their hand-over");
+  auto kern = gather_gemm_tc2_kernel<BN, STAGES, LAG>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
+      b2s_set_error("conv_tc: cannot opt in to %d bytes of shared memory", L::DYN_BYTES);
+      return -1;
+    }
+    attr_set = true;
+  }
+  const int64_t ctas = ceil_div64(n_out, 2 * BM) * (c_out / BN);
+  const int kc = c_in / BK;
+  int splits = 1;
+  if (ctas < B2S_NUM_SMS) {                      // too few output tiles for 148 SMs: split the K loop
+    splits = (int)((B2S_NUM_SMS + ctas - 1) / ctas);
+    const int max_splits = T / 16 > 0 ? T / 16 : 1;                 // >= 16 stages per split
+    if (splits > max_splits) splits = max_splits;
+  }
+  int per = (T + splits - 1) / splits;
+  per = ((per + kc - 1) / kc) * kc;
+  splits = (T + per - 1) / per;
+  if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
+  dim3 grid((unsigned)ceil_div64(n_out, 2 * BM), (unsigned)(c_out / BN), (unsigned)splits);
+  kern<<<grid, TC2_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y);
+  return 0;
+}
+
+int tc_m256() { return tc_knob(g_b2s_tc_m256, "B2S_TC_M256", 1); }
+
 template <int BN, int STAGES, bool SMALL, int LAG = 2>
 int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
@@ -771,6 +1014,16 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
                                         : launch_tma<128, 3>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
     return variant == 11 ? launch_tma<64, 8>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st)
                          : launch_tma<64, 4>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  }
+  // M = 256 tiles: measured 1.5x faster for 128-wide output tiles (0.193 -> 0.127 ms at 69.5 k rows x 128 -> 128),
+  // neutral for 64-wide ones (bound by the LSU gather, not by weight traffic) and 1.5x SLOWER for 256-wide ones
+  // (three 64 KB stages, split-K reductions) -- knob "tc_m256": 0 off, 1 = 128-wide tiles only (default), 2 = wherever
+  // it can run (tests), 3 = 64- and 128-wide tiles
+  const int m256 = tc_m256();
+  if (m256 && n_out > BM && (bn == 128 || m256 == 2 || (m256 == 3 && bn == 64))) {
+    if (bn == 256) return launch_tc2<256, 3, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    if (bn == 128) return launch_tc2<128, 4, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    return launch_tc2<64, 5, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   }
   if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   if (bn == 128) {

@@ -31,6 +31,7 @@ extern "C" int32_t b2s_device_check(void) {
 // launch-tuning knobs (wgrad_tc.cu / conv_tc.cu read them at every launch)
 int g_b2s_wg_nbp = -1, g_b2s_wg_lag = -1, g_b2s_wg_occ2 = -1, g_b2s_tc_rot = -1;
 int g_b2s_tc_ca = -1, g_b2s_tc_occ1 = -1, g_b2s_wg_ca = -1;
+int g_b2s_wg_wv = -1, g_b2s_tc_m256 = -1;
 int g_b2s_cr_v4 = -1, g_b2s_cr_cap = -1, g_b2s_cr_unroll = -1;
 
 extern "C" int32_t b2s_set_tuning(const char* key, int32_t value) {
@@ -42,6 +43,8 @@ extern "C" int32_t b2s_set_tuning(const char* key, int32_t value) {
   else if (!strcmp(key, "tc_ca")) g_b2s_tc_ca = value;
   else if (!strcmp(key, "tc_occ1")) g_b2s_tc_occ1 = value;
   else if (!strcmp(key, "wg_ca")) g_b2s_wg_ca = value;
+  else if (!strcmp(key, "wg_wv")) g_b2s_wg_wv = value;
+  else if (!strcmp(key, "tc_m256")) g_b2s_tc_m256 = value;
   else if (!strcmp(key, "cr_v4")) g_b2s_cr_v4 = value;
   else if (!strcmp(key, "cr_cap")) g_b2s_cr_cap = value;
   else if (!strcmp(key, "cr_unroll")) g_b2s_cr_unroll = value;

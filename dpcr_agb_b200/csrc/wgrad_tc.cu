@@ -24,7 +24,7 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 
-extern int g_b2s_wg_nbp, g_b2s_wg_lag, g_b2s_wg_occ2, g_b2s_wg_ca;   // lib.cu (b2s_set_tuning)
+extern int g_b2s_wg_nbp, g_b2s_wg_lag, g_b2s_wg_occ2, g_b2s_wg_ca, g_b2s_wg_wv;   // lib.cu (b2s_set_tuning)
 
 namespace {
 
@@ -575,10 +575,18 @@ int launch_group(const float* x, const float* gy, const int* nbr, int64_t n_out,
     attr_set = true;
   }
   const int64_t base = (int64_t)p.groups * p.ci_tiles * p.co_tiles;
-  // two waves of the resident CTAs; every split gets at least 16 stages of rows
-  int64_t splits = (2LL * MINB * B2S_NUM_SMS + base - 1) / base;
+  // `wv` half-waves of the resident CTAs (default 4 = two waves); every split gets at least 16 stages of rows.  More
+  // splits balance the SMs, fewer splits mean fewer partial tiles to combine with atomics (each split adds one copy
+  // of the whole gradient tile to the reduction traffic)
+  const int wv = g_b2s_wg_wv > 0 ? g_b2s_wg_wv : wg_env("B2S_WG_WV", 4);
+  int64_t splits = ((int64_t)wv * MINB * B2S_NUM_SMS / 2 + base - 1) / base;
   const int64_t max_splits = ceil_div64(n_out, 16 * G_R);
   if (splits > max_splits) splits = max_splits;
+  // reduction traffic = splits x (whole gradient tile), gathered traffic ~ n_out x k3 x c_in: where the unsplit grid
+  // already has a few dozen CTAs, keep the former below about half of the latter (the 512-channel maps with ~2k rows
+  // ran 1.3x faster with 1-2 splits than with 3-6: tools/sweep.py, wg_wv)
+  const int64_t traffic_cap = n_out / (2 * (int64_t)p.c_out);
+  if (base >= 48 && splits > traffic_cap) splits = traffic_cap;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
   int64_t rows = ceil_div64(n_out, splits);

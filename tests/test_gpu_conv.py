@@ -220,3 +220,33 @@ def test_parity_plan_and_strided_dgrad(cuda):
         dense = Fn.gather_gemm(gy, w, None, km.inv, km.n_out, km.n_in, cout, cin, km.k3, 1, impl=TC, prerounded=True)
         sparse = Fn.dgrad_strided(gy, w, km, cout, cin)
         util.assert_close(sparse, dense, tol=2e-5, what=f"parity dgrad K={K}")   # fp32 summation order only
+
+
+@pytest.mark.parametrize("n,cin,cout", [(700, 64, 64), (1300, 128, 128), (257, 64, 128), (900, 128, 64),
+                                        (300, 128, 256), (400, 256, 512)])
+def test_conv_m256_tiles(cuda, n, cin, cout):
+    """The M = 256 variant of the tcgen05 kernel (two accumulator tiles per CTA sharing every weight stage; chosen
+    automatically only for maps with >= 148 such tiles, forced here through the tuning knob): forward with bias and
+    dgrad (transposed weights, reversed kernel index) against the oracle's tf32 model, incl. a partial last tile."""
+    c, out, nbr = _maps(n, seed=7)
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((c.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) * 0.05).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    gy = rng.standard_normal((out.shape[0], cout)).astype(np.float32)
+    x32 = torch.from_numpy(x).requires_grad_()
+    with tf32_model():
+        ref = oo.conv(x32, torch.from_numpy(w), nbr, torch.from_numpy(b))
+        ref.backward(torch.from_numpy(gy))
+    ng = torch.from_numpy(nbr).to(cuda)
+    wg = torch.from_numpy(w).to(cuda)
+    L.set_tuning("tc_m256", 2)
+    try:
+        got = Fn.gather_gemm(torch.from_numpy(x).to(cuda), wg, torch.from_numpy(b).to(cuda), ng, c.shape[0],
+                             out.shape[0], cin, cout, 27, 0, impl=TC)
+        gx = Fn.gather_gemm(torch.from_numpy(gy).to(cuda), wg, None, ng, out.shape[0], c.shape[0], cout, cin, 27, 3,
+                            impl=TC)
+    finally:
+        L.set_tuning("tc_m256", -1)
+    util.assert_close(got, ref.detach(), tol=TF32_MODEL_TOL, what="M=256 forward vs tf32 model")
+    util.assert_close(gx, x32.grad, tol=TF32_MODEL_TOL, what="M=256 dgrad vs tf32 model")

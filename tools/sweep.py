@@ -58,7 +58,7 @@ for name, its, ots, K, cin, cout in layers:
     prep.append((name, km, xf, w, gy, cin, cout))
 
 
-ALL_KEYS = ("wg_nbp", "wg_lag", "wg_occ2", "wg_ca", "tc_rot", "tc_ca", "tc_occ1")
+ALL_KEYS = ("wg_nbp", "wg_lag", "wg_occ2", "wg_ca", "wg_wv", "tc_m256", "tc_rot", "tc_ca", "tc_occ1")
 
 
 def apply(cfg):
