@@ -901,10 +901,11 @@ int launch_tc2(const float* x, const float* wimg, const float* bias, const int* 
   const int64_t ctas = ceil_div64(n_out, 2 * BM) * (c_out / BN);
   const int kc = c_in / BK;
   int splits = 1;
-  if (ctas < B2S_NUM_SMS) {                      // too few output tiles for 148 SMs: split the K loop
-    splits = (int)((B2S_NUM_SMS + ctas - 1) / ctas);
+  if (ctas < B2S_NUM_SMS) {   // too few output tiles for 148 SMs: split the K loop, but stay within ONE wave (one CTA
+    splits = (int)(B2S_NUM_SMS / ctas);             // per SM: a 149th CTA would double the kernel's time)
     const int max_splits = T / 16 > 0 ? T / 16 : 1;                 // >= 16 stages per split
     if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
   }
   int per = (T + splits - 1) / splits;
   per = ((per + kc - 1) / kc) * kc;
