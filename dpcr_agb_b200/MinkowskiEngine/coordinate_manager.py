@@ -109,6 +109,10 @@ class KernelMap:
                 and all(s == t for s, t in zip(self.step, tin))
             if not ok:
                 self._plan = False
+            elif (self.in_key, self.out_key) in cm.parity_plans:
+                # the plan sorts the fine rows by their position in the coarse cell: it depends on the two maps only,
+                # so the k3 convolution and the k1 downsample convolution of a block share it
+                self._plan = cm.parity_plans[(self.in_key, self.out_key)]
             else:
                 imap = cm.maps[self.in_key]
                 rows = L.query("b2s_parity_plan_rows", imap.n)
@@ -118,6 +122,7 @@ class KernelMap:
                 scratch = torch.empty(16, dtype=torch.int32, device=dev)
                 L.call("b2s_parity_plan", imap.coords, imap.n, imap.n_dev, L.host_i32(*tout), perm, bounds, scratch)
                 self._plan = (perm, bounds)
+                cm.parity_plans[(self.in_key, self.out_key)] = self._plan
         return self._plan or None
 
     def pairs(self):
@@ -144,6 +149,7 @@ class CoordinateManager:
         self.device = device
         self.maps = {}
         self.kernel_maps = {}
+        self.parity_plans = {}
         self.capacities = dict(capacities) if capacities is not None else None
         self.static = capacities is not None
         if self.static:
@@ -164,21 +170,39 @@ class CoordinateManager:
         assert self.static and coords.dtype == torch.int32 and coords.is_contiguous() and coords.shape[1] == 4
         cap_rows = coords.shape[0]
         dev = coords.device
-        hcap = L.query("b2s_hash_capacity", cap_rows)
-        table = torch.empty(hcap * 16, dtype=torch.uint8, device=dev)
-        slot = torch.empty(max(cap_rows, 1), dtype=torch.int32, device=dev)
-        rank = torch.empty(max(cap_rows, 1), dtype=torch.int32, device=dev)
-        info = torch.empty(4, dtype=torch.int32, device=dev)
-        scan_ws = torch.empty(L.query("b2s_scan_workspace_bytes", cap_rows), dtype=torch.uint8, device=dev)
-        L.call("b2s_coordmap_insert", coords, cap_rows, n_dev, L.host_i32(1, 1, 1), table, hcap, slot, rank, info,
-               scan_ws)
         key = CoordinateMapKey(tensor_stride, tag)
-        self.maps[key] = CoordMap(coords, table, hcap, n_dev=n_dev, info=info)   # unique rows: table values == rows
-        self.maps[key].dense = dense_index
         self.device = dev
         self.checks.append((f"rows at tensor stride {key.tensor_stride[0]}", cap_rows, n_dev))
-        self.checks.append(("coordinate range flag", 0, info[1:2]))
+        if dense_index is not None and USE_DENSE_INDEX:
+            # every kernel map over these rows goes through the quantiser's occupancy index and the strided map
+            # below builds its own table: the hash of the finest map (the largest of the step) would never be probed.
+            # It is built on first use (_table_of); the coordinate range is bounded by the quantiser's box.
+            cmap = CoordMap(coords, None, 0, n_dev=n_dev, info=None)
+            cmap.dense = dense_index
+            self.maps[key] = cmap
+            return key
+        cmap = CoordMap(coords, None, 0, n_dev=n_dev, info=None)
+        self._table_of(cmap)
+        cmap.dense = dense_index
+        self.maps[key] = cmap
         return key
+
+    def _table_of(self, cmap: CoordMap):
+        """Hash table of a map whose rows are unique (table values == rows); built on first use."""
+        if cmap.table is None:
+            cap_rows, dev = cmap.coords.shape[0], cmap.coords.device
+            hcap = L.query("b2s_hash_capacity", cap_rows)
+            table = torch.empty(hcap * 16, dtype=torch.uint8, device=dev)
+            slot = torch.empty(max(cap_rows, 1), dtype=torch.int32, device=dev)
+            rank = torch.empty(max(cap_rows, 1), dtype=torch.int32, device=dev)
+            info = torch.empty(4, dtype=torch.int32, device=dev)
+            scan_ws = torch.empty(L.query("b2s_scan_workspace_bytes", cap_rows), dtype=torch.uint8, device=dev)
+            L.call("b2s_coordmap_insert", cmap.coords, cap_rows, cmap.n_dev, L.host_i32(1, 1, 1), table, hcap, slot,
+                   rank, info, scan_ws)
+            cmap.table, cmap.capacity, cmap.info = table, hcap, info
+            if self.static:
+                self.checks.append(("coordinate range flag", 0, info[1:2]))
+        return cmap.table
 
     # ------------------------------------------------------------------ map construction
     def _build(self, coords: torch.Tensor, ts_floor, want_in2out=True):
@@ -272,7 +296,8 @@ class CoordinateManager:
             L.call("b2s_kernel_map_dense", query_map.coords, n, query_map.n_dev, ws, num_plots, L.host_i32(*lo),
                    L.host_i32(*dims), L.host_i32(*kernel_size), L.host_i32(*step), sign, nbr)
             return nbr
-        L.call("b2s_kernel_map", query_map.coords, n, query_map.n_dev, table_map.table, table_map.capacity,
+        table = self._table_of(table_map)
+        L.call("b2s_kernel_map", query_map.coords, n, query_map.n_dev, table, table_map.capacity,
                L.host_i32(*kernel_size), L.host_i32(*step), sign, nbr)
         return nbr
 
