@@ -93,8 +93,10 @@ class KernelMap:
     @property
     def inv(self):
         """Transposed table ``[K^3, N_in]``: ``inv[k, i] = o`` iff ``nbr[k, o] = i`` (strided maps only)."""
+        self.manager._join(("inv", id(self)))
         if self._inv is None:
             cm = self.manager
+            cm._note(("inv", self.in_key, self.out_key, self.kernel_size))
             self._inv = cm._probe(cm.maps[self.in_key], cm.maps[self.out_key], self.kernel_size, self.step, -1)
         return self._inv
 
@@ -102,8 +104,10 @@ class KernelMap:
     def parity_plan(self):
         """(perm, bounds) of ``b2s_parity_plan`` for the fine (input) rows of a stride-2 map, or None when the map is
         not a stride-2 map with kernel sizes 1 or 3 (dgrad then takes the dense transposed table)."""
+        self.manager._join(("plan", id(self)))
         if getattr(self, "_plan", None) is None:
             cm = self.manager
+            cm._note(("plan", self.in_key, self.out_key, self.kernel_size))
             tin, tout = self.in_key.tensor_stride, self.out_key.tensor_stride
             ok = all(o == 2 * i for i, o in zip(tin, tout)) and all(k in (1, 3) for k in self.kernel_size) \
                 and all(s == t for s, t in zip(self.step, tin))
@@ -150,12 +154,75 @@ class CoordinateManager:
         self.maps = {}
         self.kernel_maps = {}
         self.parity_plans = {}
+        # Map journal: every map-building operation of a step in the order it happened.  A later step with the same
+        # network can replay it up front on a side stream (prebuild), so that the integer pipeline -- hash inserts,
+        # kernel maps, transposed tables, parity plans, per-plot counts -- overlaps the stem convolution instead of
+        # sitting between the layers.  _side: the stream whose work the first consumer of a prebuilt map must join.
+        self.journal = []
+        self._side = None
+        self._replaying = False
+        self._main_built = set()
         self.capacities = dict(capacities) if capacities is not None else None
         self.static = capacities is not None
         if self.static:
             assert num_batches is not None, "static mode needs num_batches"
         self.num_batches = int(num_batches) if num_batches is not None else 0
         self.checks = []     # static mode: (description, capacity, int32 device tensor [>=1]) to verify after a replay
+
+    # ------------------------------------------------------------------ journal / prebuild
+    def _note(self, op):
+        if not self._replaying:
+            self.journal.append(op)
+
+    def _join(self, what):
+        """Called by every map accessor: the first request for anything that was not built on the caller's stream
+        makes that stream wait for the side stream."""
+        if self._side is not None and not self._replaying and what not in self._main_built:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side = None
+
+    def _replay(self, op):
+        kind = op[0]
+        if kind == "stride":
+            self.stride(op[1], op[2])
+        elif kind == "kmap":
+            self.kernel_map(op[1], op[2], op[3], op[4])
+        elif kind in ("inv", "plan"):
+            km = next((k for k in self.kernel_maps.values()
+                       if (k.in_key, k.out_key, k.kernel_size) == (op[1], op[2], op[3])), None)
+            if km is not None:
+                _ = km.inv if kind == "inv" else km.parity_plan
+        elif kind == "invc":
+            self.inv_counts(op[1])
+
+    def prebuild(self, journal, side_stream, main_first=1):
+        """Replay a previous step's map journal: the first ``main_first`` operations (the stem's kernel map, which the
+        first convolution needs at once) on the current stream, the rest on ``side_stream`` forked from it here and
+        joined by the first consumer (``_join``).  Results are identical to building on demand -- same kernels, same
+        inputs -- only their place in the stream order changes."""
+        self._replaying = True
+        try:
+            for op in journal[:main_first]:
+                self._replay(op)
+                if op[0] == "kmap":
+                    self._main_built.add(("kmap", (op[1], op[2], op[3], op[4])))
+                elif op[0] == "stride":
+                    ts = tuple(a * b for a, b in zip(op[1].tensor_stride, _triple(op[2])))
+                    self._main_built.add(("map", CoordinateMapKey(ts, op[1].tag)))
+            main = torch.cuda.current_stream()
+            side_stream.wait_stream(main)
+            with torch.cuda.stream(side_stream):
+                for op in journal[main_first:]:
+                    self._replay(op)
+        finally:
+            self._replaying = False
+        self._side = side_stream
+
+    def join_side(self):
+        """Make the current stream wait for any outstanding prebuild work (end of a step)."""
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side = None
 
     def capacity_of(self, tensor_stride):
         ts = tensor_stride[0]
@@ -252,7 +319,9 @@ class CoordinateManager:
         stride = _triple(stride)
         ts = tuple(a * b for a, b in zip(in_key.tensor_stride, stride))
         out_key = CoordinateMapKey(ts, in_key.tag)
+        self._join(("map", out_key))
         if out_key not in self.maps:
+            self._note(("stride", in_key, stride))
             if self.static:
                 self.maps[out_key] = self._build_static(self.maps[in_key], ts)
             else:
@@ -304,8 +373,10 @@ class CoordinateManager:
     def kernel_map(self, in_key, out_key, kernel_size, dilation=(1, 1, 1)) -> KernelMap:
         kernel_size, dilation = _triple(kernel_size), _triple(dilation)
         ck = (in_key, out_key, kernel_size, dilation)
+        self._join(("kmap", ck))
         km = self.kernel_maps.get(ck)
         if km is None:
+            self._note(("kmap", in_key, out_key, kernel_size, dilation))
             step = tuple(d * t for d, t in zip(dilation, in_key.tensor_stride))
             imap, omap = self.maps[in_key], self.maps[out_key]
             nbr = self._probe(omap, imap, kernel_size, step, +1)
@@ -339,8 +410,10 @@ class CoordinateManager:
 
     def inv_counts(self, key):
         """float32 [B]: 1 / (rows of each plot) -- the average-pooling scale."""
+        self._join(("invc", key))
         m = self.maps[key]
         if m._inv_counts is None:
+            self._note(("invc", key))
             counts = torch.empty(self.num_batches, dtype=torch.int32, device=m.coords.device)
             L.call("b2s_batch_counts", m.coords, 4, m.n, m.n_dev, self.num_batches, counts)
             m._inv_counts = 1.0 / counts.clamp(min=1).float()

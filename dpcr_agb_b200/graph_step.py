@@ -75,6 +75,9 @@ class GraphStep:
         self.capture_collective = capture_collective or trainer.world == 1
         self.graph = None
         self.graph_tail = None
+        self.overlap_maps = True          # replay the map journal of the first warm-up step on a side stream
+        self.map_journal = None
+        self.side_stream = torch.cuda.Stream()
         self.status = None          # int32 device tensor: live row counts / flags recorded during capture
         self.status_meta = []
         self.launches_per_step = 0  # C-ABI calls recorded into the graph (== kernels-of-ours launches, lower bound)
@@ -88,10 +91,17 @@ class GraphStep:
         tr.opt.zero_grad()
         x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"], num_rows=vox["num_rows"],
                             capacities=self.capacities, num_batches=self.B, dense_index=vox["index"])
+        cm = x.coordinate_manager
+        if self.overlap_maps and self.map_journal is not None:
+            # build every coordinate structure of the step on a side stream while the stem convolution runs
+            cm.prebuild(self.map_journal, self.side_stream)
         pred = tr.model(x)
         loss = T.reg_loss(pred, self.inp["target"], tr.center, tr.scale)
         with tr.direct_grads():
             loss.backward()
+        cm.join_side()
+        if self.map_journal is None:
+            self.map_journal = list(cm.journal)
         self.loss.copy_(loss.detach())
         cm = x.coordinate_manager
         self.status_meta = [(what, cap) for what, cap, _ in cm.checks]
