@@ -331,7 +331,7 @@ class BatchNormFunction(torch.autograd.Function):
         if training:
             mean = torch.empty(c, dtype=torch.float32, device=dev)
             invstd = torch.empty(c, dtype=torch.float32, device=dev)
-            ws = torch.empty(2 * c, dtype=torch.float64, device=dev)
+            ws = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
             L.call("b2s_bn_stats", x, n, n_dev, c, float(eps), float(momentum), running_mean, running_var, ws, mean,
                    invstd)
         else:
@@ -354,7 +354,7 @@ class BatchNormFunction(torch.autograd.Function):
         gy = gy.contiguous()
         dev = x.device
         sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
-        ws = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        ws = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
         L.call("b2s_bn_bwd_reduce", gy, x, mean, invstd, weight, bias, n, ctx.nd, c, ctx.act, ws, sums)
         gx = None
         if ctx.needs_input_grad[0]:

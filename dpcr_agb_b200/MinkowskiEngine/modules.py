@@ -256,6 +256,23 @@ class MinkowskiLinear(nn.Module):
                 f"out_features={self.linear.out_features}, bias={self.linear.bias is not None})")
 
 
+# ``with deferred_bn_counters():`` (dpcr_agb_b200.train) -- the ``num_batches_tracked += 1`` of every batch-norm layer
+# becomes ONE multi-tensor add after the forward pass instead of one tiny launch per layer.
+DEFERRED_BN_COUNTERS = None
+
+
+class deferred_bn_counters:
+    def __enter__(self):
+        global DEFERRED_BN_COUNTERS
+        self.old, DEFERRED_BN_COUNTERS = DEFERRED_BN_COUNTERS, []
+
+    def __exit__(self, *exc):
+        global DEFERRED_BN_COUNTERS
+        pending, DEFERRED_BN_COUNTERS = DEFERRED_BN_COUNTERS, self.old
+        if pending and exc[0] is None:
+            torch._foreach_add_(pending, 1)
+
+
 class MinkowskiBatchNorm(nn.Module):
     """nn.BatchNorm1d semantics over all rows of the batch, computed by the b2s_bn_* kernels.
 
@@ -275,7 +292,10 @@ class MinkowskiBatchNorm(nn.Module):
         use_batch_stats = bn.training or bn.running_mean is None
         momentum = bn.momentum
         if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+            if DEFERRED_BN_COUNTERS is not None and momentum is not None:
+                DEFERRED_BN_COUNTERS.append(bn.num_batches_tracked)   # one fused add for all layers after the forward
+            else:
+                bn.num_batches_tracked.add_(1)
             if momentum is None:
                 momentum = 1.0 / float(bn.num_batches_tracked)
         update = bn.training and bn.track_running_stats

@@ -349,6 +349,18 @@ constexpr int CR_THREADS = 512;
 constexpr int CR_SLAB = 64;                         // channels per CTA
 constexpr int CR_TPR = CR_SLAB / 4;                 // threads per row
 constexpr int CR_RPB = CR_THREADS / CR_TPR;         // row lanes
+// What the LAST CTA of a column reduction does with the finished sums (it is elected by a ticket counter stored behind
+// the 2c accumulators; the caller zeroes accumulators and ticket with one memset): nothing, the batch-norm statistics
+// (mean / invstd / running buffers) or the fp64 -> fp32 copy of the backward sums.  Saves one dependent launch per call.
+struct CrFinal {
+  int kind;              // 0 none, 1 batch-norm statistics, 2 copy to float
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  float* out0;           // kind 1: mean [c]; kind 2: sums [2c]
+  float* out1;           // kind 1: invstd [c]
+};
+
 template <int MODE, typename ACC, int U>
 __global__ void __launch_bounds__(CR_THREADS, 1) colreduce_v4_kernel(const float* __restrict__ x,
                                                                      const float* __restrict__ g,
@@ -357,7 +369,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) colreduce_v4_kernel(const float
                                                                      const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, int64_t n,
                                                                      const int* __restrict__ n_dev, int c, int act,
-                                                                     ACC* __restrict__ ws) {
+                                                                     ACC* __restrict__ ws, CrFinal fin) {
   n = b2s_rows(n, n_dev);
   __shared__ float4 sm[2][CR_THREADS];
   const int tc = threadIdx.x % CR_TPR, tr = threadIdx.x / CR_TPR;
@@ -427,6 +439,37 @@ __global__ void __launch_bounds__(CR_THREADS, 1) colreduce_v4_kernel(const float
     const int cc = blockIdx.y * CR_SLAB + threadIdx.x;
     atomicAdd(&ws[cc], (ACC)s0[threadIdx.x]);
     if (MODE != 0) atomicAdd(&ws[c + cc], (ACC)s1[threadIdx.x]);
+  }
+  if (MODE != 0 && fin.kind != 0) {
+    __shared__ int is_last;
+    __threadfence();                                   // this CTA's atomics are visible before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned* ticket = reinterpret_cast<unsigned*>(ws + 2 * c);
+      is_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const double dn = n > 0 ? (double)n : 1.0;
+      if (fin.kind == 1) {
+        for (int ch2 = threadIdx.x; ch2 < c; ch2 += blockDim.x) {
+          const double m = (double)__ldcg(&ws[ch2]) / dn;
+          double var = (double)__ldcg(&ws[c + ch2]) / dn - m * m;
+          if (var < 0.0) var = 0.0;
+          fin.out0[ch2] = (float)m;
+          fin.out1[ch2] = (float)(1.0 / sqrt(var + (double)fin.eps));
+          if (fin.running_mean)
+            fin.running_mean[ch2] = (1.f - fin.momentum) * fin.running_mean[ch2] + fin.momentum * (float)m;
+          if (fin.running_var) {
+            const double unb = n > 1 ? var * dn / (dn - 1.0) : var;
+            fin.running_var[ch2] = (1.f - fin.momentum) * fin.running_var[ch2] + fin.momentum * (float)unb;
+          }
+        }
+      } else {
+        for (int e = threadIdx.x; e < 2 * c; e += blockDim.x) fin.out0[e] = (float)__ldcg(&ws[e]);
+      }
+    }
   }
 }
 
@@ -848,8 +891,9 @@ dim3 colgrid(int64_t n, int c) { return dim3((unsigned)ceil_div64(n, ROWS_PER_CT
 
 // column reduction launch: the float4 kernel whenever the rows are 16-byte aligned vectors, else the scalar one
 template <int MODE, typename ACC>
-void launch_colreduce(const float* x, const float* g, const float* mean, const float* invstd, const float* gamma,
-                      const float* beta, int64_t n, const int* n_dev, int c, int act, ACC* ws, cudaStream_t st) {
+bool launch_colreduce(const float* x, const float* g, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, int64_t n, const int* n_dev, int c, int act, ACC* ws, cudaStream_t st,
+                      CrFinal fin = CrFinal{}) {
   const int v4 = g_b2s_cr_v4 >= 0 ? g_b2s_cr_v4 : 1;
   if (v4 && c % CR_SLAB == 0 && vec_of(c, x, g, mean, invstd) == 4 && vec_of(c, gamma, beta) == 4) {
     // slabs x row shares ~ `cap` (default one) CTA per SM, >= 4 rows per thread
@@ -861,11 +905,12 @@ void launch_colreduce(const float* x, const float* g, const float* mean, const f
     if (shares < 1) shares = 1;
     constexpr int U = MODE == 2 ? 4 : 8;
     colreduce_v4_kernel<MODE, ACC, U><<<dim3((unsigned)shares, (unsigned)slabs), CR_THREADS, 0, st>>>(
-        x, g, mean, invstd, gamma, beta, n, n_dev, c, act, ws);
-  } else {
-    colreduce_kernel<MODE, ACC><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, g, mean, invstd, gamma, beta, n, n_dev, c, act,
-                                                                      ws);
+        x, g, mean, invstd, gamma, beta, n, n_dev, c, act, ws, fin);
+    return fin.kind != 0;
   }
+  colreduce_kernel<MODE, ACC><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, g, mean, invstd, gamma, beta, n, n_dev, c, act,
+                                                                    ws);
+  return false;
 }
 
 }  // namespace
@@ -1021,10 +1066,11 @@ extern "C" int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev,
   B2S_CHECK_ARG(n > 0 && c > 0, "n > 0 and c > 0");
   B2S_CHECK_ARG(x && stats_ws && mean && invstd, "null pointer");
   cudaStream_t st = as_stream(stream);
-  B2S_CUDA(cudaMemsetAsync(stats_ws, 0, 2 * (size_t)c * sizeof(double), st));
-  launch_colreduce<1, double>(x, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c, 0, stats_ws, st);
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(stats_ws, n, n_dev, c, eps, momentum, running_mean,
-                                                      running_var, mean, invstd);
+  B2S_CUDA(cudaMemsetAsync(stats_ws, 0, (2 * (size_t)c + 1) * sizeof(double), st));
+  CrFinal fin{1, eps, momentum, running_mean, running_var, mean, invstd};
+  if (!launch_colreduce<1, double>(x, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c, 0, stats_ws, st, fin))
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(stats_ws, n, n_dev, c, eps, momentum, running_mean,
+                                                        running_var, mean, invstd);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -1052,9 +1098,10 @@ extern "C" int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const floa
   B2S_CHECK_ARG(n > 0 && c > 0 && (act == 0 || act == 1), "bad arguments");
   B2S_CHECK_ARG(gy && x && mean && invstd && stats_ws && sums, "null pointer");
   cudaStream_t st = as_stream(stream);
-  B2S_CUDA(cudaMemsetAsync(stats_ws, 0, 2 * (size_t)c * sizeof(double), st));
-  launch_colreduce<2, double>(x, gy, mean, invstd, gamma, beta, n, n_dev, c, act, stats_ws, st);
-  double_to_float_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(stats_ws, sums, 2 * c);
+  B2S_CUDA(cudaMemsetAsync(stats_ws, 0, (2 * (size_t)c + 1) * sizeof(double), st));
+  CrFinal fin{2, 0.f, 0.f, nullptr, nullptr, sums, nullptr};
+  if (!launch_colreduce<2, double>(x, gy, mean, invstd, gamma, beta, n, n_dev, c, act, stats_ws, st, fin))
+    double_to_float_kernel<<<(2 * c + 127) / 128, 128, 0, st>>>(stats_ws, sums, 2 * c);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -95,7 +95,8 @@ class GraphStep:
         if self.overlap_maps and self.map_journal is not None:
             # build every coordinate structure of the step on a side stream while the stem convolution runs
             cm.prebuild(self.map_journal, self.side_stream)
-        pred = tr.model(x)
+        with tr.deferred_counters():
+            pred = tr.model(x)
         loss = T.reg_loss(pred, self.inp["target"], tr.center, tr.scale)
         with tr.direct_grads():
             loss.backward()

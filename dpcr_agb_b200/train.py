@@ -162,6 +162,13 @@ class Trainer:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.num_batches = 0
 
+    def deferred_counters(self):
+        mods = getattr(self.ME, "modules", None)
+        if mods is not None and hasattr(mods, "deferred_bn_counters"):
+            return mods.deferred_bn_counters()
+        import contextlib
+        return contextlib.nullcontext()
+
     def direct_grads(self):
         fn = getattr(self.ME, "MinkowskiFunctional", None)
         if fn is not None and hasattr(fn, "direct_param_grads"):
@@ -181,7 +188,8 @@ class Trainer:
         self.opt.zero_grad()
         kw = {"dense_index": dense_index} if dense_index is not None else {}
         x = self.ME.SparseTensor(features=feats, coordinates=coords, **kw)
-        pred = self.model(x)
+        with self.deferred_counters():
+            pred = self.model(x)
         loss = reg_loss(pred, target, self.center, self.scale)
         with self.direct_grads():            # .grad = views of the flat buffer zeroed above: kernels write in place
             loss.backward()

@@ -222,6 +222,8 @@ B2S_API int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float* y
  * bn_bwd_reduce : sums[0..c) = sum gy', sums[c..2c) = sum gy'*xhat  (gy' = gy through the fused act);
  *                 these are also grad_beta and grad_gamma.
  * bn_bwd_apply  : training: gx = gamma*invstd*(gy' - sums0/n - xhat*sums1/n); eval: gx = gamma*invstd*gy'.
+ * stats_ws      : caller-provided scratch of 2c + 1 doubles (2c accumulators + a ticket with which the last CTA of the
+ *                 reduction is elected to finalise: mean / invstd / running buffers, or the fp32 sums).
  * gelu_fwd/bwd  : exact erf GELU on a flat array.
  * TF32 twins     : maxpool_fwd, bn_apply, bn_bwd_apply and add_gelu_fwd take a nullable `*_tf32` output that receives
  *                 the result rounded to TF32 (round-to-nearest), i.e. the operand form b2s_round_tf32 would produce

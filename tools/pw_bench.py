@@ -51,7 +51,7 @@ for cfg in CFGS:
         mean, invstd = torch.zeros(c, device=dev), torch.ones(c, device=dev)
         gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
         rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
-        ws = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        ws = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
         sums = torch.empty(2 * c, device=dev)
         gb = torch.empty(c, device=dev)
         t_stats = graph_time(lambda i: L.call("b2s_bn_stats", xs[i], n, None, c, 1e-5, 0.1, rm, rv, ws, mean, invstd))
