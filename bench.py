@@ -232,9 +232,12 @@ def run_b200(args):
         gstep.load(d)
         return gstep.step()
 
+    last_loss = [None]
+
     def step_from_host(h):
         gstep.load(h)                                             # pinned host -> device copies of this step's inputs
-        return float(gstep.step())                                # device -> host read of the step's result
+        last_loss[0] = float(gstep.step())                        # device -> host read of the step's result
+        return last_loss[0]
 
     def timed(fn, items, steps):
         barrier()
@@ -340,7 +343,7 @@ def run_b200(args):
                         f"({'; '.join(i['instance'] for i in inst)}); {tr_['source']}")
     except Exception:
         pass
-    roofline = {"kernel": "gather_gemm_tc_kernel (b2s_conv_gather_gemm: conv forward + dgrad, tcgen05 kind::tf32)",
+    roofline = {"kernel": "gather_gemm_tc_kernel + gather_gemm_tc2_kernel (b2s_conv_gather_gemm: conv forward + dgrad, tcgen05 kind::tf32; M = 128 and M = 256 tiles)",
                 "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": achieved / tf32_peak if tf32_peak else None, "traffic": traffic, "traffic_note": traffic_note,
                 "algorithmic_bytes_per_launch": (work.get("fwd", {"bytes": 0})["bytes"]
@@ -363,7 +366,7 @@ def run_b200(args):
             "config": workload(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": calls, "gpu_launches_note": "C-ABI calls into libb200sparse.so recorded in the captured "
+            "last_loss": last_loss[0], "gpu_launches": calls, "gpu_launches_note": "C-ABI calls into libb200sparse.so recorded in the captured "
                                                         "step graph x steps (each launches 1-4 kernels of ours)",
             "row_capacities": caps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "breakdown_ms_per_step": breakdown}

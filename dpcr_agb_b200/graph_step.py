@@ -73,6 +73,8 @@ class GraphStep:
         for i, m in enumerate(self.drops):
             m.static_mask = self.drop_dev[i]
         self.capture_collective = capture_collective or trainer.world == 1
+        if not self.capture_collective:
+            trainer.overlap_comm = False      # the exchange stays outside the graph: no collective inside backward
         self.graph = None
         self.graph_tail = None
         self.overlap_maps = True          # replay the map journal of the first warm-up step on a side stream
@@ -113,7 +115,7 @@ class GraphStep:
         torch.maximum(self.status, status, out=self.status)
 
     def _tail(self):
-        T.allreduce_mean_(self.tr.opt.flat_grad, self.tr.world)
+        self.tr.exchange_gradients()
         self.tr.opt.step_from_device()
 
     def _body(self):
@@ -175,7 +177,7 @@ class GraphStep:
             self.drop_dev.copy_(self.drop_pinned, non_blocking=True)
         self.graph.replay()
         if not self.capture_collective:
-            T.allreduce_mean_(tr.opt.flat_grad, tr.world)
+            tr.exchange_gradients()
             self.graph_tail.replay()
         return self.loss
 

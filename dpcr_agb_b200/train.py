@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
@@ -161,6 +163,62 @@ class Trainer:
         self.scale = torch.tensor(target_scale, dtype=torch.float32, device=dev)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.num_batches = 0
+        # Gradient exchange overlapped with the backward pass: the parameters of the last stage and the head (85 % of
+        # MSENet's weights) sit at the END of the flat buffer and their gradients are complete EARLY in the backward
+        # pass -- as soon as the gradient of the last stage's input exists.  A tensor hook there starts the all-reduce
+        # of that slice on a second stream; the rest of the buffer follows after the backward pass.
+        self.overlap_comm = os.environ.get("B2S_OVERLAP_COMM", "0") == "1"   # opt-in: measured +0.4 % at 2 GPUs
+        self.late_offset = self._late_offset() if (self.world > 1 and dev.type == "cuda") else None
+        self.comm_stream = torch.cuda.Stream() if self.late_offset is not None else None
+        self._late_started = False
+        if self.late_offset is not None:
+            model.blocks[-1].register_forward_pre_hook(self._watch_late_input)
+
+    def _late_offset(self):
+        """Flat-buffer offset of the first parameter of the last stage (everything behind it belongs to that stage or
+        to the head), or None when the model does not have that shape."""
+        stages = getattr(self.model, "blocks", None)
+        if stages is None or len(stages) < 2:
+            return None
+        late = {id(p) for p in stages[-1].parameters()}
+        early = {id(p) for st in stages[:-1] for p in st.parameters()}
+        off, first = 0, None
+        for p in self.opt.params:
+            if first is None and id(p) in late:
+                first = off
+            elif first is not None and id(p) in early:      # an early-stage parameter behind the split point
+                return None
+            off += p.numel()
+        return first if first else None
+
+    def _watch_late_input(self, module, args):
+        x = args[0]
+        feats = getattr(x, "F", None)
+        if self.overlap_comm and torch.is_tensor(feats) and feats.requires_grad and torch.is_grad_enabled():
+            feats.register_hook(self._late_grads_ready)
+
+    def _late_grads_ready(self, grad):
+        """Autograd hook on the input of the last stage: every gradient behind ``late_offset`` is final (in-place
+        writes of the backward kernels / AccumulateGrad of the head run before this node)."""
+        if not self._late_started:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self.opt.flat_grad[self.late_offset:], op=dist.ReduceOp.SUM)
+            self._late_started = True
+        return None
+
+    def exchange_gradients(self):
+        """Average the flat gradient buffer over the ranks (finishing what the backward hook started)."""
+        if self.world <= 1:
+            return
+        g = self.opt.flat_grad
+        if self._late_started:
+            dist.all_reduce(g[:self.late_offset], op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+            self._late_started = False
+            g.mul_(1.0 / self.world)
+        else:
+            allreduce_mean_(g, self.world)
 
     def deferred_counters(self):
         mods = getattr(self.ME, "modules", None)
@@ -193,7 +251,7 @@ class Trainer:
         loss = reg_loss(pred, target, self.center, self.scale)
         with self.direct_grads():            # .grad = views of the flat buffer zeroed above: kernels write in place
             loss.backward()
-        allreduce_mean_(self.opt.flat_grad, self.world)   # == DDP's all-reduce with a single bucket
+        self.exchange_gradients()            # == DDP's all-reduce: two buckets, the big one overlapped with backward
         self.num_batches += 1
         self.opt.lr = self.sched.lr_at(self.num_batches / self.batches_per_epoch)
         self.opt.step()
