@@ -55,8 +55,12 @@ B2S_API int32_t b2s_version(void);
 B2S_API int32_t b2s_device_check(void);
 /* Diagnostic: overrides one launch-tuning knob of the convolution kernels for this process (results are unaffected,
  * only tile / pipeline shapes).  Keys: "wg_nbp", "wg_lag", "wg_occ2" (weight-gradient stage size cap in 2 KB blocks,
- * producer run-ahead in stages, 1 = two CTAs per SM), "tc_rot" (1 = every output tile starts its kernel-offset
- * loop at a different offset).  B2S_EINVAL for an unknown key.  Not part of the reference-facing surface. */
+ * producer run-ahead in stages, 1 = two CTAs per SM), "wg_wv" (half-waves of CTAs the row range is split over),
+ * "wg_ca" / "tc_ca" (1 = L1-allocating gathers), "tc_occ1" (1 = one CTA per SM), "tc_rot" (1 = every output tile
+ * starts its kernel-offset loop at a different offset), "tc_m256" (0 off, 1 = M = 256 tiles for 128-wide output tiles,
+ * 2 = wherever they can run, 3 = 64- and 128-wide), "cr_v4" / "cr_cap" (column reductions: 0 = scalar kernel; CTAs
+ * per SM).  A value < 0 restores the default.  B2S_EINVAL for an unknown key.  Not part of the reference-facing
+ * surface. */
 B2S_API int32_t b2s_set_tuning(const char* key, int32_t value);
 
 /* ---------------------------------------------------------------- (a1) voxel quantisation ----
