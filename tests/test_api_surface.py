@@ -159,3 +159,43 @@ def test_reference_senet14_equals_restatement_on_oracle():
         finally:
             for k in [k for k in sys.modules if k.startswith("torch_points3d") or k.startswith("MinkowskiEngine")]:
                 del sys.modules[k]
+
+
+def test_block_output_forms_follow_the_consumers():
+    """Host logic of the TF32-twin scheme (dpcr_agb_b200/msenet.py): a block whose output is consumed by convolutions
+    only (the next block has a downsample convolution) writes it TF32-rounded (2), one whose output also feeds an
+    identity residual writes the plain result plus the twin (1), the last block writes the plain result (0)."""
+    from dpcr_agb_b200 import MinkowskiEngine as ME
+    from dpcr_agb_b200 import msenet
+    flags = {}
+    for name in ("SENet14", "SENet50"):
+        m = msenet.MSENet(ME, name)
+        blocks = [b for st in m.blocks[1:] for b in st]
+        flags[name] = [b.out_tf32 for b in blocks]
+        for blk, nxt in zip(blocks, blocks[1:]):
+            has_down = not isinstance(nxt.downsample, torch.nn.Identity)
+            assert blk.out_tf32 == (2 if has_down else 1)
+        assert all(b._se_tail is not None for b in blocks)          # channel counts of both nets suit the fused tail
+    assert flags["SENet14"] == [2, 2, 2, 0]
+    assert flags["SENet50"] == [1, 1, 2, 1, 1, 1, 2, 1, 1, 1, 1, 1, 2, 1, 1, 0]
+
+
+def test_step_contexts_restore_their_flags():
+    """``direct_param_grads`` / ``deferred_bn_counters`` are process-wide switches used around one step: they must
+    nest and restore, and the deferred counters must be applied exactly once on exit."""
+    from dpcr_agb_b200.MinkowskiEngine import functional as Fn
+    from dpcr_agb_b200.MinkowskiEngine import modules as M
+    assert Fn.DIRECT_PARAM_GRADS is False
+    with Fn.direct_param_grads():
+        assert Fn.DIRECT_PARAM_GRADS is True
+        with Fn.direct_param_grads():
+            assert Fn.DIRECT_PARAM_GRADS is True
+        assert Fn.DIRECT_PARAM_GRADS is True
+    assert Fn.DIRECT_PARAM_GRADS is False
+    counters = [torch.zeros((), dtype=torch.long) for _ in range(3)]
+    assert M.DEFERRED_BN_COUNTERS is None
+    with M.deferred_bn_counters():
+        for t in counters:
+            M.DEFERRED_BN_COUNTERS.append(t)
+        assert all(int(t) == 0 for t in counters)
+    assert M.DEFERRED_BN_COUNTERS is None and all(int(t) == 1 for t in counters)
