@@ -132,6 +132,20 @@ def _tc(impl):
     return (CONV_IMPL if impl is None else impl) != 1
 
 
+# Shapes the tensor-core kernels cover -- mirrors b2s_conv_tc_supported / b2s_wgrad_tc_supported (csrc/conv_tc.cu,
+# wgrad_tc.cu).  Only these may be handed operands in operand form (``prerounded``): in the default split-bf16 mode
+# that form is a packed bit pattern, not a rounded float, and the library rejects it on the SIMT path.
+def _fwd_tc_ok(c_in, c_out):
+    return c_out % 64 == 0 and (c_in <= 4 or c_in % 32 == 0)
+
+
+def _wg_tc_ok(c_in, c_out, has_map):
+    if c_in <= 4:
+        return has_map and c_out % 32 == 0
+    blocks = c_in // 32
+    return c_in % 32 == 0 and c_out % 64 == 0 and (blocks >= 8 or (blocks & (blocks - 1)) == 0)
+
+
 def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None, n_out_dev=None,
                 prerounded=False):
     """y[o] = bias + sum_k x[nbr[k,o]] @ B_k  (C ABI ``b2s_conv_gather_gemm``).  ``n_out_dev``: device row count
@@ -178,10 +192,13 @@ class ConvolutionFunction(torch.autograd.Function):
         b = bias.contiguous().view(-1) if bias is not None else None
         # the tensor-core kernels consume TF32 operands: x is rounded once here and the rounded copy is what is
         # saved for wgrad (c_in <= 4: the stem pads + rounds inside the library)
-        pre = _tc(None) and c_in > 4
+        pre = _tc(None) and c_in > 4 and _fwd_tc_ok(c_in, c_out)
+        raw = feats
         if pre:
             feats = rounded_operand(feats, nd_in)
         out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0, n_out_dev=nd_out, prerounded=pre)
+        if pre and not _wg_tc_ok(c_in, c_out, kmap is not None):   # wgrad will run on the SIMT kernel: keep plain x
+            feats, pre = raw, False
         ctx.pre = pre
         ctx.kmap = kmap
         ctx.nd = (nd_in, nd_out)
@@ -200,24 +217,27 @@ class ConvolutionFunction(torch.autograd.Function):
         gy = gy.contiguous()
         nd_in, nd_out = ctx.nd
         gx = gw = gb = None
-        gyr, pre_gy = gy, False
-        if _tc(None) and c_out > 4:           # grad_out feeds dgrad and wgrad: round it once
-            gyr, pre_gy = rounded_operand(gy, nd_out), True
+        # grad_out feeds dgrad and wgrad: brought into operand form once, for whichever of the two runs on tensor cores
+        dg_ok = _tc(None) and c_out > 4 and _fwd_tc_ok(c_out, c_in) and ctx.needs_input_grad[0]
+        wg_ok = (_tc(None) and c_out % 32 == 0 and _wg_tc_ok(c_in, c_out, kmap is not None)
+                 and (ctx.pre or c_in <= 4) and ctx.needs_input_grad[1])
+        gyr = rounded_operand(gy, nd_out) if (dg_ok or wg_ok) else gy
         if ctx.needs_input_grad[0]:
+            gd, pre_gy = (gyr, True) if dg_ok else (gy, False)
             if kmap is None:
-                gx = gather_gemm(gyr, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1, n_out_dev=nd_in,
+                gx = gather_gemm(gd, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1, n_out_dev=nd_in,
                                  prerounded=pre_gy)
             elif kmap.symmetric:      # transposed map == same table with the kernel index reversed
-                gx = gather_gemm(gyr, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2, n_out_dev=nd_in,
+                gx = gather_gemm(gd, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2, n_out_dev=nd_in,
                                  prerounded=pre_gy)
             elif (USE_PARITY_DGRAD and pre_gy and CONV_IMPL == 0 and c_out % 32 == 0 and c_in % 64 == 0
                   and kmap.parity_plan is not None):
-                gx = dgrad_strided(gyr, kernel, kmap, c_out, c_in)
+                gx = dgrad_strided(gd, kernel, kmap, c_out, c_in)
             else:
-                gx = gather_gemm(gyr, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1, n_out_dev=nd_in,
+                gx = gather_gemm(gd, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1, n_out_dev=nd_in,
                                  prerounded=pre_gy)
         if ctx.needs_input_grad[1]:
-            both = pre_gy and (ctx.pre or c_in <= 4)      # feats is the rounded copy saved by forward
+            both = wg_ok                                  # feats is the operand-form copy saved by forward
             kp = ctx.params[0]
             gw = wgrad(feats, gyr if both else gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out, k3,
                        n_out_dev=nd_out, prerounded=both, out=kp.grad if _direct(kp) else None).view(kernel.shape)

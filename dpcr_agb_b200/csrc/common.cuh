@@ -40,6 +40,9 @@ void b2s_set_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
+// operand mode of the tensor-core convolutions (lib.cu): 1 = split-bf16 pairs (default), 0 = TF32
+int b2s_precise();
+
 static inline cudaStream_t as_stream(b2s_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

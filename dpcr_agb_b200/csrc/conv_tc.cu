@@ -29,6 +29,7 @@ constexpr int BK = 32;             // fp32 per K step == one 128-byte swizzle ro
 constexpr int A_STAGE_BYTES = BM * 128;
 constexpr int PRODUCERS = 128;     // warps 0..3 gather A and run the epilogue; warp 4 issues MMA
 constexpr int TC_THREADS = 160;
+constexpr int SMALL_NB = 3;        // weight images per stage of the small-c_in kernel in split-bf16 mode
 
 // ---------------------------------------------------------------------------------------------
 // weight image: img[it][n][32] (128 bytes per n, 16-byte chunks XOR-swizzled by n & 7)
@@ -37,16 +38,52 @@ constexpr int TC_THREADS = 160;
 // B_k[ci, co] = w[(k*c_in + ci)*c_out + co] (layout bit0 = 0) or w[(k*c_out + co)*c_in + ci] (bit0 = 1);
 // layout bit1 reverses the kernel index (k -> k3-1-k)
 // ---------------------------------------------------------------------------------------------
+// Split-bf16 mode (`precise`, see tc_ptx.cuh): a 128-byte image row holds 64 bf16.
+//   general: [H(32 channels) | L(32 channels)] of the same (offset, channel chunk) -- same bytes as the TF32 image;
+//   small  : per kernel offset 8 bf16 matching the operand row [h0..h3 | l0..l3], in SMALL_NB = 3 images
+//            (it*3 + j): j = 0 [H | H], j = 1 [M | M], j = 2 [L | 0] with W = H + M + L (24 bits: the k7 stem's
+//            weights need more than the 16-17 bits of a pair, and the l*M cross term, measured end to end: without
+//            them the stem kernel's own gradient is off by 4e-3 at BASELINE plot size).
+__device__ __forceinline__ float weight_at(const float* __restrict__ w, int c_in, int c_out, int k3, int w_layout, int k,
+                                           int ci, int n) {
+  if (k >= k3 || ci >= c_in) return 0.f;
+  const int kw = (w_layout & 2) ? k3 - 1 - k : k;  // bit 1: kernel index reversed (symmetric maps)
+  return !(w_layout & 1) ? w[((int64_t)kw * c_in + ci) * c_out + n] : w[((int64_t)kw * c_out + n) * c_in + ci];
+}
+
 __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restrict__ w, int c_in, int c_out, int k3,
-                                                           int w_layout, int small, int T,
+                                                           int w_layout, int small, int T, int precise,
                                                            float* __restrict__ img) {
-  const int64_t total = (int64_t)T * c_out * BK;
+  const int nb = (precise && small) ? SMALL_NB : 1;
+  const int64_t total = (int64_t)T * nb * c_out * BK;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int pos = (int)(e % BK);             // physical position inside the 128-byte row
     const int64_t rn = e / BK;
     const int n = (int)(rn % c_out);
-    const int it = (int)(rn / c_out);
+    const int itj = (int)(rn / c_out);
     const int chunk = (pos >> 2) ^ (n & 7);     // logical 16-byte chunk stored at this physical slot
+    if (precise) {
+      const int it = itj / nb, j = itj % nb;
+      const int k16 = chunk * 8 + (pos & 3) * 2;  // the two bf16 of this 4-byte slot: k16, k16 + 1
+      uint32_t out[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int kq = k16 + q;
+        uint32_t h, m, l;
+        if (small) {
+          const int s8 = kq & 7;
+          split_bf16x3(weight_at(w, c_in, c_out, k3, w_layout, it * 8 + (kq >> 3), s8 & 3, n), h, m, l);
+          out[q] = j == 0 ? h : (j == 1 ? m : (s8 < 4 ? l : 0u));
+        } else {
+          const int kc = c_in / BK;
+          split_bf16(weight_at(w, c_in, c_out, k3, w_layout, it / kc, (it % kc) * BK + (kq & 31), n), h, l);
+          out[q] = kq < 32 ? h : l;
+        }
+      }
+      img[e] = __uint_as_float(out[0] | (out[1] << 16));
+      continue;
+    }
+    const int it = itj;
     const int kk = chunk * 4 + (pos & 3);
     int k, ci;
     if (small) {
@@ -73,7 +110,7 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
 // reads that layout with ci fastest across threads -- one 32-byte sector per element.  Block = (iteration, 32 output
 // channels): rows of 32 co are read coalesced, 128-byte image rows are written coalesced.
 __global__ void __launch_bounds__(256) prep_weights_t_kernel(const float* __restrict__ w, int c_in, int c_out, int k3,
-                                                             int w_layout, float* __restrict__ img) {
+                                                             int w_layout, int precise, float* __restrict__ img) {
   __shared__ float t[32][33];
   const int it = blockIdx.x, n0 = blockIdx.y * 32, kc = c_in / BK;
   const int k = it / kc, ci0 = (it % kc) * BK;
@@ -86,25 +123,41 @@ __global__ void __launch_bounds__(256) prep_weights_t_kernel(const float* __rest
   for (int y = ty; y < 32; y += 8) {
     const int n = n0 + y;
     const int chunk = (tx >> 2) ^ (n & 7);
-    const int kk = chunk * 4 + (tx & 3);
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t[kk][y]));
+    if (precise) {
+      const int k16 = chunk * 8 + (tx & 3) * 2;   // [H(32) | L(32)]: the two bf16 of this slot
+      uint32_t h0, l0, h1, l1;
+      split_bf16(t[k16 & 31][y], h0, l0);
+      split_bf16(t[(k16 + 1) & 31][y], h1, l1);
+      r = k16 < 32 ? (h0 | (h1 << 16)) : (l0 | (l1 << 16));
+    } else {
+      const int kk = chunk * 4 + (tx & 3);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t[kk][y]));
+    }
     img[((int64_t)it * c_out + n) * BK + tx] = __uint_as_float(r);
   }
 }
 
-__global__ void __launch_bounds__(256) pad_rows4_kernel(const float* __restrict__ x, int64_t n, int c,
+__global__ void __launch_bounds__(256) pad_rows4_kernel(const float* __restrict__ x, int64_t n, int c, int precise,
                                                         float4* __restrict__ x4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (precise) {     // [h0 h1 h2 h3 | l0 l1 l2 l3] bf16
+      uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+      for (int j = 0; j < c; ++j) split_bf16(x[i * c + j], h[j], l[j]);
+      x4[i] = make_float4(__uint_as_float(h[0] | (h[1] << 16)), __uint_as_float(h[2] | (h[3] << 16)),
+                          __uint_as_float(l[0] | (l[1] << 16)), __uint_as_float(l[2] | (l[3] << 16)));
+      continue;
+    }
     for (int j = 0; j < c; ++j) v[j] = __uint_as_float(rna_tf32(__float_as_uint(x[i * c + j])));
     x4[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NB = 1>
 struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int B_IMG_BYTES = BN * 128;
+  static constexpr int B_STAGE_BYTES = NB * BN * 128;
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
   static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;  // full[S], empty[S], accum, tmem slot
@@ -125,7 +178,8 @@ struct PermArgs {
 };
 
 // LAG: a producer hands over stage (it - LAG) after issuing the copies of stage it (LAG + 1 stages of copies in flight)
-template <int BN, int STAGES, bool SMALL, int LAG, bool PERM = false>
+// flags: bit 0 = offset rotation, bit 1 = L1-allocating gathers, bit 2 = split-bf16 operands (NB > 1 implies it)
+template <int BN, int STAGES, bool SMALL, int LAG, bool PERM = false, int NB = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
@@ -133,6 +187,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                           const PermArgs pa, int flags) {
   const int rot_on = flags & 1;
   const bool l1 = (flags & 2) != 0;                // gather through L1 (cp.async.ca) instead of L2 only (.cg)
+  const bool precise = NB > 1 || (flags & 4) != 0;
   const int64_t pitch = n_out;                     // row pitch of the neighbour table (the caller's capacity)
   n_out = b2s_rows(n_out, n_out_dev);
   int cls = 0;
@@ -145,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if ((int64_t)blockIdx.x * BM >= n_out) {
     return;                                        // whole tile beyond the live rows (uniform across the CTA)
   }
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, NB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -254,8 +309,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const int git = (PERM || !SMALL) ? kof(g) * kc + cc : it0 + it;
       if (tid == 0) {
         mbar_arrive_expect_tx(full_bar(s), L::B_STAGE_BYTES);
-        bulk_g2s(b_base + s * L::B_STAGE_BYTES, wimg + ((int64_t)git * c_out + n0) * BK, L::B_STAGE_BYTES,
-                 full_bar(s));
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          bulk_g2s(b_base + s * L::B_STAGE_BYTES + j * L::B_IMG_BYTES,
+                   wimg + (((int64_t)git * NB + j) * c_out + n0) * BK, L::B_IMG_BYTES, full_bar(s));
       }
       const uint32_t a_stage = a_base + s * A_STAGE_BYTES;
 #pragma unroll
@@ -369,7 +426,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_fence_before();
   } else {
     // ===================== MMA issuer: warp 4 stays converged, lane 0 issues =====================
-    constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0);
+    constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0), IDESC16 = idesc_bf16(BM, BN, 0, 0);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < T; ++it) {
@@ -378,9 +435,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (lane == 0) {
         const uint64_t a_desc = smem_desc_sw128(a_base + s * A_STAGE_BYTES, 16, 1024);
         const uint64_t b_desc = smem_desc_sw128(b_base + s * L::B_STAGE_BYTES, 16, 1024);
+        if (!precise) {
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk)  // advance 32 bytes (8 tf32) inside the swizzle row per MMA
-          mma_tf32(tmem_d, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC, (it | kk) ? 1u : 0u);
+          for (int kk = 0; kk < BK / 8; ++kk)  // advance 32 bytes (8 tf32) inside the swizzle row per MMA
+            mma_tf32(tmem_d, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC, (it | kk) ? 1u : 0u);
+        } else if (NB == 1) {
+          // rows are [h | l] x [H | L], 32 bytes (16 bf16) per MMA: h*H (steps 0,1 x 0,1), l*H (2,3 x 0,1), h*L (0,1 x 2,3)
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            const int ak = q < 4 ? q : q - 4, bk = q < 2 ? q : q - 2;
+            mma_bf16(tmem_d, a_desc + (uint64_t)(ak * 2), b_desc + (uint64_t)(bk * 2), IDESC16, (it | q) ? 1u : 0u);
+          }
+        } else {
+          // small c_in: operand rows [h4 | l4] per offset against the images [H | H], [M | M], [L | 0]
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              mma_bf16(tmem_d, a_desc + (uint64_t)(kk * 2),
+                       b_desc + (uint64_t)((j * L::B_IMG_BYTES) >> 4) + (uint64_t)(kk * 2), IDESC16,
+                       (it | j | kk) ? 1u : 0u);
+        }
         mma_commit(empty_bar(s));
       }
       __syncwarp();
@@ -424,7 +499,7 @@ template <int BN, int STAGES, int LAG>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
     gather_gemm_tc2_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                            const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
-                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y) {
+                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y, int precise) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
   if ((int64_t)blockIdx.x * (2 * BM) >= n_out) return;
@@ -575,7 +650,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
     }
     tc_fence_before();
   } else {
-    constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0);
+    constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0), IDESC16 = idesc_bf16(BM, BN, 0, 0);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < T; ++it) {
@@ -586,10 +661,19 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           const uint64_t a_desc = smem_desc_sw128(a_base + s * L::A_STAGE + mt * A_STAGE_BYTES, 16, 1024);
+          if (!precise) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk)
-            mma_tf32(tmem_d + (uint32_t)(mt * BN), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC,
-                     (it | kk) ? 1u : 0u);
+            for (int kk = 0; kk < BK / 8; ++kk)
+              mma_tf32(tmem_d + (uint32_t)(mt * BN), a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESC,
+                       (it | kk) ? 1u : 0u);
+          } else {   // split-bf16: [h | l] x [H | L] -> h*H, l*H, h*L (see gather_gemm_tc_kernel)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              const int ak = q < 4 ? q : q - 4, bk = q < 2 ? q : q - 2;
+              mma_bf16(tmem_d + (uint32_t)(mt * BN), a_desc + (uint64_t)(ak * 2), b_desc + (uint64_t)(bk * 2), IDESC16,
+                       (it | q) ? 1u : 0u);
+            }
+          }
         }
         mma_commit(empty_bar(s));
       }
@@ -862,7 +946,7 @@ int launch_perm(const float* x, const float* wimg, const int* nbr, int64_t n_out
   }
   dim3 grid((unsigned)tiles_cap, (unsigned)(c_out / BN), 1);
   kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, nullptr, nbr, n_out, n_out_dev, c_in, c_out, k3, 0, 0, y, pa,
-                                               tc_ca() ? 2 : 0);
+                                               (tc_ca() ? 2 : 0) | (b2s_precise() ? 4 : 0));
   return 0;
 }
 
@@ -912,18 +996,19 @@ int launch_tc2(const float* x, const float* wimg, const float* bias, const int* 
   splits = (T + per - 1) / per;
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, 2 * BM), (unsigned)(c_out / BN), (unsigned)splits);
-  kern<<<grid, TC2_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y);
+  kern<<<grid, TC2_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y,
+                                                b2s_precise());
   return 0;
 }
 
 int tc_m256() { return tc_knob(g_b2s_tc_m256, "B2S_TC_M256", 1); }
 
-template <int BN, int STAGES, bool SMALL, int LAG = 2>
+template <int BN, int STAGES, bool SMALL, int LAG = 2, int NB = 1>
 int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, NB>;
   static_assert(LAG < STAGES, "producers run LAG stages ahead of their hand-over");
-  auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL, LAG>;
+  auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL, LAG, false, NB>;
   static bool attr_set = false;
   if (!attr_set) {
     constexpr int OPT_IN = L::DYN_BYTES > 116 * 1024 ? L::DYN_BYTES : 116 * 1024;
@@ -950,7 +1035,7 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
   kern<<<grid, TC_THREADS, dyn, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y, PermArgs{},
-                                      (tc_rot() ? 1 : 0) | (tc_ca() ? 2 : 0));
+                                      (tc_rot() ? 1 : 0) | (tc_ca() ? 2 : 0) | (b2s_precise() ? 4 : 0));
   return 0;
 }
 
@@ -967,8 +1052,8 @@ static inline int64_t align256(int64_t b) { return (b + 255) & ~(int64_t)255; }
 
 static int iterations(int c_in, int k3) { return c_in <= 4 ? (k3 + 7) / 8 : k3 * (c_in / BK); }
 
-int64_t b2s_conv_tc_image_bytes(int32_t c_in, int32_t c_out, int32_t k3) {
-  return align256((int64_t)iterations(c_in, k3) * c_out * 128);
+int64_t b2s_conv_tc_image_bytes(int32_t c_in, int32_t c_out, int32_t k3) {   // small c_in: room for SMALL_NB images
+  return align256((int64_t)iterations(c_in, k3) * (c_in <= 4 ? SMALL_NB : 1) * c_out * 128);
 }
 
 int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_in) {
@@ -977,11 +1062,13 @@ int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int
 
 static void launch_prep_weights(const float* w, int c_in, int c_out, int k3, int w_layout, bool small, int T, float* img,
                                 cudaStream_t st) {
+  const int precise = b2s_precise();
   if (!small && !(w_layout & 1) && c_in % BK == 0 && c_out % 32 == 0)
-    prep_weights_t_kernel<<<dim3((unsigned)T, (unsigned)(c_out / 32)), 256, 0, st>>>(w, c_in, c_out, k3, w_layout, img);
+    prep_weights_t_kernel<<<dim3((unsigned)T, (unsigned)(c_out / 32)), 256, 0, st>>>(w, c_in, c_out, k3, w_layout,
+                                                                                     precise, img);
   else
-    prep_weights_kernel<<<grid_for((int64_t)T * c_out * BK, 256), 256, 0, st>>>(w, c_in, c_out, k3, w_layout,
-                                                                               small ? 1 : 0, T, img);
+    prep_weights_kernel<<<grid_for((int64_t)T * (small && precise ? SMALL_NB : 1) * c_out * BK, 256), 256, 0, st>>>(
+        w, c_in, c_out, k3, w_layout, small ? 1 : 0, T, precise, img);
 }
 
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
@@ -995,10 +1082,15 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   const float* xin = x;
   if (small) {
     float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + b2s_conv_tc_image_bytes(c_in, c_out, k3));
-    pad_rows4_kernel<<<grid_for(n_in, 256), 256, 0, st>>>(x, n_in, c_in, x4);
+    pad_rows4_kernel<<<grid_for(n_in, 256), 256, 0, st>>>(x, n_in, c_in, b2s_precise(), x4);
     xin = reinterpret_cast<const float*>(x4);
   }
   const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
+  if (small && b2s_precise()) {   // three weight images per stage: one CTA per SM, deeper ring
+    if (bn == 256) return launch_tc<256, 2, true, 1, SMALL_NB>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
+    if (bn == 128) return launch_tc<128, 3, true, 2, SMALL_NB>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
+    return launch_tc<64, 5, true, 3, SMALL_NB>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
+  }
   if (small) {
     if (bn == 256) return launch_tc<256, 4, true>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
     if (bn == 128) return launch_tc<128, 3, true>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
@@ -1009,7 +1101,7 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
     const char* e = getenv("B2S_TC_VARIANT");
     variant = e ? atoi(e) : 0;
   }
-  if (variant >= 10 && n_in > 0) {   // TMA row gather (variant 10: default stages; 11: deeper)
+  if (variant >= 10 && n_in > 0 && !b2s_precise()) {   // TMA row gather (TF32 operands only) (variant 10: default stages; 11: deeper)
     if (bn == 256) return launch_tma<256, 4>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
     if (bn == 128) return variant == 11 ? launch_tma<128, 6>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st)
                                         : launch_tma<128, 3>(xin, n_in, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);

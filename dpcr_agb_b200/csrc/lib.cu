@@ -1,6 +1,7 @@
 // lib.cu -- library plumbing (errors, version, device check) and the convolution dispatch of the C ABI.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_last_error[512] = "";
 
@@ -33,6 +34,19 @@ int g_b2s_wg_nbp = -1, g_b2s_wg_lag = -1, g_b2s_wg_occ2 = -1, g_b2s_tc_rot = -1;
 int g_b2s_tc_ca = -1, g_b2s_tc_occ1 = -1, g_b2s_wg_ca = -1;
 int g_b2s_wg_wv = -1, g_b2s_tc_m256 = -1;
 int g_b2s_cr_v4 = -1, g_b2s_cr_cap = -1, g_b2s_cr_unroll = -1;
+int g_b2s_precise = -1;
+
+// Operand mode of the tensor-core convolutions: 1 (default) = split-bf16 pairs, 16-17 significant bits per operand,
+// three kind::f16 products per term; 0 = TF32 round-to-nearest operands, one kind::tf32 product.  Environment
+// B2S_PRECISE read once; b2s_set_tuning("precise", v) overrides.  Unlike the other knobs this one changes results.
+int b2s_precise() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("B2S_PRECISE");
+    env = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  return g_b2s_precise >= 0 ? (g_b2s_precise != 0 ? 1 : 0) : env;
+}
 
 extern "C" int32_t b2s_set_tuning(const char* key, int32_t value) {
   B2S_CHECK_ARG(key != nullptr, "key is NULL");
@@ -48,6 +62,7 @@ extern "C" int32_t b2s_set_tuning(const char* key, int32_t value) {
   else if (!strcmp(key, "cr_v4")) g_b2s_cr_v4 = value;
   else if (!strcmp(key, "cr_cap")) g_b2s_cr_cap = value;
   else if (!strcmp(key, "cr_unroll")) g_b2s_cr_unroll = value;
+  else if (!strcmp(key, "precise")) g_b2s_precise = value;
   else {
     b2s_set_error("b2s_set_tuning: unknown key '%s'", key);
     return B2S_EINVAL;
@@ -126,6 +141,11 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
                                 workspace_bytes, st))
       return B2S_ECUDA;
   } else {
+    if ((w_layout & 4) && b2s_precise()) {
+      b2s_set_error("b2s_conv_gather_gemm: operand-form (split-bf16) input on the SIMT path (c_in=%d c_out=%d impl=%d)",
+                    c_in, c_out, impl);
+      return B2S_EINVAL;
+    }
     b2s_conv_gather_gemm_simt(x, w, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, w_layout & 3, y, st);
   }
   B2S_LAUNCH_CHECK();
@@ -199,6 +219,11 @@ extern "C" int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t
     }
     if (b2s_conv_wgrad_tc(xin, gin, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, gw, workspace, st)) return B2S_ECUDA;
   } else {
+    if ((flags & 1) && b2s_precise()) {
+      b2s_set_error("b2s_conv_wgrad: operand-form (split-bf16) inputs on the SIMT path (c_in=%d c_out=%d impl=%d)", c_in,
+                    c_out, impl);
+      return B2S_EINVAL;
+    }
     b2s_conv_wgrad_simt(x, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, gw, st);
   }
   B2S_LAUNCH_CHECK();

@@ -75,6 +75,29 @@ __device__ __forceinline__ V<VEC> tf32v(const V<VEC>& a) {
   for (int j = 0; j < VEC; ++j) r.v[j] = __uint_as_float(tc::rna_tf32(__float_as_uint(a.v[j])));
   return r;
 }
+// Operand-form store of VEC consecutive channels (ch ..) of row r of an [n, c] matrix: the layout the tensor-core
+// convolutions gather.  mode 0: TF32 round-to-nearest values in place.  mode 1 (split-bf16, see tc_ptx.cuh): every
+// 32-channel block of a row keeps its 128 bytes and holds the 32 bf16 high parts in the first 64 bytes and the 32 bf16
+// residuals in the last 64 -- a 16-byte chunk is then either eight high parts or eight residuals, so that a gathered
+// row lands as [h | l] halves of a K-major tile and as separate H / L atoms of an MN-major one.
+template <int VEC>
+__device__ __forceinline__ void st_operand(float* base, int64_t r, int c, int ch, const V<VEC>& a, int mode) {
+  if (mode == 0) {
+    stv<VEC>(base + r * c + ch, tf32v<VEC>(a));
+    return;
+  }
+  char* blk = reinterpret_cast<char*>(base + r * c + (ch & ~31)) + (ch & 31) * 2;
+  uint32_t h[VEC], l[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) tc::split_bf16(a.v[j], h[j], l[j]);
+  if (VEC == 4) {
+    *reinterpret_cast<uint2*>(blk) = make_uint2(h[0] | (h[1 % VEC] << 16), h[2 % VEC] | (h[3 % VEC] << 16));
+    *reinterpret_cast<uint2*>(blk + 64) = make_uint2(l[0] | (l[1 % VEC] << 16), l[2 % VEC] | (l[3 % VEC] << 16));
+  } else {
+    *reinterpret_cast<unsigned short*>(blk) = (unsigned short)h[0];
+    *reinterpret_cast<unsigned short*>(blk + 64) = (unsigned short)l[0];
+  }
+}
 // per-channel parameter vector (nullable pointer -> constant)
 template <int VEC>
 __device__ __forceinline__ V<VEC> ldparam(const float* p, int ch, float dflt) {
@@ -118,7 +141,7 @@ __global__ void __launch_bounds__(PW_THREADS) maxpool_fwd_kernel(const float* __
                                                                  const int* __restrict__ nbr, int64_t n_out,
                                                                  const int* __restrict__ n_dev, int c, int k3,
                                                                  float* __restrict__ y, int* __restrict__ arg,
-                                                                 float* __restrict__ y_tf32) {
+                                                                 float* __restrict__ y_tf32, int opm) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_dev);
   const RowMap m = row_map<VEC>(c);
@@ -148,7 +171,7 @@ __global__ void __launch_bounds__(PW_THREADS) maxpool_fwd_kernel(const float* __
         arg[o * c + ch + j] = bi[j];
       }
       stv<VEC>(y + o * c + ch, best);
-      if (y_tf32) stv<VEC>(y_tf32 + o * c + ch, tf32v<VEC>(best));
+      if (y_tf32) st_operand<VEC>(y_tf32, o, c, ch, best, opm);
     }
   }
 }
@@ -505,7 +528,8 @@ __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __res
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int64_t n,
                                                               const int* __restrict__ n_dev, int c, int act,
-                                                              float* __restrict__ y, float* __restrict__ y_tf32) {
+                                                              float* __restrict__ y, float* __restrict__ y_tf32,
+                                                              int opm) {
   n = b2s_rows(n, n_dev);
   const RowMap m = row_map<VEC>(c);
   if (!m.active) return;
@@ -522,7 +546,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __res
         v.v[j] = act == 1 ? gelu_f(t) : t;
       }
       if (y) stv<VEC>(y + r * c + ch, v);
-      if (y_tf32) stv<VEC>(y_tf32 + r * c + ch, tf32v<VEC>(v));
+      if (y_tf32) st_operand<VEC>(y_tf32, r, c, ch, v, opm);
     }
   }
 }
@@ -532,7 +556,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ sums, int64_t n, const int* __restrict__ n_dev, int c, int act, int training,
-    float* __restrict__ gx, float* __restrict__ gx_tf32) {
+    float* __restrict__ gx, float* __restrict__ gx_tf32, int opm) {
   n = b2s_rows(n, n_dev);
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
   const RowMap m = row_map<VEC>(c);
@@ -558,7 +582,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
         g.v[j] = t * ga.v[j] * is.v[j];
       }
       stv<VEC>(gx + r * c + ch, g);
-      if (gx_tf32) stv<VEC>(gx_tf32 + r * c + ch, tf32v<VEC>(g));
+      if (gx_tf32) st_operand<VEC>(gx_tf32, r, c, ch, g, opm);
     }
   }
 }
@@ -568,7 +592,7 @@ template <int VEC, int OP>  // OP 0: y = gelu(x)   1: gx = gy * gelu'(x)   2: s 
 __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                           int64_t n, const int* __restrict__ n_dev, int c,
                                                           float* __restrict__ o0, float* __restrict__ o1,
-                                                          float* __restrict__ o2) {
+                                                          float* __restrict__ o2, int opm) {
   n = b2s_rows(n, n_dev);
   const int64_t total = n * c / VEC;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -579,9 +603,7 @@ __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restric
       for (int j = 0; j < VEC; ++j) r0.v[j] = gelu_f(av.v[j]);
       stv<VEC>(o0 + e * VEC, r0);
     } else if (OP == 3) {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) r0.v[j] = __uint_as_float(tc::rna_tf32(__float_as_uint(av.v[j])));
-      stv<VEC>(o0 + e * VEC, r0);
+      st_operand<VEC>(o0, (e * VEC) / c, c, (int)((e * VEC) % c), av, opm);
     } else if (OP == 1) {
       const V<VEC> bv = ldv<VEC>(b + e * VEC);
 #pragma unroll
@@ -596,7 +618,7 @@ __global__ void __launch_bounds__(PW_THREADS) flat_kernel(const float* __restric
       }
       stv<VEC>(o0 + e * VEC, r0);
       if (o1) stv<VEC>(o1 + e * VEC, r1);
-      if (o2) stv<VEC>(o2 + e * VEC, tf32v<VEC>(r1));
+      if (o2) st_operand<VEC>(o2, (e * VEC) / c, c, (int)((e * VEC) % c), r1, opm);
     }
   }
 }
@@ -748,7 +770,7 @@ template <int VEC>
 __global__ void __launch_bounds__(PW_THREADS) gated_add_gelu_fwd_kernel(
     const float* __restrict__ u, const float* __restrict__ gate_eff, const float* __restrict__ res,
     const int* __restrict__ rb, int stride, int64_t n, const int* __restrict__ n_dev, int c, float* __restrict__ s,
-    float* __restrict__ y, float* __restrict__ y_tf32) {
+    float* __restrict__ y, float* __restrict__ y_tf32, int opm) {
   n = b2s_rows(n, n_dev);
   const RowMap m = row_map<VEC>(c);
   if (!m.active) return;
@@ -766,7 +788,7 @@ __global__ void __launch_bounds__(PW_THREADS) gated_add_gelu_fwd_kernel(
       }
       stv<VEC>(s + r * c + ch, sv);
       if (y) stv<VEC>(y + r * c + ch, yv);
-      if (y_tf32) stv<VEC>(y_tf32 + r * c + ch, tf32v<VEC>(yv));
+      if (y_tf32) st_operand<VEC>(y_tf32, r, c, ch, yv, opm);
     }
   }
 }
@@ -929,6 +951,10 @@ bool launch_colreduce(const float* x, const float* g, const float* mean, const f
 
 }  // namespace
 
+// operand form written by the `*_tf32` outputs: split-bf16 blocks need whole 32-channel blocks (what the tensor-core
+// convolutions require of their operands anyway); other widths keep TF32 values
+static inline int operand_mode(int c) { return (b2s_precise() && c % 32 == 0) ? 1 : 0; }
+
 // ================================================================= C ABI ======================
 extern "C" int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_out, const int32_t* n_out_dev,
                                    int32_t c, int32_t k3, float* y, int32_t* arg, float* y_tf32,
@@ -939,10 +965,10 @@ extern "C" int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n
   cudaStream_t st = as_stream(stream);
   if (vec_of(c, x, y, y_tf32) == 4)
     maxpool_fwd_kernel<4><<<rows_grid(n_out, c, 4), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg,
-                                                                         y_tf32);
+                                                                         y_tf32, operand_mode(c));
   else
     maxpool_fwd_kernel<1><<<rows_grid(n_out, c, 1), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg,
-                                                                         y_tf32);
+                                                                         y_tf32, operand_mode(c));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -1098,10 +1124,10 @@ extern "C" int32_t b2s_bn_apply(const float* x, const float* mean, const float* 
   cudaStream_t st = as_stream(stream);
   if (vec_of(c, x, y, mean, invstd) == 4 && vec_of(c, gamma, beta, y_tf32) == 4)
     bn_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
-                                                                  y_tf32);
+                                                                  y_tf32, operand_mode(c));
   else
     bn_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
-                                                                  y_tf32);
+                                                                  y_tf32, operand_mode(c));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -1130,10 +1156,10 @@ extern "C" int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float
   cudaStream_t st = as_stream(stream);
   if (vec_of(c, gy, x, gx, mean) == 4 && vec_of(c, invstd, gamma, beta, sums) == 4 && vec_of(c, gx_tf32) == 4)
     bn_bwd_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(gy, x, mean, invstd, gamma, beta, sums, n,
-                                                                      n_dev, c, act, training, gx, gx_tf32);
+                                                                      n_dev, c, act, training, gx, gx_tf32, operand_mode(c));
   else
     bn_bwd_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(gy, x, mean, invstd, gamma, beta, sums, n,
-                                                                      n_dev, c, act, training, gx, gx_tf32);
+                                                                      n_dev, c, act, training, gx, gx_tf32, operand_mode(c));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -1142,9 +1168,11 @@ template <int OP>
 static int32_t launch_flat(const float* a, const float* b, int64_t n, const int32_t* n_dev, int32_t c, float* o0,
                            float* o1, cudaStream_t st, float* o2 = nullptr) {
   if (vec_of(c, a, b, o0, o1) == 4 && vec_of(c, o2) == 4)
-    flat_kernel<4, OP><<<grid_for(n * c / 4, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1, o2);
+    flat_kernel<4, OP><<<grid_for(n * c / 4, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1, o2,
+                                                                               operand_mode(c));
   else
-    flat_kernel<1, OP><<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1, o2);
+    flat_kernel<1, OP><<<grid_for(n * c, PW_THREADS), PW_THREADS, 0, st>>>(a, b, n, n_dev, c, o0, o1, o2,
+                                                                               operand_mode(c));
   return 0;
 }
 
@@ -1237,10 +1265,12 @@ extern "C" int32_t b2s_gated_add_gelu_fwd(const float* u, const float* gate_eff,
   cudaStream_t st = as_stream(stream);
   if (vec_of(c, u, res, sum, gate_eff) == 4 && vec_of(c, y, y_tf32) == 4)
     gated_add_gelu_fwd_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(u, gate_eff, res, row_batch,
-                                                                            row_batch_stride, n, n_dev, c, sum, y, y_tf32);
+                                                                            row_batch_stride, n, n_dev, c, sum, y, y_tf32,
+                                                                            operand_mode(c));
   else
     gated_add_gelu_fwd_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(u, gate_eff, res, row_batch,
-                                                                            row_batch_stride, n, n_dev, c, sum, y, y_tf32);
+                                                                            row_batch_stride, n, n_dev, c, sum, y, y_tf32,
+                                                                            operand_mode(c));
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

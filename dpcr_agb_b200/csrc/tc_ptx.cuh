@@ -121,6 +121,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, kind::f16 (here: bf16 inputs, fp32 accumulate; K = 16 per instruction) -- the split-bf16 operand mode
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all tcgen05 ops issued so far by this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -176,6 +186,34 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_base32(uint32_t saddr, uint3
 __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::f16 with bf16 inputs and fp32 accumulate: A / B format 1 = BF16, otherwise the same fields
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ split-bf16 operands ------
+// "Precise" operand mode (b2s_set_tuning("precise", 1), the default): an fp32 value v travels as the bf16 pair
+// (h, l) with h = bf16(v), l = bf16(v - h), i.e. 16-17 significant bits in the same four bytes, and a product is
+// evaluated as h*H + l*H + h*L on the kind::f16 tensor-core path (bf16 products are exact in the fp32 accumulator).
+// Per operand the error is <= 2^-17 |v| against 2^-11 |v| of a TF32 operand, which is what it takes to hold 1e-3 on
+// every gradient of a training step END TO END (tests/test_gpu_model.py::test_full_size_training_parity_fp32).
+// h and l are returned in the low 16 bits.
+__device__ __forceinline__ uint32_t bf16_rn_bits(float v) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 t;\n\tcvt.rn.bf16.f32 t, %1;\n\tmov.b32 %0, {t, 0};\n\t}" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void split_bf16(float v, uint32_t& h, uint32_t& l) {
+  h = bf16_rn_bits(v);
+  l = bf16_rn_bits(v - __uint_as_float(h << 16));
+}
+// three-term split (24 significant bits) for the k7 stem's weights
+__device__ __forceinline__ void split_bf16x3(float v, uint32_t& h, uint32_t& m, uint32_t& l) {
+  split_bf16(v, h, m);
+  l = bf16_rn_bits((v - __uint_as_float(h << 16)) - __uint_as_float(m << 16));
 }
 
 // byte offset of 16-byte chunk `chunk` (0..7) of 128-byte row `row` inside a 128B-swizzled tile

@@ -89,6 +89,7 @@ struct G2Params {
   int lag;             // stages a producer keeps in flight behind the one it is issuing (< stages)
   int use_atomic;
   int l1;              // 1: gather the x rows through L1 (offsets of a group re-read the same rows within a stage)
+  int precise;         // 1: split-bf16 operands (see below), 0: TF32 operands
   int64_t rows_per_split;
 };
 
@@ -153,7 +154,18 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
     const int a_rounds = NBP >> 1;                  // NBP blocks, two per round (NBP is a multiple of 4)
     constexpr int B_ROUNDS = BN / 64;
     const int cb_mask = p.CB - 1, cb_shift = 31 - __clz(p.CB);   // CB is a power of two
-    const uint32_t dst0 = (uint32_t)h * G_BLOCK + g_offset(r, l8);
+    // Split-bf16 mode: a gathered 128-byte run is [h of 32 channels | l of 32 channels] (chunks 0-3 / 4-7).  The H and L
+    // halves go to separate regions of the stage (first / second half of the A part, likewise of the B part), each laid
+    // out as MN-major SWIZZLE_128B atoms of 64 channels x 8 rows: two 32-channel blocks side by side per 128-byte atom
+    // row, 16-byte chunks XOR-ed with (row & 7), the next 8 rows 1 KB further, the next 64 channels 2 KB further.
+    const int prc = p.precise;
+    const uint32_t in_atom = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                             (uint32_t)((((h << 2) | (l8 & 3)) ^ (r & 7)) << 4);
+    const uint32_t dst0 = prc ? (uint32_t)(l8 >> 2) * (a_stage_bytes >> 1) + in_atom
+                              : (uint32_t)h * G_BLOCK + g_offset(r, l8);
+    const uint32_t dstb0 = prc ? a_stage_bytes + (uint32_t)(l8 >> 2) * (b_stage_bytes >> 1) + in_atom
+                               : a_stage_bytes + dst0;
+    const uint32_t rstride = prc ? (uint32_t)G_BLOCK : (uint32_t)(2 * G_BLOCK);   // per round of two blocks
     unsigned valid = 0;                              // bit j: round j addresses a real (offset, channel block)
 #pragma unroll
     for (int j = 0; j < MAXR; ++j) {
@@ -189,14 +201,15 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
       const int s = it % p.stages;
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       mbar_wait(empty_bar(s), ph ^ 1u);
-      const uint32_t a_dst = base + (uint32_t)s * stage_bytes + dst0, b_dst = a_dst + a_stage_bytes;
+      const uint32_t a_dst = base + (uint32_t)s * stage_bytes + dst0;
+      const uint32_t b_dst = base + (uint32_t)s * stage_bytes + dstb0;
       const int64_t o = r_begin + (int64_t)it * G_R + r;
 #pragma unroll
       for (int j = 0; j < MAXR; ++j) {
         if (j < a_rounds) {
           const int i = cur[j];
           const float* src = x_l + (int64_t)(i >= 0 ? i : 0) * p.c_in + ((2 * j + h) & cb_mask) * 32;
-          cp_async16_sel(a_dst + (uint32_t)j * (2 * G_BLOCK), src, i >= 0 ? 16u : 0u, l1);
+          cp_async16_sel(a_dst + (uint32_t)j * rstride, src, i >= 0 ? 16u : 0u, l1);
         }
       }
       {
@@ -204,7 +217,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
         const float* src = gy_l + (live ? o : 0) * p.c_out;
 #pragma unroll
         for (int j = 0; j < B_ROUNDS; ++j)
-          cp_async16(b_dst + (uint32_t)j * (2 * G_BLOCK), src + j * 64, live ? 16u : 0u);
+          cp_async16(b_dst + (uint32_t)j * rstride, src + j * 64, live ? 16u : 0u);
       }
       cp_async_commit();
       load_idx(it + 2, fill);             // overlaps with two stages of copies (the table streams from HBM)
@@ -262,6 +275,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
   } else {
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_tf32(WG_BM, BN, 1, 1);  // both operands MN-major
+    constexpr uint32_t IDESC16 = idesc_bf16(WG_BM, BN, 1, 1);
     for (int it = 0; it < T; ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -270,6 +284,16 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
       if (lane == 0) {
         const uint32_t a_stage = base + (uint32_t)s * stage_bytes, b_stage = a_stage + a_stage_bytes;
         for (int mt = 0; mt < p.MT; ++mt) {
+          if (p.precise) {
+            // one kind::f16 MMA (K = 16 rows) per term: xh*gh + xl*gh + xh*gl into the tile's accumulator
+            const uint32_t ah = a_stage + (uint32_t)mt * (2 * G_BLOCK), al = ah + (a_stage_bytes >> 1);
+            const uint32_t bh = b_stage, bl = b_stage + (b_stage_bytes >> 1);
+            const uint32_t d = tmem_d + (uint32_t)(mt * BN);
+            mma_bf16(d, smem_desc_sw128(ah, G_BLOCK, 1024), smem_desc_sw128(bh, G_BLOCK, 1024), IDESC16, it ? 1u : 0u);
+            mma_bf16(d, smem_desc_sw128(al, G_BLOCK, 1024), smem_desc_sw128(bh, G_BLOCK, 1024), IDESC16, 1u);
+            mma_bf16(d, smem_desc_sw128(ah, G_BLOCK, 1024), smem_desc_sw128(bl, G_BLOCK, 1024), IDESC16, 1u);
+            continue;
+          }
 #pragma unroll
           for (int g = 0; g < G_R / 8; ++g) {
             const uint64_t a_desc =
@@ -314,8 +338,12 @@ template <int STAGES>
 __global__ void __launch_bounds__(WG_THREADS, 1)
     wgrad_small_tc_kernel(const float4* __restrict__ x4, const float* __restrict__ gy, const int* __restrict__ nbr,
                           int64_t n_out, const int* __restrict__ n_out_dev, int c_in, int c_out, int k3, int co_tiles,
-                          int64_t rows_per_split, int l1_on, float* __restrict__ gw) {
+                          int64_t rows_per_split, int l1_on, int precise, float* __restrict__ gw) {
+  // Split-bf16 mode: the operand row of a neighbour is 8 bf16 [h0..h3 | l0..l3], so an offset takes 8 columns of N and
+  // a CTA owns 32 offsets (N = 256); gy rows are [h | l] per 32 channels and go to separate H / L atoms
+  // (MN-major SWIZZLE_128B, see wgrad_group_kernel).  D = (gh + gl)^T [xh | xl]; the epilogue adds the h and l columns.
   const bool l1 = l1_on != 0;
+  const int KPG = precise ? 32 : 64;             // kernel offsets per CTA
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
   using L = WgSmallSmem<STAGES>;
@@ -332,7 +360,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cot = blockIdx.x % co_tiles;
-  const int k0 = (blockIdx.x / co_tiles) * 64;
+  const int k0 = (blockIdx.x / co_tiles) * KPG;
   const int co0 = cot * WG_BM;
   const int co_valid = min(WG_BM, c_out - co0);
   const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
@@ -364,13 +392,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     // consecutive entries of one neighbour-table row (128 B) and -- rows being sorted along x -- mostly consecutive
     // 16-byte feature rows, instead of 32 scattered sectors per instruction with lanes walking the offsets of one row.
     constexpr int NK = 16;
-    const int kw = k0 + warp * NK;
+    const int nk = precise ? 8 : NK;               // offsets of this warp
+    const int kw = k0 + warp * nk;
     // neighbour rows are fetched two stages ahead of their gather (the table streams from HBM)
     auto load_nbr = [&](int it, int (&da)[NK]) {
       const int64_t o = r_begin + (int64_t)it * WG_ROWS + lane;
       const bool live = o < r_end;
 #pragma unroll
-      for (int p = 0; p < NK; ++p) da[p] = (live && kw + p < k3) ? __ldg(&nbr[(int64_t)(kw + p) * pitch + o]) : -1;
+      for (int p = 0; p < NK; ++p)
+        da[p] = (live && p < nk && kw + p < k3) ? __ldg(&nbr[(int64_t)(kw + p) * pitch + o]) : -1;
     };
     auto stage = [&](int it, const int (&cur)[NK], int (&fill)[NK]) {
       const int s = it % STAGES;
@@ -384,13 +414,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           const int row = p * 4 + warp;
           const int64_t o = r0 + row;
           const bool live = o < r_end;
-          cp_async16(a_stage + mn_offset(row, lane), gy + (live ? o : 0) * c_out + co0 + lane * 4, live ? 16u : 0u);
+          // split-bf16: chunk `lane` of the row = block lane / 8, chunks 0-3 h / 4-7 l; atom = 64 channels x 8 rows
+          const uint32_t dst =
+              precise ? (uint32_t)((lane >> 2) & 1) * 8192u + (uint32_t)(lane >> 4) * 4096u + (uint32_t)(row >> 3) * 1024u +
+                            (uint32_t)(row & 7) * 128u + (uint32_t)((((((lane >> 3) & 1) << 2) | (lane & 3)) ^ (row & 7)) << 4)
+                      : mn_offset(row, lane);
+          cp_async16(a_stage + dst, gy + (live ? o : 0) * c_out + co0 + lane * 4, live ? 16u : 0u);
         }
       }
 #pragma unroll
       for (int p = 0; p < NK; ++p) {
+        if (p >= nk) break;
         const int v = cur[p];
-        cp_async16_sel(b_stage + mn_offset(lane, warp * NK + p), x4 + (v >= 0 ? v : 0), v >= 0 ? 16u : 0u, l1);
+        const uint32_t dst = precise ? (uint32_t)warp * 4096u + (uint32_t)(lane >> 3) * 1024u + (uint32_t)(lane & 7) * 128u +
+                                           (uint32_t)((p ^ (lane & 7)) << 4)
+                                     : mn_offset(lane, warp * NK + p);
+        cp_async16_sel(b_stage + dst, x4 + (v >= 0 ? v : 0), v >= 0 ? 16u : 0u, l1);
       }
       cp_async_commit();
       load_nbr(it + 2, fill);
@@ -426,7 +465,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       uint32_t v[32];
       tmem_ld32(t_lane + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (co < co_valid) {
+      if (co < co_valid && precise) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int k = k0 + ((c0 + g8 * 8) >> 3);
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci)
+            if (ci < c_in && k < k3)
+              atomicAdd(&gw[((int64_t)k * c_in + ci) * c_out + co0 + co],
+                        __uint_as_float(v[g8 * 8 + ci]) + __uint_as_float(v[g8 * 8 + 4 + ci]));
+        }
+      } else if (co < co_valid) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           const int col = c0 + jj;
@@ -438,12 +487,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     tc_fence_before();
   } else {
     constexpr uint32_t IDESC = idesc_tf32(WG_BM, SM_BN, 1, 1);
+    constexpr uint32_t IDESC16 = idesc_bf16(WG_BM, SM_BN, 1, 1);
     for (int it = 0; it < T; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (lane == 0 && precise) {
+#pragma unroll
+        for (int g = 0; g < WG_ROWS / 16; ++g) {      // K = 16 rows per MMA; A terms gh, gl against [xh | xl]
+          const uint64_t b_desc = smem_desc_sw128(b_base + s * SM_B_STAGE + g * 2048, 4096, 1024);
+          mma_bf16(tmem_d, smem_desc_sw128(a_base + s * WG_A_STAGE + g * 2048, 4096, 1024), b_desc, IDESC16,
+                   (it | g) ? 1u : 0u);
+          mma_bf16(tmem_d, smem_desc_sw128(a_base + s * WG_A_STAGE + 8192 + g * 2048, 4096, 1024), b_desc, IDESC16, 1u);
+        }
+        mma_commit(empty_bar(s));
+      } else if (lane == 0) {
 #pragma unroll
         for (int g = 0; g < WG_ROWS / 8; ++g) {
           const uint64_t a_desc = smem_desc_sw128_base32(a_base + s * WG_A_STAGE + g * ATOM_BYTES, LBO_BYTES, SBO_BYTES);
@@ -467,10 +526,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
 int wg_ca_knob();
 
-__global__ void __launch_bounds__(256) wg_pad_rows4_kernel(const float* __restrict__ x, int64_t n, int c,
+__global__ void __launch_bounds__(256) wg_pad_rows4_kernel(const float* __restrict__ x, int64_t n, int c, int precise,
                                                            float4* __restrict__ x4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (precise) {     // [h0 h1 h2 h3 | l0 l1 l2 l3] bf16
+      uint32_t h[4] = {0, 0, 0, 0}, l[4] = {0, 0, 0, 0};
+      for (int j = 0; j < c; ++j) split_bf16(x[i * c + j], h[j], l[j]);
+      x4[i] = make_float4(__uint_as_float(h[0] | (h[1] << 16)), __uint_as_float(h[2] | (h[3] << 16)),
+                          __uint_as_float(l[0] | (l[1] << 16)), __uint_as_float(l[2] | (l[3] << 16)));
+      continue;
+    }
     for (int j = 0; j < c; ++j) v[j] = __uint_as_float(rna_tf32(__float_as_uint(x[i * c + j])));
     x4[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -490,8 +556,10 @@ int launch_wgrad_small(const float* x, const float* gy, const int* nbr, int64_t 
     attr_set = true;
   }
   float4* x4 = reinterpret_cast<float4*>(workspace);
-  wg_pad_rows4_kernel<<<grid_for(n_in, 256), 256, 0, st>>>(x, n_in, c_in, x4);
-  const int co_tiles = (c_out + WG_BM - 1) / WG_BM, groups = (k3 + 63) / 64;
+  const int precise = b2s_precise();
+  wg_pad_rows4_kernel<<<grid_for(n_in, 256), 256, 0, st>>>(x, n_in, c_in, precise, x4);
+  const int kpg = precise ? 32 : 64;
+  const int co_tiles = (c_out + WG_BM - 1) / WG_BM, groups = (k3 + kpg - 1) / kpg;
   const int64_t base = (int64_t)groups * co_tiles;
   int64_t splits = (3LL * B2S_NUM_SMS + base - 1) / base;
   const int64_t max_splits = ceil_div64(n_out, 8 * WG_ROWS);
@@ -504,7 +572,7 @@ int launch_wgrad_small(const float* x, const float* gy, const int* nbr, int64_t 
   cudaMemsetAsync(gw, 0, (size_t)k3 * c_in * c_out * sizeof(float), st);
   dim3 grid((unsigned)base, (unsigned)splits);
   kern<<<grid, WG_THREADS, L::DYN_BYTES, st>>>(x4, gy, nbr, n_out, n_out_dev, c_in, c_out, k3, co_tiles, rows,
-                                               wg_ca_knob(), gw);
+                                               wg_ca_knob(), precise, gw);
   return 0;
 }
 
@@ -557,6 +625,7 @@ int launch_group(const float* x, const float* gy, const int* nbr, int64_t n_out,
   }
   p.stages = stages;
   p.l1 = wg_tuning().ca;
+  p.precise = b2s_precise();
   // default: leave one stage being consumed and one being filled beyond the in-flight ones when the ring allows it
   int lag = wg_tuning().lag > 0 ? wg_tuning().lag : (stages >= 4 ? stages - 2 : stages - 1);
   if (lag > stages - 1) lag = stages - 1;

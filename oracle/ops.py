@@ -25,6 +25,11 @@ def _as_long(a):
 # TF32 (10-bit mantissa, round-to-nearest, ties away from zero == PTX cvt.rna.tf32.f32), products and sums in
 # fp32 -- in the forward (x, W), in dgrad (grad_out, W) and in wgrad (x, grad_out).  The parity tests hold the
 # CUDA path to 1e-3 against "fp32" per op (the north_star tolerance) and to a much tighter bound against "tf32".
+# "bf16x2" restates the kernels' default ("precise") operand mode: every operand v travels as the bf16 pair
+# h = bf16(v), l = bf16(v - h) (round-to-nearest-even, 16-17 significant bits) and a product a*b is evaluated as
+# ah*bh + al*bh + ah*bl with fp32 accumulation -- in the forward (x, W), in dgrad (grad_out, W) and in wgrad
+# (x, grad_out).  Where c_in <= 4 (the k7 stem) the weights are split three ways, W = H + M + L, and the forward is
+# (xh + xl)*(H + M) + xh*L; its wgrad keeps all four terms (xh + xl) * (gh + gl).
 CONV_PRECISION = "fp32"
 
 
@@ -34,6 +39,14 @@ def round_tf32(t: torch.Tensor) -> torch.Tensor:
         return t
     bits = t.detach().contiguous().view(torch.int32)
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def split_bf16(t: torch.Tensor):
+    """(h, l) with h = bf16(t), l = bf16(t - h), both returned as fp32 tensors."""
+    t = t.detach()
+    h = t.to(torch.bfloat16).to(torch.float32)
+    l = (t - h).to(torch.bfloat16).to(torch.float32)
+    return h, l
 
 
 def _conv_fp32(x, weight, nbr):
@@ -73,6 +86,46 @@ class _ConvTF32(torch.autograd.Function):
         return gx, gw, None
 
 
+class _ConvBF16x2(torch.autograd.Function):
+    """The same sum with split-bf16 operands in all three passes (see CONV_PRECISION)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, nbr):
+        ctx.save_for_backward(x, weight)
+        ctx.nbr = nbr
+        xh, xl = split_bf16(x)
+        wh, wl = split_bf16(weight)
+        if weight.shape[-2] <= 4:       # three-way weight split W = H + M + L; only xl*L is dropped
+            w3, _ = split_bf16(weight - wh - wl)
+            return _conv_fp32(xh + xl, wh + wl, nbr) + _conv_fp32(xh, w3, nbr)
+        return _conv_fp32(xh + xl, wh, nbr) + _conv_fp32(xh, wl, nbr)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gh, gl = split_bf16(gy)
+        xh, xl = split_bf16(x)
+        wh, wl = split_bf16(weight)
+        gx = gw = None
+        with torch.enable_grad():
+            if ctx.needs_input_grad[0]:
+                xv = torch.zeros_like(x).requires_grad_()
+                (g1,) = torch.autograd.grad(_conv_fp32(xv, wh, ctx.nbr), xv, gh + gl)
+                xv = torch.zeros_like(x).requires_grad_()
+                (g2,) = torch.autograd.grad(_conv_fp32(xv, wl, ctx.nbr), xv, gh)
+                gx = g1 + g2
+            if ctx.needs_input_grad[1]:
+                wv = torch.zeros_like(weight).requires_grad_()
+                if weight.shape[-2] <= 4:
+                    (gw,) = torch.autograd.grad(_conv_fp32(xh + xl, wv, ctx.nbr), wv, gh + gl)
+                else:
+                    (g1,) = torch.autograd.grad(_conv_fp32(xh + xl, wv, ctx.nbr), wv, gh)
+                    wv = torch.zeros_like(weight).requires_grad_()
+                    (g2,) = torch.autograd.grad(_conv_fp32(xh, wv, ctx.nbr), wv, gl)
+                    gw = g1 + g2
+        return gx, gw, None
+
+
 def conv(x: torch.Tensor, weight: torch.Tensor, nbr, bias: torch.Tensor | None = None) -> torch.Tensor:
     """MinkowskiConvolution forward: ``out[o] = bias + sum_k sum_{(i->o) in M_k} x[i] @ W[k]``.
 
@@ -83,6 +136,8 @@ def conv(x: torch.Tensor, weight: torch.Tensor, nbr, bias: torch.Tensor | None =
         nbr = _as_long(nbr)
     if CONV_PRECISION == "tf32" and x.dtype == torch.float32:
         out = _ConvTF32.apply(x, weight, nbr)
+    elif CONV_PRECISION == "bf16x2" and x.dtype == torch.float32:
+        out = _ConvBF16x2.apply(x, weight, nbr)
     else:
         out = _conv_fp32(x, weight, nbr)
     if bias is not None:

@@ -1,8 +1,9 @@
 """GPU parity of the convolution kernels (a6-a8) against the oracle, SIMT and tcgen05 paths, through
-the C ABI.  Two bars for the tcgen05 kernels: 1e-3 relative (max|a-b| / max|b|) against the fp32/fp64 oracle --
-the fp32/TF32 tolerance of BASELINE.json -- and TF32_MODEL_TOL against the oracle's "tf32" precision model
-(operands rounded to TF32 with round-to-nearest, fp32 accumulation), which restates exactly what the kernels
-compute and leaves only the summation order free."""
+the C ABI.  The tcgen05 kernels run in both operand modes (``b2s_set_tuning("precise", ...)``): the default
+split-bf16 mode ("bf16x2": 16-17 significant bits per operand) and the TF32 mode.  Two bars each: against the
+fp32/fp64 oracle -- 1e-3 relative (max|a-b| / max|b|), the fp32/TF32 tolerance of BASELINE.json, for TF32 and
+5e-5 for split-bf16 -- and MODEL_TOL against the oracle's precision model of the same mode (oracle/ops.py
+CONV_PRECISION), which restates exactly what the kernels compute and leaves only the summation order free."""
 import numpy as np
 import pytest
 import torch
@@ -17,16 +18,31 @@ pytestmark = pytest.mark.gpu
 
 SIMT, TC = 1, 2
 TF32_MODEL_TOL = 2e-5
+FP32_TOL = {"tf32": 1e-3, "bf16x2": 5e-5}     # tcgen05 kernels against the fp32 / fp64 oracle, per operand mode
+_MODEL = ["bf16x2"]
+
+
+@pytest.fixture(params=["bf16x2", "tf32"], autouse=True)
+def opmode(request):
+    """Runs every test of this file in both operand modes of the tensor-core kernels."""
+    _MODEL[0] = request.param
+    L.set_tuning("precise", 1 if request.param == "bf16x2" else 0)
+    yield request.param
+    L.set_tuning("precise", -1)
 
 
 class tf32_model:
-    """Context manager: evaluate the oracle convolution under its "tf32" precision model (fp32 tensors)."""
+    """Context manager: evaluate the oracle convolution under the precision model of the current operand mode."""
 
     def __enter__(self):
-        self.old, oo.CONV_PRECISION = oo.CONV_PRECISION, "tf32"
+        self.old, oo.CONV_PRECISION = oo.CONV_PRECISION, _MODEL[0]
 
     def __exit__(self, *a):
         oo.CONV_PRECISION = self.old
+
+
+def _tol(impl):
+    return FP32_TOL[_MODEL[0]] if impl != SIMT else 2e-5
 
 
 def _maps(n, nb=2, extent=9, seed=0, K=3, strided=False):
@@ -65,7 +81,7 @@ def test_conv_forward(cuda, impl, n, cin, cout, K, strided):
     b = rng.standard_normal(cout).astype(np.float32)
     ref = oo.conv(torch.from_numpy(x).double(), torch.from_numpy(w).double(), nbr, torch.from_numpy(b).double())
     got = _run_fwd(x, w, b, nbr, c.shape[0], out.shape[0], impl, cuda)
-    util.assert_close(got, ref, what=f"conv fwd impl={impl}")
+    util.assert_close(got, ref, tol=_tol(impl), what=f"conv fwd impl={impl}")
     if impl == SIMT:   # fp32 SIMT must be far tighter than the TF32 bar
         util.assert_close(got, ref, tol=2e-5, what="conv fwd simt fp32")
     else:
@@ -81,7 +97,7 @@ def test_conv_use_mm_identity_map(cuda, impl):
     x = rng.standard_normal((n, cin)).astype(np.float32)
     w = (rng.standard_normal((1, cin, cout)) * 0.05).astype(np.float32)
     got = _run_fwd(x, w, None, None, n, n, impl, cuda)
-    util.assert_close(got, torch.from_numpy(x).double() @ torch.from_numpy(w[0]).double(), what="use_mm")
+    util.assert_close(got, torch.from_numpy(x).double() @ torch.from_numpy(w[0]).double(), tol=_tol(impl), what="use_mm")
 
 
 @pytest.mark.parametrize("impl", [SIMT, TC])
@@ -116,8 +132,8 @@ def test_conv_backward(cuda, impl, n, cin, cout, strided):
         y.backward(torch.from_numpy(gy).to(cuda))
     finally:
         Fn.CONV_IMPL = old
-    util.assert_close(xg.grad, xr.grad, what="dgrad")
-    util.assert_close(wg.grad, wr.grad, what="wgrad")
+    util.assert_close(xg.grad, xr.grad, tol=_tol(impl), what="dgrad")
+    util.assert_close(wg.grad, wr.grad, tol=_tol(impl), what="wgrad")
     util.assert_close(bg.grad, br.grad, what="bias grad")
     if impl == TC:
         x32 = torch.from_numpy(x).requires_grad_()
@@ -140,7 +156,7 @@ def test_stem_wgrad_small_cin(cuda, impl):
     n = c.shape[0]
     got = Fn.wgrad(torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda), torch.from_numpy(nbr).to(cuda),
                    n, n, 3, 64, 343, impl=impl)
-    util.assert_close(got, wr.grad, what=f"stem wgrad impl={impl}")
+    util.assert_close(got, wr.grad, tol=_tol(impl), what=f"stem wgrad impl={impl}")
     if impl == TC:
         w32 = torch.zeros((343, 3, 64), requires_grad=True)
         with tf32_model():
@@ -178,7 +194,7 @@ def test_wgrad_tcgen05(cuda, n, cin, cout, K, strided):
     got_tc = Fn.wgrad(*args, impl=TC)
     got_simt = Fn.wgrad(*args, impl=SIMT)
     util.assert_close(got_simt, wr.grad, tol=2e-5, what="wgrad simt")
-    util.assert_close(got_tc, wr.grad, what="wgrad tcgen05")
+    util.assert_close(got_tc, wr.grad, tol=_tol(TC), what="wgrad tcgen05")
     w32 = torch.zeros((K ** 3, cin, cout), requires_grad=True)
     with tf32_model():
         oo.conv(torch.from_numpy(x), w32, nbr).backward(torch.from_numpy(gy))
@@ -191,7 +207,8 @@ def test_wgrad_tcgen05_null_map(cuda):
     x = rng.standard_normal((n, cin)).astype(np.float32)
     gy = rng.standard_normal((n, cout)).astype(np.float32)
     got = Fn.wgrad(torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda), None, n, n, cin, cout, 1, impl=TC)
-    util.assert_close(got[0], torch.from_numpy(x).double().T @ torch.from_numpy(gy).double(), what="wgrad use_mm")
+    util.assert_close(got[0], torch.from_numpy(x).double().T @ torch.from_numpy(gy).double(), tol=_tol(TC),
+                      what="wgrad use_mm")
 
 
 def test_parity_plan_and_strided_dgrad(cuda):

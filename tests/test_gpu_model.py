@@ -30,12 +30,20 @@ pytestmark = pytest.mark.gpu
 #     The bounds below are that amplified noise floor, not a kernel tolerance;
 #   * tcgen05 kernels, training mode at BASELINE plot size (4 x 16 000 points, 0.0125 grid) -- the configuration
 #     the benchmark runs -- where the coarse maps hold hundreds of rows (test_full_size_training_parity).
-E2E_OUT_TOL = {("tc", False): 1e-3, ("tc", True): 1e-2, ("simt", False): 1e-3, ("simt", True): 1e-3}
-E2E_GRAD_TOL = {("tc", False): 2e-3, ("tc", True): 1e-1, ("simt", False): 1e-3, ("simt", True): 1e-3}
-E2E_BUF_TOL = {"tc": 1e-2, "simt": 1e-3}
+#   * "tc" = the tcgen05 kernels in their default split-bf16 operand mode (16-17 significant bits per operand):
+#     held to the SAME 1e-3 as the SIMT path on these small plots, and to 1e-3 on outputs and EVERY gradient
+#     against the fp32 oracle at BASELINE plot size (test_full_size_training_parity_fp32) -- the end-to-end bar of
+#     BASELINE.json; "tc_tf32" = the same kernels with TF32 operands (``b2s_set_tuning("precise", 0)``), the
+#     faster mode whose end-to-end training error is what single-rounded 10-bit operands give (2e-3 .. 2.5e-2).
+E2E_OUT_TOL = {("tc_tf32", False): 1e-3, ("tc_tf32", True): 1e-2, ("simt", False): 1e-3, ("simt", True): 1e-3,
+               ("tc", False): 1e-3, ("tc", True): 1e-3}
+E2E_GRAD_TOL = {("tc_tf32", False): 2e-3, ("tc_tf32", True): 1e-1, ("simt", False): 1e-3, ("simt", True): 1e-3,
+                ("tc", False): 1e-3, ("tc", True): 1e-3}
+E2E_BUF_TOL = {"tc_tf32": 1e-2, "simt": 1e-3, "tc": 1e-3}
 # absolute slack of the gradient check as a fraction of the largest gradient of the whole model (scalar bias
 # gradients are sums with heavy cancellation)
-E2E_GRAD_ABS = {("tc", False): 2e-5, ("tc", True): 2e-3, ("simt", False): 2e-5, ("simt", True): 2e-5}
+E2E_GRAD_ABS = {("tc_tf32", False): 2e-5, ("tc_tf32", True): 2e-3, ("simt", False): 2e-5, ("simt", True): 2e-5,
+                ("tc", False): 2e-5, ("tc", True): 2e-5}
 
 
 def _report(name, **vals):
@@ -81,7 +89,7 @@ def _grad_check(mine, ref, tol, abs_slack=2e-5):
     return worst, worst_name
 
 
-CASES = [("simt", "fp32"), ("tc", "tf32"), ("tc", "fp32")]
+CASES = [("simt", "fp32"), ("tc", "bf16x2"), ("tc", "fp32"), ("tc_tf32", "tf32"), ("tc_tf32", "fp32")]
 
 
 @pytest.mark.parametrize("name,n_points,size", [("SENet14", 2500, 0.04), ("SENet50", 2000, 0.04)])
@@ -91,28 +99,62 @@ def test_msenet_forward_backward(cuda, name, n_points, size, training, impl, mod
     _run_parity(cuda, name, 4, n_points, size, training, impl, model, cfg=7)
 
 
-def test_full_size_training_parity(cuda):
-    """MSENet14 training-mode forward + backward on BASELINE-size plots (4 x 16 000 points, grid 0.0125) against
-    the oracle's tf32 model: outputs, loss, every gradient, BN running statistics."""
-    _run_parity(cuda, "SENet14", 4, 16000, 0.0125, True, "tc", "tf32", cfg=2, out_tol=2e-3, grad_tol=1e-2,
+def test_full_size_training_parity_fp32(cuda):
+    """The end-to-end bar of BASELINE.json where the benchmark runs: MSENet14 TRAINING-mode forward + backward on
+    BASELINE-size plots (4 x 16 000 points, grid 0.0125), tcgen05 kernels in their default (split-bf16) operand mode,
+    against the FP32 oracle: outputs, loss, BN running statistics and EVERY gradient within 1e-3 -- in the
+    max|a-b| / max|b| norm and in SURVEY.md 8(c)'s element-wise norm max |a-b| / max(|b|, eps * max|b|), eps = 0.1."""
+    _run_parity(cuda, "SENet14", 4, 16000, 0.0125, True, "tc", "fp32", cfg=2, out_tol=1e-3, grad_tol=1e-3,
+                buf_tol=1e-3, elementwise_eps=0.1)
+
+
+def test_full_size_training_parity_tf32_mode(cuda):
+    """Same configuration with TF32 operands (``precise`` = 0) against the oracle's tf32 model: the bound single-
+    rounded 10-bit operands reach end to end (documented in DESIGN.md; not the default mode)."""
+    _run_parity(cuda, "SENet14", 4, 16000, 0.0125, True, "tc_tf32", "tf32", cfg=2, out_tol=2e-3, grad_tol=1e-2,
                 buf_tol=1e-3)
 
 
 def _run_parity(cuda, name, num_plots, n_points, size, training, impl, model, cfg, out_tol=None, grad_tol=None,
-                buf_tol=None):
+                buf_tol=None, elementwise_eps=None):
+    from dpcr_agb_b200 import lib
     from dpcr_agb_b200.MinkowskiEngine import functional as Fn
     from oracle import ops as oo
     old_p, oo.CONV_PRECISION = oo.CONV_PRECISION, model
     old_i, Fn.CONV_IMPL = Fn.CONV_IMPL, (1 if impl == "simt" else 0)
+    lib.set_tuning("precise", 0 if impl == "tc_tf32" else 1)
     try:
         _parity_body(cuda, name, num_plots, n_points, size, training, impl, model, cfg,
                      out_tol or E2E_OUT_TOL[(impl, training)], grad_tol or E2E_GRAD_TOL[(impl, training)],
-                     buf_tol or E2E_BUF_TOL[impl])
+                     buf_tol or E2E_BUF_TOL[impl], elementwise_eps)
     finally:
         oo.CONV_PRECISION, Fn.CONV_IMPL = old_p, old_i
+        lib.set_tuning("precise", -1)
 
 
-def _parity_body(cuda, name, num_plots, n_points, size, training, impl, model, cfg, out_tol, grad_tol, buf_tol):
+def _elementwise_check(mine, ref, ym, yr, tol, eps):
+    """max over elements of |a-b| / max(|b|, eps * max|b|), per tensor; parameters whose oracle
+    gradient is numerically zero (a bias in front of a training-mode batch norm: < 1e-5 of the largest gradient of
+    the model) are compared absolutely against that scale."""
+    def err(a, b, floor=0.0):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        den = torch.clamp(b.abs(), min=max(eps * b.abs().max().item(), floor, 1e-300))
+        return ((a - b).abs() / den).max().item()
+    worst, worst_name = err(ym, yr), "output"
+    assert worst <= tol, f"output: element-wise error {worst:.3e} > {tol:.1e}"
+    gmax = max(p.grad.abs().max().item() for p in ref.parameters() if p.grad is not None)
+    for (n1, p1), (_, p2) in zip(mine.named_parameters(), ref.named_parameters()):
+        if p2.grad is None:
+            continue
+        e = err(p1.grad, p2.grad, floor=1e-5 * gmax)
+        assert e <= tol, f"grad of {n1}: element-wise error {e:.3e} > {tol:.1e}"
+        if e > worst:
+            worst, worst_name = e, n1
+    return worst, worst_name
+
+
+def _parity_body(cuda, name, num_plots, n_points, size, training, impl, model, cfg, out_tol, grad_tol, buf_tol,
+                 elementwise_eps=None):
     batch = util.make_points(num_plots, n_points, cfg=cfg)
     c, f, _, _, _ = util.oracle_quantize(batch, size)
     ref, mine = _pair(name, drop_path=0.2)
@@ -136,7 +178,11 @@ def _parity_body(cuda, name, num_plots, n_points, size, training, impl, model, c
             worst_grad=worst_name)
     util.assert_close(ym, yr, tol=out_tol, what=f"{name} output")
     util.assert_close(lm, lr, tol=out_tol, what=f"{name} loss")
-    _grad_check(mine, ref, grad_tol, E2E_GRAD_ABS[(impl, training)] if n_points < 16000 else 1e-4)
+    _grad_check(mine, ref, grad_tol, E2E_GRAD_ABS[(impl, training)] if n_points < 16000 else
+                (1e-5 if impl == "tc" else 1e-4))
+    if elementwise_eps is not None:
+        ew, ew_name = _elementwise_check(mine, ref, ym, yr, grad_tol, elementwise_eps)
+        _report(tag + "-elementwise", eps=elementwise_eps, worst=ew, worst_tensor=ew_name)
     if training:   # BN running statistics followed the same batches
         for (n1, b1), (n2, b2) in zip(mine.named_buffers(), ref.named_buffers()):
             if b2.dtype.is_floating_point:
