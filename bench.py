@@ -49,7 +49,11 @@ def parse():
     ap.add_argument("--model", default="SENet14")
     ap.add_argument("--plots-per-gpu", type=int, default=PLOTS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-plots", type=int, default=2)
+    ap.add_argument("--cpu-sample-plots", type=int, default=0,
+                    help="plots per CPU-arm step; 0 = the GPU arm's batch (--plots-per-gpu): like for like")
+    ap.add_argument("--precision", default="bf16x2", choices=["bf16x2", "tf32"],
+                    help="operand mode of the tensor-core convolutions: bf16x2 = split-bf16 pairs (default; holds "
+                         "1e-3 on every gradient end to end against the fp32 oracle), tf32 = single TF32 operands")
     return ap.parse_args()
 
 
@@ -86,8 +90,10 @@ def cpu_arm(args, steps, warmup, sample_plots):
             times.append(dt)
     med = float(np.median(times))
     return {"value": sample_plots / med, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} timed steps (median) of a {sample_plots}-plot batch x {POINTS_PER_PLOT} points after "
-                      f"{warmup} warm-up, whole step from raw points (quantise+maps+fwd+bwd+AdaBelief), "
+            "plots_per_step": sample_plots,
+            "sample": f"{steps} timed step(s) (median) of a {sample_plots}-plot batch x {POINTS_PER_PLOT} points "
+                      f"{'(the GPU arm batch size)' if sample_plots == args.plots_per_gpu else '(SMALLER than the GPU arm batch of ' + str(args.plots_per_gpu) + ')'} "
+                      f"after {warmup} warm-up, whole step from raw points (quantise+maps+fwd+bwd+AdaBelief), fp32, "
                       f"oracle restatement of the ME-CPU algorithm on torch-CPU with {cores} threads",
             "ms_per_step": med * 1e3}
 
@@ -96,13 +102,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = max(1, args.cpu_sample_plots)
+    sample = args.cpu_sample_plots if args.cpu_sample_plots > 0 else args.plots_per_gpu
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     cb = cpu_arm(args, steps, warmup, sample)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload(args),
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload(args),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "plots_per_step")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference MinkowskiEngine (CPU build, env_cpu.yml) is an un-vendored pip dependency and cannot "
                     "be built offline; this arm is the oracle port of its algorithm on the host cores"}
@@ -184,6 +191,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib.load()
+    lib.set_tuning("precise", 1 if args.precision == "bf16x2" else 0)
     B = args.plots_per_gpu
 
     torch.manual_seed(0)
@@ -357,12 +365,14 @@ def run_b200(args):
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_arm(args, steps=2, warmup=1, sample_plots=args.cpu_sample_plots)
-        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb = cpu_arm(args, steps=1, warmup=1,
+                     sample_plots=args.cpu_sample_plots if args.cpu_sample_plots > 0 else args.plots_per_gpu)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "plots_per_step")}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+            "vs_baseline": None, "dtype": ("bf16x2 (fp32 storage; conv operands as split-bf16 pairs, 3 kind::f16 products, fp32 accumulate)"
+                                       if args.precision == "bf16x2" else "tf32 (fp32 storage, fp32 accumulate)"), "data": "synthetic",
             "config": workload(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},

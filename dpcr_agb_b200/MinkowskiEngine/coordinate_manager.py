@@ -344,6 +344,7 @@ class CoordinateManager:
         out = torch.empty((cap_out, 4), dtype=torch.int32, device=dev)
         L.call("b2s_coordmap_fill", imap.coords, n, imap.n_dev, tsh, table, hcap, slot, rank, out, cap_out, None)
         self.checks.append((f"rows at tensor stride {ts[0]}", cap_out, info[0:1]))
+        self.checks.append((f"coordinate range flag at tensor stride {ts[0]}", 0, info[1:2]))
         return CoordMap(out, table, hcap, n_dev=info[0:1], info=info)
 
     def origin(self, key=None):
@@ -401,6 +402,8 @@ class CoordinateManager:
         out = {}
         for (what, cap, _), v in zip(self.checks, vals):
             out[what] = v
+            if v < 0:
+                raise L.B2SError(f"{what}: the device reported {v} (a point outside the voxel bounds)")
             if cap == 0:
                 if v != 0:
                     raise L.B2SError(f"{what} raised on the device (B2S_EOVERFLOW)")

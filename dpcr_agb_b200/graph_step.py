@@ -69,7 +69,7 @@ class GraphStep:
         self.drops = [m for m in trainer.model.modules() if isinstance(m, DropPath)]
         nd = max(len(self.drops), 1)
         self.drop_dev = torch.ones((nd, self.B, 1), dtype=torch.float32, device=dev)
-        self.drop_pinned = torch.ones((nd, self.B, 1), dtype=torch.float32).pin_memory()
+        self.drop_ring = T.PinnedRing((nd, self.B, 1), torch.float32)
         for i, m in enumerate(self.drops):
             m.static_mask = self.drop_dev[i]
         self.capture_collective = capture_collective or trainer.world == 1
@@ -111,8 +111,16 @@ class GraphStep:
         status = torch.cat([t.reshape(-1)[:1] for _, _, t in cm.checks])
         if self.status is None:
             self.status = torch.zeros_like(status)
-        # running maximum over replays since the last verify()
+            self.status_min = torch.zeros_like(status)
+            self.caps_dev = torch.tensor([cap for _, cap in self.status_meta], dtype=torch.int32, device=status.device)
+        # running maximum AND minimum over replays since the last verify(): a negative row count is the quantiser's
+        # "point outside the voxel box" flag and must not be folded away by the maximum
         torch.maximum(self.status, status, out=self.status)
+        torch.minimum(self.status_min, status, out=self.status_min)
+        # a step whose coordinate structures overflowed (or saw no valid batch) must not train: route the condition
+        # into the optimiser kernel's skip flag (the GradScaler inf-skip path), evaluated on the device
+        bad = (status < 0) | torch.where(self.caps_dev > 0, status > self.caps_dev, status != 0)
+        self.tr.opt.found_inf.copy_(bad.any().to(torch.float32).reshape(1))
 
     def _tail(self):
         self.tr.exchange_gradients()
@@ -146,6 +154,7 @@ class GraphStep:
         for b, saved in buffers:
             b.copy_(saved)
         self.status.zero_()
+        self.status_min.zero_()
         calls0 = L.launch_count
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -167,18 +176,17 @@ class GraphStep:
     def step(self):
         """Replay the captured step on the data currently in the input buffers; returns the on-device loss."""
         tr = self.tr
-        tr.num_batches += 1
-        tr.opt.lr = tr.sched.lr_at(tr.num_batches / tr.batches_per_epoch)
-        tr.opt.upload_hyper()
+        tr.opt.upload_hyper()                      # this step runs at the current lr ...
         if self.drops:
-            for i, m in enumerate(self.drops):
-                vals = m.draw(self.B) if tr.model.training else [1.0] * self.B
-                self.drop_pinned[i, :, 0] = torch.tensor(vals)
-            self.drop_dev.copy_(self.drop_pinned, non_blocking=True)
+            vals = [m.draw(self.B) if tr.model.training else [1.0] * self.B for m in self.drops]
+            self.drop_ring.upload(torch.tensor(vals, dtype=torch.float32), self.drop_dev)
         self.graph.replay()
         if not self.capture_collective:
             tr.exchange_gradients()
             self.graph_tail.replay()
+        # ... then the scheduler steps with the un-incremented batch counter, as the reference does
+        tr.opt.lr = tr.sched.lr_at(tr.num_batches / tr.batches_per_epoch)
+        tr.num_batches += 1
         return self.loss
 
     def release(self):
@@ -195,11 +203,16 @@ class GraphStep:
     def verify(self):
         """One host read: raises if any replay since the last call exceeded a row capacity or left the packed
         coordinate range; returns {description: largest value seen}."""
-        vals = self.status.tolist()
+        both = torch.stack([self.status, self.status_min]).tolist()
+        vals, lows = both
         self.status.zero_()
+        self.status_min.zero_()
         out = {}
-        for (what, cap), v in zip(self.status_meta, vals):
+        for (what, cap), v, lo in zip(self.status_meta, vals, lows):
             out[what] = v
+            if lo < 0:
+                raise L.B2SError(f"{what}: the device reported {lo} (a point outside the voxel bounds / an invalid "
+                                 f"batch); the optimiser update of that step was skipped")
             if cap == 0:
                 if v != 0:
                     raise L.B2SError(f"{what} raised on the device (B2S_EOVERFLOW)")

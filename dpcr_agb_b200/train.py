@@ -55,10 +55,15 @@ class FlatAdaBelief:
                 off += k
         self.lr, self.betas, self.eps, self.weight_decay, self.grad_clip = lr, betas, eps, weight_decay, grad_clip
         self.step_count = 0
+        # factor applied to every gradient inside the update kernel (before the clip): 1 / world_size turns the SUM the
+        # data-parallel exchange leaves in ``flat_grad`` into the mean without a separate pass over the buffer
+        self.grad_scale = 1.0
         self.found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
-        # device copy of the hyper-parameter block (captured-graph replays read it; see graph_step.py)
+        # device copy of the hyper-parameter block (captured-graph replays read it; see graph_step.py), fed through a
+        # ring of pinned staging buffers: the host may run several replays ahead of the device, and a buffer is only
+        # rewritten after the copy that read it has completed (event per slot)
         self.hyper_dev = torch.zeros(16, dtype=torch.float32, device=dev)
-        self.hyper_pinned = torch.zeros(16, dtype=torch.float32).pin_memory() if torch.cuda.is_available() else None
+        self.hyper_ring = PinnedRing((16,), torch.float32) if torch.cuda.is_available() else None
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -85,6 +90,7 @@ class FlatAdaBelief:
 
     def step(self, inv_scale=1.0, check_inf=False):
         self.step_count += 1
+        inv_scale = float(inv_scale) * self.grad_scale
         found = None
         if check_inf:
             L.call("b2s_grad_check", self.flat_grad, self.numel, float(inv_scale), self.found_inf)
@@ -97,13 +103,64 @@ class FlatAdaBelief:
         """Advance the step count and copy this step's hyper-parameters to the device (stream-ordered); the
         captured graph's ``step_from_device`` launch reads them."""
         self.step_count += 1
-        self.hyper_pinned.copy_(torch.tensor(self.hyper_values(inv_scale), dtype=torch.float32))
-        self.hyper_dev.copy_(self.hyper_pinned, non_blocking=True)
+        self.hyper_ring.upload(torch.tensor(self.hyper_values(float(inv_scale) * self.grad_scale), dtype=torch.float32),
+                               self.hyper_dev)
 
-    def step_from_device(self):
-        """AdaBelief update with the hyper-parameters read from ``hyper_dev`` (capturable)."""
+    def state_dict(self):
+        """Optimiser state for checkpoint / resume (the reference saves ``optimizer.state_dict()`` with the model:
+        metrics/model_checkpoint.py:182-193): the two moment buffers per parameter, in parameter order, plus the step
+        count and the hyper-parameters."""
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            state[i] = {"step": self.step_count, "exp_avg": self.exp_avg[off:off + k].view_as(p).clone(),
+                        "exp_avg_var": self.exp_avg_var[off:off + k].view_as(p).clone()}
+            off += k
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
+                 "grad_clip": self.grad_clip, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        off = 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            st = sd["state"].get(i)
+            if st is not None:
+                self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_var[off:off + k].copy_(st["exp_avg_var"].reshape(-1))
+                self.step_count = int(st["step"])
+            off += k
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
+        self.weight_decay, self.grad_clip = g["weight_decay"], g.get("grad_clip", self.grad_clip)
+
+    def step_from_device(self, skip_flag=True):
+        """AdaBelief update with the hyper-parameters read from ``hyper_dev`` (capturable).  ``found_inf`` (device
+        float, nonzero = skip the update) is honoured: the captured step sets it when a capacity check failed."""
         L.call("b2s_adabelief_step", self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_var, self.numel,
-               None, self.hyper_dev, None)
+               None, self.hyper_dev, self.found_inf if skip_flag else None)
+
+
+class PinnedRing:
+    """Small ring of pinned host staging buffers for per-step uploads that are issued with ``non_blocking=True``: a
+    slot is rewritten only after the device copy that last read it has completed (one CUDA event per slot), so the
+    host can run ahead of the device without a later step's values overtaking an earlier step's copy."""
+
+    def __init__(self, shape, dtype, slots=4):
+        self.bufs = [torch.zeros(shape, dtype=dtype).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.i = 0
+
+    def upload(self, host_values, dst):
+        i = self.i
+        self.i = (i + 1) % len(self.bufs)
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        self.bufs[i].copy_(host_values.reshape(self.bufs[i].shape))
+        dst.copy_(self.bufs[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
 
 
 class CosineAnnealingWarmRestarts:
@@ -162,6 +219,7 @@ class Trainer:
         self.center = torch.tensor(target_center, dtype=torch.float32, device=dev)
         self.scale = torch.tensor(target_scale, dtype=torch.float32, device=dev)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.opt.grad_scale = 1.0 / self.world     # the exchange sums; the update kernel applies the mean
         self.num_batches = 0
         # Gradient exchange overlapped with the backward pass: the parameters of the last stage and the head (85 % of
         # MSENet's weights) sit at the END of the flat buffer and their gradients are complete EARLY in the backward
@@ -208,7 +266,9 @@ class Trainer:
         return None
 
     def exchange_gradients(self):
-        """Average the flat gradient buffer over the ranks (finishing what the backward hook started)."""
+        """SUM the flat gradient buffer over the ranks (finishing what the backward hook started); the division by
+        the world size rides in the optimiser kernel (``FlatAdaBelief.grad_scale``), so the exchange is exactly one
+        collective and no extra pass over the 57.8 MB buffer."""
         if self.world <= 1:
             return
         g = self.opt.flat_grad
@@ -216,9 +276,8 @@ class Trainer:
             dist.all_reduce(g[:self.late_offset], op=dist.ReduceOp.SUM)
             torch.cuda.current_stream().wait_stream(self.comm_stream)
             self._late_started = False
-            g.mul_(1.0 / self.world)
         else:
-            allreduce_mean_(g, self.world)
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
 
     def deferred_counters(self):
         mods = getattr(self.ME, "modules", None)
@@ -252,7 +311,9 @@ class Trainer:
         with self.direct_grads():            # .grad = views of the flat buffer zeroed above: kernels write in place
             loss.backward()
         self.exchange_gradients()            # == DDP's all-reduce: two buckets, the big one overlapped with backward
-        self.num_batches += 1
-        self.opt.lr = self.sched.lr_at(self.num_batches / self.batches_per_epoch)
+        # the reference updates with the current lr, THEN steps the scheduler with the un-incremented batch counter
+        # (base_model.py:219-226, 246-256): batch 0 and 1 run at base_lr, batch k at lr_at((k - 1) / batches_per_epoch)
         self.opt.step()
+        self.opt.lr = self.sched.lr_at(self.num_batches / self.batches_per_epoch)
+        self.num_batches += 1
         return loss.detach()
