@@ -129,6 +129,23 @@ class KernelMap:
                 cm.parity_plans[(self.in_key, self.out_key)] = self._plan
         return self._plan or None
 
+    def transposed(self):
+        """The same pairs seen from the other side: a KernelMap whose "out" rows are this map's in rows -- the map of
+        ``MinkowskiConvolutionTranspose`` / ``MinkowskiPoolingTranspose`` from the coarse rows back onto the fine map
+        (MinkowskiEngine builds the forward kernel map fine -> coarse and swaps its sides).  ``nbr`` of the view is this
+        map's transposed table, and vice versa; the offset index k keeps its meaning."""
+        if getattr(self, "_tview", None) is None:
+            tv = KernelMap.__new__(KernelMap)
+            tv.manager, tv.in_key, tv.out_key = self.manager, self.out_key, self.in_key
+            tv.kernel_size, tv.step, tv.k3 = self.kernel_size, self.step, self.k3
+            tv.n_in, tv.n_out, tv.n_in_dev, tv.n_out_dev = self.n_out, self.n_in, self.n_out_dev, self.n_in_dev
+            tv.nbr, tv._inv = self.inv, self.nbr
+            tv.symmetric = False
+            tv._plan = False                 # no parity plan: dgrad of the view walks this map's forward table
+            tv._tview = self
+            self._tview = tv
+        return self._tview
+
     def pairs(self):
         """MinkowskiEngine's pair-list form: (in_idx, out_idx, offsets[K^3+1]); sorted by out row per offset."""
         assert self.n_out_dev is None, "pairs() needs exact row counts (dynamic mode)"
@@ -346,6 +363,22 @@ class CoordinateManager:
         self.checks.append((f"rows at tensor stride {ts[0]}", cap_out, info[0:1]))
         self.checks.append((f"coordinate range flag at tensor stride {ts[0]}", 0, info[1:2]))
         return CoordMap(out, table, hcap, n_dev=info[0:1], info=info)
+
+    def union(self, key_a, key_b):
+        """Union map of two maps of the same tensor stride (``SparseTensor.__add__`` across coordinate maps): the rows
+        of ``key_a`` in their order, then the rows only ``key_b`` has.  Returns (key, rows of a, rows of b) as int64
+        index tensors.  Dynamic mode only (one host sync for the row count)."""
+        if self.static:
+            raise L.B2SError("union maps are built in dynamic mode only")
+        assert key_a.tensor_stride == key_b.tensor_stride, "union of maps with different tensor strides"
+        a, b = self.maps[key_a], self.maps[key_b]
+        both = torch.cat([a.coords, b.coords])
+        cmap, in2out, _ = self._build(both, (1, 1, 1))
+        if in2out is None:          # disjoint: the concatenation is already unique
+            in2out = torch.arange(both.shape[0], dtype=torch.int32, device=both.device)
+        key = CoordinateMapKey(key_a.tensor_stride, f"union({key_a.tag}|{key_b.tag}|{len(self.maps)})")
+        self.maps[key] = cmap
+        return key, in2out[:a.n].long(), in2out[a.n:].long()
 
     def origin(self, key=None):
         """Key of the per-plot origin map (one row per batch id), as MinkowskiGlobalPooling returns."""

@@ -283,6 +283,34 @@ class MaxPoolFunction(torch.autograd.Function):
         return gx, None, None
 
 
+class LocalPoolFunction(torch.autograd.Function):
+    """MinkowskiSumPooling / MinkowskiAvgPooling (networks.py:29): ``y[o] = scale[o] * sum_k x[nbr[k, o]]`` with
+    ``scale = 1 / #inputs under the kernel`` for the average (C ABI ``b2s_sumpool`` / ``b2s_nbr_inv_counts``);
+    backward = the same kernel on the transposed table with the scale applied per gathered row."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, feats, kmap, average):
+        feats = feats.contiguous()
+        c = feats.shape[1]
+        y = torch.empty((kmap.n_out, c), dtype=torch.float32, device=feats.device)
+        inv = None
+        if average:
+            inv = torch.empty(kmap.n_out, dtype=torch.float32, device=feats.device)
+            L.call("b2s_nbr_inv_counts", kmap.nbr, kmap.k3, kmap.n_out, kmap.n_out_dev, inv)
+        L.call("b2s_sumpool", feats, kmap.nbr, None, inv, kmap.n_out, kmap.n_out_dev, c, kmap.k3, y)
+        ctx.kmap, ctx.inv, ctx.c = kmap, inv, c
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy):
+        kmap = ctx.kmap
+        gx = torch.empty((kmap.n_in, ctx.c), dtype=torch.float32, device=gy.device)
+        L.call("b2s_sumpool", gy.contiguous(), kmap.inv, ctx.inv, None, kmap.n_in, kmap.n_in_dev, ctx.c, kmap.k3, gx)
+        return gx, None, None
+
+
 class GlobalPoolFunction(torch.autograd.Function):
     """MinkowskiGlobal{Sum,Avg}Pooling / MinkowskiGlobalPooling (senet_block.py:43; common.py:44-48)."""
 
@@ -303,6 +331,53 @@ class GlobalPoolFunction(torch.autograd.Function):
         gx = torch.empty((n, c), dtype=torch.float32, device=gy.device)
         L.call("b2s_segment_bcast", gy.contiguous(), ctx.coords, 4, n, ctx.nd, c, ctx.scale, gx)
         return gx, None, None, None, None
+
+
+class GlobalMaxPoolFunction(torch.autograd.Function):
+    """MinkowskiGlobalMaxPooling (networks.py:39; PointNet.py:28 via GLOBAL_POOL["max"])."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, feats, coords, num_batches, n_dev=None):
+        feats = feats.contiguous()
+        n, c = feats.shape
+        y = torch.empty((num_batches, c), dtype=torch.float32, device=feats.device)
+        arg = torch.empty((num_batches, c), dtype=torch.int32, device=feats.device)
+        L.call("b2s_segment_max", feats, coords, 4, n, n_dev, c, num_batches, y, arg)
+        ctx.save_for_backward(arg)
+        ctx.dims = (n, c, num_batches)
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, gy):
+        (arg,) = ctx.saved_tensors
+        n, c, nb = ctx.dims
+        gx = torch.empty((n, c), dtype=torch.float32, device=gy.device)
+        L.call("b2s_segment_max_bwd", gy.contiguous(), arg, n, c, nb, gx)
+        return gx, None, None, None
+
+
+class BroadcastFunction(torch.autograd.Function):
+    """MinkowskiBroadcast / MinkowskiBroadcastAddition: ``out[i] = (x[i] +) y[batch(i)]``; backward of the broadcast
+    operand = per-plot sum."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, y, coords, n, n_dev=None):
+        y = y.contiguous()
+        out = torch.empty((n, y.shape[1]), dtype=torch.float32, device=y.device)
+        L.call("b2s_segment_bcast", y, coords, 4, n, n_dev, y.shape[1], None, out)
+        ctx.coords, ctx.nd, ctx.nb = coords, n_dev, y.shape[0]
+        return out
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        g = g.contiguous()
+        gy = torch.empty((ctx.nb, g.shape[1]), dtype=torch.float32, device=g.device)
+        L.call("b2s_segment_sum", g, ctx.coords, 4, g.shape[0], ctx.nd, g.shape[1], ctx.nb, None, gy)
+        return gy, None, None, None
 
 
 class BroadcastMulFunction(torch.autograd.Function):

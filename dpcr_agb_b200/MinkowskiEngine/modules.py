@@ -119,33 +119,94 @@ class MinkowskiConvolution(MinkowskiModuleBase):
 
 
 class _NotOnHotPath(MinkowskiModuleBase):
-    """Names that must exist for the reference package to import (``common.py:157-212``, ``networks.py``,
-    ``modules.py``) but that MSENet14/50 never call -- SURVEY.md 8(f) rank 3."""
+    """Names that must exist for the reference package to import but that none of its networks call."""
 
     def __init__(self, *args, **kwargs):
         super().__init__()
 
     def forward(self, *args, **kwargs):
-        raise NotImplementedError(f"{type(self).__name__} is outside the MSENet hot path (SURVEY.md 8f rank 3)")
+        raise NotImplementedError(f"{type(self).__name__} is not used by any network of the reference")
 
 
-class MinkowskiConvolutionTranspose(_NotOnHotPath):
-    pass
+def _fine_key(x: SparseTensor, stride):
+    """Key of the EXISTING finer map a transposed op lands on (tensor stride / stride, same tag): the encoder map of a
+    U-Net (``networks.py:155-245``).  Generating new coordinates (``expand_coordinates``) is not implemented."""
+    cm, in_key = x.coordinate_manager, x.coordinate_map_key
+    ts = in_key.tensor_stride
+    if any(t % s for t, s in zip(ts, stride)):
+        raise ValueError(f"tensor stride {ts} is not divisible by the transposed stride {stride}")
+    from .coordinate_manager import CoordinateMapKey
+    key = CoordinateMapKey(tuple(t // s for t, s in zip(ts, stride)), in_key.tag)
+    if key not in cm.maps:
+        raise NotImplementedError(f"transposed op onto tensor stride {list(key.tensor_stride)}: no such coordinate map "
+                                  f"in this manager (generative transposed convolution is not implemented)")
+    return key
 
 
-class MinkowskiAvgPooling(_NotOnHotPath):
-    pass
+class MinkowskiConvolutionTranspose(MinkowskiConvolution):
+    """Non-generative transposed convolution (``networks.py:155-176``: the decoder of MinkUNet): the output lives on
+    the existing finer map; ``out[f] = bias + sum_k in[c] @ W[k]`` over the pairs of the forward convolution
+    fine -> coarse with the two sides swapped.  Runs on the same gather-GEMM / wgrad kernels as the convolution: its
+    forward table is the transposed table of that forward map (``KernelMap.transposed``)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=None, dimension=None):
+        if expand_coordinates:
+            raise NotImplementedError("expand_coordinates (generative transposed convolution) is not implemented")
+        super().__init__(in_channels, out_channels, kernel_size, stride, dilation, bias, kernel_generator, False,
+                         convolution_mode, dimension)
+        self.is_transpose = True
+        if self.use_mm:          # K=1, stride=1: the transposed op is the same matmul; keep ME's [K^3, Cin, Cout] shape
+            self.use_mm = False
+            self.kernel = nn.Parameter(torch.empty((self.kernel_volume, in_channels, out_channels)))
+        self.reset_parameters(True)
+
+    def forward(self, input: SparseTensor, coordinates=None):
+        cm = input.coordinate_manager
+        out_key = _fine_key(input, self.stride)
+        fwd_map = cm.kernel_map(out_key, input.coordinate_map_key, self.kernel_size, self.dilation)
+        out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, fwd_map.transposed())
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
 
 
-class MinkowskiSumPooling(_NotOnHotPath):
-    pass
+class MinkowskiSumPooling(MinkowskiModuleBase):
+    """Local sum pooling over the kernel region; ``AVERAGE`` (MinkowskiAvgPooling, ``networks.py:29``) divides by the
+    number of inputs under the kernel, as MinkowskiEngine does."""
+    AVERAGE = False
+
+    def __init__(self, kernel_size, stride=1, dilation=1, kernel_generator=None, dimension=None):
+        super().__init__()
+        assert dimension == 3
+        self.kernel_size, self.stride, self.dilation = _triple(kernel_size), _triple(stride), _triple(dilation)
+
+    def forward(self, input: SparseTensor, coordinates=None):
+        cm = input.coordinate_manager
+        out_key = _out_key(input, self.stride)
+        kmap = cm.kernel_map(input.coordinate_map_key, out_key, self.kernel_size, self.dilation)
+        out = Fn.LocalPoolFunction.apply(input.F, kmap, self.AVERAGE)
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
+
+    def __repr__(self):
+        return f"{type(self).__name__}(kernel_size={list(self.kernel_size)}, stride={list(self.stride)})"
+
+
+class MinkowskiAvgPooling(MinkowskiSumPooling):
+    AVERAGE = True
+
+
+class MinkowskiPoolingTranspose(MinkowskiSumPooling):
+    """Unpooling onto the existing finer map: ``out[f] = sum_k in[c]`` over the transposed pairs of the forward
+    pooling fine -> coarse."""
+
+    def forward(self, input: SparseTensor, coordinates=None):
+        cm = input.coordinate_manager
+        out_key = _fine_key(input, self.stride)
+        fwd_map = cm.kernel_map(out_key, input.coordinate_map_key, self.kernel_size, self.dilation)
+        out = Fn.LocalPoolFunction.apply(input.F, fwd_map.transposed(), False)
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
 
 
 class MinkowskiAvgUnpooling(_NotOnHotPath):
-    pass
-
-
-class MinkowskiPoolingTranspose(_NotOnHotPath):
     pass
 
 
@@ -202,17 +263,15 @@ class MinkowskiGlobalPooling(_GlobalPoolBase):
 
 
 class MinkowskiGlobalMaxPooling(MinkowskiModuleBase):
-    """Not used by the README configs (``global_pool: sum``); torch CUDA scatter-amax on the batch column."""
+    """Per-plot maximum (``networks.py:39``, ``PointNet.py:28``): ``b2s_segment_max`` over the batch-sorted rows."""
 
     def __init__(self, mode=None):
         super().__init__()
 
     def forward(self, input: SparseTensor, coordinates=None):
         cm = input.coordinate_manager
-        b = cm.coords(input.coordinate_map_key)[:, 0].long()
-        f = input.F
-        out = torch.full((cm.num_batches, f.shape[1]), -float("inf"), dtype=f.dtype, device=f.device)
-        out = out.scatter_reduce(0, b[:, None].expand_as(f), f, reduce="amax", include_self=True)
+        key = input.coordinate_map_key
+        out = Fn.GlobalMaxPoolFunction.apply(input.F, cm.coords(key), cm.num_batches, cm.n_dev(key))
         return SparseTensor(out, coordinate_map_key=cm.origin(), coordinate_manager=cm)
 
 
@@ -227,18 +286,16 @@ class MinkowskiBroadcastMultiplication(MinkowskiModuleBase):
         return type(self).__name__ + "()"
 
 
-class MinkowskiBroadcastAddition(MinkowskiModuleBase):
-    def forward(self, input: SparseTensor, input_glob: SparseTensor):
-        cm = input.coordinate_manager
-        b = cm.coords(input.coordinate_map_key)[:, 0].long()
-        return input._wrap(input.F + input_glob.F[b])
-
-
 class MinkowskiBroadcast(MinkowskiModuleBase):
     def forward(self, input: SparseTensor, input_glob: SparseTensor):
         cm = input.coordinate_manager
-        b = cm.coords(input.coordinate_map_key)[:, 0].long()
-        return input._wrap(input_glob.F[b])
+        key = input.coordinate_map_key
+        return input._wrap(Fn.BroadcastFunction.apply(input_glob.F, cm.coords(key), input.F.shape[0], cm.n_dev(key)))
+
+
+class MinkowskiBroadcastAddition(MinkowskiBroadcast):
+    def forward(self, input: SparseTensor, input_glob: SparseTensor):
+        return input._wrap(input.F + super().forward(input, input_glob).F)
 
 
 class MinkowskiLinear(nn.Module):

@@ -132,11 +132,20 @@ class SparseTensor:
         return other.coordinate_manager is self.coordinate_manager and \
             other.coordinate_map_key == self.coordinate_map_key
 
+    def _union_add(self, other, sign=1.0):
+        """``a + b`` for tensors on DIFFERENT coordinate maps of one manager: features land on the union map
+        (rows of ``a``, then the rows only ``b`` has); every union row receives at most one row of each operand."""
+        cm = self.coordinate_manager
+        assert other.coordinate_manager is cm, "tensors of different coordinate managers"
+        key, ra, rb = cm.union(self.coordinate_map_key, other.coordinate_map_key)
+        out = self._F.new_zeros((cm.coords(key).shape[0], self._F.shape[1]))
+        out = out.index_add(0, ra, self._F).index_add(0, rb, other._F if sign == 1.0 else -other._F)
+        return SparseTensor(out, coordinate_map_key=key, coordinate_manager=cm)
+
     def __add__(self, other):
         if isinstance(other, SparseTensor):
             if not self._same_map(other):
-                raise NotImplementedError("adding tensors on different coordinate maps (union map) is not on the "
-                                          "MSENet hot path (SURVEY.md 8f rank 3)")
+                return self._union_add(other)
             return self._wrap(self._F + other._F)
         return self._wrap(self._F + other)
 
@@ -144,7 +153,8 @@ class SparseTensor:
 
     def __sub__(self, other):
         if isinstance(other, SparseTensor):
-            assert self._same_map(other)
+            if not self._same_map(other):
+                return self._union_add(other, -1.0)
             return self._wrap(self._F - other._F)
         return self._wrap(self._F - other)
 

@@ -179,8 +179,11 @@ struct PermArgs {
 
 // LAG: a producer hands over stage (it - LAG) after issuing the copies of stage it (LAG + 1 stages of copies in flight)
 // flags: bit 0 = offset rotation, bit 1 = L1-allocating gathers, bit 2 = split-bf16 operands (NB > 1 implies it)
-template <int BN, int STAGES, bool SMALL, int LAG, bool PERM = false, int NB = 1>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// PW: producer warps (4, or 8 in SMALL mode: threads 128.. take the second half of a stage's kernel offsets -- the
+// split-bf16 stem keeps three weight images per stage and therefore one CTA per SM; eight gathering warps restore the
+// number of copies in flight that two 4-warp CTAs had).  Warp PW issues the MMAs; warps 0-3 run the epilogue.
+template <int BN, int STAGES, bool SMALL, int LAG, bool PERM = false, int NB = 1, int PW = 4>
+__global__ void __launch_bounds__((PW + 1) * 32, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y,
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const int T = min(it_per_split, T_total - it0);
   if (T <= 0) {
     if (PERM) {   // a class without any offset (K = 1: rows off the coarse lattice): its rows are zero
-      for (int e = tid; e < BM * (BN / 4); e += TC_THREADS) {
+      for (int e = tid; e < BM * (BN / 4); e += (PW + 1) * 32) {
         const int o = __ldg(&pa.perm[m0 + e / (BN / 4)]);
         if (o >= 0) reinterpret_cast<float4*>(y + (int64_t)o * c_out + n0)[e % (BN / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -233,20 +236,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), PRODUCERS + 1);  // 128 gather arrivals + 1 arrive.expect_tx for the B bulk copy
+      mbar_init(full_bar(s), PW * 32 + 1);    // gather arrivals + 1 arrive.expect_tx for the B bulk copy
       mbar_init(empty_bar(s), 1);             // one tcgen05.commit
     }
     mbar_init(accum_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<BN>(tmem_slot);
+  static_assert(PW == 4 || (PW == 8 && SMALL), "eight producer warps: SMALL mode only");
+  if (warp == PW) tmem_alloc<BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_ptr;
 
-  if (warp < 4) {
+  if (warp < PW) {
     // ===================== producers: gather A, fetch B =====================
+    constexpr int NPT = SMALL ? 32 / PW : 8;        // SMALL: kernel offsets of a stage handled by this thread
+    const int srow = tid & 127;                      // SMALL: tile row of this thread
+    const int pbase = SMALL ? (tid >> 7) * NPT : 0;  // SMALL: first of its offsets
     const int chunk = tid & 7;   // 16-byte chunk inside the 128-byte row
     const int rsub = tid >> 3;   // rows rsub + 16 p
     const int kc = SMALL ? 1 : c_in / BK;
@@ -272,10 +279,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         // thread = tile row, p = the 8 kernel offsets of the stage: a warp reads 32 consecutive entries of one table
         // row (128 B) and, rows being sorted along x, gathers mostly consecutive feature rows -- instead of 32
         // scattered 16-byte sectors per instruction when the lanes of a warp walk the offsets of one row
-        const int64_t o = m0 + tid;
+        const int64_t o = m0 + srow;
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const int k = g * 8 + p;
+        for (int p = 0; p < NPT; ++p) {
+          const int k = g * 8 + pbase + p;
           dst[p] = (k < k3 && o < n_out) ? (nbr ? __ldg(nbr + (int64_t)k * pitch + o) : (int)o) : -1;
         }
         return;
@@ -316,12 +323,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       const uint32_t a_stage = a_base + s * A_STAGE_BYTES;
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const int row = SMALL ? tid : rsub + 16 * p;
+      for (int p = 0; p < NPT; ++p) {
+        const int row = SMALL ? srow : rsub + 16 * p;
         const int i = cur[p];
         const float* src = SMALL ? x + (int64_t)(i >= 0 ? i : 0) * 4
                                  : x + (int64_t)(i >= 0 ? i : 0) * c_in + cc * BK + chunk * 4;
-        cp_async16_sel(a_stage + sw128_offset(row, SMALL ? p : chunk), src, i >= 0 ? 16u : 0u, l1);
+        cp_async16_sel(a_stage + sw128_offset(row, SMALL ? pbase + p : chunk), src, i >= 0 ? 16u : 0u, l1);
       }
       cp_async_commit();
     };
@@ -394,6 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 
     // ===================== epilogue: TMEM -> registers -> y =====================
+    if (warp < 4) {
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int64_t o = PERM ? (int64_t)__ldg(&pa.perm[m0 + warp * 32 + lane]) : m0 + warp * 32 + lane;
@@ -424,8 +432,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
     tc_fence_before();
+    }
   } else {
-    // ===================== MMA issuer: warp 4 stays converged, lane 0 issues =====================
+    // ===================== MMA issuer: warp PW stays converged, lane 0 issues =====================
     constexpr uint32_t IDESC = idesc_tf32(BM, BN, 0, 0), IDESC16 = idesc_bf16(BM, BN, 0, 0);
     int s = 0;
     uint32_t ph = 0;
@@ -468,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == PW) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<BN>(tmem_d);
@@ -1003,12 +1012,12 @@ int launch_tc2(const float* x, const float* wimg, const float* bias, const int* 
 
 int tc_m256() { return tc_knob(g_b2s_tc_m256, "B2S_TC_M256", 1); }
 
-template <int BN, int STAGES, bool SMALL, int LAG = 2, int NB = 1>
+template <int BN, int STAGES, bool SMALL, int LAG = 2, int NB = 1, int PW = 4>
 int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, NB>;
   static_assert(LAG < STAGES, "producers run LAG stages ahead of their hand-over");
-  auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL, LAG, false, NB>;
+  auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL, LAG, false, NB, PW>;
   static bool attr_set = false;
   if (!attr_set) {
     constexpr int OPT_IN = L::DYN_BYTES > 116 * 1024 ? L::DYN_BYTES : 116 * 1024;
@@ -1034,7 +1043,7 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
   splits = (T + per - 1) / per;
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
-  kern<<<grid, TC_THREADS, dyn, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y, PermArgs{},
+  kern<<<grid, (PW + 1) * 32, dyn, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y, PermArgs{},
                                       (tc_rot() ? 1 : 0) | (tc_ca() ? 2 : 0) | (b2s_precise() ? 4 : 0));
   return 0;
 }
@@ -1087,9 +1096,9 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   }
   const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
   if (small && b2s_precise()) {   // three weight images per stage: one CTA per SM, deeper ring
-    if (bn == 256) return launch_tc<256, 2, true, 1, SMALL_NB>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
-    if (bn == 128) return launch_tc<128, 3, true, 2, SMALL_NB>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
-    return launch_tc<64, 5, true, 3, SMALL_NB>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
+    if (bn == 256) return launch_tc<256, 2, true, 1, SMALL_NB, 8>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
+    if (bn == 128) return launch_tc<128, 3, true, 2, SMALL_NB, 8>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
+    return launch_tc<64, 5, true, 3, SMALL_NB, 8>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
   }
   if (small) {
     if (bn == 256) return launch_tc<256, 4, true>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);

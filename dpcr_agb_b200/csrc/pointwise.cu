@@ -176,6 +176,55 @@ __global__ void __launch_bounds__(PW_THREADS) maxpool_fwd_kernel(const float* __
   }
 }
 
+// ---------------------------------------------------------------- local sum / average pooling --
+// y[o,:] = post[o] * sum_k pre[i] * x[i,:], i = nbr[k,o] >= 0 (pre / post nullable).  Forward of MinkowskiSumPooling /
+// MinkowskiAvgPooling (post = 1 / #neighbours) on the forward table, and their backward on the TRANSPOSED table with
+// pre = the same per-out-row factor (gx[i] = sum over the out rows o that pooled i of gy[o] / count[o]).
+template <int VEC>
+__global__ void __launch_bounds__(PW_THREADS) sumpool_kernel(const float* __restrict__ x, const int* __restrict__ nbr,
+                                                             const float* __restrict__ pre,
+                                                             const float* __restrict__ post, int64_t n_out,
+                                                             const int* __restrict__ n_dev, int c, int k3,
+                                                             float* __restrict__ y) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_dev);
+  const RowMap m = row_map<VEC>(c);
+  if (!m.active) return;
+  for (int v0 = m.tc; v0 < m.cv; v0 += m.tpr) {
+    const int ch = v0 * VEC;
+    B2S_ROW_LOOP(m, n_out, o) {
+      V<VEC> acc = splat<VEC>(0.f);
+      for (int k = 0; k < k3; ++k) {
+        const int i = __ldg(&nbr[(int64_t)k * pitch + o]);
+        if (i < 0) continue;
+        const V<VEC> v = ldgv<VEC>(x + (int64_t)i * c + ch);
+        const float f = pre ? __ldg(&pre[i]) : 1.f;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc.v[j] = fmaf(v.v[j], f, acc.v[j]);
+      }
+      if (post) {
+        const float f = __ldg(&post[o]);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc.v[j] *= f;
+      }
+      stv<VEC>(y + o * c + ch, acc);
+    }
+  }
+}
+
+// inv[o] = 1 / max(1, number of k with nbr[k,o] >= 0)
+__global__ void __launch_bounds__(PW_THREADS) nbr_inv_counts_kernel(const int* __restrict__ nbr, int k3, int64_t n,
+                                                                    const int* __restrict__ n_dev,
+                                                                    float* __restrict__ inv) {
+  const int64_t pitch = n;
+  n = b2s_rows(n, n_dev);
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
+    int cnt = 0;
+    for (int k = 0; k < k3; ++k) cnt += __ldg(&nbr[(int64_t)k * pitch + o]) >= 0;
+    inv[o] = 1.f / (float)(cnt > 0 ? cnt : 1);
+  }
+}
+
 __global__ void __launch_bounds__(PW_THREADS) maxpool_bwd_kernel(const float* __restrict__ gy,
                                                                  const int* __restrict__ arg, int64_t n_out,
                                                                  const int* __restrict__ n_dev, int c,
@@ -247,6 +296,76 @@ __global__ void __launch_bounds__(PW_THREADS) scale_rows_kernel(float* __restric
                                                                 int nb, int c) {
   const int total = nb * c;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) y[e] *= scale[e / c];
+}
+
+// Per-plot maximum (MinkowskiGlobalMaxPooling, R:networks.py:39, R:PointNet.py:28): y[b, c] = max over the rows of plot b,
+// arg[b, c] = the lowest row holding it (-1 and y = 0 for a plot without rows).  Rows are batch-sorted, so a CTA =
+// (plot, 64-channel slab) finds its row range by bisection of the batch column and reduces it without atomics:
+// 16 row lanes x 16 channel quads, then a shared-memory fold over the row lanes.  Deterministic.
+__global__ void __launch_bounds__(256) segment_max_kernel(const float* __restrict__ x, const int* __restrict__ rb,
+                                                          int stride, int64_t n, const int* __restrict__ n_dev, int c,
+                                                          float* __restrict__ y, int* __restrict__ arg) {
+  n = b2s_rows(n, n_dev);
+  const int b = blockIdx.x, c0 = blockIdx.y * 64;
+  auto lower = [&](int key) {       // first row with batch id >= key
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(&rb[mid * stride]) < key) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo;
+  };
+  const int64_t r0 = lower(b), r1 = lower(b + 1);
+  const int q = threadIdx.x & 15, lane = threadIdx.x >> 4;       // channel quad, row lane
+  float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int bi[4] = {-1, -1, -1, -1};
+  const int ch = c0 + q * 4;
+  if (ch < c) {
+    for (int64_t r = r0 + lane; r < r1; r += 16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (ch + j < c) {
+          const float v = __ldg(&x[r * c + ch + j]);
+          if (bi[j] < 0 || v > best[j]) {          // rows ascend per lane: strict > keeps the lowest row on ties
+            best[j] = v;
+            bi[j] = (int)r;
+          }
+        }
+      }
+    }
+  }
+  __shared__ float sv[16][64];
+  __shared__ int si[16][64];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sv[lane][q * 4 + j] = best[j];
+    si[lane][q * 4 + j] = bi[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64 && c0 + threadIdx.x < c) {
+    float v = -INFINITY;
+    int i = -1;
+    for (int l = 0; l < 16; ++l) {
+      const int il = si[l][threadIdx.x];
+      const float vl = sv[l][threadIdx.x];
+      if (il >= 0 && (i < 0 || vl > v || (vl == v && il < i))) {
+        v = vl;
+        i = il;
+      }
+    }
+    y[(int64_t)b * c + c0 + threadIdx.x] = i >= 0 ? v : 0.f;
+    arg[(int64_t)b * c + c0 + threadIdx.x] = i;
+  }
+}
+
+// gx[arg[b, c], c] = gy[b, c] into a zeroed gx
+__global__ void __launch_bounds__(256) segment_max_bwd_kernel(const float* __restrict__ gy, const int* __restrict__ arg,
+                                                              int64_t total, int c, float* __restrict__ gx) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = arg[e];
+    if (i >= 0) gx[(int64_t)i * c + (e % c)] = gy[e];
+  }
 }
 
 // out[r, :] = y[batch(r), :] * scale[batch(r)]
@@ -973,6 +1092,33 @@ extern "C" int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n
   return B2S_OK;
 }
 
+extern "C" int32_t b2s_sumpool(const float* x, const int32_t* nbr, const float* pre_scale, const float* post_scale,
+                               int64_t n_out, const int32_t* n_out_dev, int32_t c, int32_t k3, float* y,
+                               b2s_stream_t stream) {
+  B2S_CHECK_ARG(n_out >= 0 && c > 0 && k3 > 0, "bad sizes");
+  if (n_out == 0) return B2S_OK;
+  B2S_CHECK_ARG(x && nbr && y, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (vec_of(c, x, y) == 4)
+    sumpool_kernel<4><<<rows_grid(n_out, c, 4), PW_THREADS, 0, st>>>(x, nbr, pre_scale, post_scale, n_out, n_out_dev, c,
+                                                                     k3, y);
+  else
+    sumpool_kernel<1><<<rows_grid(n_out, c, 1), PW_THREADS, 0, st>>>(x, nbr, pre_scale, post_scale, n_out, n_out_dev, c,
+                                                                     k3, y);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_nbr_inv_counts(const int32_t* nbr, int32_t k3, int64_t n, const int32_t* n_dev, float* inv,
+                                      b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && k3 > 0, "bad sizes");
+  if (n == 0) return B2S_OK;
+  B2S_CHECK_ARG(nbr && inv, "null pointer");
+  nbr_inv_counts_kernel<<<grid_for(n, PW_THREADS), PW_THREADS, 0, as_stream(stream)>>>(nbr, k3, n, n_dev, inv);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 extern "C" int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t n_in, int64_t n_out,
                                    const int32_t* n_out_dev, int32_t c, float* gx, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c > 0, "bad sizes");
@@ -1027,6 +1173,31 @@ extern "C" int32_t b2s_segment_sum(const float* x, const int32_t* row_batch, int
   segment_sum_kernel<false><<<colgrid(n, c), PW_THREADS, 0, st>>>(x, nullptr, row_batch, row_batch_stride, n, n_dev,
                                                                   c, num_batches, y);
   if (scale) scale_rows_kernel<<<grid_for((int64_t)num_batches * c, PW_THREADS), PW_THREADS, 0, st>>>(y, scale, num_batches, c);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_segment_max(const float* x, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
+                                   const int32_t* n_dev, int32_t c, int32_t num_batches, float* y, int32_t* arg,
+                                   b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0 && num_batches >= 0 && row_batch_stride > 0, "bad arguments");
+  if (num_batches == 0) return B2S_OK;
+  B2S_CHECK_ARG((x || n == 0) && (row_batch || n == 0) && y && arg, "null pointer");
+  segment_max_kernel<<<dim3((unsigned)num_batches, (unsigned)((c + 63) / 64)), 256, 0, as_stream(stream)>>>(
+      x, row_batch, row_batch_stride, n, n_dev, c, y, arg);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_segment_max_bwd(const float* gy, const int32_t* arg, int64_t n, int32_t c, int32_t num_batches,
+                                       float* gx, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && c > 0 && num_batches >= 0, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (n > 0) B2S_CUDA(cudaMemsetAsync(gx, 0, (size_t)n * c * sizeof(float), st));
+  if (n == 0 || num_batches == 0) return B2S_OK;
+  B2S_CHECK_ARG(gy && arg && gx, "null pointer");
+  const int64_t total = (int64_t)num_batches * c;
+  segment_max_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>(gy, arg, total, c, gx);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

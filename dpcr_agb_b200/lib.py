@@ -47,8 +47,12 @@ SIGNATURES = {
     "b2s_colsum": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_maxpool_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b2s_maxpool_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp]),
+    "b2s_sumpool": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "b2s_nbr_inv_counts": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "b2s_batch_counts": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "b2s_segment_sum": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2s_segment_max": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2s_segment_max_bwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "b2s_segment_bcast": (_i32, [_vp, _vp, _i32, _i64, _vp, _i32, _vp, _vp, _vp]),
     "b2s_bcast_mul_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp]),
     "b2s_bcast_mul_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),

@@ -195,6 +195,18 @@ B2S_API int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n_ou
 B2S_API int32_t b2s_maxpool_bwd(const float* gy, const int32_t* arg, int64_t n_in, int64_t n_out,
                                 const int32_t* n_out_dev, int32_t c, float* gx, b2s_stream_t stream);
 
+/* ---------------------------------------------------------------- (f3) local sum / average pooling --
+ * R:modules/MinkowskiEngine/networks.py:29 (ME.MinkowskiAvgPooling(kernel_size=2, stride=2) of ResNetBase) and
+ * MinkowskiSumPooling.  y[o,:] = post_scale[o] * sum_k pre_scale[i] * x[i,:] over i = nbr[k,o] >= 0; both scales
+ * nullable.  Average pooling: post_scale = b2s_nbr_inv_counts(nbr) (1 / number of inputs under the kernel, as
+ * MinkowskiEngine divides); its backward is the same kernel on the transposed table with pre_scale = that vector.
+ */
+B2S_API int32_t b2s_sumpool(const float* x, const int32_t* nbr, const float* pre_scale, const float* post_scale,
+                            int64_t n_out, const int32_t* n_out_dev, int32_t c, int32_t k3, float* y,
+                            b2s_stream_t stream);
+B2S_API int32_t b2s_nbr_inv_counts(const int32_t* nbr, int32_t k3, int64_t n, const int32_t* n_dev, float* inv,
+                                   b2s_stream_t stream);
+
 /* ---------------------------------------------------------------- (a5,a10,a11) per-plot ops --
  * R:modules/MinkowskiEngine/senet_block.py:43-50; common.py:44-48; SENet.py:63,117.
  * row_batch points at the batch id of row 0 and is read with `row_batch_stride` int32s per row (the
@@ -205,6 +217,13 @@ B2S_API int32_t b2s_batch_counts(const int32_t* row_batch, int32_t row_batch_str
 B2S_API int32_t b2s_segment_sum(const float* x, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
                                 const int32_t* n_dev, int32_t c, int32_t num_batches, const float* scale, float* y,
                                 b2s_stream_t stream);
+/* per-plot maximum (MinkowskiGlobalMaxPooling: R:modules/MinkowskiEngine/networks.py:39, PointNet.py:28): rows must be
+ * batch-sorted; arg int32 [B, c] = winning row (lowest on ties, -1 for an empty plot -> y = 0); bwd scatters gy to it. */
+B2S_API int32_t b2s_segment_max(const float* x, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
+                                const int32_t* n_dev, int32_t c, int32_t num_batches, float* y, int32_t* arg,
+                                b2s_stream_t stream);
+B2S_API int32_t b2s_segment_max_bwd(const float* gy, const int32_t* arg, int64_t n, int32_t c, int32_t num_batches,
+                                    float* gx, b2s_stream_t stream);
 B2S_API int32_t b2s_segment_bcast(const float* y, const int32_t* row_batch, int32_t row_batch_stride, int64_t n,
                                   const int32_t* n_dev, int32_t c, const float* scale, float* x_out,
                                   b2s_stream_t stream);

@@ -113,6 +113,27 @@ class CoordinateManager:
             self.kmaps[ck] = oc.kernel_map_table(self.maps[in_key], self.maps[out_key], kernel_size, step)
         return self.kmaps[ck]
 
+    def transposed_kernel_map(self, coarse_key, fine_key, kernel_size, dilation):
+        """Table of a transposed convolution / pooling from ``coarse_key`` rows to ``fine_key`` rows:
+        ``nbr[k, f] = c`` iff ``fine[f] == coarse[c] + delta_k`` with the offsets of the FORWARD op fine -> coarse
+        (step = dilation * fine tensor stride) -- MinkowskiEngine builds the forward kernel map and swaps its sides."""
+        ck = ("T", coarse_key, fine_key, kernel_size, dilation)
+        if ck not in self.kmaps:
+            step = tuple(d * t for d, t in zip(dilation, fine_key.tensor_stride))
+            self.kmaps[ck] = oc.kernel_map_table(self.maps[coarse_key], self.maps[fine_key], kernel_size, step, sign=-1)
+        return self.kmaps[ck]
+
+    def union(self, key_a, key_b):
+        """Union coordinate map of two maps of the same tensor stride (``SparseTensor.__add__`` across maps): rows of
+        ``key_a`` in their order, then the rows only ``key_b`` has, in its order.  Returns (key, rows of a, rows of b)."""
+        assert key_a.tensor_stride == key_b.tensor_stride
+        both = np.concatenate([self.maps[key_a], self.maps[key_b]])
+        first, inv = oc.unique_first(both)
+        key = CoordinateMapKey(key_a.tensor_stride, f"union({key_a.tag}|{key_b.tag}|{len(self.maps)})")
+        self.maps[key] = both[first]
+        na = self.maps[key_a].shape[0]
+        return key, inv[:na].astype(np.int64), inv[na:].astype(np.int64)
+
 
 class SparseTensor:
     """``ME.SparseTensor`` as the reference uses it (``models/instance/minkowski.py:74``,
@@ -187,10 +208,18 @@ class SparseTensor:
     def _wrap(self, f):
         return SparseTensor(f, coordinate_map_key=self.coordinate_map_key, coordinate_manager=self.coordinate_manager)
 
+    def _union_add(self, other, sign=1.0):
+        cm = self.coordinate_manager
+        key, ra, rb = cm.union(self.coordinate_map_key, other.coordinate_map_key)
+        out = self._F.new_zeros((cm.coords(key).shape[0], self._F.shape[1]))
+        out = out.index_add(0, torch.from_numpy(ra), self._F).index_add(0, torch.from_numpy(rb), sign * other._F)
+        return SparseTensor(out, coordinate_map_key=key, coordinate_manager=cm)
+
     def __add__(self, other):
         if isinstance(other, SparseTensor):
-            assert other.coordinate_map_key == self.coordinate_map_key and \
-                other.coordinate_manager is self.coordinate_manager, "oracle: union-map add not restated"
+            assert other.coordinate_manager is self.coordinate_manager
+            if other.coordinate_map_key != self.coordinate_map_key:
+                return self._union_add(other)
             return self._wrap(self._F + other._F)
         return self._wrap(self._F + other)
 
@@ -259,11 +288,33 @@ class MinkowskiConvolution(MinkowskiModuleBase):
 
 
 class MinkowskiConvolutionTranspose(MinkowskiModuleBase):
-    def __init__(self, *a, **kw):
+    """Non-generative transposed convolution (``modules/MinkowskiEngine/networks.py:155-176``): the output lives on
+    the EXISTING map of tensor stride ``ts_in / stride`` (the encoder map of a U-Net);
+    ``out[f] = bias + sum_k in[c] @ W[k]`` over the pairs (f, c, k) of the forward op fine -> coarse, sides swapped."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
+                 kernel_generator=None, expand_coordinates=False, convolution_mode=None, dimension=None):
         super().__init__()
+        assert dimension == 3 and not expand_coordinates
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.dilation = _triple(kernel_size), _triple(stride), _triple(dilation)
+        self.kernel_volume = int(np.prod(self.kernel_size))
+        self.kernel = nn.Parameter(torch.empty(self.kernel_volume, in_channels, out_channels))
+        self.bias = nn.Parameter(torch.empty(1, out_channels)) if bias else None
+        with torch.no_grad():
+            std = 1.0 / np.sqrt(out_channels * self.kernel_volume)
+            self.kernel.uniform_(-std, std)
+            if self.bias is not None:
+                self.bias.uniform_(-std, std)
 
     def forward(self, x):
-        raise NotImplementedError("oracle: transposed convolution is outside the MSENet hot path")
+        cm, in_key = x.coordinate_manager, x.coordinate_map_key
+        ts = tuple(t // s for t, s in zip(in_key.tensor_stride, self.stride))
+        out_key = CoordinateMapKey(ts, in_key.tag)
+        assert out_key in cm.maps, "oracle: transposed convolution onto an existing (encoder) map only"
+        nbr = cm.transposed_kernel_map(in_key, out_key, self.kernel_size, self.dilation)
+        return SparseTensor(oo.conv(x.F, self.kernel, nbr, self.bias), coordinate_map_key=out_key,
+                            coordinate_manager=cm)
 
 
 class MinkowskiMaxPooling(MinkowskiModuleBase):
@@ -286,12 +337,30 @@ class _NotOnPath(MinkowskiModuleBase):
         raise NotImplementedError(f"oracle: {type(self).__name__} is outside the MSENet hot path")
 
 
-class MinkowskiAvgPooling(_NotOnPath):
-    pass
+class MinkowskiSumPooling(MinkowskiModuleBase):
+    """Local sum pooling; ``AVERAGE`` divides by the number of inputs under the kernel (MinkowskiAvgPooling,
+    ``networks.py:29``)."""
+    AVERAGE = False
+
+    def __init__(self, kernel_size, stride=1, dilation=1, kernel_generator=None, dimension=None):
+        super().__init__()
+        self.kernel_size, self.stride, self.dilation = _triple(kernel_size), _triple(stride), _triple(dilation)
+
+    def forward(self, x):
+        cm, in_key = x.coordinate_manager, x.coordinate_map_key
+        out_key = in_key if self.stride == (1, 1, 1) else cm.stride(in_key, self.stride)
+        nbr = torch.from_numpy(cm.kernel_map(in_key, out_key, self.kernel_size, self.dilation).astype(np.int64))
+        out = x.F.new_zeros((nbr.shape[1], x.F.shape[1]))
+        for k in range(nbr.shape[0]):
+            o = torch.nonzero(nbr[k] >= 0).squeeze(1)
+            out = out.index_add(0, o, x.F[nbr[k, o]])
+        if self.AVERAGE:
+            out = out / (nbr >= 0).sum(0).clamp(min=1).to(out.dtype)[:, None]
+        return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
 
 
-class MinkowskiSumPooling(_NotOnPath):
-    pass
+class MinkowskiAvgPooling(MinkowskiSumPooling):
+    AVERAGE = True
 
 
 class MinkowskiAvgUnpooling(_NotOnPath):

@@ -199,3 +199,74 @@ def test_step_contexts_restore_their_flags():
             M.DEFERRED_BN_COUNTERS.append(t)
         assert all(int(t) == 0 for t in counters)
     assert M.DEFERRED_BN_COUNTERS is None and all(int(t) == 1 for t in counters)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present on this machine")
+def test_reference_pointnet_resnet_minkunet_run_over_the_oracle():
+    """SURVEY.md 8(f) ranks 3-4 on the oracle side: the UNCHANGED reference ``MinkowskiPointNet`` equals our
+    restatement (state-dict keys and forward), and the unchanged ``ResNet14`` (k5s2 conv, k2s2 average pooling, k3s3
+    conv, global max pooling) and ``MinkUNet14A`` (k2s2 transposed convolutions onto the encoder maps, ``ME.cat``)
+    of ``networks.py`` / ``api_modules`` run forward + backward over it."""
+    import numpy as np
+    from dpcr_agb_b200 import plots, pointnet
+    from oracle import coords as oc
+    from oracle import me_cpu
+    for k in [k for k in sys.modules if k.startswith("torch_points3d") or k.startswith("MinkowskiEngine")]:
+        del sys.modules[k]
+    me_cpu.install()
+    _stub_reference_imports()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from torch_points3d.modules.MinkowskiEngine import PointNet, networks
+        try:
+            b = plots.synth_batch(0, 0, 2, n_points=600)
+            c, f, _, _, _ = oc.quantize_batch([b["pos"][b["batch"] == i] for i in range(2)],
+                                              [b["feats"][b["batch"] == i] for i in range(2)], 0.05)
+            x6 = np.concatenate([c[:, 1:].astype(np.float32) * 0.05, f], 1)
+            torch.manual_seed(0)
+            ref = PointNet.MinkowskiPointNet(3, 2, activation="gelu", global_pool="max", embedding_channel=256)
+            mine = pointnet.MinkowskiPointNet(me_cpu, 3, 2, activation="gelu", global_pool="max", embedding_channel=256)
+            assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == \
+                {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+            mine.load_state_dict(ref.state_dict())
+            yr = ref(me_cpu.SparseTensor(torch.from_numpy(x6), coordinates=torch.from_numpy(c))).F
+            ym = mine(me_cpu.SparseTensor(torch.from_numpy(x6), coordinates=torch.from_numpy(c))).F
+            assert torch.equal(yr, ym)
+            for cls in (networks.ResNet14, networks.MinkUNet14A):
+                torch.manual_seed(1)
+                net = cls(3, 4, D=3)
+                x = me_cpu.SparseTensor(torch.from_numpy(f).clone().requires_grad_(), coordinates=torch.from_numpy(c))
+                y = net(x)
+                assert y.F.shape[1] == 4 and torch.isfinite(y.F).all()
+                if cls is networks.MinkUNet14A:
+                    assert y.F.shape[0] == c.shape[0] and y.coordinate_map_key == x.coordinate_map_key
+                y.F.square().sum().backward()
+                assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+        finally:
+            for k in [k for k in sys.modules if k.startswith("torch_points3d") or k.startswith("MinkowskiEngine")]:
+                del sys.modules[k]
+
+
+def test_checkpoint_layout_round_trip(tmp_path):
+    """``dpcr_agb_b200.checkpoint`` writes the dict layout of ``metrics/model_checkpoint.py:24-61`` (models / optimizer /
+    schedulers / stats / run_config) with the backbone under ``model.`` as ``MinkowskiBaselineModel`` saves it, and
+    loads both layouts back."""
+    from dpcr_agb_b200 import MinkowskiEngine as ME
+    from dpcr_agb_b200 import checkpoint, msenet
+    torch.manual_seed(0)
+    a = msenet.MSENet(ME, "SENet14")
+    path = str(tmp_path / "SENet14.pt")
+    obj = checkpoint.save(path, a, run_config={"model_name": "SENet14"}, extra_models={"best_loss": a.state_dict()})
+    assert set(obj) >= {"run_config", "models", "stats", "optimizer", "schedulers", "grad_scale", "dataset_properties"}
+    assert set(obj["models"]) == {"latest", "best_loss"}
+    assert all(k.startswith("model.") for k in obj["models"]["latest"])
+    assert "model.blocks.0.0.conv.kernel" in obj["models"]["latest"] and "model.final.linears.1.bias" in obj["models"]["latest"]
+    torch.manual_seed(1)
+    b = msenet.MSENet(ME, "SENet14")
+    checkpoint.load(path, b, weight_name="best_miou")            # unknown name -> latest (model_checkpoint.py:237-243)
+    for (k, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(va, vb), k
+    torch.save({"models": {"latest": a.state_dict()}}, path)      # a file without the model. prefix loads too
+    checkpoint.load(path, b)

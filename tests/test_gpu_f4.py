@@ -1,0 +1,146 @@
+"""GPU coverage of SURVEY.md 8(f) rank 4: the sibling networks of the reference (SENet18 / 34 / 101, MinkowskiPointNet)
+against the oracle, the per-plot max pooling / broadcast ops they add, the call pattern of the reference's own
+``MinkowskiDropPath`` (``common.py:353-366``), and checkpoint files in the reference's layout incl. optimiser state."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from dpcr_agb_b200 import MinkowskiEngine as ME
+from dpcr_agb_b200 import checkpoint, msenet, pointnet, train
+from oracle import me_cpu
+from oracle import train as otrain
+import b2s_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def _voxels(num_plots=3, n_points=1500, size=0.05, cfg=5):
+    batch = util.make_points(num_plots, n_points, cfg=cfg)
+    c, f, _, _, _ = util.oracle_quantize(batch, size)
+    return batch, c, f
+
+
+@pytest.mark.parametrize("name", ["SENet18", "SENet34", "SENet101"])
+def test_sibling_senets_match_the_oracle(cuda, name):
+    """Eval-mode forward + backward of the deeper SENets (``SENet.py:121-194``) through the product path."""
+    batch, c, f = _voxels()
+    torch.manual_seed(0)
+    ref = msenet.MSENet(me_cpu, name, drop_path=0.0).eval()
+    mine = msenet.MSENet(ME, name, drop_path=0.0)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(cuda).eval()
+    target = torch.from_numpy(batch["target"])
+    center, scale = torch.tensor([107.0, 200.0]), torch.tensor([103.0, 194.0])
+    yr = ref(me_cpu.SparseTensor(torch.from_numpy(f), coordinates=torch.from_numpy(c)))
+    otrain.reg_loss(yr, target, center, scale).backward()
+    ym = mine(ME.SparseTensor(features=torch.from_numpy(f), coordinates=torch.from_numpy(c), device=cuda))
+    train.reg_loss(ym, target.to(cuda), center.to(cuda), scale.to(cuda)).backward()
+    util.assert_close(ym, yr, tol=1e-3, what=f"{name} output")
+    gmax = max(p.grad.abs().max().item() for p in ref.parameters() if p.grad is not None)
+    for (n1, p1), (_, p2) in zip(mine.named_parameters(), ref.named_parameters()):
+        if p2.grad is None:
+            continue
+        err = (p1.grad.cpu() - p2.grad).abs().max().item()
+        assert err <= 1e-3 * p2.grad.abs().max().item() + 2e-5 * gmax, f"{name} grad of {n1}: {err:.3e}"
+
+
+@pytest.mark.parametrize("pool", ["max", "sum", "mean"])
+def test_pointnet_matches_the_oracle(cuda, pool):
+    """``MinkowskiPointNet`` (``PointNet.py:9-49``), training-mode batch norm, forward + backward."""
+    _, c, f = _voxels(cfg=6)
+    x6 = np.concatenate([c[:, 1:].astype(np.float32) * 0.05, f], 1)
+    torch.manual_seed(0)
+    ref = pointnet.MinkowskiPointNet(me_cpu, 3, 2, activation="gelu", global_pool=pool, embedding_channel=256)
+    mine = pointnet.MinkowskiPointNet(ME, 3, 2, activation="gelu", global_pool=pool, embedding_channel=256)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(cuda)
+    yr = ref(me_cpu.SparseTensor(torch.from_numpy(x6), coordinates=torch.from_numpy(c))).F
+    ym = mine(ME.SparseTensor(features=torch.from_numpy(x6), coordinates=torch.from_numpy(c), device=cuda)).F
+    util.assert_close(ym, yr, tol=1e-4, what="PointNet output")
+    g = torch.randn(yr.shape, generator=torch.Generator().manual_seed(1))
+    yr.backward(g)
+    ym.backward(g.to(cuda))
+    gmax = max(p.grad.abs().max().item() for p in ref.parameters())
+    for (n1, p1), (_, p2) in zip(mine.named_parameters(), ref.named_parameters()):
+        err = (p1.grad.cpu() - p2.grad).abs().max().item()
+        assert err <= 1e-3 * p2.grad.abs().max().item() + 2e-5 * gmax, f"PointNet grad of {n1}: {err:.3e}"
+    for (n1, b1), (_, b2) in zip(mine.named_buffers(), ref.named_buffers()):
+        if b2.dtype.is_floating_point:
+            util.assert_close(b1, b2, tol=1e-4, what=f"buffer {n1}")
+
+
+def test_global_max_pool_and_broadcast_ops(cuda):
+    rng = np.random.default_rng(3)
+    c = util.random_coords(rng, 900, nb=4, extent=8)
+    c = c[c[:, 0] != 2]                                    # plot 2 has no rows: y = 0, arg = -1, no gradient
+    f = rng.standard_normal((c.shape[0], 70)).astype(np.float32)
+    f[5] = f[3]                                            # a tie between rows of plot 0: the lower row wins
+    xr = me_cpu.SparseTensor(torch.from_numpy(f).clone().requires_grad_(), coordinates=torch.from_numpy(c))
+    xg = ME.SparseTensor(torch.from_numpy(f).to(cuda).requires_grad_(), coordinates=torch.from_numpy(c).to(cuda))
+    b = torch.from_numpy(c[:, 0].astype(np.int64))
+    yg = ME.MinkowskiGlobalMaxPooling()(xg)
+    ref = torch.zeros((4, 70))
+    for p in (0, 1, 3):
+        ref[p] = torch.from_numpy(f)[b == p].max(0).values
+    assert torch.equal(yg.F.detach().cpu(), ref)
+    g = torch.randn(4, 70)
+    yg.F.backward(g.to(cuda))
+    yr = xr.F[b == 0].max(0).values
+    yr.backward(g[0])
+    assert torch.equal(xg.F.grad.cpu()[b == 0], xr.F.grad[b == 0])       # same arg-max rows incl. the tie
+    assert torch.count_nonzero(xg.F.grad) == 3 * 70
+    glob = ME.SparseTensor(torch.randn(4, 70, device=cuda).requires_grad_(), coordinate_map_key=yg.coordinate_map_key,
+                           coordinate_manager=yg.coordinate_manager)
+    out = ME.MinkowskiBroadcastAddition()(xg, glob)
+    assert torch.equal(out.F.detach().cpu(), (xg.F.detach() + glob.F.detach()[b.to(cuda)]).cpu())
+    out.F.sum().backward()
+    assert torch.allclose(glob.F.grad.cpu(), torch.bincount(b, minlength=4).float()[:, None].expand(4, 70))
+    assert torch.equal(ME.MinkowskiBroadcast()(xg, glob).F.detach(), glob.F.detach()[b.to(cuda)])
+
+
+def test_reference_drop_path_call_pattern(cuda):
+    """What the reference's own ``MinkowskiDropPath.forward`` does with a SparseTensor (``common.py:353-366``):
+    ``decomposed_coordinates`` (one entry per plot, ascending batch id), a per-row mask concatenated in batch order,
+    ``x.F * mask`` re-wrapped with the same key and manager -- must agree with our per-plot broadcast formulation."""
+    _, c, f = _voxels()
+    x = ME.SparseTensor(features=torch.from_numpy(f), coordinates=torch.from_numpy(c), device=cuda)
+    dec = x.decomposed_coordinates
+    counts = np.bincount(c[:, 0], minlength=3)
+    assert [d.shape[0] for d in dec] == counts.tolist()
+    assert all(torch.equal(d.cpu(), torch.from_numpy(c[c[:, 0] == i][:, 1:])) for i, d in enumerate(dec))
+    random.seed(7)
+    keep = 0.7
+    mask = torch.cat([torch.ones(len(d), 1) / keep if random.uniform(0, 1) > 0.3 else torch.zeros(len(d), 1)
+                      for d in dec]).to(cuda)
+    ref_style = ME.SparseTensor(x.F * mask, coordinate_map_key=x.coordinate_map_key,
+                                coordinate_manager=x.coordinate_manager)
+    dp = msenet.DropPath(ME, 0.3).train()
+    random.seed(7)
+    ours = dp(x)
+    assert torch.equal(ours.F, ref_style.F) and ours.coordinate_map_key == x.coordinate_map_key
+
+
+def test_checkpoint_with_optimiser_state_resumes(cuda, tmp_path):
+    """Save after two steps, load into a fresh model + optimiser, take the third step on both: identical parameters
+    (the reference checkpoints ``optimizer.state_dict()`` next to the weights, ``model_checkpoint.py:41-55``)."""
+    batch, c, f = _voxels(num_plots=2, n_points=1200)
+    cg, fg = torch.from_numpy(c).to(cuda), torch.from_numpy(f).to(cuda)
+    target = torch.from_numpy(batch["target"]).to(cuda)
+    torch.manual_seed(0)
+    a = train.Trainer(msenet.build(ME, "SENet14", drop_path=0.0).to(cuda), ME, lr=1e-3)
+    for _ in range(2):
+        a.step(cg, fg, target)
+    path = str(tmp_path / "ckpt.pt")
+    checkpoint.save(path, a.model, optimizer=a.opt)
+    torch.manual_seed(1)
+    b = train.Trainer(msenet.build(ME, "SENet14", drop_path=0.0).to(cuda), ME, lr=1e-3)
+    obj = checkpoint.load(path, b.model, optimizer=b.opt)
+    assert obj["optimizer"][0] == "AdaBelief" and b.opt.step_count == 2
+    b.num_batches = a.num_batches
+    b.opt.lr = a.opt.lr
+    la, lb = a.step(cg, fg, target), b.step(cg, fg, target)
+    torch.cuda.synchronize()
+    assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(la))
+    util.assert_close(b.opt.flat_param, a.opt.flat_param, tol=1e-5, what="parameters after the resumed step")

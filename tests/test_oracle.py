@@ -146,3 +146,39 @@ def test_stride_map_properties(rows, ts):
         o = np.nonzero(fwd[k] >= 0)[0]
         assert np.array_equal(tr[k][fwd[k, o]], o)
     assert int((fwd >= 0).sum()) == int((tr >= 0).sum())
+
+
+def test_transposed_conv_is_the_adjoint_and_pooling_counts():
+    """Self-consistency of the SURVEY 8(f) rank-3 oracle ops: the non-generative transposed convolution with kernel
+    W^T is the adjoint of the strided convolution with kernel W on the same pair of maps; average pooling of ones is
+    one; the union map keeps the rows of the first operand first."""
+    import torch
+    from oracle import me_cpu
+    rng = np.random.default_rng(0)
+    seen, rows = set(), []
+    while len(rows) < 500:
+        r = (int(rng.integers(2)), *(int(v) for v in rng.integers(-8, 8, 3)))
+        if r not in seen:
+            seen.add(r)
+            rows.append(r)
+    c = np.asarray(sorted(rows, key=lambda r: r[0]), dtype=np.int32)
+    f = torch.randn(500, 8)
+    x = me_cpu.SparseTensor(f, coordinates=torch.from_numpy(c))
+    down = me_cpu.MinkowskiConvolution(8, 6, kernel_size=2, stride=2, dimension=3)
+    up = me_cpu.MinkowskiConvolutionTranspose(6, 8, kernel_size=2, stride=2, dimension=3)
+    with torch.no_grad():
+        up.kernel.copy_(down.kernel.transpose(1, 2))
+        y = down(x)
+        a = torch.randn_like(y.F)
+        ua = up(me_cpu.SparseTensor(a, coordinate_map_key=y.coordinate_map_key, coordinate_manager=y.coordinate_manager))
+    assert ua.coordinate_map_key == x.coordinate_map_key
+    lhs, rhs = float((ua.F * f).sum()), float((a * y.F).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs))
+    ones = me_cpu.SparseTensor(torch.ones(500, 2), coordinates=torch.from_numpy(c))
+    avg = me_cpu.MinkowskiAvgPooling(kernel_size=2, stride=2, dimension=3)(ones).F
+    assert torch.equal(avg, torch.ones_like(avg))
+    cm = x.coordinate_manager
+    kb = cm.insert(c[::-1][:300] + np.array([0, 1, 0, 0], np.int32), (1, 1, 1), tag="b")
+    ukey, ra, rb = cm.union(x.coordinate_map_key, kb)
+    assert np.array_equal(cm.coords(ukey)[:500], c) and np.array_equal(ra, np.arange(500))
+    assert np.array_equal(cm.coords(ukey)[rb], cm.coords(kb))

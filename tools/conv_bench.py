@@ -14,6 +14,8 @@ from dpcr_agb_b200.MinkowskiEngine import functional as Fn
 from dpcr_agb_b200.quantize import GridSampling3D
 
 dev = torch.device("cuda:0")
+PRECISE = int(os.environ.get("PRECISE", "1"))      # operand mode: 1 = split-bf16 (default), 0 = TF32
+lib.set_tuning("precise", PRECISE)
 B = int(os.environ.get("PLOTS", "32"))
 b = plots.synth_batch(2, 0, B, n_points=16000)
 d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in b.items()}
@@ -87,4 +89,5 @@ for name, its, ots, K, cin, cout in layers:
     print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in row.items()})
 res["layers"] = out
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/conv_bench.json", "w"), indent=1)
+res["precise"] = PRECISE
+json.dump(res, open(f"gpurun_out/conv_bench_{'bf16x2' if PRECISE else 'tf32'}.json", "w"), indent=1)
