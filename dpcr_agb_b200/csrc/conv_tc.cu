@@ -243,7 +243,12 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
     fence_mbar_init();
   }
   static_assert(PW == 4 || (PW == 8 && SMALL), "eight producer warps: SMALL mode only");
-  if (warp == PW) tmem_alloc<BN>(tmem_slot);
+  // WIDE: the NB weight images of a stage are consecutive rows of shared memory, so ONE MMA of N = NB * BN reads the
+  // A stage once for all of them (N = 64 MMAs re-read the 16 KB A stage per image: the split-bf16 stem was bound by
+  // shared-memory operand reads); the accumulator holds NB column groups that the epilogue adds.
+  constexpr bool WIDE = NB > 1 && NB * BN <= 256;
+  constexpr int TCOLS = WIDE ? 256 : BN;
+  if (warp == PW) tmem_alloc<TCOLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -412,6 +417,16 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
       uint32_t v[32];
       tmem_ld32(t_lane + (uint32_t)c0, v);
       tmem_ld_wait();
+      if (WIDE) {            // add the column groups of the other weight images
+#pragma unroll
+        for (int j = 1; j < NB; ++j) {
+          uint32_t u[32];
+          tmem_ld32(t_lane + (uint32_t)(j * BN + c0), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
+        }
+      }
       if (o_ok) {
         float* dst = y + o * c_out + n0 + c0;
         const bool add_bias = bias && it0 == 0;
@@ -455,6 +470,11 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
             const int ak = q < 4 ? q : q - 4, bk = q < 2 ? q : q - 2;
             mma_bf16(tmem_d, a_desc + (uint64_t)(ak * 2), b_desc + (uint64_t)(bk * 2), IDESC16, (it | q) ? 1u : 0u);
           }
+        } else if (WIDE) {
+          constexpr uint32_t IDESCW = idesc_bf16(BM, WIDE ? NB * BN : BN, 0, 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            mma_bf16(tmem_d, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), IDESCW, (it | kk) ? 1u : 0u);
         } else {
           // small c_in: operand rows [h4 | l4] per offset against the images [H | H], [M | M], [L | 0]
 #pragma unroll
@@ -480,7 +500,7 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
   if (warp == PW) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<BN>(tmem_d);
+    tmem_dealloc<TCOLS>(tmem_d);
   }
 }
 

@@ -833,3 +833,276 @@ extern "C" int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
+
+// =============================================================================================
+// (f2) GPU input pipeline -- the arithmetic transforms the reference runs per sample on the CPU before the quantiser
+// (R:conf/data/instance/NFI/transforms/sparse-xy.yaml:105-152 test_transform; the same ops sit inside train_transform):
+//   ScalePos(op="div")           R:core/data_transform/transforms.py:590-598   pos = pos / (sx, sy, sz)
+//   MoveCenterPosPerSample       :722-739                                      pos += (cx, cy, cz)
+//   StartZFromZero               :766-769                                      z -= min z of the plot
+//   Polygon2dExtend              :1489-1496  keep the points whose (x, y) lies inside the polygon (matplotlib
+//                                            Path.contains_points == the crossings test restated below, in double)
+//   MaxPoints                    :1772-1791  choice = randperm(n)[:num], rows in choice order
+//   AddOnes / XYZFeature(z) / AddXYDistanceToCenter / AddFeatsByKeys   R:core/data_transform/features.py:307-383
+//                                            x = [1, z, ||(x, y) - centre + 1e-6||_2]  (torch PairwiseDistance)
+//   RandomCoordsFlip(ignored z) / ShiftVoxels   :1046-1054 / R:core/data_transform/sparse_transforms.py:49-55
+//                                            on the quantised coordinates, per plot
+// Points of a plot are contiguous (collated batch); every kernel takes the device point count.
+// =============================================================================================
+namespace {
+
+// order-preserving map float -> uint32 (for atomicMin on floats of either sign)
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+constexpr int PP_CHUNK = 64;   // consecutive points per thread: one atomic per plot change instead of one per point
+
+__global__ void __launch_bounds__(256) plot_minz_kernel(const float* __restrict__ pos, const int* __restrict__ plot,
+                                                        int64_t n, const int* __restrict__ n_dev, float sz, float cz,
+                                                        unsigned* __restrict__ minz) {
+  n = b2s_rows(n, n_dev);
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PP_CHUNK;
+  int cur = -1;
+  unsigned best = 0xFFFFFFFFu;
+  for (int64_t i = i0; i < n && i < i0 + PP_CHUNK; ++i) {
+    const int p = __ldg(&plot[i]);
+    if (p != cur) {
+      if (cur >= 0) atomicMin(&minz[cur], best);
+      cur = p;
+      best = 0xFFFFFFFFu;
+    }
+    const unsigned o = f2ord(__fadd_rn(__fdiv_rn(__ldg(&pos[i * 3 + 2]), sz), cz));
+    best = o < best ? o : best;
+  }
+  if (cur >= 0) atomicMin(&minz[cur], best);
+}
+
+struct Polygon {
+  int nv;
+  double vx[16], vy[16];
+};
+
+// matplotlib's point_in_path (src/_path.h, the crossings test of the comp.graphics.algorithms FAQ) for one closed
+// polygon, in double like Path.contains_points
+__device__ __forceinline__ bool inside_polygon(const Polygon& pg, double tx, double ty) {
+  bool inside = false;
+  double x0 = pg.vx[pg.nv - 1], y0 = pg.vy[pg.nv - 1];
+  bool yflag0 = y0 >= ty;
+  for (int j = 0; j < pg.nv; ++j) {
+    const double x1 = pg.vx[j], y1 = pg.vy[j];
+    const bool yflag1 = y1 >= ty;
+    if (yflag0 != yflag1) {
+      if (((y1 - ty) * (x0 - x1) >= (x1 - tx) * (y0 - y1)) == yflag1) inside = !inside;
+    }
+    yflag0 = yflag1;
+    x0 = x1;
+    y0 = y1;
+  }
+  return inside;
+}
+
+__global__ void __launch_bounds__(256) plot_transform_kernel(const float* __restrict__ pos, const int* __restrict__ plot,
+                                                             int64_t n, const int* __restrict__ n_dev, float sx,
+                                                             float sy, float sz, float cx, float cy, float cz,
+                                                             const unsigned* __restrict__ minz, const Polygon pg,
+                                                             float* __restrict__ out_pos, int* __restrict__ keep) {
+  n = b2s_rows(n, n_dev);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __fadd_rn(__fdiv_rn(__ldg(&pos[i * 3]), sx), cx);
+    const float y = __fadd_rn(__fdiv_rn(__ldg(&pos[i * 3 + 1]), sy), cy);
+    const float z = __fsub_rn(__fadd_rn(__fdiv_rn(__ldg(&pos[i * 3 + 2]), sz), cz), ord2f(__ldg(&minz[__ldg(&plot[i])])));
+    out_pos[i * 3] = x;
+    out_pos[i * 3 + 1] = y;
+    out_pos[i * 3 + 2] = z;
+    keep[i] = (pg.nv < 3 || inside_polygon(pg, (double)x, (double)y)) ? 1 : 0;
+  }
+}
+
+// stable compaction: rows with keep != 0 move to their exclusive-scan position
+__global__ void __launch_bounds__(256) compact_points_kernel(const float* __restrict__ pos, const int* __restrict__ plot,
+                                                             const int* __restrict__ keep, const int* __restrict__ idx,
+                                                             int64_t n, const int* __restrict__ n_dev,
+                                                             float* __restrict__ out_pos, int* __restrict__ out_plot) {
+  n = b2s_rows(n, n_dev);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!keep[i]) continue;
+    const int64_t o = idx[i];
+    out_pos[o * 3] = pos[i * 3];
+    out_pos[o * 3 + 1] = pos[i * 3 + 1];
+    out_pos[o * 3 + 2] = pos[i * 3 + 2];
+    out_plot[o] = plot[i];
+  }
+}
+
+// feats = [1, z, ||(x, y) - (cx, cy) + 1e-6||]: torch.nn.PairwiseDistance(eps=1e-6) evaluates
+// sqrt(fma(dy, dy, dx*dx)) with dx, dy = (x - cx) + eps in fp32 on the CPU (checked bit for bit, tests/test_oracle.py)
+__global__ void __launch_bounds__(256) point_features_kernel(const float* __restrict__ pos, int64_t n,
+                                                             const int* __restrict__ n_dev, float cx, float cy,
+                                                             float* __restrict__ feats) {
+  n = b2s_rows(n, n_dev);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float dx = __fadd_rn(__fsub_rn(pos[i * 3], cx), 1e-6f), dy = __fadd_rn(__fsub_rn(pos[i * 3 + 1], cy), 1e-6f);
+    feats[i * 3] = 1.0f;
+    feats[i * 3 + 1] = pos[i * 3 + 2];
+    feats[i * 3 + 2] = __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+  }
+}
+
+// MaxPoints: point i of plot p with rank r = rank[i] (its position in the plot's random permutation) goes to row
+// offsets[p] + r if r < num; offsets = exclusive sum of min(count, num)
+__global__ void capped_offsets_kernel(const int* __restrict__ counts, int num_plots, int num, int* __restrict__ offsets) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int s = 0;
+    for (int p = 0; p < num_plots; ++p) {
+      offsets[p] = s;
+      s += counts[p] < num ? counts[p] : num;
+    }
+    offsets[num_plots] = s;
+  }
+}
+__global__ void __launch_bounds__(256) select_by_rank_kernel(const float* __restrict__ pos, const int* __restrict__ plot,
+                                                             const int* __restrict__ rank, int64_t n,
+                                                             const int* __restrict__ n_dev, int num,
+                                                             const int* __restrict__ offsets,
+                                                             float* __restrict__ out_pos, int* __restrict__ out_plot) {
+  n = b2s_rows(n, n_dev);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = rank[i];
+    if (r < 0 || r >= num) continue;
+    const int p = plot[i];
+    const int64_t o = (int64_t)offsets[p] + r;
+    out_pos[o * 3] = pos[i * 3];
+    out_pos[o * 3 + 1] = pos[i * 3 + 1];
+    out_pos[o * 3 + 2] = pos[i * 3 + 2];
+    out_plot[o] = p;
+  }
+}
+
+// per-plot maximum of the x and y voxel coordinates (RandomCoordsFlip flips about the maximum of the sample)
+__global__ void __launch_bounds__(256) coords_max_kernel(const int* __restrict__ coords, int64_t m,
+                                                         const int* __restrict__ m_dev, int* __restrict__ maxc) {
+  m = b2s_rows(m, m_dev);
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * PP_CHUNK;
+  int cur = -1, bx = INT_MIN, by = INT_MIN;
+  for (int64_t i = i0; i < m && i < i0 + PP_CHUNK; ++i) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + i);
+    if (c.x != cur) {
+      if (cur >= 0) {
+        atomicMax(&maxc[cur * 2], bx);
+        atomicMax(&maxc[cur * 2 + 1], by);
+      }
+      cur = c.x;
+      bx = by = INT_MIN;
+    }
+    bx = max(bx, c.y);
+    by = max(by, c.z);
+  }
+  if (cur >= 0) {
+    atomicMax(&maxc[cur * 2], bx);
+    atomicMax(&maxc[cur * 2 + 1], by);
+  }
+}
+// aug int32 [B, 5] = (flip_x, flip_y, shift_x, shift_y, shift_z) per plot
+__global__ void __launch_bounds__(256) coords_augment_kernel(int* __restrict__ coords, int64_t m,
+                                                             const int* __restrict__ m_dev, const int* __restrict__ aug,
+                                                             const int* __restrict__ maxc) {
+  m = b2s_rows(m, m_dev);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    int4 c = reinterpret_cast<int4*>(coords)[i];
+    const int* a = aug + c.x * 5;
+    if (a[0]) c.y = maxc[c.x * 2] - c.y;
+    if (a[1]) c.z = maxc[c.x * 2 + 1] - c.z;
+    c.y += a[2];
+    c.z += a[3];
+    c.w += a[4];
+    reinterpret_cast<int4*>(coords)[i] = c;
+  }
+}
+
+}  // namespace
+
+extern "C" int32_t b2s_plot_transform(const float* pos, const int32_t* plot_of_point, int64_t n, const int32_t* n_dev,
+                                      int32_t num_plots, const float* scale_host, const float* center_host,
+                                      const double* polygon_host, int32_t num_vertices, uint32_t* minz_scratch,
+                                      float* out_pos, int32_t* keep, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && num_plots > 0 && scale_host && center_host && num_vertices >= 0 && num_vertices <= 16,
+                "bad arguments (at most 16 polygon vertices)");
+  B2S_CHECK_ARG(num_vertices == 0 || polygon_host, "polygon is NULL");
+  if (n == 0) return B2S_OK;
+  B2S_CHECK_ARG(pos && plot_of_point && minz_scratch && out_pos && keep, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  Polygon pg{};
+  pg.nv = num_vertices;
+  for (int j = 0; j < num_vertices; ++j) {
+    pg.vx[j] = polygon_host[2 * j];
+    pg.vy[j] = polygon_host[2 * j + 1];
+  }
+  B2S_CUDA(cudaMemsetAsync(minz_scratch, 0xFF, (size_t)num_plots * sizeof(uint32_t), st));
+  plot_minz_kernel<<<grid_for(ceil_div64(n, PP_CHUNK), 256), 256, 0, st>>>(pos, plot_of_point, n, n_dev, scale_host[2],
+                                                                          center_host[2], minz_scratch);
+  plot_transform_kernel<<<grid_for(n, 256), 256, 0, st>>>(pos, plot_of_point, n, n_dev, scale_host[0], scale_host[1],
+                                                          scale_host[2], center_host[0], center_host[1], center_host[2],
+                                                          minz_scratch, pg, out_pos, keep);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_compact_points(const float* pos, const int32_t* plot_of_point, const int32_t* keep, int64_t n,
+                                      const int32_t* n_dev, int32_t* index_scratch, void* scan_workspace,
+                                      float* out_pos, int32_t* out_plot, int32_t* num_kept_dev, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && num_kept_dev, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {
+    B2S_CUDA(cudaMemsetAsync(num_kept_dev, 0, sizeof(int32_t), st));
+    return B2S_OK;
+  }
+  B2S_CHECK_ARG(pos && plot_of_point && keep && index_scratch && scan_workspace && out_pos && out_plot, "null pointer");
+  launch_exclusive_scan(keep, index_scratch, n, n_dev, num_kept_dev, scan_workspace, st);
+  compact_points_kernel<<<grid_for(n, 256), 256, 0, st>>>(pos, plot_of_point, keep, index_scratch, n, n_dev, out_pos,
+                                                          out_plot);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_point_features(const float* pos, int64_t n, const int32_t* n_dev, float center_x, float center_y,
+                                      float* feats, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0, "n >= 0");
+  if (n == 0) return B2S_OK;
+  B2S_CHECK_ARG(pos && feats, "null pointer");
+  point_features_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(pos, n, n_dev, center_x, center_y, feats);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_select_by_rank(const float* pos, const int32_t* plot_of_point, const int32_t* rank, int64_t n,
+                                      const int32_t* n_dev, int32_t num_plots, int32_t num, const int32_t* counts,
+                                      int32_t* offsets, float* out_pos, int32_t* out_plot, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n >= 0 && num_plots > 0 && num > 0 && counts && offsets, "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  capped_offsets_kernel<<<1, 32, 0, st>>>(counts, num_plots, num, offsets);
+  if (n > 0) {
+    B2S_CHECK_ARG(pos && plot_of_point && rank && out_pos && out_plot, "null pointer");
+    select_by_rank_kernel<<<grid_for(n, 256), 256, 0, st>>>(pos, plot_of_point, rank, n, n_dev, num, offsets, out_pos,
+                                                            out_plot);
+  }
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_coords_augment(int32_t* coords, int64_t m, const int32_t* m_dev, int32_t num_plots,
+                                      const int32_t* aug_dev, int32_t* max_scratch, b2s_stream_t stream) {
+  B2S_CHECK_ARG(m >= 0 && num_plots > 0, "bad arguments");
+  if (m == 0) return B2S_OK;
+  B2S_CHECK_ARG(coords && aug_dev && max_scratch, "null pointer");
+  cudaStream_t st = as_stream(stream);
+  B2S_CUDA(cudaMemsetAsync(max_scratch, 0x80, (size_t)num_plots * 2 * sizeof(int32_t), st));   // 0x80808080 < any coord
+  coords_max_kernel<<<grid_for(ceil_div64(m, PP_CHUNK), 256), 256, 0, st>>>(coords, m, m_dev, max_scratch);
+  coords_augment_kernel<<<grid_for(m, 256), 256, 0, st>>>(coords, m, m_dev, aug_dev, max_scratch);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}

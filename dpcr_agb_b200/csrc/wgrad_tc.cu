@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
   const int k0 = (blockIdx.x / co_tiles) * KPG;
   const int co0 = cot * WG_BM;
   const int co_valid = min(WG_BM, c_out - co0);
+  const bool stack_hl = precise && co_valid <= 64;   // split-bf16: [gh ; gl] stacked along M (see the producers)
   const int64_t r_begin = (int64_t)blockIdx.y * rows_per_split;
   const int64_t r_end = min(r_begin + rows_per_split, n_out);
   const int T = (int)((r_end - r_begin + WG_ROWS - 1) / WG_ROWS);
@@ -415,8 +416,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           const int64_t o = r0 + row;
           const bool live = o < r_end;
           // split-bf16: chunk `lane` of the row = block lane / 8, chunks 0-3 h / 4-7 l; atom = 64 channels x 8 rows
+          // (<= 64 output channels: the l parts take the second 64-lane atom of M instead of a second region, so
+          // that ONE M = 128 MMA covers gh and gl)
+          const uint32_t l_off = stack_hl ? 4096u : 8192u;
           const uint32_t dst =
-              precise ? (uint32_t)((lane >> 2) & 1) * 8192u + (uint32_t)(lane >> 4) * 4096u + (uint32_t)(row >> 3) * 1024u +
+              precise ? (uint32_t)((lane >> 2) & 1) * l_off + (uint32_t)(lane >> 4) * 4096u + (uint32_t)(row >> 3) * 1024u +
                             (uint32_t)(row & 7) * 128u + (uint32_t)((((((lane >> 3) & 1) << 2) | (lane & 3)) ^ (row & 7)) << 4)
                       : mn_offset(row, lane);
           cp_async16(a_stage + dst, gy + (live ? o : 0) * c_out + co0 + lane * 4, live ? 16u : 0u);
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int co = warp * 32 + lane;
+    const int co = stack_hl ? ((warp * 32 + lane) & 63) : warp * 32 + lane;   // stacked: lanes 64.. hold the gl terms
     const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < SM_BN; c0 += 32) {
@@ -499,7 +503,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
           const uint64_t b_desc = smem_desc_sw128(b_base + s * SM_B_STAGE + g * 2048, 4096, 1024);
           mma_bf16(tmem_d, smem_desc_sw128(a_base + s * WG_A_STAGE + g * 2048, 4096, 1024), b_desc, IDESC16,
                    (it | g) ? 1u : 0u);
-          mma_bf16(tmem_d, smem_desc_sw128(a_base + s * WG_A_STAGE + 8192 + g * 2048, 4096, 1024), b_desc, IDESC16, 1u);
+          if (!stack_hl)
+            mma_bf16(tmem_d, smem_desc_sw128(a_base + s * WG_A_STAGE + 8192 + g * 2048, 4096, 1024), b_desc, IDESC16, 1u);
         }
         mma_commit(empty_bar(s));
       } else if (lane == 0) {

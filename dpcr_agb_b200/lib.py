@@ -27,6 +27,11 @@ SIGNATURES = {
     "b2s_quantize_count": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
     "b2s_quantize_fill": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "b2s_gather_rows": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp]),
+    "b2s_plot_transform": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "b2s_compact_points": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2s_select_by_rank": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b2s_point_features": (_i32, [_vp, _i64, _vp, _f32, _f32, _vp, _vp]),
+    "b2s_coords_augment": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp, _vp]),
     "b2s_hash_capacity": (_i64, [_i64]),
     "b2s_scan_workspace_bytes": (_i64, [_i64]),
     "b2s_coordmap_insert": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -141,6 +146,10 @@ def host_i32(*vals):
 
 def host_f32(*vals):
     return (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def host_f64(*vals):
+    return (ctypes.c_double * len(vals))(*[float(v) for v in vals])
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)

@@ -91,6 +91,40 @@ B2S_API int32_t b2s_quantize_fill(const int32_t* qcoords, const int32_t* plot_of
 B2S_API int32_t b2s_gather_rows(const float* in, const int32_t* idx, int64_t m, const int32_t* m_dev, int32_t c,
                                 float* out, b2s_stream_t stream);
 
+/* ---------------------------------------------------------------- (f2) input transforms -------
+ * The arithmetic transforms the reference applies per sample on the CPU before the quantiser
+ * (R:../conf/data/instance/NFI/transforms/sparse-xy.yaml:105-152), on a collated batch (points of a plot contiguous):
+ * b2s_plot_transform : ScalePos(div) + MoveCenterPosPerSample + StartZFromZero
+ *                      (R:core/data_transform/transforms.py:590-598, 722-739, 766-769): out = pos / scale + center,
+ *                      z -= min z of the plot (minz_scratch: uint32 [num_plots]); keep[i] = 1 iff (x, y) lies inside
+ *                      the polygon (Polygon2dExtend :1489-1496, matplotlib's crossings test in double; <= 16 vertices
+ *                      as (x, y) pairs, 0 vertices = keep all).
+ * b2s_compact_points : stable removal of the points with keep == 0 (apply_mask :1090-1095); index_scratch int32 [n],
+ *                      scan_workspace of b2s_scan_workspace_bytes(n); *num_kept_dev = surviving points.
+ * b2s_select_by_rank : MaxPoints (:1772-1791, choice = randperm(n)[:num]): rank[i] = position of point i in its plot's
+ *                      permutation; rows land in permutation order at offsets[plot] + rank (offsets int32
+ *                      [num_plots + 1] written here from the per-plot point counts).
+ * b2s_point_features : x = [1, z, ||(x, y) - centre + 1e-6||]  (AddOnes, XYZFeature(z), AddXYDistanceToCenter,
+ *                      AddFeatsByKeys: R:core/data_transform/features.py:307-383).
+ * b2s_coords_augment : RandomCoordsFlip(ignored z) + ShiftVoxels on quantised coordinates (transforms.py:1046-1054,
+ *                      sparse_transforms.py:49-55): aug_dev int32 [num_plots, 5] = (flip_x, flip_y, shift_x, shift_y,
+ *                      shift_z) per plot; a flip maps c -> max_c(plot) - c; max_scratch int32 [num_plots, 2].
+ */
+B2S_API int32_t b2s_plot_transform(const float* pos, const int32_t* plot_of_point, int64_t n, const int32_t* n_dev,
+                                   int32_t num_plots, const float* scale_host, const float* center_host,
+                                   const double* polygon_host, int32_t num_vertices, uint32_t* minz_scratch,
+                                   float* out_pos, int32_t* keep, b2s_stream_t stream);
+B2S_API int32_t b2s_compact_points(const float* pos, const int32_t* plot_of_point, const int32_t* keep, int64_t n,
+                                   const int32_t* n_dev, int32_t* index_scratch, void* scan_workspace, float* out_pos,
+                                   int32_t* out_plot, int32_t* num_kept_dev, b2s_stream_t stream);
+B2S_API int32_t b2s_select_by_rank(const float* pos, const int32_t* plot_of_point, const int32_t* rank, int64_t n,
+                                   const int32_t* n_dev, int32_t num_plots, int32_t num, const int32_t* counts,
+                                   int32_t* offsets, float* out_pos, int32_t* out_plot, b2s_stream_t stream);
+B2S_API int32_t b2s_point_features(const float* pos, int64_t n, const int32_t* n_dev, float center_x, float center_y,
+                                   float* feats, b2s_stream_t stream);
+B2S_API int32_t b2s_coords_augment(int32_t* coords, int64_t m, const int32_t* m_dev, int32_t num_plots,
+                                   const int32_t* aug_dev, int32_t* max_scratch, b2s_stream_t stream);
+
 /* ---------------------------------------------------------------- (a2,a3) coordinate maps ----
  * R:models/instance/minkowski.py:74 (ME.SparseTensor -> hash build) and every stride-2 op
  * (R:modules/MinkowskiEngine/SENet.py:53,94-97; resnet_block.py:48-50).

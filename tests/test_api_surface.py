@@ -39,13 +39,16 @@ def test_product_path_has_no_cpu_fallback():
         ME.SparseTensor(features=torch.zeros(2, 3), coordinates=torch.zeros(2, 4, dtype=torch.int32))
     with pytest.raises(lib.B2SError):
         lib.call("b2s_gelu_fwd", torch.zeros(4), 1, None, 4, torch.zeros(4))
-    # nothing of the product imports the oracle
-    for mod in list(sys.modules):
-        if mod.startswith("dpcr_agb_b200"):
-            src = getattr(sys.modules[mod], "__file__", None)
-            if src and src.endswith(".py"):
-                assert "oracle" not in open(src).read().replace("oracle.me_cpu", "").replace("CPU oracle", "") \
-                    or mod.endswith("msenet"), mod
+    # nothing of the product imports (or loads by path) the oracle: every .py file of the package is scanned
+    import glob
+    import re
+    pkg = os.path.dirname(os.path.abspath(lib.__file__))
+    files = glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True)
+    assert len(files) >= 15
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b|from\s+\.+\s*oracle\b)|import_module\([\"']oracle|__import__\([\"']oracle",
+                     re.M)
+    for f in files:
+        assert not pat.search(open(f).read()), f"{f} imports the oracle"
 
 
 ME_NAMES = """SparseTensor MinkowskiConvolution MinkowskiConvolutionTranspose MinkowskiMaxPooling MinkowskiAvgPooling

@@ -182,3 +182,31 @@ def test_transposed_conv_is_the_adjoint_and_pooling_counts():
     ukey, ra, rb = cm.union(x.coordinate_map_key, kb)
     assert np.array_equal(cm.coords(ukey)[:500], c) and np.array_equal(ra, np.arange(500))
     assert np.array_equal(cm.coords(ukey)[rb], cm.coords(kb))
+
+
+def test_input_transform_restatements():
+    """``oracle/transforms.py``: the hexagon test agrees with the geometric definition away from the boundary; the
+    distance feature is torch's own PairwiseDistance; ``sqrt(fma(dy, dy, dx*dx))`` in fp32 -- the arithmetic the GPU
+    kernel uses -- reproduces it to one ulp (bit for bit where torch's CPU kernel fuses the same way)."""
+    import torch
+    from oracle import transforms as ot
+    rng = np.random.default_rng(1)
+    xy = rng.uniform(-0.1, 1.1, (20000, 2)).astype(np.float32)
+    got = ot.contains_points(ot.HEXAGON, xy)
+    # regular hexagon centred at (0.5, 0.5) with circumradius 0.5 and two vertices on the x axis
+    dx, dy = np.abs(xy[:, 0].astype(np.float64) - 0.5), np.abs(xy[:, 1].astype(np.float64) - 0.5)
+    h = 0.9330127 - 0.5
+    geo = (dy < h) & (h * dx + 0.25 * dy < 0.5 * h)
+    near = (np.abs(dy - h) < 1e-5) | (np.abs(h * dx + 0.25 * dy - 0.5 * h) < 1e-5)
+    assert np.array_equal(got[~near], geo[~near]) and 0.4 < got.mean() < 0.6
+    pos = torch.rand(50000, 3)
+    f = ot.features(pos)
+    d = (pos[:, :2] - torch.tensor([[0.5, 0.5]])) + 1e-6
+    a = d.numpy().astype(np.float64)
+    fused = np.sqrt((np.float32(a[:, 0] * a[:, 0]).astype(np.float64) + a[:, 1] * a[:, 1]).astype(np.float32)
+                    .astype(np.float64)).astype(np.float32)
+    assert np.abs(fused - f[:, 2].numpy()).max() <= 1.2e-7 * float(f[:, 2].max())
+    assert torch.equal(f[:, 0], torch.ones(50000)) and torch.equal(f[:, 1], pos[:, 2])
+    raw = torch.from_numpy(rng.uniform(-15, 15, (1000, 3)).astype(np.float32))
+    p, x = ot.test_transform(raw, num=400, perm=torch.randperm)
+    assert p.shape[0] <= 400 and float(p[:, 2].min()) >= 0.0 and x.shape == (p.shape[0], 3)
