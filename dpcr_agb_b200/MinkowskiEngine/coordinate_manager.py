@@ -20,6 +20,7 @@ from dpcr_agb_b200 import lib as L
 
 
 USE_DENSE_INDEX = True   # tests flip this to compare the occupancy-index kernel map with the hash one
+USE_LINES = True         # tests flip this to compare the x-line convolution kernels with the table-driven ones
 
 
 def _triple(v):
@@ -83,12 +84,59 @@ class KernelMap:
     def __init__(self, manager, in_key, out_key, kernel_size, step, nbr, n_in, n_out, n_in_dev=None, n_out_dev=None):
         self.manager, self.in_key, self.out_key = manager, in_key, out_key
         self.kernel_size, self.step = kernel_size, step
-        self.nbr, self.n_in, self.n_out = nbr, n_in, n_out
+        self._nbr, self.n_in, self.n_out = nbr, n_in, n_out
         self.n_in_dev, self.n_out_dev = n_in_dev, n_out_dev
         self.k3 = kernel_size[0] * kernel_size[1] * kernel_size[2]
         # stride-1 odd kernels are point-symmetric: the transposed table is nbr with k reversed
         self.symmetric = in_key == out_key and all(k % 2 == 1 for k in kernel_size)
         self._inv = None
+        self._lines = None
+
+    @property
+    def nbr(self):
+        """Neighbour table ``[K^3, N_out]``.  Maps that have the x-line form (``lines_ok``) build it on first use only:
+        the k7 stem never asks for it."""
+        if self._nbr is None:
+            cm = self.manager
+            self._nbr = cm._probe(cm.maps[self.out_key], cm.maps[self.in_key], self.kernel_size, self.step, +1)
+        return self._nbr
+
+    @nbr.setter
+    def nbr(self, value):
+        self._nbr = value
+
+    @property
+    def lines_ok(self):
+        """The x-line form exists: a stride-1 map of the quantiser's own rows (sorted by cell), at most 8 offsets along
+        x with an x step of 1, fewer than 2^24 rows (C ABI ``b2s_kernel_map_lines``)."""
+        m = self.manager.maps[self.in_key]
+        return (USE_LINES and USE_DENSE_INDEX and self.in_key == self.out_key and m.dense is not None
+                and self.kernel_size[0] <= 8 and self.step[0] == 1 and m.n < (1 << 24))
+
+    @property
+    def lines(self):
+        """uint32-in-int32 ``[K1*K2, N]`` line words ``(base << 8) | mask`` (include/b200sparse.h), built on first use."""
+        if self._lines is None:
+            assert self.lines_ok
+            cm = self.manager
+            m = cm.maps[self.in_key]
+            ws, lo, dims, num_plots = m.dense
+            nl = self.kernel_size[1] * self.kernel_size[2]
+            self._lines = torch.empty((nl, m.n), dtype=torch.int32, device=m.coords.device)
+            L.call("b2s_kernel_map_lines", m.coords, m.n, m.n_dev, ws, num_plots, L.host_i32(*lo), L.host_i32(*dims),
+                   L.host_i32(*self.kernel_size), L.host_i32(*self.step), self._lines)
+        return self._lines
+
+    def num_pairs(self, n_rows=None):
+        """Number of (in, out) pairs of the map (host sync; statistics only)."""
+        n_rows = self.n_out if n_rows is None else n_rows
+        if self._nbr is None and self._lines is not None:
+            masks = (self._lines[:, :n_rows] & 0xFF).to(torch.uint8)
+            bits = torch.zeros_like(masks, dtype=torch.int64)
+            for b in range(8):
+                bits += (masks >> b) & 1
+            return int(bits.sum().item())
+        return int((self.nbr[:, :n_rows] >= 0).sum().item())
 
     @property
     def inv(self):
@@ -139,7 +187,7 @@ class KernelMap:
             tv.manager, tv.in_key, tv.out_key = self.manager, self.out_key, self.in_key
             tv.kernel_size, tv.step, tv.k3 = self.kernel_size, self.step, self.k3
             tv.n_in, tv.n_out, tv.n_in_dev, tv.n_out_dev = self.n_out, self.n_in, self.n_out_dev, self.n_in_dev
-            tv.nbr, tv._inv = self.inv, self.nbr
+            tv._nbr, tv._inv, tv._lines = self.inv, self.nbr, None
             tv.symmetric = False
             tv._plan = False                 # no parity plan: dgrad of the view walks this map's forward table
             tv._tview = self
@@ -413,8 +461,9 @@ class CoordinateManager:
             self._note(("kmap", in_key, out_key, kernel_size, dilation))
             step = tuple(d * t for d, t in zip(dilation, in_key.tensor_stride))
             imap, omap = self.maps[in_key], self.maps[out_key]
-            nbr = self._probe(omap, imap, kernel_size, step, +1)
-            km = KernelMap(self, in_key, out_key, kernel_size, step, nbr, imap.n, omap.n, imap.n_dev, omap.n_dev)
+            km = KernelMap(self, in_key, out_key, kernel_size, step, None, imap.n, omap.n, imap.n_dev, omap.n_dev)
+            if not km.lines_ok:          # maps with an x-line form build either table on first use (KernelMap.nbr / .lines)
+                km.nbr = self._probe(omap, imap, kernel_size, step, +1)
             self.kernel_maps[ck] = km
         return km
 

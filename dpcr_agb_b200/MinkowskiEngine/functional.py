@@ -23,12 +23,16 @@ USE_PARITY_DGRAD = True   # tests flip this to compare the parity-plan dgrad wit
 WORK_STATS = None
 
 
-def _account(kind, nbr, n_rows, c_in, c_out, k3, n_dev=None):
+def _account(kind, nbr, n_rows, c_in, c_out, k3, n_dev=None, kmap=None):
+    """``kmap``: count the pairs through the map object (x-line maps never build ``nbr``)."""
     if WORK_STATS is None:
         return
     if n_dev is not None:
         n_rows = min(int(n_rows), int(n_dev.item()))
-    pairs = int((nbr[:, :n_rows] >= 0).sum().item()) if nbr is not None else int(n_rows)
+    if kmap is not None:
+        pairs = kmap.num_pairs(n_rows)
+    else:
+        pairs = int((nbr[:, :n_rows] >= 0).sum().item()) if nbr is not None else int(n_rows)
     st = WORK_STATS.setdefault(kind, {"launches": 0, "pairs": 0, "flops": 0, "bytes": 0})
     st["launches"] += 1
     st["pairs"] += pairs
@@ -169,6 +173,36 @@ def wgrad(x, gy, nbr, n_in, n_out, c_in, c_out, k3, impl=None, n_out_dev=None, p
     return gw
 
 
+def lines_path(kmap, c_in, c_out):
+    """True when the convolution runs through the x-line form of its map (C ABI ``b2s_conv_lines_*``: few input
+    channels on the quantiser's rows, split-bf16 mode -- the k7 stem)."""
+    return (kmap is not None and _tc(None) and c_in <= 4 and kmap.lines_ok
+            and L.query("b2s_conv_lines_supported", c_in, c_out, L.host_i32(*kmap.kernel_size)) == 1)
+
+
+def lines_fwd(x, w, bias, kmap, c_in, c_out):
+    y = torch.empty((kmap.n_out, c_out), dtype=torch.float32, device=x.device)
+    _account("fwd", None, kmap.n_out, c_in, c_out, kmap.k3, kmap.n_out_dev, kmap=kmap)
+    ks = L.host_i32(*kmap.kernel_size)
+    nbytes = L.query("b2s_conv_lines_workspace_bytes", kmap.n_in, c_in, c_out, ks)
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+    L.call("b2s_conv_lines_fwd", x, w, bias, kmap.lines, kmap.n_in, kmap.n_out, kmap.n_out_dev, c_in, c_out, ks, y, ws,
+           nbytes)
+    return y
+
+
+def lines_wgrad(x, gy_operand, kmap, c_in, c_out, out=None):
+    gw = out.view(kmap.k3, c_in, c_out) if out is not None else torch.empty((kmap.k3, c_in, c_out), dtype=torch.float32,
+                                                                           device=x.device)
+    _account("wgrad", None, kmap.n_out, c_in, c_out, kmap.k3, kmap.n_out_dev, kmap=kmap)
+    ks = L.host_i32(*kmap.kernel_size)
+    nbytes = L.query("b2s_conv_lines_workspace_bytes", kmap.n_in, c_in, c_out, ks)
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
+    L.call("b2s_conv_lines_wgrad", x, gy_operand, kmap.lines, kmap.n_in, kmap.n_out, kmap.n_out_dev, c_in, c_out, ks,
+           gw, ws, nbytes)
+    return gw
+
+
 class ConvolutionFunction(torch.autograd.Function):
     """MinkowskiConvolution fwd / dgrad / wgrad (reference call sites: SENet.py:49-52,94-97;
     resnet_block.py:48-54,95-107).  ``kmap`` is None for the K=1, stride=1 ``use_mm`` case."""
@@ -181,15 +215,24 @@ class ConvolutionFunction(torch.autograd.Function):
         feats = feats.contiguous()
         kernel = kernel.contiguous()
         c_in, c_out = kernel.shape[-2], kernel.shape[-1]
+        use_lines = lines_path(kmap, c_in, c_out)
         if kmap is None:
             n_in = n_out = feats.shape[0]
             nbr, k3 = None, 1
             nd_in = nd_out = n_dev
         else:
-            n_in, n_out, nbr, k3 = kmap.n_in, kmap.n_out, kmap.nbr, kmap.k3
+            n_in, n_out, k3 = kmap.n_in, kmap.n_out, kmap.k3
+            nbr = None if use_lines else kmap.nbr
             nd_in, nd_out = kmap.n_in_dev, kmap.n_out_dev
         assert feats.shape == (n_in, c_in), f"feature shape {tuple(feats.shape)} does not match the map ({n_in},{c_in})"
         b = bias.contiguous().view(-1) if bias is not None else None
+        ctx.lines = use_lines
+        if use_lines:
+            out = lines_fwd(feats, kernel, b, kmap, c_in, c_out)
+            ctx.pre, ctx.kmap, ctx.nd, ctx.dims = False, kmap, (nd_in, nd_out), (n_in, n_out, c_in, c_out, k3)
+            ctx.has_bias, ctx.params = bias is not None, (kernel, bias)
+            ctx.save_for_backward(feats, kernel)
+            return out
         # the tensor-core kernels consume TF32 operands: x is rounded once here and the rounded copy is what is
         # saved for wgrad (c_in <= 4: the stem pads + rounds inside the library)
         pre = _tc(None) and c_in > 4 and _fwd_tc_ok(c_in, c_out)
@@ -239,8 +282,12 @@ class ConvolutionFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             both = wg_ok                                  # feats is the operand-form copy saved by forward
             kp = ctx.params[0]
-            gw = wgrad(feats, gyr if both else gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out, k3,
-                       n_out_dev=nd_out, prerounded=both, out=kp.grad if _direct(kp) else None).view(kernel.shape)
+            if ctx.lines and wg_ok:
+                gw = lines_wgrad(feats, gyr, kmap, c_in, c_out, out=kp.grad if _direct(kp) else None).view(kernel.shape)
+            else:
+                gw = wgrad(feats, gyr if both else gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out,
+                           k3, n_out_dev=nd_out, prerounded=both,
+                           out=kp.grad if _direct(kp) else None).view(kernel.shape)
             if _direct(kp):
                 gw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:

@@ -627,6 +627,46 @@ __global__ void __launch_bounds__(256) kernel_map_dense_kernel(const int4* __res
   }
 }
 
+// x-line form of a stride-1 kernel map over a quantised (cell-sorted) map: ONE 32-bit word per (query row, line of
+// K[0] x-consecutive kernel offsets):  word = (base << 8) | mask,  mask bit ix set <=> the cell of offset ix of the
+// line is occupied, base = row of the lowest occupied cell of the window.  Rows are sorted by cell (plot, z, y, x), so
+// the occupied cells of a line are CONSECUTIVE rows base, base + 1, ...: row(ix) = base + popc(mask & below(ix)).
+// 49 words per row instead of the 343 table entries of the k7 stem (83 MB instead of 580 MB at batch 32), built from
+// at most two bitmap words and one prefix entry per line.
+__global__ void __launch_bounds__(256) kernel_map_lines_kernel(const int4* __restrict__ query, int64_t n,
+                                                               const int* __restrict__ n_dev,
+                                                               const unsigned* __restrict__ bitmap,
+                                                               const int* __restrict__ prefix, QBox box,
+                                                               int num_plots, KmParams p, int nlines,
+                                                               unsigned* __restrict__ lines) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= b2s_rows(n, n_dev)) return;
+  const int4 c = query[q];
+  const int l0 = blockIdx.y * p.group;
+  const int l1 = min(l0 + p.group, nlines);
+  const int hx = (p.K[0] & 1) ? p.K[0] / 2 : 0, hy = (p.K[1] & 1) ? p.K[1] / 2 : 0, hz = (p.K[2] & 1) ? p.K[2] / 2 : 0;
+  const bool plot_ok = (unsigned)c.x < (unsigned)num_plots;
+  const int xlo = c.y - box.lo[0] - hx;                                    // cell x of offset ix = 0
+  const int xa = max(xlo, 0), xb = min(xlo + p.K[0] - 1, box.dim[0] - 1);
+  for (int l = l0; l < l1; ++l) {
+    const int iy = l % p.K[1], iz = l / p.K[1];
+    const int y = c.z + (iy - hy) * p.step[1] - box.lo[1];
+    const int z = c.w + (iz - hz) * p.step[2] - box.lo[2];
+    unsigned word = 0;
+    if (plot_ok && xa <= xb && (unsigned)y < (unsigned)box.dim[1] && (unsigned)z < (unsigned)box.dim[2]) {
+      const int64_t c0 = (((int64_t)c.x * box.dim[2] + z) * box.dim[1] + y) * box.dim[0] + xa;
+      const int64_t wi = c0 >> 5;
+      const unsigned b0 = (unsigned)(c0 & 31);
+      const unsigned w0 = __ldg(&bitmap[wi]);
+      unsigned bits = w0 >> b0;
+      if (((c0 + (xb - xa)) >> 5) != wi) bits |= __ldg(&bitmap[wi + 1]) << (32u - b0);   // b0 > 0 here
+      bits &= (1u << (xb - xa + 1)) - 1u;
+      if (bits) word = ((unsigned)(__ldg(&prefix[wi]) + __popc(w0 & ((1u << b0) - 1u))) << 8) | (bits << (xa - xlo));
+    }
+    lines[(int64_t)l * n + q] = word;
+  }
+}
+
 __global__ void __launch_bounds__(256) pair_count_kernel(const int* __restrict__ nbr, int64_t n,
                                                          int* __restrict__ counts) {
   const int k = blockIdx.y;
@@ -720,6 +760,44 @@ extern "C" int32_t b2s_kernel_map_dense(const int32_t* query_coords, int64_t n_q
   kernel_map_dense_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const int4*>(query_coords), n_query,
                                                                n_query_dev, l.bitmap, l.prefix, box, num_plots, p,
                                                                nbr);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
+extern "C" int32_t b2s_kernel_map_lines(const int32_t* query_coords, int64_t n_query, const int32_t* n_query_dev,
+                                        const void* quantize_workspace, int32_t num_plots, const int32_t* lo_host,
+                                        const int32_t* dims_host, const int32_t* kernel_size_host,
+                                        const int32_t* step_host, uint32_t* lines, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n_query >= 0 && kernel_size_host && step_host && quantize_workspace && lo_host && dims_host,
+                "bad arguments");
+  QWs l;
+  B2S_CHECK_ARG(quantize_layout(num_plots, dims_host, const_cast<void*>(quantize_workspace), &l), "bad voxel box");
+  KmParams p;
+  for (int d = 0; d < 3; ++d) {
+    B2S_CHECK_ARG(kernel_size_host[d] >= 1 && kernel_size_host[d] <= 15 && step_host[d] >= 1, "kernel size 1..15");
+    p.K[d] = kernel_size_host[d];
+    p.step[d] = step_host[d];
+  }
+  B2S_CHECK_ARG(p.K[0] <= 8 && p.step[0] == 1, "x-lines need kernel_size[0] <= 8 and an x step of 1");
+  if (n_query >= ((int64_t)1 << 24)) {
+    b2s_set_error("b2s_kernel_map_lines: %lld rows do not fit the 24-bit row field of a line word", (long long)n_query);
+    return B2S_EOVERFLOW;
+  }
+  p.sign = 1;
+  p.k3 = p.K[0] * p.K[1] * p.K[2];
+  if (n_query == 0) return B2S_OK;
+  B2S_CHECK_ARG(query_coords && lines, "null pointer");
+  const int nlines = p.K[1] * p.K[2];
+  int64_t row_blocks = ceil_div64(n_query, 256);
+  int groups = 1;
+  while (row_blocks * groups < 2 * B2S_NUM_SMS * 8 && groups < nlines) ++groups;
+  p.group = (nlines + groups - 1) / groups;
+  groups = (nlines + p.group - 1) / p.group;
+  QBox box{{lo_host[0], lo_host[1], lo_host[2]}, {dims_host[0], dims_host[1], dims_host[2]}};
+  dim3 grid((unsigned)row_blocks, (unsigned)groups);
+  kernel_map_lines_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const int4*>(query_coords), n_query,
+                                                               n_query_dev, l.bitmap, l.prefix, box, num_plots, p,
+                                                               nlines, lines);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -38,6 +38,7 @@ SIGNATURES = {
     "b2s_coordmap_fill": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "b2s_kernel_map": (_i32, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp]),
     "b2s_kernel_map_dense": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "b2s_kernel_map_lines": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2s_kernel_map_pair_counts": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "b2s_kernel_map_pairs_fill": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b2s_conv_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),
@@ -45,6 +46,10 @@ SIGNATURES = {
     "b2s_conv_gather_gemm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32,
                                     _vp]),
     "b2s_conv_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "b2s_conv_lines_supported": (_i32, [_i32, _i32, _vp]),
+    "b2s_conv_lines_workspace_bytes": (_i64, [_i64, _i32, _i32, _vp]),
+    "b2s_conv_lines_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "b2s_conv_lines_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "b2s_parity_plan_rows": (_i64, [_i64]),
     "b2s_parity_plan": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2s_conv_dgrad_strided_workspace_bytes": (_i64, [_i32, _i32, _i32]),

@@ -166,6 +166,16 @@ B2S_API int32_t b2s_kernel_map_dense(const int32_t* query_coords, int64_t n_quer
                                      const void* quantize_workspace, int32_t num_plots, const int32_t* lo_host,
                                      const int32_t* dims_host, const int32_t* kernel_size_host,
                                      const int32_t* step_host, int32_t sign, int32_t* nbr, b2s_stream_t stream);
+/* x-LINE form of a stride-1 kernel map over the quantiser's rows (the k7 stem of R:modules/MinkowskiEngine/SENet.py:49-52
+ * reads its 343 offsets as 49 lines of 7 x-consecutive cells): lines[l*n_query + q], l = iy + K[1]*iz, holds
+ * (base << 8) | mask -- mask bit ix set <=> offset (ix, iy, iz) of row q has a neighbour, and because the rows are
+ * sorted by (plot, z, y, x) those neighbours are the CONSECUTIVE rows base, base+1, ...:
+ * nbr[(ix + K[0]*l), q] = base + popc(mask & ((1 << ix) - 1)).  Needs kernel_size[0] <= 8, step[0] == 1 and fewer than
+ * 2^24 rows (B2S_EOVERFLOW otherwise).  12 % of the bytes of the [K^3, n] table for K = 7. */
+B2S_API int32_t b2s_kernel_map_lines(const int32_t* query_coords, int64_t n_query, const int32_t* n_query_dev,
+                                     const void* quantize_workspace, int32_t num_plots, const int32_t* lo_host,
+                                     const int32_t* dims_host, const int32_t* kernel_size_host,
+                                     const int32_t* step_host, uint32_t* lines, b2s_stream_t stream);
 B2S_API int32_t b2s_kernel_map_pair_counts(const int32_t* nbr, int32_t k3, int64_t n_query, int32_t* counts,
                                    b2s_stream_t stream);
 B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_t n_query, const int64_t* offsets,
@@ -202,6 +212,25 @@ B2S_API int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* n
                                const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw,
                                void* workspace, int64_t workspace_bytes, int32_t impl, int32_t flags,
                                b2s_stream_t stream);
+/* Convolution of a FEW input channels (c_in <= 4: the k7 stem, R:modules/MinkowskiEngine/SENet.py:49-52) through the
+ * x-line table of b2s_kernel_map_lines: forward and weight gradient, split-bf16 operand mode only, c_out % 64 == 0.
+ * A pipeline stage is one line: the producers read one line word per row, load only the EXISTING neighbours (89 % of
+ * the stem's 343 offsets are empty) and store the operand tile to shared memory; no [K^3, n] table is read or built.
+ * b2s_conv_lines_supported: 1 when the library is in split-bf16 mode and the shape is covered, else 0 (callers then
+ * use b2s_kernel_map_dense + b2s_conv_gather_gemm / b2s_conv_wgrad, which give the same results).
+ * x is plain fp32 [n_in, c_in]; gy of b2s_conv_lines_wgrad must be in operand form (b2s_round_tf32 in split-bf16 mode).
+ * Same results as b2s_conv_gather_gemm / b2s_conv_wgrad on the expanded table. */
+B2S_API int32_t b2s_conv_lines_supported(int32_t c_in, int32_t c_out, const int32_t* kernel_size_host);
+B2S_API int64_t b2s_conv_lines_workspace_bytes(int64_t n_in, int32_t c_in, int32_t c_out,
+                                               const int32_t* kernel_size_host);
+B2S_API int32_t b2s_conv_lines_fwd(const float* x, const float* w, const float* bias, const uint32_t* lines,
+                                   int64_t n_in, int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out,
+                                   const int32_t* kernel_size_host, float* y, void* workspace, int64_t workspace_bytes,
+                                   b2s_stream_t stream);
+B2S_API int32_t b2s_conv_lines_wgrad(const float* x, const float* gy, const uint32_t* lines, int64_t n_in,
+                                     int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out,
+                                     const int32_t* kernel_size_host, float* gw, void* workspace,
+                                     int64_t workspace_bytes, b2s_stream_t stream);
 /* dgrad of a STRIDE-2 convolution (gx[i] = sum_k gy[inv[k,i]] W[k]^T) without gathering zero rows.  In the
  * transposed map a fine row has partners only at the offsets whose parity matches its position inside the 2x2x2 coarse
  * cell (27/8 offsets on average).  b2s_parity_plan sorts the fine rows of `coords` by that position into tile-aligned

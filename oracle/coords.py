@@ -185,6 +185,42 @@ def kernel_map_table(in_coords: np.ndarray, out_coords: np.ndarray, kernel_size,
     return nbr
 
 
+def kernel_map_lines(nbr: np.ndarray, kernel_size) -> np.ndarray:
+    """x-LINE form of a stride-1 neighbour table over rows sorted by (batch, z, y, x) -- the layout the k7 stem
+    kernels read (include/b200sparse.h ``b2s_kernel_map_lines``; call site of the layer: ME/SENet.py:49-52).
+
+    ``lines uint32 [K1*K2, N]``: line ``l = iy + K1*iz`` of row q packs its ``K0`` x-consecutive offsets as
+    ``(base << 8) | mask`` with mask bit ix set iff ``nbr[ix + K0*l, q] >= 0`` and base = the smallest of those rows.
+    Because the in rows are sorted with x fastest, the existing neighbours of a line are consecutive rows, so the
+    table is recovered exactly by :func:`lines_to_table` (asserted here)."""
+    K = np.broadcast_to(np.asarray(kernel_size, dtype=np.int64), (3,))
+    k0, nl = int(K[0]), int(K[1] * K[2])
+    assert k0 <= 8 and nbr.shape[0] == k0 * nl and nbr.shape[1] < (1 << 24)
+    t = nbr.reshape(nl, k0, -1).astype(np.int64)
+    valid = t >= 0
+    mask = (valid * (1 << np.arange(k0, dtype=np.int64))[None, :, None]).sum(1)
+    base = np.where(valid, t, np.iinfo(np.int64).max).min(1)
+    base = np.where(mask != 0, base, 0)
+    rank = np.cumsum(valid, 1) - valid                     # number of existing neighbours below ix
+    assert np.all(np.where(valid, t == base[:, None, :] + rank, True)), "rows of a line are not consecutive"
+    return ((base << 8) | mask).astype(np.uint32)
+
+
+def lines_to_table(lines: np.ndarray, kernel_size) -> np.ndarray:
+    """Inverse of :func:`kernel_map_lines`: ``nbr[ix + K0*l, q] = base + popcount(mask & ((1 << ix) - 1))``."""
+    K = np.broadcast_to(np.asarray(kernel_size, dtype=np.int64), (3,))
+    k0 = int(K[0])
+    w = lines.astype(np.int64)
+    mask, base = w & 0xFF, w >> 8
+    out = np.full((lines.shape[0], k0, lines.shape[1]), -1, dtype=np.int32)
+    below = np.zeros_like(mask)
+    for ix in range(k0):
+        bit = (mask >> ix) & 1
+        out[:, ix, :] = np.where(bit == 1, base + below, -1)
+        below = below + bit
+    return out.reshape(lines.shape[0] * k0, lines.shape[1])
+
+
 def table_to_pairs(nbr: np.ndarray):
     """Pair-list form: per offset k the (in,out) pairs sorted by out row; ``offsets int64 [K^3+1]``."""
     ins, outs, offsets = [], [], [0]

@@ -3,6 +3,7 @@ properties of the integer stages (SURVEY.md section 4 test plan (i) and (iii))."
 import os
 
 import numpy as np
+import pytest
 import torch
 from hypothesis import given, settings
 from hypothesis import strategies as st
@@ -10,6 +11,7 @@ from hypothesis import strategies as st
 from oracle import coords as oc
 from oracle import me_cpu
 from oracle import ops as oo
+import b2s_testutil as util
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -210,3 +212,30 @@ def test_input_transform_restatements():
     raw = torch.from_numpy(rng.uniform(-15, 15, (1000, 3)).astype(np.float32))
     p, x = ot.test_transform(raw, num=400, perm=torch.randperm)
     assert p.shape[0] <= 400 and float(p[:, 2].min()) >= 0.0 and x.shape == (p.shape[0], 3)
+
+
+@pytest.mark.parametrize("K", [(7, 7, 7), (3, 3, 3), (8, 3, 2), (1, 5, 5)])
+def test_kernel_map_lines_roundtrip(K):
+    """The x-line form of a stride-1 map over cell-sorted rows: lines -> table is exact, a hand case pins the packing,
+    and unsorted rows are rejected (the form relies on the existing neighbours of a line being consecutive rows)."""
+    batch = util.make_points(2, 1500, cfg=11)
+    c, _, _, _, _ = util.oracle_quantize(batch, 0.05)
+    assert np.all(np.diff(oc.pack_keys(c)) > 0)                                  # (plot, z, y, x), x fastest
+    nbr = oc.kernel_map_table(c, c, K, (1, 1, 1))
+    lines = oc.kernel_map_lines(nbr, K)
+    assert lines.shape == (K[1] * K[2], c.shape[0]) and lines.dtype == np.uint32
+    assert np.array_equal(oc.lines_to_table(lines, K), nbr)
+    assert int(sum(bin(int(v) & 0xFF).count("1") for v in lines.ravel())) == int((nbr >= 0).sum())
+
+
+def test_kernel_map_lines_hand_case():
+    # one plot, one x-line: cells x = 0, 1, 3 -> rows 0, 1, 2; K = (3, 1, 1)
+    c = np.array([[0, 0, 0, 0], [0, 1, 0, 0], [0, 3, 0, 0]], dtype=np.int32)
+    nbr = oc.kernel_map_table(c, c, (3, 1, 1), (1, 1, 1))
+    lines = oc.kernel_map_lines(nbr, (3, 1, 1))
+    # row 0: offsets (-1, 0, +1) -> (none, row 0, row 1): mask 0b110, base 0
+    # row 1: (row 0, row 1, none): mask 0b011, base 0;  row 2 (x = 3): (none, row 2, none): mask 0b010, base 2
+    assert lines.tolist() == [[(0 << 8) | 0b110, (0 << 8) | 0b011, (2 << 8) | 0b010]]
+    shuffled = c[[1, 0, 2]]
+    with pytest.raises(AssertionError):
+        oc.kernel_map_lines(oc.kernel_map_table(shuffled, shuffled, (3, 1, 1), (1, 1, 1)), (3, 1, 1))

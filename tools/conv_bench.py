@@ -60,19 +60,39 @@ layers = [("stem k7 3->64 @ts1", 1, 1, 7, 3, 64), ("pool k3s2 ts1->2", 1, 2, 3, 
           ("L3 k3s2 128->256 ts4->8", 4, 8, 3, 128, 256), ("L3 k3 256->256 @ts8", 8, 8, 3, 256, 256),
           ("L4 k3s2 256->512 ts8->16", 8, 16, 3, 256, 512), ("L4 k3 512->512 @ts16", 16, 16, 3, 512, 512)]
 out = []
+if os.environ.get("ONLY_STEM"):
+    layers = layers[:1]
 for name, its, ots, K, cin, cout in layers:
     t_map = timeit(lambda: build_map(its, ots, K), reps=3)
     km = build_map(its, ots, K)
-    pairs = int((km.nbr >= 0).sum().item())
+    lines = cin and Fn.lines_path(km, cin, cout)
+    if lines:                                   # x-line form: what the stem really builds per step
+        def build_lines():
+            cm.kernel_maps.clear()
+            return cm.kernel_map(keys[its], keys[ots], K).lines
+        t_map = timeit(build_lines, reps=3)
+        _ = km.lines
+    pairs = km.num_pairs()
     row = {"layer": name, "n_in": km.n_in, "n_out": km.n_out, "k3": km.k3, "pairs": pairs,
            "fill": pairs / (km.n_out * km.k3), "kernel_map_ms": t_map,
            "kernel_map_GBps": (16 * km.n_out + 4 * km.k3 * km.n_out) / t_map / 1e6}
+    if lines:
+        row["kernel_map_GBps"] = (16 * km.n_out + 4 * km.kernel_size[1] * km.kernel_size[2] * km.n_out) / t_map / 1e6
     if cin:
         xf = Fn.round_tf32(torch.randn(km.n_in, cin, device=dev))          # operands pre-rounded, as the autograd
         w = torch.randn(km.k3, cin, cout, device=dev) * 0.02                # Function hands them to the kernels
         gy = Fn.round_tf32(torch.randn(km.n_out, cout, device=dev))
         pre = cin > 4
         flops = 2.0 * pairs * cin * cout
+        if lines:
+            xp = torch.randn(km.n_in, cin, device=dev)
+            t = timeit(lambda: Fn.lines_fwd(xp, w, None, km, cin, cout))
+            row.update(fwd_ms=t, fwd_tflops=flops / t / 1e9, path="x-lines")
+            t = timeit(lambda: Fn.lines_wgrad(xp, gy, km, cin, cout))
+            row.update(wgrad_ms=t, wgrad_tflops=flops / t / 1e9)
+            out.append(row)
+            print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in row.items()})
+            continue
         t = timeit(lambda: Fn.gather_gemm(xf, w, None, km.nbr, km.n_in, km.n_out, cin, cout, km.k3, 0, prerounded=pre))
         row.update(fwd_ms=t, fwd_tflops=flops / t / 1e9)
         if cin >= 32:
