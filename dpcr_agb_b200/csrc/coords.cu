@@ -648,22 +648,34 @@ __global__ void __launch_bounds__(256) kernel_map_lines_kernel(const int4* __res
   const bool plot_ok = (unsigned)c.x < (unsigned)num_plots;
   const int xlo = c.y - box.lo[0] - hx;                                    // cell x of offset ix = 0
   const int xa = max(xlo, 0), xb = min(xlo + p.K[0] - 1, box.dim[0] - 1);
-  for (int l = l0; l < l1; ++l) {
-    const int iy = l % p.K[1], iz = l / p.K[1];
-    const int y = c.z + (iy - hy) * p.step[1] - box.lo[1];
-    const int z = c.w + (iz - hz) * p.step[2] - box.lo[2];
+  const bool row_ok = plot_ok && xa <= xb;
+  const unsigned span = (unsigned)(xb - xa), wmask = (2u << span) - 1u, shl = (unsigned)(xa - xlo);
+  // cell of (xa, y, z) = plot_base + (z * dim1 + y) * dim0 + xa, walked with additions: iy fastest
+  const int64_t plot_base = (int64_t)c.x * box.dim[2] * box.dim[1] * box.dim[0] + xa;
+  int iy = l0 % p.K[1], iz = l0 / p.K[1];
+  int y = c.z + (iy - hy) * p.step[1] - box.lo[1];
+  int z = c.w + (iz - hz) * p.step[2] - box.lo[2];
+  const int y_first = c.z - hy * p.step[1] - box.lo[1];
+  unsigned* out = lines + (int64_t)l0 * n + q;
+  for (int l = l0; l < l1; ++l, out += n) {
     unsigned word = 0;
-    if (plot_ok && xa <= xb && (unsigned)y < (unsigned)box.dim[1] && (unsigned)z < (unsigned)box.dim[2]) {
-      const int64_t c0 = (((int64_t)c.x * box.dim[2] + z) * box.dim[1] + y) * box.dim[0] + xa;
+    if (row_ok && (unsigned)y < (unsigned)box.dim[1] && (unsigned)z < (unsigned)box.dim[2]) {
+      const int64_t c0 = plot_base + ((int64_t)z * box.dim[1] + y) * box.dim[0];
       const int64_t wi = c0 >> 5;
-      const unsigned b0 = (unsigned)(c0 & 31);
+      const unsigned b0 = (unsigned)c0 & 31u;
       const unsigned w0 = __ldg(&bitmap[wi]);
       unsigned bits = w0 >> b0;
-      if (((c0 + (xb - xa)) >> 5) != wi) bits |= __ldg(&bitmap[wi + 1]) << (32u - b0);   // b0 > 0 here
-      bits &= (1u << (xb - xa + 1)) - 1u;
-      if (bits) word = ((unsigned)(__ldg(&prefix[wi]) + __popc(w0 & ((1u << b0) - 1u))) << 8) | (bits << (xa - xlo));
+      if (b0 + span > 31u) bits |= __ldg(&bitmap[wi + 1]) << (32u - b0);   // the window crosses into the next word
+      bits &= wmask;
+      if (bits) word = ((unsigned)(__ldg(&prefix[wi]) + __popc(w0 & ((1u << b0) - 1u))) << 8) | (bits << shl);
     }
-    lines[(int64_t)l * n + q] = word;
+    *out = word;
+    y += p.step[1];
+    if (++iy == p.K[1]) {
+      iy = 0;
+      y = y_first;
+      z += p.step[2];
+    }
   }
 }
 

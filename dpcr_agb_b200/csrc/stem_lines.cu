@@ -253,6 +253,219 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// forward, operand tile in TENSOR MEMORY.  The kernel above is bound by shared-memory bandwidth, not by the tensor
+// pipe: per stage the MMAs read 2 x 4 x (4 KB of A + 6 KB of B) = 80 KB of operands from shared memory, the producers
+// write 32 KB of A and the bulk copy 24 KB of B -- 136 KB at 128 B/clk = 1 090 clocks against 768 clocks of MMA.
+// Here a producer thread (= out row = TMEM lane) writes its 128-byte operand row straight into tensor memory
+// (tcgen05.st 32x32b.x32, 256 B/clk) and the MMA takes A from TMEM, so shared memory carries the weight stages only
+// (48 KB of reads + 24 KB of writes per stage).  TMEM: accumulators 2 x 192 columns, operand ring 2 stages x 2 tiles x
+// 32 columns = 512.  Weights: a ring of SB stages filled by their own warp (the bulk copies need ~1 300 clocks, more
+// than one stage of MMA).
+// ---------------------------------------------------------------------------------------------
+constexpr int LT_THREADS = 320;              // 8 producer / epilogue warps, warp 8 = MMA issuer, warp 9 = weight loader
+constexpr int LT_SA = 2;
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint4 (&d)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(d[0].x), "r"(d[0].y), "r"(d[0].z), "r"(d[0].w), "r"(d[1].x), "r"(d[1].y), "r"(d[1].z), "r"(d[1].w),
+      "r"(d[2].x), "r"(d[2].y), "r"(d[2].z), "r"(d[2].w), "r"(d[3].x), "r"(d[3].y), "r"(d[3].z), "r"(d[3].w),
+      "r"(d[4].x), "r"(d[4].y), "r"(d[4].z), "r"(d[4].w), "r"(d[5].x), "r"(d[5].y), "r"(d[5].z), "r"(d[5].w),
+      "r"(d[6].x), "r"(d[6].y), "r"(d[6].z), "r"(d[6].w), "r"(d[7].x), "r"(d[7].y), "r"(d[7].z), "r"(d[7].w)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_bf16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int SB>
+struct LtSmem {
+  static constexpr int B_OFF = 0;
+  static constexpr int BAR_OFF = SB * LF_B_STAGE;
+  static constexpr int NBAR = 2 * LT_SA + 2 * SB + 2;
+  static constexpr int TOTAL = BAR_OFF + NBAR * 8;
+  static constexpr int DYN_BYTES = (TOTAL + 1024) > 120 * 1024 ? (TOTAL + 1024) : 120 * 1024;   // one CTA per SM (TMEM)
+};
+
+template <int SB, int DEPTH>
+__global__ void __launch_bounds__(LT_THREADS, 1)
+    conv_lines_fwd_tmem_kernel(const uint4* __restrict__ x4, const uint32_t* __restrict__ wimg,
+                               const float* __restrict__ bias, const uint32_t* __restrict__ lines, int64_t n_out,
+                               const int* __restrict__ n_out_dev, int c_out, int nlines, float* __restrict__ y) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
+  const int64_t m0 = (int64_t)blockIdx.x * 256;
+  if (m0 >= n_out) return;                       // uniform across the CTA
+  const int n0 = blockIdx.y * LF_BN;
+  using L = LtSmem<SB>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t b_base = base + L::B_OFF, bar_base = base + L::BAR_OFF;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (LT_SA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * LT_SA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * LT_SA + SB + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * LT_SA + 2 * SB);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * LT_SA + 2 * SB + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + 8 * (2 * LT_SA + 2 * SB + 1));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = nlines;
+
+  if (tid == 0) {
+    for (int s = 0; s < LT_SA; ++s) {
+      mbar_init(a_full(s), 256);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<512>(tmem_slot);     // D tile 0: columns 0..191, D tile 1: 192..383, operands: 384..511
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+  constexpr uint32_t A_COL = 384;
+
+  if (warp < 8) {
+    // ===================== producers: thread = out row = TMEM lane =====================
+    const int64_t o = m0 + tid;
+    const bool live = o < n_out;
+    const uint32_t* lt = lines + o;
+    const int tile = warp >> 2;
+    const uint32_t t_row = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    auto ldw = [&](int l) -> uint32_t { return (live && l < T) ? __ldg(lt + (int64_t)l * pitch) : 0u; };
+    uint4 d[DEPTH][8];
+    uint32_t wq[DEPTH];
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) wq[j] = ldw(j);
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) {
+      load_line(x4, wq[j], d[j]);
+      wq[j] = ldw(j + DEPTH);
+    }
+#pragma unroll 1
+    for (int it0 = 0; it0 < T; it0 += DEPTH) {
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j) {
+        const int it = it0 + j;
+        if (it < T) {
+          const int sa = it & 1;
+          mbar_wait(a_empty(sa), (((uint32_t)it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          tmem_st32(t_row + A_COL + (uint32_t)((sa * 2 + tile) * 32), d[j]);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(a_full(sa));
+          load_line(x4, wq[j], d[j]);            // stage it + DEPTH
+          wq[j] = ldw(it + 2 * DEPTH);
+        }
+      }
+    }
+    // ===================== epilogue: warp = (tile, lane quadrant) =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int64_t orow = m0 + tid;
+    const uint32_t t_lane = t_row + (uint32_t)(tile * 192);
+#pragma unroll 1
+    for (int c0 = 0; c0 < LF_BN; c0 += 32) {
+      uint32_t v[32], u[32];
+      tmem_ld32(t_lane + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 1; i < 3; ++i) {
+        tmem_ld32(t_lane + (uint32_t)(i * LF_BN + c0), u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+      }
+      if (orow < n_out) {
+        float* dst = y + orow * c_out + n0 + c0;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          float4 r;
+          r.x = __uint_as_float(v[e]) + (bias ? __ldg(&bias[n0 + c0 + e]) : 0.f);
+          r.y = __uint_as_float(v[e + 1]) + (bias ? __ldg(&bias[n0 + c0 + e + 1]) : 0.f);
+          r.z = __uint_as_float(v[e + 2]) + (bias ? __ldg(&bias[n0 + c0 + e + 2]) : 0.f);
+          r.w = __uint_as_float(v[e + 3]) + (bias ? __ldg(&bias[n0 + c0 + e + 3]) : 0.f);
+          *reinterpret_cast<float4*>(dst + e) = r;
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = idesc_bf16(128, 3 * LF_BN, 0, 0);
+    int sb = 0;
+    uint32_t phb = 0;
+    for (int it = 0; it < T; ++it) {
+      const int sa = it & 1;
+      mbar_wait(b_full(sb), phb);
+      mbar_wait(a_full(sa), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t b_desc = smem_desc_sw128(b_base + sb * LF_B_STAGE, 16, 1024);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t a_t = tmem_d + A_COL + (uint32_t)((sa * 2 + t) * 32);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)         // K = 16 bf16 = 8 TMEM columns = two slots per MMA
+            mma_bf16_ta(tmem_d + (uint32_t)(t * 192), a_t + (uint32_t)(kk * 8), b_desc + (uint64_t)(kk * 2), IDESC,
+                        (it | kk) ? 1u : 0u);
+        }
+        mma_commit(a_empty(sa));
+        mma_commit(b_empty(sb));
+      }
+      __syncwarp();
+      if (++sb == SB) {
+        sb = 0;
+        phb ^= 1u;
+      }
+    }
+    if (lane == 0) mma_commit(accum_bar);
+    __syncwarp();
+  } else if (lane == 0) {
+    // ===================== weight loader =====================
+    int sb = 0;
+    uint32_t phb = 0;
+    for (int it = 0; it < T; ++it) {
+      mbar_wait(b_empty(sb), phb ^ 1u);
+      mbar_arrive_expect_tx(b_full(sb), LF_B_STAGE);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        bulk_g2s(b_base + sb * LF_B_STAGE + i * LF_B_IMG, wimg + (((int64_t)it * 3 + i) * c_out + n0) * 32, LF_B_IMG,
+                 b_full(sb));
+      if (++sb == SB) {
+        sb = 0;
+        phb ^= 1u;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_d);
+  }
+}
+
 // =============================================================================================
 // weight gradient
 // =============================================================================================
@@ -323,7 +536,11 @@ __global__ void __launch_bounds__(LW_THREADS, 1)
     // A: the two 16-byte chunks (rows ra, ra + 16) of the stage's gy rows this thread moves.  A gy row of 64 channels
     // in operand form is [h 0..31 | l 0..31 | h 32..63 | l 32..63]; h chunks go to the first 4 KB (M rows 0..63), l
     // chunks to the second (M rows 64..127), each as atoms of 64 channels x 8 rows
-    const int c16 = tid & 15, ra = tid >> 4;
+    // (chunk order inside the 16 lanes of a row: lanes 0-7 take the eight h chunks of both 32-channel blocks, lanes
+    // 8-15 the l chunks, so that a quarter-warp -- the unit a 16-byte shared store is processed in -- writes eight
+    // different chunk columns; [block | h/l | chunk] order put h and l of one chunk, 4 KB apart, on the same banks)
+    const int l16 = tid & 15, ra = tid >> 4;
+    const int c16 = ((l16 & 4) << 1) | ((l16 & 8) >> 1) | (l16 & 3);
     const uint32_t a_chunk = (uint32_t)((((c16 >> 3) & 1) << 2) | (c16 & 3));
     auto a_off = [&](int row) -> uint32_t {
       return (uint32_t)((c16 >> 2) & 1) * 4096u + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u +
@@ -509,11 +726,24 @@ extern "C" int32_t b2s_conv_lines_fwd(const float* x, const float* w, const floa
     }                                                                                                           \
     kern<<<grid, LF_THREADS, LfSmem<S>::DYN_BYTES, st>>>(x4, img, bias, lines, n_out, n_out_dev, c_out, nlines, y); \
   } while (0)
+#define LT_LAUNCH(SB, D)                                                                                        \
+  do {                                                                                                          \
+    auto kern = conv_lines_fwd_tmem_kernel<SB, D>;                                                              \
+    static bool attr_set = false;                                                                               \
+    if (!attr_set) {                                                                                            \
+      B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LtSmem<SB>::DYN_BYTES)); \
+      attr_set = true;                                                                                          \
+    }                                                                                                           \
+    kern<<<grid, LT_THREADS, LtSmem<SB>::DYN_BYTES, st>>>(x4, img, bias, lines, n_out, n_out_dev, c_out, nlines, y); \
+  } while (0)
   if (variant == 1) LF_LAUNCH(3, 2);
   else if (variant == 2) LF_LAUNCH(4, 3);
-  else if (variant == 3) LF_LAUNCH(4, 4);
-  else LF_LAUNCH(3, 3);
+  else if (variant == 3) LF_LAUNCH(3, 3);
+  else if (variant == 4) LT_LAUNCH(4, 3);
+  else if (variant == 5) LT_LAUNCH(6, 2);
+  else LT_LAUNCH(6, 3);
 #undef LF_LAUNCH
+#undef LT_LAUNCH
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

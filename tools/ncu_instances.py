@@ -35,8 +35,16 @@ def main(raw, manifest_path, out_path, peaks_path=None):
             groups.append(cur)
         elif cur is not None:
             cur.append(r)
-    groups = [g for g in groups if g]
     inst = man["instances"]
+    if len(groups) == len(inst) + 1 and not groups[-1]:
+        groups = groups[:-1]                                  # the closing marker opens an empty group
+    # an instance may launch nothing (a lazily built map): keep its (empty) group, drop it from the report
+    if len(groups) == len(inst):
+        keep = [i for i, g in enumerate(groups) if g]
+        groups, inst = [groups[i] for i in keep], [inst[i] for i in keep]
+    else:
+        groups = [g for g in groups if g]
+        inst = [m for m in inst if m.get("kernels_expected", 1) != 0]
     assert len(groups) == len(inst), f"{len(groups)} marker-delimited groups for {len(inst)} manifest instances"
     out = []
     for m, g in zip(inst, groups):

@@ -54,20 +54,44 @@ k2 = instance("strided map ts1 -> ts2 (hash insert + fill)", lambda: cm.stride(k
 N2 = cm.coords(k2).shape[0]
 manifest[-1]["alg_bytes"] = 16 * M + 16 * N2 + 4 * M
 k4 = cm.stride(k2, 2)
-km7 = instance("kernel map k7 stem (occupancy index, dense table)", lambda: cm.kernel_map(k1, k1, 7), "hbm")
-P7 = int((km7.nbr >= 0).sum())
-manifest[-1]["alg_bytes"] = 16 * M + 8 * P7
-manifest[-1]["note"] = f"16 N_out + 8 P (P = {P7}); the kernel WRITES the dense table 4 * 343 * N_out = {4 * 343 * M} bytes"
+LINES = Fn.lines_path(cm.kernel_map(k1, k1, 7), 3, 64)
+cm.kernel_maps.clear()
+if LINES:
+    km7 = instance("kernel map k7 stem (occupancy index, x-line table)", lambda: cm.kernel_map(k1, k1, 7), "hbm")
+    manifest[-1]["kernels_expected"] = 0            # the map object is lazy: the table is the next instance's launch
+    instance("x-line table of the k7 stem map", lambda: km7.lines, "hbm")
+    P7 = km7.num_pairs()
+    manifest[-1]["alg_bytes"] = 16 * M + 8 * P7
+    manifest[-1]["note"] = f"16 N_out + 8 P (P = {P7}); the kernel WRITES 4 * 49 * N_out = {4 * 49 * M} bytes of line words"
+else:
+    km7 = instance("kernel map k7 stem (occupancy index, dense table)", lambda: cm.kernel_map(k1, k1, 7), "hbm")
+    P7 = int((km7.nbr >= 0).sum())
+    manifest[-1]["alg_bytes"] = 16 * M + 8 * P7
+    manifest[-1]["note"] = f"16 N_out + 8 P (P = {P7}); the kernel WRITES the dense table 4 * 343 * N_out = {4 * 343 * M} bytes"
 km2 = instance("kernel map k3 @ts2 (hash probes)", lambda: cm.kernel_map(k2, k2, 3), "hbm")
 P2 = int((km2.nbr >= 0).sum())
 manifest[-1]["alg_bytes"] = 16 * N2 + 8 * P2
 w7 = torch.randn(343, 3, 64, device=dev) * 0.02
 f1 = vox["tensors"][0]
-y = instance("conv fwd stem k7 3->64 @ts1", lambda: Fn.gather_gemm(f1, w7, None, km7.nbr, M, M, 3, 64, 343, 0), "tensor",
+if LINES:
+    y = instance("conv fwd stem k7 3->64 @ts1 (x-lines)", lambda: Fn.lines_fwd(f1, w7, None, km7, 3, 64), "tensor",
+                 conv_bytes(M, M, 3, 64, 343, P7), 2 * P7 * 3 * 64)
+    gy1 = Fn.round_tf32(torch.randn_like(y))
+    instance("conv wgrad stem k7 3->64 @ts1 (x-lines)", lambda: Fn.lines_wgrad(f1, gy1, km7, 3, 64), "tensor",
              conv_bytes(M, M, 3, 64, 343, P7), 2 * P7 * 3 * 64)
-gy1 = Fn.round_tf32(torch.randn_like(y))
-instance("conv wgrad stem k7 3->64 @ts1", lambda: Fn.wgrad(f1, gy1, km7.nbr, M, M, 3, 64, 343, prerounded=True),
-         "tensor", conv_bytes(M, M, 3, 64, 343, P7), 2 * P7 * 3 * 64)
+else:
+    y = instance("conv fwd stem k7 3->64 @ts1", lambda: Fn.gather_gemm(f1, w7, None, km7.nbr, M, M, 3, 64, 343, 0),
+                 "tensor", conv_bytes(M, M, 3, 64, 343, P7), 2 * P7 * 3 * 64)
+    gy1 = Fn.round_tf32(torch.randn_like(y))
+    instance("conv wgrad stem k7 3->64 @ts1", lambda: Fn.wgrad(f1, gy1, km7.nbr, M, M, 3, 64, 343, prerounded=True),
+             "tensor", conv_bytes(M, M, 3, 64, 343, P7), 2 * P7 * 3 * 64)
+if os.environ.get("ONLY_STEM"):
+    lib.call("b2s_gelu_fwd", one, 1, None, 1, one)
+    torch.cuda.synchronize()
+    json.dump({"plots": B, "precise": PRECISE, "rows": {"ts1": M, "ts2": N2}, "instances": manifest},
+              open("gpurun_out/ncu_manifest.json", "w"), indent=1)
+    print("done", len(manifest), "instances")
+    sys.exit(0)
 for key, c, name in ((k2, 64, "L1 k3 64->64 @ts2"), (k4, 128, "L2 k3 128->128 @ts4")):
     km = cm.kernel_map(key, key, 3)
     P = int((km.nbr >= 0).sum())
