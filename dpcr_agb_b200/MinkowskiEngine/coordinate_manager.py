@@ -22,6 +22,18 @@ from dpcr_agb_b200 import lib as L
 USE_DENSE_INDEX = True   # tests flip this to compare the occupancy-index kernel map with the hash one
 USE_LINES = True         # tests flip this to compare the x-line convolution kernels with the table-driven ones
 
+# bench.py sets this to a dict to collect the ALGORITHMIC bytes of the integer stages per entry point (SURVEY.md 8d:
+# kernel map 16 N_out + 8 P, strided map 16 N_in + 16 N_out + 4 N_in); pair counts cost a host sync per map, so this
+# is only ever enabled in an untimed statistics pass
+MAP_STATS = None
+
+
+def _map_account(name, nbytes):
+    if MAP_STATS is not None:
+        st = MAP_STATS.setdefault(name, {"calls": 0, "bytes": 0})
+        st["calls"] += 1
+        st["bytes"] += int(nbytes)
+
 
 def _triple(v):
     if isinstance(v, torch.Tensor):
@@ -125,6 +137,8 @@ class KernelMap:
             self._lines = torch.empty((nl, m.n), dtype=torch.int32, device=m.coords.device)
             L.call("b2s_kernel_map_lines", m.coords, m.n, m.n_dev, ws, num_plots, L.host_i32(*lo), L.host_i32(*dims),
                    L.host_i32(*self.kernel_size), L.host_i32(*self.step), self._lines)
+            if MAP_STATS is not None:
+                _map_account("b2s_kernel_map_lines", 16 * m.n + 8 * self.num_pairs())
         return self._lines
 
     def num_pairs(self, n_rows=None):
@@ -359,6 +373,7 @@ class CoordinateManager:
         out = torch.empty((n_unique, 4), dtype=torch.int32, device=dev)
         in2out = torch.empty(max(n, 1), dtype=torch.int32, device=dev) if want_in2out else None
         L.call("b2s_coordmap_fill", coords, n, None, ts, table, cap, slot, rank, out, n_unique, in2out)
+        _map_account("strided map (b2s_coordmap_insert + _fill)", 16 * n + 16 * n_unique + 4 * n)
         return CoordMap(out, table, cap), (in2out[:n] if want_in2out else None), n_unique
 
     def insert(self, coords: torch.Tensor, tensor_stride=(1, 1, 1), tag="", dense_index=None):
@@ -446,10 +461,14 @@ class CoordinateManager:
             ws, lo, dims, num_plots = table_map.dense
             L.call("b2s_kernel_map_dense", query_map.coords, n, query_map.n_dev, ws, num_plots, L.host_i32(*lo),
                    L.host_i32(*dims), L.host_i32(*kernel_size), L.host_i32(*step), sign, nbr)
+            if MAP_STATS is not None:
+                _map_account("b2s_kernel_map_dense", 16 * n + 8 * int((nbr >= 0).sum().item()))
             return nbr
         table = self._table_of(table_map)
         L.call("b2s_kernel_map", query_map.coords, n, query_map.n_dev, table, table_map.capacity,
                L.host_i32(*kernel_size), L.host_i32(*step), sign, nbr)
+        if MAP_STATS is not None:
+            _map_account("b2s_kernel_map", 16 * n + 8 * int((nbr >= 0).sum().item()))
         return nbr
 
     def kernel_map(self, in_key, out_key, kernel_size, dilation=(1, 1, 1)) -> KernelMap:

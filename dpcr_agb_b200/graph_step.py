@@ -219,3 +219,91 @@ class GraphStep:
             elif v > cap:
                 raise L.B2SError(f"{what}: {v} exceeds the planned capacity {cap}; re-plan with larger capacities")
         return out
+
+
+class GraphForward:
+    """Captured EVAL forward of a batch of plots: raw points -> quantise -> maps -> network -> prediction, one CUDA
+    graph, no host sync (BASELINE.json configs[0] on the GPU: MSENet14 inference on one 16k-point plot; the reference
+    runs it as ``eval.py`` -> ``model.forward`` under ``torch.no_grad``, models/base_model.py:153-160).  Same static
+    coordinate manager as :class:`GraphStep`; ``verify()`` reports capacity overflows."""
+
+    def __init__(self, model, ME, gs: GridSampling3D, num_plots, n_points, bounds, capacities, feat_dim=3, out_dim=2):
+        self.model, self.ME, self.gs = model, ME, gs
+        self.B, self.n_points, self.bounds = int(num_plots), int(n_points), bounds
+        self.capacities = dict(capacities)
+        dev = next(model.parameters()).device
+        self.dev = dev
+        self.inp = {
+            "pos": torch.zeros((n_points, 3), dtype=torch.float32, device=dev),
+            "feats": torch.zeros((n_points, feat_dim), dtype=torch.float32, device=dev),
+            "batch": torch.zeros(n_points, dtype=torch.int32, device=dev),
+            "perm": torch.arange(n_points, dtype=torch.int32, device=dev),
+        }
+        self.n_points_dev = torch.full((1,), n_points, dtype=torch.int32, device=dev)
+        self.pred = torch.zeros((num_plots, out_dim), dtype=torch.float32, device=dev)
+        self.pred_host = torch.zeros((num_plots, out_dim), dtype=torch.float32).pin_memory()
+        self.graph = None
+        self.status = self.status_min = None
+        self.status_meta = []
+        self.launches_per_step = 0
+
+    def _body(self):
+        vox = self.gs(self.inp["pos"], self.inp["batch"], tensors=(self.inp["feats"],), order=self.inp["perm"],
+                      num_plots=self.B, bounds=self.bounds, capacity=self.capacities[1],
+                      n_points_dev=self.n_points_dev)
+        x = self.ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"], num_rows=vox["num_rows"],
+                                 capacities=self.capacities, num_batches=self.B, dense_index=vox["index"])
+        with torch.no_grad():
+            pred = self.model(x)
+        self.pred.copy_(pred.reshape(self.pred.shape))
+        cm = x.coordinate_manager
+        self.status_meta = [(what, cap) for what, cap, _ in cm.checks]
+        status = torch.cat([t.reshape(-1)[:1] for _, _, t in cm.checks])
+        if self.status is None:
+            self.status, self.status_min = torch.zeros_like(status), torch.zeros_like(status)
+        torch.maximum(self.status, status, out=self.status)
+        torch.minimum(self.status_min, status, out=self.status_min)
+
+    def capture(self, warmup=2):
+        self.model.eval()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.status.zero_()
+        self.status_min.zero_()
+        calls0 = L.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches_per_step = L.launch_count - calls0
+        return self
+
+    def load(self, host_batch, non_blocking=True):
+        for k, dst in self.inp.items():
+            dst.copy_(host_batch[k], non_blocking=non_blocking)
+
+    def step(self):
+        """Replay on the loaded points; returns the on-device prediction ``[B, out_dim]``."""
+        self.graph.replay()
+        return self.pred
+
+    def verify(self):
+        vals, lows = torch.stack([self.status, self.status_min]).tolist()
+        self.status.zero_()
+        self.status_min.zero_()
+        out = {}
+        for (what, cap), v, lo in zip(self.status_meta, vals, lows):
+            out[what] = v
+            if lo < 0:
+                raise L.B2SError(f"{what}: the device reported {lo} (a point outside the voxel bounds)")
+            if (cap == 0 and v != 0) or (cap > 0 and v > cap):
+                raise L.B2SError(f"{what}: {v} against capacity {cap} (0 = flag)")
+        return out
+
+    def release(self):
+        torch.cuda.synchronize()
+        self.graph = None

@@ -100,3 +100,27 @@ def cpu_training_step(model, opt, batch, size, center, scale):
             p.grad.clamp_(-100.0, 100.0)
     opt.step()
     return float(loss)
+
+
+def cpu_inference_step(model, batch, size):
+    """Eval forward of a batch on the CPU oracle from raw points (BASELINE.json configs[0]: the reference's CPU
+    MinkowskiEngine case, ``eval.py`` -> ``model.forward`` under no_grad, models/base_model.py:153-160)."""
+    import numpy as np
+
+    from . import coords as oc
+    from . import me_cpu
+
+    nb = int(batch["batch"].max()) + 1
+    pos_l, feat_l, perm_l, base = [], [], [], 0
+    for b in range(nb):
+        sel = batch["batch"] == b
+        n = int(sel.sum())
+        pos_l.append(batch["pos"][sel])
+        feat_l.append(batch["feats"][sel])
+        perm_l.append(batch["perm"][base:base + n] - base)
+        base += n
+    c, f, _, _, _ = oc.quantize_batch(pos_l, feat_l, size, perm_l)
+    x = me_cpu.SparseTensor(torch.from_numpy(np.ascontiguousarray(f)), coordinates=torch.from_numpy(c))
+    model.eval()
+    with torch.no_grad():
+        return model(x)
