@@ -603,9 +603,14 @@ struct WgTuning {
   int nbp_cap, lag, occ2, ca;
 };
 WgTuning wg_tuning() {
-  static const WgTuning env = {wg_env("B2S_WG_NBP", 16), wg_env("B2S_WG_LAG", 2), wg_env("B2S_WG_OCC2", 1),
+  // defaults measured per operand mode (tools/sweep.py, profiles/r02_sweep_bf16x2.json): with split-bf16 operands a
+  // stage is three MMAs per M tile instead of two, and ONE CTA per SM with a hand-over lag of one stage runs the 64->64
+  // layers 20 % faster (0.48 -> 0.385 ms) than two CTAs per SM with a lag of two, which is the better choice for TF32
+  static const WgTuning env = {wg_env("B2S_WG_NBP", 16), wg_env("B2S_WG_LAG", -1), wg_env("B2S_WG_OCC2", -1),
                                wg_env("B2S_WG_CA", 0)};
   WgTuning t = env;
+  if (t.lag < 0) t.lag = b2s_precise() ? 1 : 2;
+  if (t.occ2 < 0) t.occ2 = b2s_precise() ? 0 : 1;
   if (g_b2s_wg_nbp >= 0) t.nbp_cap = g_b2s_wg_nbp;
   if (g_b2s_wg_lag >= 0) t.lag = g_b2s_wg_lag;
   if (g_b2s_wg_occ2 >= 0) t.occ2 = g_b2s_wg_occ2;

@@ -48,6 +48,8 @@ layers = [("stem k7 3->64 ts1", 1, 1, 7, 3, 64), ("L1 64->64 ts2", 2, 2, 3, 64, 
 calls = {"stem k7 3->64 ts1": 1, "L1 64->64 ts2": 4, "L2 s2 64->128": 1, "L2 128->128 ts4": 3, "L3 s2 128->256": 1, "L3 256->256 ts8": 3,
          "L4 s2 256->512": 1, "L4 512->512 ts16": 3}
 prep = []
+if os.environ.get("SKIP_STEM"):
+    layers = layers[1:]
 for name, its, ots, K, cin, cout in layers:
     km = cm.kernel_map(keys[its], keys[ots], K)
     xf = torch.randn(km.n_in, cin, device=dev)
