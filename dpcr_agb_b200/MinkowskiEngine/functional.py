@@ -62,6 +62,30 @@ def round_tf32(x, n_dev=None):
 # b2s_round_tf32 pass.  A tensor that IS the rounded result (no plain copy was written) is marked ``_b2s_is_tf32``.
 # Nothing depends on the attribute surviving: without it the convolution rounds as before.
 TWINS = True
+FUSE_BIAS_GRAD = True   # bn_bwd_apply accumulates the column sums of its gx (the bias gradient of the conv in front)
+FUSE_BN_STATS = True    # a convolution's epilogue accumulates the column sums / sums of squares of its output: the
+#                         statistics of the batch norm behind it (C ABI: col_stats of b2s_conv_gather_gemm / _lines_fwd)
+
+
+def new_col_stats(c_out, device):
+    """Workspace for the fused batch-norm statistics of a convolution output, or None when they are not wanted (no
+    gradient mode: inference normalises with the running statistics)."""
+    if not (FUSE_BN_STATS and torch.is_grad_enabled()):
+        return None
+    return torch.empty(2 * c_out + 1, dtype=torch.float64, device=device)
+
+
+def attach_col_stats(y, stats):
+    if stats is not None:
+        y._b2s_colstats = (stats, y._version)
+    return y
+
+
+def col_stats_of(x, c):
+    st = getattr(x, "_b2s_colstats", None)
+    if st is not None and st[1] == x._version and st[0].numel() == 2 * c + 1:
+        return st[0]
+    return None
 
 
 def twins_on():
@@ -151,14 +175,15 @@ def _wg_tc_ok(c_in, c_out, has_map):
 
 
 def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None, n_out_dev=None,
-                prerounded=False):
+                prerounded=False, col_stats=None):
     """y[o] = bias + sum_k x[nbr[k,o]] @ B_k  (C ABI ``b2s_conv_gather_gemm``).  ``n_out_dev``: device row count
-    (then ``n_out`` is the capacity / pitch of ``nbr``).  ``prerounded``: x is already TF32-representable."""
+    (then ``n_out`` is the capacity / pitch of ``nbr``).  ``prerounded``: x is already TF32-representable.
+    ``col_stats``: float64 [2 c_out + 1] that receives the column sums / sums of squares of y."""
     y = torch.empty((n_out, c_out), dtype=torch.float32, device=x.device)
     _account("dgrad" if (w_layout & 1) else "fwd", nbr, n_out, c_in, c_out, k3, n_out_dev)
     ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device, prerounded)
     L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3,
-           w_layout | (4 if prerounded else 0), y, ws, nbytes, CONV_IMPL if impl is None else impl)
+           w_layout | (4 if prerounded else 0), y, ws, nbytes, CONV_IMPL if impl is None else impl, col_stats)
     return y
 
 
@@ -180,14 +205,14 @@ def lines_path(kmap, c_in, c_out):
             and L.query("b2s_conv_lines_supported", c_in, c_out, L.host_i32(*kmap.kernel_size)) == 1)
 
 
-def lines_fwd(x, w, bias, kmap, c_in, c_out):
+def lines_fwd(x, w, bias, kmap, c_in, c_out, col_stats=None):
     y = torch.empty((kmap.n_out, c_out), dtype=torch.float32, device=x.device)
     _account("fwd", None, kmap.n_out, c_in, c_out, kmap.k3, kmap.n_out_dev, kmap=kmap)
     ks = L.host_i32(*kmap.kernel_size)
     nbytes = L.query("b2s_conv_lines_workspace_bytes", kmap.n_in, c_in, c_out, ks)
     ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=x.device)
     L.call("b2s_conv_lines_fwd", x, w, bias, kmap.lines, kmap.n_in, kmap.n_out, kmap.n_out_dev, c_in, c_out, ks, y, ws,
-           nbytes)
+           nbytes, col_stats)
     return y
 
 
@@ -209,9 +234,9 @@ class ConvolutionFunction(torch.autograd.Function):
 
     @staticmethod
     @_fwd
-    def forward(ctx, feats, kernel, bias, kmap, n_dev=None):
+    def forward(ctx, feats, kernel, bias, kmap, n_dev=None, col_stats=None):
         """``n_dev``: device row count of the (identity-map) input when ``kmap`` is None; a KernelMap carries its
-        own device counts."""
+        own device counts.  ``col_stats``: see :func:`gather_gemm` (filled as a side effect, not differentiable)."""
         feats = feats.contiguous()
         kernel = kernel.contiguous()
         c_in, c_out = kernel.shape[-2], kernel.shape[-1]
@@ -228,7 +253,7 @@ class ConvolutionFunction(torch.autograd.Function):
         b = bias.contiguous().view(-1) if bias is not None else None
         ctx.lines = use_lines
         if use_lines:
-            out = lines_fwd(feats, kernel, b, kmap, c_in, c_out)
+            out = lines_fwd(feats, kernel, b, kmap, c_in, c_out, col_stats)
             ctx.pre, ctx.kmap, ctx.nd, ctx.dims = False, kmap, (nd_in, nd_out), (n_in, n_out, c_in, c_out, k3)
             ctx.has_bias, ctx.params = bias is not None, (kernel, bias)
             ctx.save_for_backward(feats, kernel)
@@ -239,7 +264,8 @@ class ConvolutionFunction(torch.autograd.Function):
         raw = feats
         if pre:
             feats = rounded_operand(feats, nd_in)
-        out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0, n_out_dev=nd_out, prerounded=pre)
+        out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0, n_out_dev=nd_out, prerounded=pre,
+                          col_stats=col_stats)
         if pre and not _wg_tc_ok(c_in, c_out, kmap is not None):   # wgrad will run on the SIMT kernel: keep plain x
             feats, pre = raw, False
         ctx.pre = pre
@@ -292,12 +318,20 @@ class ConvolutionFunction(torch.autograd.Function):
                 gw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             bp = ctx.params[1]
-            gb = bp.grad.view(1, c_out) if _direct(bp) else torch.empty((1, c_out), dtype=torch.float32,
-                                                                         device=gy.device)
-            L.call("b2s_colsum", gy, n_out, nd_out, c_out, gb)
-            if _direct(bp):
-                gb = None
-        return gx, gw, gb, None, None
+            pre = getattr(gy, "_b2s_colsum", None)      # column sums already accumulated by the producer of gy
+            if pre is not None and pre[1] == gy._version and pre[0].numel() == c_out:
+                if _direct(bp):
+                    bp.grad.view(-1).copy_(pre[0])
+                    gb = None
+                else:
+                    gb = pre[0].view(1, c_out).clone()
+            else:
+                gb = bp.grad.view(1, c_out) if _direct(bp) else torch.empty((1, c_out), dtype=torch.float32,
+                                                                             device=gy.device)
+                L.call("b2s_colsum", gy, n_out, nd_out, c_out, gb)
+                if _direct(bp):
+                    gb = None
+        return gx, gw, gb, None, None, None
 
 
 class MaxPoolFunction(torch.autograd.Function):
@@ -465,17 +499,22 @@ class BatchNormFunction(torch.autograd.Function):
     @staticmethod
     @_fwd
     def forward(ctx, x, weight, bias, running_mean, running_var, training, momentum, eps, act, n_dev=None,
-                tf32_only=False):
-        """``tf32_only``: the result is written TF32-rounded and nothing else (its only consumer is a convolution)."""
+                tf32_only=False, col_stats=None):
+        """``tf32_only``: the result is written TF32-rounded and nothing else (its only consumer is a convolution).
+        ``col_stats``: column sums / sums of squares of x already accumulated by the convolution that produced it."""
         x = x.contiguous()
         n, c = x.shape
         dev = x.device
         if training:
             mean = torch.empty(c, dtype=torch.float32, device=dev)
             invstd = torch.empty(c, dtype=torch.float32, device=dev)
-            ws = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
-            L.call("b2s_bn_stats", x, n, n_dev, c, float(eps), float(momentum), running_mean, running_var, ws, mean,
-                   invstd)
+            if col_stats is not None and n > 0:
+                L.call("b2s_bn_finalize", col_stats, n, n_dev, c, float(eps), float(momentum), running_mean,
+                       running_var, mean, invstd)
+            else:
+                ws = torch.empty(2 * c + 1, dtype=torch.float64, device=dev)
+                L.call("b2s_bn_stats", x, n, n_dev, c, float(eps), float(momentum), running_mean, running_var, ws,
+                       mean, invstd)
         else:
             mean = running_mean
             invstd = torch.rsqrt(running_var + eps)
@@ -504,10 +543,14 @@ class BatchNormFunction(torch.autograd.Function):
             # the input gradient of a batch norm is the output gradient of the convolution in front of it: write
             # the TF32 operand for its dgrad / wgrad alongside
             gxr = torch.empty_like(x) if (twins_on() and c > 4) else None
+            # ... and its column sums are that convolution's bias gradient: accumulated here while gx is written
+            cs = torch.empty(c, dtype=torch.float32, device=dev) if FUSE_BIAS_GRAD else None
             L.call("b2s_bn_bwd_apply", gy, x, mean, invstd, weight, bias, sums, n, ctx.nd, c, ctx.act,
-                   1 if ctx.training else 0, gx, gxr)
+                   1 if ctx.training else 0, gx, gxr, cs)
             if gxr is not None:
                 attach_twin(gx, gxr)
+            if cs is not None:
+                gx._b2s_colsum = (cs, gx._version)
         gw = gb = None
         if weight is not None and ctx.needs_input_grad[1]:
             if _direct(weight):
@@ -519,7 +562,7 @@ class BatchNormFunction(torch.autograd.Function):
                 bias.grad.copy_(sums[:c])
             else:
                 gb = sums[:c].clone()
-        return gx, gw, gb, None, None, None, None, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None, None, None, None, None
 
 
 class GELUFunction(torch.autograd.Function):

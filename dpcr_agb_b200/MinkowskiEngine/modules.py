@@ -105,12 +105,16 @@ class MinkowskiConvolution(MinkowskiModuleBase):
 
     def forward(self, input: SparseTensor, coordinates=None):
         cm = input.coordinate_manager
+        # every convolution of the reference's networks feeds a batch norm: its statistics ride in the epilogue
+        stats = Fn.new_col_stats(self.out_channels, input.F.device) if self.training else None
         if self.use_mm:
-            out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, None, input.n_dev)
+            out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, None, input.n_dev, stats)
+            Fn.attach_col_stats(out, stats)
             return SparseTensor(out, coordinate_map_key=input.coordinate_map_key, coordinate_manager=cm)
         out_key = _out_key(input, self.stride)
         kmap = cm.kernel_map(input.coordinate_map_key, out_key, self.kernel_size, self.dilation)
-        out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, kmap)
+        out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, kmap, None, stats)
+        Fn.attach_col_stats(out, stats)
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)
 
     def __repr__(self):
@@ -360,7 +364,8 @@ class MinkowskiBatchNorm(nn.Module):
                                          bn.running_mean if (update or not use_batch_stats) else None,
                                          bn.running_var if (update or not use_batch_stats) else None,
                                          use_batch_stats, 0.0 if momentum is None else momentum, bn.eps, act,
-                                         input.n_dev, tf32_only)
+                                         input.n_dev, tf32_only,
+                                         Fn.col_stats_of(input.F, input.F.shape[1]) if use_batch_stats else None)
         if tf32_only:
             Fn.mark_rounded(out)
         return input._wrap(out)

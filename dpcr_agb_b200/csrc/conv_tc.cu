@@ -187,7 +187,7 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y,
-                          const PermArgs pa, int flags) {
+                          const PermArgs pa, int flags, double* __restrict__ col_stats) {
   const int rot_on = flags & 1;
   const bool l1 = (flags & 2) != 0;                // gather through L1 (cp.async.ca) instead of L2 only (.cg)
   const bool precise = NB > 1 || (flags & 4) != 0;
@@ -427,6 +427,13 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
           for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
         }
       }
+      if (col_stats) {     // batch-norm statistics of the output (host: only when the tile is final, i.e. no split-K)
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          r[j] = o_ok ? __uint_as_float(v[j]) + (bias ? __ldg(&bias[n0 + c0 + j]) : 0.f) : 0.f;
+        epilogue_col_stats(r, lane, reinterpret_cast<float2*>(smem + L::A_OFF) + warp * BN + c0);
+      }
       if (o_ok) {
         float* dst = y + o * c_out + n0 + c0;
         const bool add_bias = bias && it0 == 0;
@@ -444,6 +451,20 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
           else
             *reinterpret_cast<float4*>(dst + j) = r;
         }
+      }
+    }
+    if (col_stats) {       // the four epilogue warps combine their per-column sums: one fp64 atomic pair per column
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float2* red = reinterpret_cast<const float2*>(smem + L::A_OFF);
+      for (int c = tid; c < BN; c += 128) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) {
+          s1 += red[wq * BN + c].x;
+          s2 += red[wq * BN + c].y;
+        }
+        atomicAdd(&col_stats[n0 + c], (double)s1);
+        atomicAdd(&col_stats[c_out + n0 + c], (double)s2);
       }
     }
     tc_fence_before();
@@ -528,7 +549,8 @@ template <int BN, int STAGES, int LAG>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
     gather_gemm_tc2_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                            const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
-                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y, int precise) {
+                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y, int precise,
+                           double* __restrict__ col_stats) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
   if ((int64_t)blockIdx.x * (2 * BM) >= n_out) return;
@@ -658,6 +680,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
       uint32_t v[32];
       tmem_ld32(t_lane + (uint32_t)c0, v);
       tmem_ld_wait();
+      if (col_stats) {
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          r[j] = o < n_out ? __uint_as_float(v[j]) + (bias ? __ldg(&bias[n0 + c0 + j]) : 0.f) : 0.f;
+        epilogue_col_stats(r, lane, reinterpret_cast<float2*>(smem + L::A_OFF) + warp * BN + c0);
+      }
       if (o < n_out) {
         float* dst = y + o * c_out + n0 + c0;
         const bool add_bias = bias && it0 == 0;
@@ -675,6 +704,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
           else
             *reinterpret_cast<float4*>(dst + j) = r;
         }
+      }
+    }
+    if (col_stats) {       // all eight epilogue warps (two row tiles) combine their per-column sums
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2* red = reinterpret_cast<const float2*>(smem + L::A_OFF);
+      for (int c = tid; c < BN; c += 256) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) {
+          s1 += red[wq * BN + c].x;
+          s2 += red[wq * BN + c].y;
+        }
+        atomicAdd(&col_stats[n0 + c], (double)s1);
+        atomicAdd(&col_stats[c_out + n0 + c], (double)s2);
       }
     }
     tc_fence_before();
@@ -975,7 +1018,7 @@ int launch_perm(const float* x, const float* wimg, const int* nbr, int64_t n_out
   }
   dim3 grid((unsigned)tiles_cap, (unsigned)(c_out / BN), 1);
   kern<<<grid, TC_THREADS, L::DYN_BYTES, st>>>(x, wimg, nullptr, nbr, n_out, n_out_dev, c_in, c_out, k3, 0, 0, y, pa,
-                                               (tc_ca() ? 2 : 0) | (b2s_precise() ? 4 : 0));
+                                               (tc_ca() ? 2 : 0) | (b2s_precise() ? 4 : 0), nullptr);
   return 0;
 }
 
@@ -999,7 +1042,8 @@ int tc_rot() {
 
 template <int BN, int STAGES, int LAG>
 int launch_tc2(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
-               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
+               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st, double* col_stats = nullptr,
+               bool* stats_fused = nullptr) {
   using L = SmemLayout2<BN, STAGES>;
   static_assert(LAG < STAGES, "producers run LAG stages ahead of their hand-over");
   auto kern = gather_gemm_tc2_kernel<BN, STAGES, LAG>;
@@ -1025,8 +1069,10 @@ int launch_tc2(const float* x, const float* wimg, const float* bias, const int* 
   splits = (T + per - 1) / per;
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, 2 * BM), (unsigned)(c_out / BN), (unsigned)splits);
+  const bool fuse = col_stats != nullptr && splits == 1;      // split-K tiles are partial sums: no statistics there
+  if (stats_fused) *stats_fused = fuse;
   kern<<<grid, TC2_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y,
-                                                b2s_precise());
+                                                b2s_precise(), fuse ? col_stats : nullptr);
   return 0;
 }
 
@@ -1034,7 +1080,8 @@ int tc_m256() { return tc_knob(g_b2s_tc_m256, "B2S_TC_M256", 1); }
 
 template <int BN, int STAGES, bool SMALL, int LAG = 2, int NB = 1, int PW = 4>
 int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
-              int c_in, int c_out, int k3, int T, float* y, cudaStream_t st) {
+              int c_in, int c_out, int k3, int T, float* y, cudaStream_t st, double* col_stats = nullptr,
+              bool* stats_fused = nullptr) {
   using L = SmemLayout<BN, STAGES, NB>;
   static_assert(LAG < STAGES, "producers run LAG stages ahead of their hand-over");
   auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL, LAG, false, NB, PW>;
@@ -1063,8 +1110,11 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
   splits = (T + per - 1) / per;
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
+  const bool fuse = col_stats != nullptr && splits == 1;      // split-K tiles are partial sums: no statistics there
+  if (stats_fused) *stats_fused = fuse;
   kern<<<grid, (PW + 1) * 32, dyn, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y, PermArgs{},
-                                      (tc_rot() ? 1 : 0) | (tc_ca() ? 2 : 0) | (b2s_precise() ? 4 : 0));
+                                      (tc_rot() ? 1 : 0) | (tc_ca() ? 2 : 0) | (b2s_precise() ? 4 : 0),
+                                      fuse ? col_stats : nullptr);
   return 0;
 }
 
@@ -1102,8 +1152,10 @@ static void launch_prep_weights(const float* w, int c_in, int c_out, int k3, int
 
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                             int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
-                            void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                            void* workspace, int64_t workspace_bytes, cudaStream_t st, double* col_stats,
+                            bool* stats_fused) {
   (void)workspace_bytes;
+  if (stats_fused) *stats_fused = false;
   const bool small = c_in <= 4;
   const int T = iterations(c_in, k3);
   float* img = reinterpret_cast<float*>(workspace);
@@ -1143,21 +1195,21 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   // it can run (tests), 3 = 64- and 128-wide tiles
   const int m256 = tc_m256();
   if (m256 && n_out > BM && (bn == 128 || m256 == 2 || (m256 == 3 && bn == 64))) {
-    if (bn == 256) return launch_tc2<256, 3, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
-    if (bn == 128) return launch_tc2<128, 4, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
-    return launch_tc2<64, 5, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    if (bn == 256) return launch_tc2<256, 3, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
+    if (bn == 128) return launch_tc2<128, 4, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
+    return launch_tc2<64, 5, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
   }
-  if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
   if (bn == 128) {
     if (variant == 1) return launch_tc<128, 3, false, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
     if (variant == 2) return launch_tc<128, 6, false, 4>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
     if (variant == 3) return launch_tc<128, 6, false, 5>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
-    return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+    return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
   }
   if (variant == 1) return launch_tc<64, 3, false, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   if (variant == 2) return launch_tc<64, 4, false, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   if (variant == 3) return launch_tc<64, 8, false, 6>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
-  return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
+  return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
 }
 
 

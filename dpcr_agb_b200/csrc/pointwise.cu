@@ -670,12 +670,17 @@ __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __res
   }
 }
 
-template <int VEC>
+// COLSUM: also accumulate the column sums of gx (the bias gradient of the convolution in front of the batch norm, which
+// otherwise re-reads gx in its own b2s_colsum launch): per-thread partial sums over the thread's rows, a shared-memory
+// tree over the row lanes of the block, one fp32 atomic per channel and block.  Needs every thread of the block active
+// and the same number of channel passes for all of them (the launcher checks: blockDim % tpr == 0, cv % tpr == 0).
+template <int VEC, bool COLSUM>
 __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ sums, int64_t n, const int* __restrict__ n_dev, int c, int act, int training,
-    float* __restrict__ gx, float* __restrict__ gx_tf32, int opm) {
+    float* __restrict__ gx, float* __restrict__ gx_tf32, int opm, float* __restrict__ colsum) {
+  __shared__ float red[COLSUM ? PW_THREADS * VEC : 1];
   n = b2s_rows(n, n_dev);
   const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
   const RowMap m = row_map<VEC>(c);
@@ -685,6 +690,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
     const V<VEC> mu = ldgv<VEC>(mean + ch), is = ldgv<VEC>(invstd + ch);
     const V<VEC> ga = ldparam<VEC>(gamma, ch, 1.f), be = ldparam<VEC>(beta, ch, 0.f);
     V<VEC> s0 = splat<VEC>(0.f), s1 = splat<VEC>(0.f);
+    V<VEC> cs = splat<VEC>(0.f);
     if (training) {
       s0 = ldgv<VEC>(sums + ch);
       s1 = ldgv<VEC>(sums + c + ch);
@@ -699,9 +705,27 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
         if (act == 1) t *= gelu_grad_f(xh * ga.v[j] + be.v[j]);
         if (training) t = t - s0.v[j] * inv_n - xh * s1.v[j] * inv_n;
         g.v[j] = t * ga.v[j] * is.v[j];
+        if (COLSUM) cs.v[j] += g.v[j];
       }
       stv<VEC>(gx + r * c + ch, g);
       if (gx_tf32) st_operand<VEC>(gx_tf32, r, c, ch, g, opm);
+    }
+    if (COLSUM) {
+      __syncthreads();                     // the previous channel pass has read its sums
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red[threadIdx.x * VEC + j] = cs.v[j];
+      __syncthreads();
+      for (int sft = m.rpb >> 1; sft > 0; sft >>= 1) {   // rpb is a power of two here
+        if (m.tr < sft) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) red[threadIdx.x * VEC + j] += red[(threadIdx.x + sft * m.tpr) * VEC + j];
+        }
+        __syncthreads();
+      }
+      if (m.tr == 0) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) atomicAdd(&colsum[ch + j], red[threadIdx.x * VEC + j]);
+      }
     }
   }
 }
@@ -1286,6 +1310,23 @@ extern "C" int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev,
   return B2S_OK;
 }
 
+// column sums and sums of squares of x accumulated into col_stats (no finalisation): the fallback of the statistics a
+// convolution epilogue accumulates (split-K launches, SIMT path)
+void b2s_launch_col_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, double* col_stats, cudaStream_t st) {
+  if (n <= 0) return;
+  launch_colreduce<1, double>(x, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c, 0, col_stats, st);
+}
+
+extern "C" int32_t b2s_bn_finalize(const double* col_stats, int64_t n, const int32_t* n_dev, int32_t c, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* mean,
+                                   float* invstd, b2s_stream_t stream) {
+  B2S_CHECK_ARG(n > 0 && c > 0 && col_stats && mean && invstd, "bad arguments");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(col_stats, n, n_dev, c, eps, momentum, running_mean,
+                                                                    running_var, mean, invstd);
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
+
 extern "C" int32_t b2s_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma,
                                 const float* beta, int64_t n, const int32_t* n_dev, int32_t c, int32_t act, float* y,
                                 float* y_tf32, b2s_stream_t stream) {
@@ -1320,17 +1361,32 @@ extern "C" int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const floa
 extern "C" int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd,
                                     const float* gamma, const float* beta, const float* sums, int64_t n,
                                     const int32_t* n_dev, int32_t c, int32_t act, int32_t training, float* gx,
-                                    float* gx_tf32, b2s_stream_t stream) {
+                                    float* gx_tf32, float* gx_colsum, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && (act == 0 || act == 1), "bad arguments");
+  cudaStream_t st = as_stream(stream);
+  if (gx_colsum) B2S_CUDA(cudaMemsetAsync(gx_colsum, 0, c * sizeof(float), st));
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(gy && x && mean && invstd && gx && (sums || !training), "null pointer");
-  cudaStream_t st = as_stream(stream);
-  if (vec_of(c, gy, x, gx, mean) == 4 && vec_of(c, invstd, gamma, beta, sums) == 4 && vec_of(c, gx_tf32) == 4)
-    bn_bwd_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(gy, x, mean, invstd, gamma, beta, sums, n,
-                                                                      n_dev, c, act, training, gx, gx_tf32, operand_mode(c));
-  else
-    bn_bwd_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(gy, x, mean, invstd, gamma, beta, sums, n,
-                                                                      n_dev, c, act, training, gx, gx_tf32, operand_mode(c));
+  bool colsum_done = false;
+  if (vec_of(c, gy, x, gx, mean) == 4 && vec_of(c, invstd, gamma, beta, sums) == 4 && vec_of(c, gx_tf32) == 4) {
+    const int cv = c / 4, tpr = cv < PW_THREADS ? cv : PW_THREADS;
+    const int rpb = PW_THREADS / tpr;
+    // the fused column sums need all threads active, equal channel passes and a power-of-two tree over the row lanes
+    if (gx_colsum && PW_THREADS % tpr == 0 && cv % tpr == 0 && (rpb & (rpb - 1)) == 0 &&
+        (reinterpret_cast<uintptr_t>(gx_colsum) & 3) == 0) {
+      bn_bwd_apply_kernel<4, true><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(
+          gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), gx_colsum);
+      colsum_done = true;
+    } else {
+      bn_bwd_apply_kernel<4, false><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(
+          gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), nullptr);
+    }
+  } else {
+    bn_bwd_apply_kernel<1, false><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(
+        gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), nullptr);
+  }
+  if (gx_colsum && !colsum_done)       // shapes the fused form does not cover: the separate column reduction
+    launch_colreduce<0, float>(gx, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c, 0, gx_colsum, st);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

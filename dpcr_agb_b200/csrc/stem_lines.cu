@@ -23,6 +23,8 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 
+void b2s_launch_col_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, double* col_stats, cudaStream_t st);
+
 namespace {
 
 using namespace tc;
@@ -302,7 +304,8 @@ template <int SB, int DEPTH>
 __global__ void __launch_bounds__(LT_THREADS, 1)
     conv_lines_fwd_tmem_kernel(const uint4* __restrict__ x4, const uint32_t* __restrict__ wimg,
                                const float* __restrict__ bias, const uint32_t* __restrict__ lines, int64_t n_out,
-                               const int* __restrict__ n_out_dev, int c_out, int nlines, float* __restrict__ y) {
+                               const int* __restrict__ n_out_dev, int c_out, int nlines, float* __restrict__ y,
+                               double* __restrict__ col_stats) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
   const int64_t m0 = (int64_t)blockIdx.x * 256;
@@ -396,6 +399,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
       }
+      if (col_stats) {     // batch-norm statistics of the output, accumulated while the tile is in registers
+        float r[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          r[e] = orow < n_out ? __uint_as_float(v[e]) + (bias ? __ldg(&bias[n0 + c0 + e]) : 0.f) : 0.f;
+        epilogue_col_stats(r, lane, reinterpret_cast<float2*>(smem + L::B_OFF) + warp * LF_BN + c0);
+      }
       if (orow < n_out) {
         float* dst = y + orow * c_out + n0 + c0;
 #pragma unroll
@@ -407,6 +417,20 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
           r.w = __uint_as_float(v[e + 3]) + (bias ? __ldg(&bias[n0 + c0 + e + 3]) : 0.f);
           *reinterpret_cast<float4*>(dst + e) = r;
         }
+      }
+    }
+    if (col_stats) {       // the eight epilogue warps (two row tiles) combine: one fp64 atomic pair per column
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float2* red = reinterpret_cast<const float2*>(smem + L::B_OFF);
+      if (tid < LF_BN) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) {
+          s1 += red[wq * LF_BN + tid].x;
+          s2 += red[wq * LF_BN + tid].y;
+        }
+        atomicAdd(&col_stats[n0 + tid], (double)s1);
+        atomicAdd(&col_stats[c_out + n0 + tid], (double)s2);
       }
     }
     tc_fence_before();
@@ -695,8 +719,10 @@ extern "C" int64_t b2s_conv_lines_workspace_bytes(int64_t n_in, int32_t c_in, in
 extern "C" int32_t b2s_conv_lines_fwd(const float* x, const float* w, const float* bias, const uint32_t* lines,
                                       int64_t n_in, int64_t n_out, const int32_t* n_out_dev, int32_t c_in,
                                       int32_t c_out, const int32_t* ks, float* y, void* workspace,
-                                      int64_t workspace_bytes, b2s_stream_t stream) {
+                                      int64_t workspace_bytes, double* col_stats, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && ks, "bad sizes");
+  if (col_stats && c_out > 0)
+    B2S_CUDA(cudaMemsetAsync(col_stats, 0, (2 * (size_t)c_out + 1) * sizeof(double), as_stream(stream)));
   if (!b2s_conv_lines_supported(c_in, c_out, ks)) {
     b2s_set_error("b2s_conv_lines_fwd: shape c_in=%d c_out=%d or operand mode not covered (see b2s_conv_lines_supported)",
                   c_in, c_out);
@@ -716,6 +742,7 @@ extern "C" int32_t b2s_conv_lines_fwd(const float* x, const float* w, const floa
   lines_pad_rows_kernel<<<grid_for(n_in, 256), 256, 0, st>>>(x, n_in, c_in, x4);
   dim3 grid((unsigned)ceil_div64(n_out, 256), (unsigned)(c_out / LF_BN));
   static const int variant = lines_env("B2S_LINES_FWD", 0);
+  bool stats_fused = false;
 #define LF_LAUNCH(S, D)                                                                                         \
   do {                                                                                                          \
     auto kern = conv_lines_fwd_kernel<S, D>;                                                                    \
@@ -734,7 +761,9 @@ extern "C" int32_t b2s_conv_lines_fwd(const float* x, const float* w, const floa
       B2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LtSmem<SB>::DYN_BYTES)); \
       attr_set = true;                                                                                          \
     }                                                                                                           \
-    kern<<<grid, LT_THREADS, LtSmem<SB>::DYN_BYTES, st>>>(x4, img, bias, lines, n_out, n_out_dev, c_out, nlines, y); \
+    kern<<<grid, LT_THREADS, LtSmem<SB>::DYN_BYTES, st>>>(x4, img, bias, lines, n_out, n_out_dev, c_out, nlines, y, \
+                                                          col_stats);                                           \
+    stats_fused = true;                                                                                         \
   } while (0)
   if (variant == 1) LF_LAUNCH(3, 2);
   else if (variant == 2) LF_LAUNCH(4, 3);
@@ -744,6 +773,7 @@ extern "C" int32_t b2s_conv_lines_fwd(const float* x, const float* w, const floa
   else LT_LAUNCH(6, 3);
 #undef LF_LAUNCH
 #undef LT_LAUNCH
+  if (col_stats && !stats_fused) b2s_launch_col_stats(y, n_out, n_out_dev, c_out, col_stats, st);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

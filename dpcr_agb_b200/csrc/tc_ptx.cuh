@@ -216,6 +216,35 @@ __device__ __forceinline__ void split_bf16x3(float v, uint32_t& h, uint32_t& m, 
   l = bf16_rn_bits((v - __uint_as_float(h << 16)) - __uint_as_float(m << 16));
 }
 
+// Column sums of a 32 x 32 register tile held one row per lane: on return lane j holds the total of v[j] over the 32
+// lanes (butterfly transpose-reduce: 31 shuffles instead of 32 x 5).  v is clobbered.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// Batch-norm statistics in a convolution epilogue: a warp holds 32 rows x 32 columns of final output values (lane =
+// row, invalid rows zeroed); per column the sum and the sum of squares over the warp's rows go to `red[warp][col]`.
+__device__ __forceinline__ void epilogue_col_stats(const float (&r)[32], int lane, float2* red_row) {
+  float f[32], q[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    f[j] = r[j];
+    q[j] = r[j] * r[j];
+  }
+  const float s1 = warp_transpose_sum(f, lane), s2 = warp_transpose_sum(q, lane);
+  red_row[lane] = make_float2(s1, s2);
+}
+
 // byte offset of 16-byte chunk `chunk` (0..7) of 128-byte row `row` inside a 128B-swizzled tile
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {
   return row * 128u + ((chunk ^ (row & 7u)) << 4);

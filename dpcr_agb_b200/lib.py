@@ -44,11 +44,11 @@ SIGNATURES = {
     "b2s_conv_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),
     "b2s_round_tf32": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_conv_gather_gemm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32,
-                                    _vp]),
+                                    _vp, _vp]),
     "b2s_conv_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
     "b2s_conv_lines_supported": (_i32, [_i32, _i32, _vp]),
     "b2s_conv_lines_workspace_bytes": (_i64, [_i64, _i32, _i32, _vp]),
-    "b2s_conv_lines_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "b2s_conv_lines_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
     "b2s_conv_lines_wgrad": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "b2s_parity_plan_rows": (_i64, [_i64]),
     "b2s_parity_plan": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -67,9 +67,10 @@ SIGNATURES = {
     "b2s_bcast_mul_fwd": (_i32, [_vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp]),
     "b2s_bcast_mul_bwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2s_bn_stats": (_i32, [_vp, _i64, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2s_bn_finalize": (_i32, [_vp, _i64, _vp, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "b2s_bn_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2s_bn_bwd_reduce": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
-    "b2s_bn_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b2s_bn_bwd_apply": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b2s_gelu_fwd": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_gelu_bwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_se_gate_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -200,6 +200,13 @@ B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_
  *                        wgrad, grad_out by dgrad and wgrad) is rounded once by the caller and flagged pre-rounded,
  *                        otherwise the entry points round internally into `workspace`.
  * b2s_conv_workspace_bytes: prerounded != 0 sizes the workspace for calls that set the pre-rounded flags.
+ * col_stats (b2s_conv_gather_gemm, b2s_conv_lines_fwd; nullable): double [2 c_out + 1] -- the workspace layout of
+ *     b2s_bn_stats.  The call zeroes it and leaves the column sums of y in [0, c_out) and the column sums of y^2 in
+ *     [c_out, 2 c_out): the statistics of the batch norm that follows every convolution of the reference's networks
+ *     (ME/SENet.py:49-52, resnet_block.py:48-55), accumulated in the convolution's epilogue while the output tile is in
+ *     registers (one fp64 atomic pair per column and CTA) instead of re-reading y; launches whose tiles are partial
+ *     sums (split-K) and the SIMT path run the column reduction afterwards.  b2s_bn_finalize turns them into
+ *     mean / invstd / running statistics.
  */
 B2S_API int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3,
                                          int32_t prerounded);
@@ -207,7 +214,7 @@ B2S_API int32_t b2s_round_tf32(const float* x, int64_t n, const int32_t* n_dev, 
 B2S_API int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                                      int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3,
                                      int32_t w_layout, float* y, void* workspace, int64_t workspace_bytes,
-                                     int32_t impl, b2s_stream_t stream);
+                                     int32_t impl, double* col_stats, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
                                const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw,
                                void* workspace, int64_t workspace_bytes, int32_t impl, int32_t flags,
@@ -226,7 +233,7 @@ B2S_API int64_t b2s_conv_lines_workspace_bytes(int64_t n_in, int32_t c_in, int32
 B2S_API int32_t b2s_conv_lines_fwd(const float* x, const float* w, const float* bias, const uint32_t* lines,
                                    int64_t n_in, int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out,
                                    const int32_t* kernel_size_host, float* y, void* workspace, int64_t workspace_bytes,
-                                   b2s_stream_t stream);
+                                   double* col_stats, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_lines_wgrad(const float* x, const float* gy, const uint32_t* lines, int64_t n_in,
                                      int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out,
                                      const int32_t* kernel_size_host, float* gw, void* workspace,
@@ -315,10 +322,16 @@ B2S_API int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float* y
  *                 the result rounded to TF32 (round-to-nearest), i.e. the operand form b2s_round_tf32 would produce
  *                 for the convolution that consumes it -- the separate rounding pass disappears.  Where the plain
  *                 result has no other consumer (bn_apply, add_gelu_fwd) `y` may be NULL and only the twin is written.
+ * gx_colsum      : nullable float [c] output of bn_bwd_apply = column sums of gx, i.e. the bias gradient of the
+ *                 convolution in front of the batch norm (ME/SENet.py:49-52, resnet_block.py:48-55: conv -> norm),
+ *                 accumulated while gx is written instead of re-reading gx in a b2s_colsum launch.
  */
 B2S_API int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float eps, float momentum,
                              float* running_mean, float* running_var, double* stats_ws, float* mean, float* invstd,
                              b2s_stream_t stream);
+B2S_API int32_t b2s_bn_finalize(const double* col_stats, int64_t n, const int32_t* n_dev, int32_t c, float eps,
+                                float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                                b2s_stream_t stream);
 B2S_API int32_t b2s_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
                              int64_t n, const int32_t* n_dev, int32_t c, int32_t act, float* y, float* y_tf32,
                              b2s_stream_t stream);
@@ -327,7 +340,8 @@ B2S_API int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const float* 
                                   int32_t act, double* stats_ws, float* sums, b2s_stream_t stream);
 B2S_API int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd, const float* gamma,
                                  const float* beta, const float* sums, int64_t n, const int32_t* n_dev, int32_t c,
-                                 int32_t act, int32_t training, float* gx, float* gx_tf32, b2s_stream_t stream);
+                                 int32_t act, int32_t training, float* gx, float* gx_tf32, float* gx_colsum,
+                                 b2s_stream_t stream);
 /* elementwise over n rows of c floats */
 B2S_API int32_t b2s_gelu_fwd(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y, b2s_stream_t stream);
 /* sum = a + b, y = gelu(sum): the residual join out = act(drop_path(out) + residual); backward = gelu_bwd(gy, sum)

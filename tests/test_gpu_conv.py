@@ -169,9 +169,9 @@ def test_conv_rejects_bad_arguments(cuda):
     w = torch.zeros((27, 8, 8), device=cuda)
     y = torch.zeros((4, 8), device=cuda)
     with pytest.raises(L.B2SError):   # nbr may be null only for k3 == 1
-        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, None, 8, 8, 27, 0, y, None, 0, 1)
+        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, None, 8, 8, 27, 0, y, None, 0, 1, None)
     with pytest.raises(L.B2SError):   # tcgen05 kernel does not cover c_out = 8
-        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, None, 8, 8, 1, 0, y, None, 0, 2)
+        L.call("b2s_conv_gather_gemm", x, w, None, None, 4, 4, None, 8, 8, 1, 0, y, None, 0, 2, None)
 
 
 @pytest.mark.parametrize("n,cin,cout,K,strided", [
@@ -267,3 +267,37 @@ def test_conv_m256_tiles(cuda, n, cin, cout):
         L.set_tuning("tc_m256", -1)
     util.assert_close(got, ref.detach(), tol=TF32_MODEL_TOL, what="M=256 forward vs tf32 model")
     util.assert_close(gx, x32.grad, tol=TF32_MODEL_TOL, what="M=256 dgrad vs tf32 model")
+
+
+@pytest.mark.parametrize("n,cin,cout,K", [
+    (3000, 64, 64, 3),        # M = 128 kernel, 64-wide tiles
+    (3000, 64, 128, 3),       # M = 256 kernel (two row tiles per CTA)
+    (200, 128, 256, 3),       # few row tiles: split-K launch -> the statistics come from the fallback reduction
+    (1300, 64, 256, 1),       # K = 1 through a table
+])
+def test_conv_epilogue_batch_norm_statistics(cuda, n, cin, cout, K):
+    """``col_stats`` of b2s_conv_gather_gemm: column sums and sums of squares of the output (bias included, rows beyond
+    the live count excluded), whichever way the launch produces them -- the input of b2s_bn_finalize."""
+    c, out, nbr = _maps(n, K=K, seed=9)
+    rng = np.random.default_rng(4)
+    x = torch.from_numpy(rng.standard_normal((c.shape[0], cin)).astype(np.float32)).to(cuda)
+    w = torch.from_numpy((rng.standard_normal((K ** 3, cin, cout)) * 0.05).astype(np.float32)).to(cuda)
+    b = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).to(cuda)
+    ng = torch.from_numpy(nbr).to(cuda)
+    for live in (None, n - 77):
+        stats = torch.full((2 * cout + 1,), 123.0, dtype=torch.float64, device=cuda)
+        n_dev = None if live is None else torch.tensor([live], dtype=torch.int32, device=cuda)
+        y = Fn.gather_gemm(x, w, b, ng, n, n, cin, cout, K ** 3, 0, impl=TC, n_out_dev=n_dev, col_stats=stats)
+        rows = n if live is None else live
+        yd = y[:rows].double()
+        s1, s2 = yd.sum(0), (yd * yd).sum(0)
+        assert (stats[:cout] - s1).abs().max().item() <= 1e-5 * yd.abs().sum(0).max().item()
+        assert (stats[cout:2 * cout] - s2).abs().max().item() <= 1e-5 * s2.max().item()
+        # ... and b2s_bn_finalize turns them into what b2s_bn_stats computes from y itself
+        mean, invstd = torch.empty(cout, device=cuda), torch.empty(cout, device=cuda)
+        mean2, invstd2 = torch.empty(cout, device=cuda), torch.empty(cout, device=cuda)
+        L.call("b2s_bn_finalize", stats, n, n_dev, cout, 1e-5, 0.1, None, None, mean, invstd)
+        ws = torch.empty(2 * cout + 1, dtype=torch.float64, device=cuda)
+        L.call("b2s_bn_stats", y, n, n_dev, cout, 1e-5, 0.1, None, None, ws, mean2, invstd2)
+        util.assert_close(mean, mean2, tol=1e-6, what="fused mean")
+        util.assert_close(invstd, invstd2, tol=1e-5, what="fused invstd")

@@ -54,10 +54,8 @@ def _worker(rank, world, port, out):
         trainer.broadcast_parameters()
         model.eval()
         gs = GridSampling3D(0.02)
-        per = PLOTS // world
-        mine = train.shard_plots([N_POINTS] * PLOTS, rank, world)
-        assert mine == list(range(rank * per, (rank + 1) * per))       # equal weights: contiguous deal
-        loss_r = _grads(trainer, ME, gs, plots.synth_batch(CFG, mine[0], per, n_points=N_POINTS), dev, per)
+        per = PLOTS // world                                           # rank r owns plots [r * per, (r + 1) * per)
+        loss_r = _grads(trainer, ME, gs, plots.synth_batch(CFG, rank * per, per, n_points=N_POINTS), dev, per)
         trainer.exchange_gradients()                                   # NCCL sum over the ranks
         mean_grad = (trainer.opt.flat_grad * trainer.opt.grad_scale).clone()   # the 1/world the optimiser kernel applies
         losses = [None] * world
@@ -67,6 +65,9 @@ def _worker(rank, world, port, out):
             joint = trainer.opt.flat_grad
             err = ((mean_grad - joint).abs().max() / joint.abs().max()).item()
             out.put((err, float(np.mean(losses)), loss_j, float(joint.abs().max())))
+    except Exception as e:                                             # fail fast: the parent must not wait for a timeout
+        out.put(("error", f"rank {rank}: {type(e).__name__}: {e}", 0.0, 0.0))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -80,7 +81,13 @@ def test_two_rank_gradients_equal_joint_batch_gradients():
     procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
-    err, loss_mean, loss_joint, gmax = out.get(timeout=600)
+    err, loss_mean, loss_joint, gmax = out.get(timeout=240)
+    if err == "error":
+        for p in procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
+        pytest.fail(str(loss_mean))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

@@ -184,4 +184,21 @@ def test_line_path_is_off_in_tf32_mode_and_for_wide_inputs(cuda):
     with pytest.raises(L.B2SError):
         ws = torch.empty(1 << 20, dtype=torch.uint8, device=cuda)
         L.call("b2s_conv_lines_fwd", vox["tensors"][0], torch.zeros(343, 3, 48, device=cuda), None, km.lines, km.n_in,
-               km.n_out, None, 3, 48, L.host_i32(7, 7, 7), torch.empty(km.n_out, 48, device=cuda), ws, 1 << 20)
+               km.n_out, None, 3, 48, L.host_i32(7, 7, 7), torch.empty(km.n_out, 48, device=cuda), ws, 1 << 20, None)
+
+
+def test_line_conv_epilogue_batch_norm_statistics(cuda):
+    """col_stats of b2s_conv_lines_fwd == column sums / sums of squares of its output over the live rows."""
+    L.set_tuning("precise", 1)
+    try:
+        vox = _voxels(cuda, 2, 3000, 0.02)
+        cm, km = _stem_map(cuda, vox, 7)
+        w, b, _ = _conv_inputs(vox, 64, 7)
+        stats = torch.full((129,), -5.0, dtype=torch.float64, device=cuda)
+        y = Fn.lines_fwd(vox["tensors"][0], torch.from_numpy(w).to(cuda), torch.from_numpy(b).to(cuda), km, 3, 64,
+                         col_stats=stats)
+        yd = y.double()
+        assert (stats[:64] - yd.sum(0)).abs().max().item() <= 1e-5 * yd.abs().sum(0).max().item()
+        assert (stats[64:128] - (yd * yd).sum(0)).abs().max().item() <= 1e-5 * (yd * yd).sum(0).max().item()
+    finally:
+        L.set_tuning("precise", -1)

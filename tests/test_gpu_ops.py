@@ -108,6 +108,29 @@ def test_batch_norm_fwd_bwd(cuda, act, training):
     util.assert_close(rvg, rvr, tol=1e-5, what="running var")
 
 
+@pytest.mark.parametrize("n,ch,training", [(5000, 64, False), (3001, 256, False), (777, 2048, False), (5000, 96, False),
+                                           (4000, 128, True)])
+def test_bn_backward_column_sums_of_gx(cuda, n, ch, training):
+    """b2s_bn_bwd_apply's gx_colsum output (the bias gradient of the convolution in front of the norm) equals the
+    column sums of gx: fused form (power-of-two channel counts), the internal fallback (96 channels), and the
+    training-mode case where the sums cancel to rounding noise.  ConvolutionFunction picks the attribute up."""
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy((rng.standard_normal((n, ch)) + 1.0).astype(np.float32)).to(cuda).requires_grad_()
+    w = torch.from_numpy(rng.standard_normal(ch).astype(np.float32)).to(cuda).requires_grad_()
+    b = torch.from_numpy(rng.standard_normal(ch).astype(np.float32)).to(cuda).requires_grad_()
+    rm, rv = torch.zeros(ch, device=cuda), torch.ones(ch, device=cuda)
+    y = Fn.BatchNormFunction.apply(x, w, b, rm, rv, training, 0.1, 1e-5, 1)
+    g = torch.from_numpy(rng.standard_normal((n, ch)).astype(np.float32)).to(cuda)
+    seen = {}
+    x.register_hook(lambda gx: seen.update(cs=getattr(gx, "_b2s_colsum", None), gx=gx))
+    y.backward(g)
+    cs, gx = seen["cs"], seen["gx"]
+    assert cs is not None and cs[1] == gx._version and cs[0].shape == (ch,)
+    ref = gx.double().sum(0)
+    scale = gx.double().abs().sum(0).max().item()               # the sums cancel in training mode: compare on this scale
+    assert (cs[0].double() - ref).abs().max().item() <= 2e-6 * scale
+
+
 def test_gelu_fwd_bwd(cuda):
     x = torch.linspace(-6, 6, 10001)
     g = torch.randn(10001, generator=torch.Generator().manual_seed(0))
