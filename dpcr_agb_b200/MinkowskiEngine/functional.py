@@ -63,16 +63,20 @@ def round_tf32(x, n_dev=None):
 # Nothing depends on the attribute surviving: without it the convolution rounds as before.
 TWINS = True
 FUSE_BIAS_GRAD = True   # bn_bwd_apply accumulates the column sums of its gx (the bias gradient of the conv in front)
-FUSE_BN_STATS = True    # a convolution's epilogue accumulates the column sums / sums of squares of its output: the
-#                         statistics of the batch norm behind it (C ABI: col_stats of b2s_conv_gather_gemm / _lines_fwd)
+# A convolution's epilogue can accumulate the column sums / sums of squares of its output -- the statistics of the batch
+# norm behind it (C ABI: col_stats of b2s_conv_gather_gemm / _lines_fwd).  OFF by default: measured on the B200 the
+# transposing reduction in the (not overlapped) epilogue adds 0.27 ms to the convolutions of an MSENet14 step while the
+# b2s_bn_stats passes it replaces cost 0.22 ms at 4 TB/s (profiles/r02_fusion_experiments.txt).
+FUSE_BN_STATS = os.environ.get("B2S_FUSE_BN_STATS", "0") == "1"
 
 
-def new_col_stats(c_out, device):
-    """Workspace for the fused batch-norm statistics of a convolution output, or None when they are not wanted (no
-    gradient mode: inference normalises with the running statistics)."""
-    if not (FUSE_BN_STATS and torch.is_grad_enabled()):
+def new_col_stats(n_out, c_out, device):
+    """Buffer for the batch-norm statistics a convolution accumulates over its output (partial rows, see
+    include/b200sparse.h ``col_stats``), or None when they are not wanted (no gradient mode: inference normalises with
+    the running statistics)."""
+    if not (FUSE_BN_STATS and torch.is_grad_enabled()) or n_out <= 0:
         return None
-    return torch.empty(2 * c_out + 1, dtype=torch.float64, device=device)
+    return torch.empty(L.query("b2s_conv_col_stats_elems", n_out, c_out), dtype=torch.float32, device=device)
 
 
 def attach_col_stats(y, stats):
@@ -83,7 +87,7 @@ def attach_col_stats(y, stats):
 
 def col_stats_of(x, c):
     st = getattr(x, "_b2s_colstats", None)
-    if st is not None and st[1] == x._version and st[0].numel() == 2 * c + 1:
+    if st is not None and st[1] == x._version and st[0].numel() == L.query("b2s_conv_col_stats_elems", x.shape[0], c):
         return st[0]
     return None
 
@@ -319,12 +323,12 @@ class ConvolutionFunction(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             bp = ctx.params[1]
             pre = getattr(gy, "_b2s_colsum", None)      # column sums already accumulated by the producer of gy
-            if pre is not None and pre[1] == gy._version and pre[0].numel() == c_out:
+            if pre is not None and pre[1] == gy._version and pre[0].dim() == 2 and pre[0].shape[1] == c_out:
                 if _direct(bp):
-                    bp.grad.view(-1).copy_(pre[0])
+                    torch.sum(pre[0], 0, keepdim=True, out=bp.grad.view(1, c_out))
                     gb = None
                 else:
-                    gb = pre[0].view(1, c_out).clone()
+                    gb = pre[0].sum(0, keepdim=True)
             else:
                 gb = bp.grad.view(1, c_out) if _direct(bp) else torch.empty((1, c_out), dtype=torch.float32,
                                                                              device=gy.device)
@@ -544,7 +548,9 @@ class BatchNormFunction(torch.autograd.Function):
             # the TF32 operand for its dgrad / wgrad alongside
             gxr = torch.empty_like(x) if (twins_on() and c > 4) else None
             # ... and its column sums are that convolution's bias gradient: accumulated here while gx is written
-            cs = torch.empty(c, dtype=torch.float32, device=dev) if FUSE_BIAS_GRAD else None
+            cs = None
+            if FUSE_BIAS_GRAD:          # one partial row per block of the launch; the consumer adds them
+                cs = torch.empty((L.query("b2s_bn_bwd_colsum_rows", n, c), c), dtype=torch.float32, device=dev)
             L.call("b2s_bn_bwd_apply", gy, x, mean, invstd, weight, bias, sums, n, ctx.nd, c, ctx.act,
                    1 if ctx.training else 0, gx, gxr, cs)
             if gxr is not None:

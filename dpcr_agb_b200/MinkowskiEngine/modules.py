@@ -106,13 +106,14 @@ class MinkowskiConvolution(MinkowskiModuleBase):
     def forward(self, input: SparseTensor, coordinates=None):
         cm = input.coordinate_manager
         # every convolution of the reference's networks feeds a batch norm: its statistics ride in the epilogue
-        stats = Fn.new_col_stats(self.out_channels, input.F.device) if self.training else None
         if self.use_mm:
+            stats = Fn.new_col_stats(input.F.shape[0], self.out_channels, input.F.device) if self.training else None
             out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, None, input.n_dev, stats)
             Fn.attach_col_stats(out, stats)
             return SparseTensor(out, coordinate_map_key=input.coordinate_map_key, coordinate_manager=cm)
         out_key = _out_key(input, self.stride)
         kmap = cm.kernel_map(input.coordinate_map_key, out_key, self.kernel_size, self.dilation)
+        stats = Fn.new_col_stats(kmap.n_out, self.out_channels, input.F.device) if self.training else None
         out = Fn.ConvolutionFunction.apply(input.F, self.kernel, self.bias, kmap, None, stats)
         Fn.attach_col_stats(out, stats)
         return SparseTensor(out, coordinate_map_key=out_key, coordinate_manager=cm)

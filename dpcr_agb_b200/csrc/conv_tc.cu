@@ -187,7 +187,7 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
     gather_gemm_tc_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
                           int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y,
-                          const PermArgs pa, int flags, double* __restrict__ col_stats) {
+                          const PermArgs pa, int flags, float* __restrict__ col_stats) {
   const int rot_on = flags & 1;
   const bool l1 = (flags & 2) != 0;                // gather through L1 (cp.async.ca) instead of L2 only (.cg)
   const bool precise = NB > 1 || (flags & 4) != 0;
@@ -453,9 +453,12 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
         }
       }
     }
-    if (col_stats) {       // the four epilogue warps combine their per-column sums: one fp64 atomic pair per column
+    if (col_stats) {       // the four epilogue warps combine their per-column sums into this row tile's partial row
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const float2* red = reinterpret_cast<const float2*>(smem + L::A_OFF);
+      float* part = col_stats + (int64_t)blockIdx.x * 2 * c_out;
+      if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)    // header behind the partial rows: rows per partial row
+        col_stats[((pitch + 127) / 128) * 2 * c_out] = (float)BM;
       for (int c = tid; c < BN; c += 128) {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -463,8 +466,8 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
           s1 += red[wq * BN + c].x;
           s2 += red[wq * BN + c].y;
         }
-        atomicAdd(&col_stats[n0 + c], (double)s1);
-        atomicAdd(&col_stats[c_out + n0 + c], (double)s2);
+        part[n0 + c] = s1;
+        part[c_out + n0 + c] = s2;
       }
     }
     tc_fence_before();
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
     gather_gemm_tc2_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                            const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
                            int c_out, int k3, int T_total, int it_per_split, float* __restrict__ y, int precise,
-                           double* __restrict__ col_stats) {
+                           float* __restrict__ col_stats) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
   if ((int64_t)blockIdx.x * (2 * BM) >= n_out) return;
@@ -709,6 +712,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
     if (col_stats) {       // all eight epilogue warps (two row tiles) combine their per-column sums
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float2* red = reinterpret_cast<const float2*>(smem + L::A_OFF);
+      float* part = col_stats + (int64_t)blockIdx.x * 2 * c_out;
+      if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) col_stats[((pitch + 127) / 128) * 2 * c_out] = (float)(2 * BM);
       for (int c = tid; c < BN; c += 256) {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -716,8 +721,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
           s1 += red[wq * BN + c].x;
           s2 += red[wq * BN + c].y;
         }
-        atomicAdd(&col_stats[n0 + c], (double)s1);
-        atomicAdd(&col_stats[c_out + n0 + c], (double)s2);
+        part[n0 + c] = s1;
+        part[c_out + n0 + c] = s2;
       }
     }
     tc_fence_before();
@@ -1042,8 +1047,8 @@ int tc_rot() {
 
 template <int BN, int STAGES, int LAG>
 int launch_tc2(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
-               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st, double* col_stats = nullptr,
-               bool* stats_fused = nullptr) {
+               int c_in, int c_out, int k3, int T, float* y, cudaStream_t st, float* col_stats = nullptr,
+               int* stats_rows = nullptr) {
   using L = SmemLayout2<BN, STAGES>;
   static_assert(LAG < STAGES, "producers run LAG stages ahead of their hand-over");
   auto kern = gather_gemm_tc2_kernel<BN, STAGES, LAG>;
@@ -1070,7 +1075,7 @@ int launch_tc2(const float* x, const float* wimg, const float* bias, const int* 
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, 2 * BM), (unsigned)(c_out / BN), (unsigned)splits);
   const bool fuse = col_stats != nullptr && splits == 1;      // split-K tiles are partial sums: no statistics there
-  if (stats_fused) *stats_fused = fuse;
+  if (stats_rows) *stats_rows = fuse ? 2 * BM : 0;            // rows per partial row of col_stats (0: not produced)
   kern<<<grid, TC2_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y,
                                                 b2s_precise(), fuse ? col_stats : nullptr);
   return 0;
@@ -1080,8 +1085,8 @@ int tc_m256() { return tc_knob(g_b2s_tc_m256, "B2S_TC_M256", 1); }
 
 template <int BN, int STAGES, bool SMALL, int LAG = 2, int NB = 1, int PW = 4>
 int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
-              int c_in, int c_out, int k3, int T, float* y, cudaStream_t st, double* col_stats = nullptr,
-              bool* stats_fused = nullptr) {
+              int c_in, int c_out, int k3, int T, float* y, cudaStream_t st, float* col_stats = nullptr,
+              int* stats_rows = nullptr) {
   using L = SmemLayout<BN, STAGES, NB>;
   static_assert(LAG < STAGES, "producers run LAG stages ahead of their hand-over");
   auto kern = gather_gemm_tc_kernel<BN, STAGES, SMALL, LAG, false, NB, PW>;
@@ -1111,7 +1116,7 @@ int launch_tc(const float* x, const float* wimg, const float* bias, const int* n
   if (splits > 1) cudaMemsetAsync(y, 0, (size_t)n_out * c_out * sizeof(float), st);
   dim3 grid((unsigned)ceil_div64(n_out, BM), (unsigned)(c_out / BN), (unsigned)splits);
   const bool fuse = col_stats != nullptr && splits == 1;      // split-K tiles are partial sums: no statistics there
-  if (stats_fused) *stats_fused = fuse;
+  if (stats_rows) *stats_rows = fuse ? BM : 0;
   kern<<<grid, (PW + 1) * 32, dyn, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, per, y, PermArgs{},
                                       (tc_rot() ? 1 : 0) | (tc_ca() ? 2 : 0) | (b2s_precise() ? 4 : 0),
                                       fuse ? col_stats : nullptr);
@@ -1152,10 +1157,10 @@ static void launch_prep_weights(const float* w, int c_in, int c_out, int k3, int
 
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                             int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
-                            void* workspace, int64_t workspace_bytes, cudaStream_t st, double* col_stats,
-                            bool* stats_fused) {
+                            void* workspace, int64_t workspace_bytes, cudaStream_t st, float* col_stats,
+                            int* stats_rows) {
   (void)workspace_bytes;
-  if (stats_fused) *stats_fused = false;
+  if (stats_rows) *stats_rows = 0;
   const bool small = c_in <= 4;
   const int T = iterations(c_in, k3);
   float* img = reinterpret_cast<float*>(workspace);
@@ -1195,21 +1200,21 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   // it can run (tests), 3 = 64- and 128-wide tiles
   const int m256 = tc_m256();
   if (m256 && n_out > BM && (bn == 128 || m256 == 2 || (m256 == 3 && bn == 64))) {
-    if (bn == 256) return launch_tc2<256, 3, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
-    if (bn == 128) return launch_tc2<128, 4, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
-    return launch_tc2<64, 5, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
+    if (bn == 256) return launch_tc2<256, 3, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_rows);
+    if (bn == 128) return launch_tc2<128, 4, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_rows);
+    return launch_tc2<64, 5, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_rows);
   }
-  if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
+  if (bn == 256) return launch_tc<256, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_rows);
   if (bn == 128) {
     if (variant == 1) return launch_tc<128, 3, false, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
     if (variant == 2) return launch_tc<128, 6, false, 4>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
     if (variant == 3) return launch_tc<128, 6, false, 5>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
-    return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
+    return launch_tc<128, 3, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_rows);
   }
   if (variant == 1) return launch_tc<64, 3, false, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   if (variant == 2) return launch_tc<64, 4, false, 3>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
   if (variant == 3) return launch_tc<64, 8, false, 6>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st);
-  return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_fused);
+  return launch_tc<64, 4, false>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, T, y, st, col_stats, stats_rows);
 }
 
 

@@ -80,10 +80,10 @@ bool b2s_conv_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_ou
 int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_in);
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                             int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
-                            void* workspace, int64_t workspace_bytes, cudaStream_t st, double* col_stats,
-                            bool* stats_fused);
-// pointwise.cu: col_stats[0:c] += column sums of x, col_stats[c:2c] += column sums of x^2 (fp64 atomics)
-void b2s_launch_col_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, double* col_stats, cudaStream_t st);
+                            void* workspace, int64_t workspace_bytes, cudaStream_t st, float* col_stats,
+                            int* stats_rows);
+// pointwise.cu: per-128-row partial column sums / sums of squares of x into col_stats, and the header of that buffer
+void b2s_launch_col_partials(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* col_stats, cudaStream_t st);
 bool b2s_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_out, bool has_map);
 int64_t b2s_wgrad_tc_workspace_bytes(int32_t c_in, int64_t n_in);
 int b2s_conv_wgrad_tc(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
@@ -113,11 +113,9 @@ extern "C" int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t
 extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr,
                                         int64_t n_in, int64_t n_out, const int32_t* n_out_dev, int32_t c_in,
                                         int32_t c_out, int32_t k3, int32_t w_layout, float* y, void* workspace,
-                                        int64_t workspace_bytes, int32_t impl, double* col_stats,
+                                        int64_t workspace_bytes, int32_t impl, float* col_stats,
                                         b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0, "bad sizes");
-  if (col_stats)   // [sum | sum of squares | ticket] as b2s_bn_stats lays its workspace out
-    B2S_CUDA(cudaMemsetAsync(col_stats, 0, (2 * (size_t)c_out + 1) * sizeof(double), as_stream(stream)));
   B2S_CHECK_ARG(w_layout >= 0 && w_layout <= 7, "w_layout must be in 0..7");
   B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
   B2S_CHECK_ARG(nbr || (k3 == 1 && n_in == n_out), "nbr may be null only for the identity map (k3 == 1)");
@@ -143,11 +141,11 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
       b2s_launch_round_tf32(x, n_in, nullptr, c_in, xr, st);
       xin = xr;
     }
-    bool fused = false;
+    int stats_rows = 0;
     if (b2s_conv_gather_gemm_tc(xin, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout & 3, y, workspace,
-                                workspace_bytes, st, col_stats, &fused))
+                                workspace_bytes, st, col_stats, &stats_rows))
       return B2S_ECUDA;
-    if (col_stats && !fused) b2s_launch_col_stats(y, n_out, n_out_dev, c_out, col_stats, st);
+    if (col_stats && stats_rows == 0) b2s_launch_col_partials(y, n_out, n_out_dev, c_out, col_stats, st);
   } else {
     if ((w_layout & 4) && b2s_precise()) {
       b2s_set_error("b2s_conv_gather_gemm: operand-form (split-bf16) input on the SIMT path (c_in=%d c_out=%d impl=%d)",
@@ -155,7 +153,7 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
       return B2S_EINVAL;
     }
     b2s_conv_gather_gemm_simt(x, w, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, w_layout & 3, y, st);
-    if (col_stats) b2s_launch_col_stats(y, n_out, n_out_dev, c_out, col_stats, st);
+    if (col_stats) b2s_launch_col_partials(y, n_out, n_out_dev, c_out, col_stats, st);
   }
   B2S_LAUNCH_CHECK();
   return B2S_OK;

@@ -672,8 +672,9 @@ __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __res
 
 // COLSUM: also accumulate the column sums of gx (the bias gradient of the convolution in front of the batch norm, which
 // otherwise re-reads gx in its own b2s_colsum launch): per-thread partial sums over the thread's rows, a shared-memory
-// tree over the row lanes of the block, one fp32 atomic per channel and block.  Needs every thread of the block active
-// and the same number of channel passes for all of them (the launcher checks: blockDim % tpr == 0, cv % tpr == 0).
+// tree over the row lanes of the block, one partial ROW per block (row blockIdx.x of colsum; the consumer adds the
+// rows -- ~1 000 same-address atomics per channel serialised in L2 and cost more than the pass they replaced).  Needs
+// every thread of the block active and the same number of channel passes for all of them (the launcher checks).
 template <int VEC, bool COLSUM>
 __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ mean,
@@ -722,9 +723,9 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
         }
         __syncthreads();
       }
-      if (m.tr == 0) {
+      if (m.tr == 0) {                     // this block's partial row (plain stores; the consumer adds the rows)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) atomicAdd(&colsum[ch + j], red[threadIdx.x * VEC + j]);
+        for (int j = 0; j < VEC; ++j) colsum[(int64_t)blockIdx.x * c + ch + j] = red[threadIdx.x * VEC + j];
       }
     }
   }
@@ -1310,19 +1311,95 @@ extern "C" int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev,
   return B2S_OK;
 }
 
-// column sums and sums of squares of x accumulated into col_stats (no finalisation): the fallback of the statistics a
-// convolution epilogue accumulates (split-K launches, SIMT path)
-void b2s_launch_col_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, double* col_stats, cudaStream_t st) {
-  if (n <= 0) return;
-  launch_colreduce<1, double>(x, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c, 0, col_stats, st);
+// ---- batch-norm statistics from a convolution's partial rows ----------------------------------------------------
+// col_stats (float): P_cap = ceil(n / 128) partial rows of [sums (c) | sums of squares (c)], then one header float =
+// the number of out rows a partial row covers (128 or 256: the row tile of the kernel that wrote them).  The
+// convolution epilogues write one partial row per row tile with plain stores -- no atomics: thousands of same-address
+// fp64 atomics serialise at ~20 ns each in L2, which cost more than the statistics pass they replaced.
+// Fallback producer (split-K launches, SIMT path): 128 rows per block, thread = channel.
+__global__ void __launch_bounds__(256) col_partials_kernel(const float* __restrict__ x, int64_t n,
+                                                           const int* __restrict__ n_dev, int c,
+                                                           float* __restrict__ col_stats) {
+  const int64_t pitch = n;
+  n = b2s_rows(n, n_dev);
+  if (blockIdx.x == 0 && threadIdx.x == 0) col_stats[((pitch + 127) / 128) * 2 * c] = 128.f;
+  const int64_t r0 = (int64_t)blockIdx.x * 128, r1 = min(r0 + 128, n);
+  if (r0 >= n) return;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const float v = x[r * c + ch];
+      s1 += v;
+      s2 += v * v;
+    }
+    col_stats[(int64_t)blockIdx.x * 2 * c + ch] = s1;
+    col_stats[(int64_t)blockIdx.x * 2 * c + c + ch] = s2;
+  }
 }
 
-extern "C" int32_t b2s_bn_finalize(const double* col_stats, int64_t n, const int32_t* n_dev, int32_t c, float eps,
+void b2s_launch_col_partials(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* col_stats,
+                             cudaStream_t st) {
+  if (n <= 0) return;
+  col_partials_kernel<<<(unsigned)ceil_div64(n, 128), 256, 0, st>>>(x, n, n_dev, c, col_stats);
+}
+
+// block = 32 channels x 32 partial-row lanes: fp64 sums over the live partial rows, then the finalisation of b2s_bn_stats
+__global__ void __launch_bounds__(1024) bn_finalize_partials_kernel(const float* __restrict__ col_stats, int64_t n,
+                                                                    const int* __restrict__ n_dev, int c, float eps,
+                                                                    float momentum, float* __restrict__ running_mean,
+                                                                    float* __restrict__ running_var,
+                                                                    float* __restrict__ mean,
+                                                                    float* __restrict__ invstd) {
+  __shared__ double sh[2][32][33];
+  const int64_t pitch = n;
+  n = b2s_rows(n, n_dev);
+  const int lane_c = threadIdx.x & 31, lane_p = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane_c;
+  int rpt = (int)col_stats[((pitch + 127) / 128) * 2 * c];
+  if (rpt <= 0) rpt = 128;
+  const int64_t P = (n + rpt - 1) / rpt;
+  double s1 = 0.0, s2 = 0.0;
+  if (ch < c) {
+#pragma unroll 4
+    for (int64_t p = lane_p; p < P; p += 32) {
+      s1 += (double)__ldg(&col_stats[p * 2 * c + ch]);
+      s2 += (double)__ldg(&col_stats[p * 2 * c + c + ch]);
+    }
+  }
+  sh[0][lane_p][lane_c] = s1;
+  sh[1][lane_p][lane_c] = s2;
+  __syncthreads();
+  if (lane_p == 0 && ch < c) {
+#pragma unroll
+    for (int j = 1; j < 32; ++j) {
+      s1 += sh[0][j][lane_c];
+      s2 += sh[1][j][lane_c];
+    }
+    const double dn = n > 0 ? (double)n : 1.0;
+    const double m = s1 / dn;
+    double var = s2 / dn - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[ch] = (float)m;
+    invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+    if (running_var) {
+      const double unb = n > 1 ? var * dn / (dn - 1.0) : var;
+      running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unb;
+    }
+  }
+}
+
+extern "C" int64_t b2s_conv_col_stats_elems(int64_t n_out, int32_t c_out) {
+  if (n_out < 0 || c_out <= 0) return -1;
+  return ceil_div64(n_out > 0 ? n_out : 1, 128) * 2 * c_out + 4;
+}
+
+extern "C" int32_t b2s_bn_finalize(const float* col_stats, int64_t n, const int32_t* n_dev, int32_t c, float eps,
                                    float momentum, float* running_mean, float* running_var, float* mean,
                                    float* invstd, b2s_stream_t stream) {
   B2S_CHECK_ARG(n > 0 && c > 0 && col_stats && mean && invstd, "bad arguments");
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(col_stats, n, n_dev, c, eps, momentum, running_mean,
-                                                                    running_var, mean, invstd);
+  bn_finalize_partials_kernel<<<(c + 31) / 32, 1024, 0, as_stream(stream)>>>(col_stats, n, n_dev, c, eps, momentum,
+                                                                            running_mean, running_var, mean, invstd);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -1358,14 +1435,23 @@ extern "C" int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const floa
   return B2S_OK;
 }
 
+// rows of the gx_colsum output of b2s_bn_bwd_apply: one partial row per block of its launch
+extern "C" int64_t b2s_bn_bwd_colsum_rows(int64_t n, int32_t c) {
+  if (n < 0 || c <= 0) return -1;
+  return c % 4 == 0 ? rows_grid(n > 0 ? n : 1, c, 4) : 1;
+}
+
 extern "C" int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd,
                                     const float* gamma, const float* beta, const float* sums, int64_t n,
                                     const int32_t* n_dev, int32_t c, int32_t act, int32_t training, float* gx,
                                     float* gx_tf32, float* gx_colsum, b2s_stream_t stream) {
   B2S_CHECK_ARG(n >= 0 && c > 0 && (act == 0 || act == 1), "bad arguments");
   cudaStream_t st = as_stream(stream);
-  if (gx_colsum) B2S_CUDA(cudaMemsetAsync(gx_colsum, 0, c * sizeof(float), st));
-  if (n == 0) return B2S_OK;
+  const int64_t cs_rows = gx_colsum ? b2s_bn_bwd_colsum_rows(n, c) : 0;
+  if (n == 0) {
+    if (gx_colsum) B2S_CUDA(cudaMemsetAsync(gx_colsum, 0, (size_t)cs_rows * c * sizeof(float), st));
+    return B2S_OK;
+  }
   B2S_CHECK_ARG(gy && x && mean && invstd && gx && (sums || !training), "null pointer");
   bool colsum_done = false;
   if (vec_of(c, gy, x, gx, mean) == 4 && vec_of(c, invstd, gamma, beta, sums) == 4 && vec_of(c, gx_tf32) == 4) {
@@ -1385,8 +1471,10 @@ extern "C" int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float
     bn_bwd_apply_kernel<1, false><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(
         gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), nullptr);
   }
-  if (gx_colsum && !colsum_done)       // shapes the fused form does not cover: the separate column reduction
+  if (gx_colsum && !colsum_done) {     // shapes the fused form does not cover: the separate column reduction into row 0
+    B2S_CUDA(cudaMemsetAsync(gx_colsum, 0, (size_t)cs_rows * c * sizeof(float), st));
     launch_colreduce<0, float>(gx, nullptr, nullptr, nullptr, nullptr, nullptr, n, n_dev, c, 0, gx_colsum, st);
+  }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -23,7 +23,7 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 
-void b2s_launch_col_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, double* col_stats, cudaStream_t st);
+void b2s_launch_col_partials(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* col_stats, cudaStream_t st);
 
 namespace {
 
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
     conv_lines_fwd_tmem_kernel(const uint4* __restrict__ x4, const uint32_t* __restrict__ wimg,
                                const float* __restrict__ bias, const uint32_t* __restrict__ lines, int64_t n_out,
                                const int* __restrict__ n_out_dev, int c_out, int nlines, float* __restrict__ y,
-                               double* __restrict__ col_stats) {
+                               float* __restrict__ col_stats) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
   const int64_t m0 = (int64_t)blockIdx.x * 256;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         }
       }
     }
-    if (col_stats) {       // the eight epilogue warps (two row tiles) combine: one fp64 atomic pair per column
+    if (col_stats) {       // the eight epilogue warps (two row tiles) combine their per-column sums
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const float2* red = reinterpret_cast<const float2*>(smem + L::B_OFF);
       if (tid < LF_BN) {
@@ -429,8 +429,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
           s1 += red[wq * LF_BN + tid].x;
           s2 += red[wq * LF_BN + tid].y;
         }
-        atomicAdd(&col_stats[n0 + tid], (double)s1);
-        atomicAdd(&col_stats[c_out + n0 + tid], (double)s2);
+        float* part = col_stats + (int64_t)blockIdx.x * 2 * c_out;     // this 256-row tile's partial row
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) col_stats[((pitch + 127) / 128) * 2 * c_out] = 256.f;
+        part[n0 + tid] = s1;
+        part[c_out + n0 + tid] = s2;
       }
     }
     tc_fence_before();
@@ -719,10 +721,8 @@ extern "C" int64_t b2s_conv_lines_workspace_bytes(int64_t n_in, int32_t c_in, in
 extern "C" int32_t b2s_conv_lines_fwd(const float* x, const float* w, const float* bias, const uint32_t* lines,
                                       int64_t n_in, int64_t n_out, const int32_t* n_out_dev, int32_t c_in,
                                       int32_t c_out, const int32_t* ks, float* y, void* workspace,
-                                      int64_t workspace_bytes, double* col_stats, b2s_stream_t stream) {
+                                      int64_t workspace_bytes, float* col_stats, b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && ks, "bad sizes");
-  if (col_stats && c_out > 0)
-    B2S_CUDA(cudaMemsetAsync(col_stats, 0, (2 * (size_t)c_out + 1) * sizeof(double), as_stream(stream)));
   if (!b2s_conv_lines_supported(c_in, c_out, ks)) {
     b2s_set_error("b2s_conv_lines_fwd: shape c_in=%d c_out=%d or operand mode not covered (see b2s_conv_lines_supported)",
                   c_in, c_out);
@@ -773,7 +773,7 @@ extern "C" int32_t b2s_conv_lines_fwd(const float* x, const float* w, const floa
   else LT_LAUNCH(6, 3);
 #undef LF_LAUNCH
 #undef LT_LAUNCH
-  if (col_stats && !stats_fused) b2s_launch_col_stats(y, n_out, n_out_dev, c_out, col_stats, st);
+  if (col_stats && !stats_fused) b2s_launch_col_partials(y, n_out, n_out_dev, c_out, col_stats, st);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

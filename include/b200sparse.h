@@ -200,21 +200,23 @@ B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_
  *                        wgrad, grad_out by dgrad and wgrad) is rounded once by the caller and flagged pre-rounded,
  *                        otherwise the entry points round internally into `workspace`.
  * b2s_conv_workspace_bytes: prerounded != 0 sizes the workspace for calls that set the pre-rounded flags.
- * col_stats (b2s_conv_gather_gemm, b2s_conv_lines_fwd; nullable): double [2 c_out + 1] -- the workspace layout of
- *     b2s_bn_stats.  The call zeroes it and leaves the column sums of y in [0, c_out) and the column sums of y^2 in
- *     [c_out, 2 c_out): the statistics of the batch norm that follows every convolution of the reference's networks
+ * col_stats (b2s_conv_gather_gemm, b2s_conv_lines_fwd; nullable): float [b2s_conv_col_stats_elems(n_out, c_out)] that
+ *     receives the statistics of the batch norm that follows every convolution of the reference's networks
  *     (ME/SENet.py:49-52, resnet_block.py:48-55), accumulated in the convolution's epilogue while the output tile is in
- *     registers (one fp64 atomic pair per column and CTA) instead of re-reading y; launches whose tiles are partial
- *     sums (split-K) and the SIMT path run the column reduction afterwards.  b2s_bn_finalize turns them into
- *     mean / invstd / running statistics.
+ *     registers instead of re-reading y: ceil(n_out / 128) partial rows [column sums | column sums of squares], one
+ *     per row tile, written with plain stores (thousands of same-address atomics serialise in L2: measured slower than
+ *     the pass they replace), then one header float = out rows per partial row.  Launches whose tiles are partial sums
+ *     (split-K) and the SIMT path fill the same layout with a reduction over y.  b2s_bn_finalize adds the live partial
+ *     rows in fp64 and produces mean / invstd / running statistics exactly as b2s_bn_stats does.
  */
 B2S_API int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3,
                                          int32_t prerounded);
+B2S_API int64_t b2s_conv_col_stats_elems(int64_t n_out, int32_t c_out);
 B2S_API int32_t b2s_round_tf32(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                                      int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3,
                                      int32_t w_layout, float* y, void* workspace, int64_t workspace_bytes,
-                                     int32_t impl, double* col_stats, b2s_stream_t stream);
+                                     int32_t impl, float* col_stats, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_wgrad(const float* x, const float* gy, const int32_t* nbr, int64_t n_in, int64_t n_out,
                                const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, float* gw,
                                void* workspace, int64_t workspace_bytes, int32_t impl, int32_t flags,
@@ -233,7 +235,7 @@ B2S_API int64_t b2s_conv_lines_workspace_bytes(int64_t n_in, int32_t c_in, int32
 B2S_API int32_t b2s_conv_lines_fwd(const float* x, const float* w, const float* bias, const uint32_t* lines,
                                    int64_t n_in, int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out,
                                    const int32_t* kernel_size_host, float* y, void* workspace, int64_t workspace_bytes,
-                                   double* col_stats, b2s_stream_t stream);
+                                   float* col_stats, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_lines_wgrad(const float* x, const float* gy, const uint32_t* lines, int64_t n_in,
                                      int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out,
                                      const int32_t* kernel_size_host, float* gw, void* workspace,
@@ -322,14 +324,15 @@ B2S_API int32_t b2s_bcast_mul_bwd(const float* g, const float* x, const float* y
  *                 the result rounded to TF32 (round-to-nearest), i.e. the operand form b2s_round_tf32 would produce
  *                 for the convolution that consumes it -- the separate rounding pass disappears.  Where the plain
  *                 result has no other consumer (bn_apply, add_gelu_fwd) `y` may be NULL and only the twin is written.
- * gx_colsum      : nullable float [c] output of bn_bwd_apply = column sums of gx, i.e. the bias gradient of the
- *                 convolution in front of the batch norm (ME/SENet.py:49-52, resnet_block.py:48-55: conv -> norm),
- *                 accumulated while gx is written instead of re-reading gx in a b2s_colsum launch.
+ * gx_colsum      : nullable float [b2s_bn_bwd_colsum_rows(n, c), c] output of bn_bwd_apply: partial rows whose sum over
+ *                 the rows is the column sum of gx, i.e. the bias gradient of the convolution in front of the batch
+ *                 norm (ME/SENet.py:49-52, resnet_block.py:48-55: conv -> norm), accumulated while gx is written
+ *                 instead of re-reading gx in a b2s_colsum launch (one row per block, plain stores, no atomics).
  */
 B2S_API int32_t b2s_bn_stats(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float eps, float momentum,
                              float* running_mean, float* running_var, double* stats_ws, float* mean, float* invstd,
                              b2s_stream_t stream);
-B2S_API int32_t b2s_bn_finalize(const double* col_stats, int64_t n, const int32_t* n_dev, int32_t c, float eps,
+B2S_API int32_t b2s_bn_finalize(const float* col_stats, int64_t n, const int32_t* n_dev, int32_t c, float eps,
                                 float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
                                 b2s_stream_t stream);
 B2S_API int32_t b2s_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
@@ -338,6 +341,7 @@ B2S_API int32_t b2s_bn_apply(const float* x, const float* mean, const float* inv
 B2S_API int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const float* mean, const float* invstd,
                                   const float* gamma, const float* beta, int64_t n, const int32_t* n_dev, int32_t c,
                                   int32_t act, double* stats_ws, float* sums, b2s_stream_t stream);
+B2S_API int64_t b2s_bn_bwd_colsum_rows(int64_t n, int32_t c);
 B2S_API int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd, const float* gamma,
                                  const float* beta, const float* sums, int64_t n, const int32_t* n_dev, int32_t c,
                                  int32_t act, int32_t training, float* gx, float* gx_tf32, float* gx_colsum,

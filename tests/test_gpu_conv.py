@@ -285,19 +285,28 @@ def test_conv_epilogue_batch_norm_statistics(cuda, n, cin, cout, K):
     b = torch.from_numpy(rng.standard_normal(cout).astype(np.float32)).to(cuda)
     ng = torch.from_numpy(nbr).to(cuda)
     for live in (None, n - 77):
-        stats = torch.full((2 * cout + 1,), 123.0, dtype=torch.float64, device=cuda)
+        elems = L.query("b2s_conv_col_stats_elems", n, cout)
+        stats = torch.full((elems,), 123.0, dtype=torch.float32, device=cuda)
         n_dev = None if live is None else torch.tensor([live], dtype=torch.int32, device=cuda)
         y = Fn.gather_gemm(x, w, b, ng, n, n, cin, cout, K ** 3, 0, impl=TC, n_out_dev=n_dev, col_stats=stats)
         rows = n if live is None else live
         yd = y[:rows].double()
+        rpt = int(stats[-4].item())                                  # header: out rows per partial row
+        assert rpt in (128, 256)
+        live_parts = -(-rows // rpt)
+        parts = stats[:live_parts * 2 * cout].double().view(live_parts, 2, cout)
         s1, s2 = yd.sum(0), (yd * yd).sum(0)
-        assert (stats[:cout] - s1).abs().max().item() <= 1e-5 * yd.abs().sum(0).max().item()
-        assert (stats[cout:2 * cout] - s2).abs().max().item() <= 1e-5 * s2.max().item()
+        assert (parts[:, 0].sum(0) - s1).abs().max().item() <= 1e-5 * yd.abs().sum(0).max().item()
+        assert (parts[:, 1].sum(0) - s2).abs().max().item() <= 1e-5 * s2.max().item()
         # ... and b2s_bn_finalize turns them into what b2s_bn_stats computes from y itself
         mean, invstd = torch.empty(cout, device=cuda), torch.empty(cout, device=cuda)
         mean2, invstd2 = torch.empty(cout, device=cuda), torch.empty(cout, device=cuda)
-        L.call("b2s_bn_finalize", stats, n, n_dev, cout, 1e-5, 0.1, None, None, mean, invstd)
+        rm, rv = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+        rm2, rv2 = torch.zeros(cout, device=cuda), torch.ones(cout, device=cuda)
+        L.call("b2s_bn_finalize", stats, n, n_dev, cout, 1e-5, 0.1, rm, rv, mean, invstd)
         ws = torch.empty(2 * cout + 1, dtype=torch.float64, device=cuda)
-        L.call("b2s_bn_stats", y, n, n_dev, cout, 1e-5, 0.1, None, None, ws, mean2, invstd2)
+        L.call("b2s_bn_stats", y, n, n_dev, cout, 1e-5, 0.1, rm2, rv2, ws, mean2, invstd2)
         util.assert_close(mean, mean2, tol=1e-6, what="fused mean")
         util.assert_close(invstd, invstd2, tol=1e-5, what="fused invstd")
+        util.assert_close(rm, rm2, tol=1e-6, what="fused running mean")
+        util.assert_close(rv, rv2, tol=1e-5, what="fused running var")

@@ -194,11 +194,14 @@ def test_line_conv_epilogue_batch_norm_statistics(cuda):
         vox = _voxels(cuda, 2, 3000, 0.02)
         cm, km = _stem_map(cuda, vox, 7)
         w, b, _ = _conv_inputs(vox, 64, 7)
-        stats = torch.full((129,), -5.0, dtype=torch.float64, device=cuda)
+        n = km.n_out
+        stats = torch.full((L.query("b2s_conv_col_stats_elems", n, 64),), -5.0, dtype=torch.float32, device=cuda)
         y = Fn.lines_fwd(vox["tensors"][0], torch.from_numpy(w).to(cuda), torch.from_numpy(b).to(cuda), km, 3, 64,
                          col_stats=stats)
         yd = y.double()
-        assert (stats[:64] - yd.sum(0)).abs().max().item() <= 1e-5 * yd.abs().sum(0).max().item()
-        assert (stats[64:128] - (yd * yd).sum(0)).abs().max().item() <= 1e-5 * (yd * yd).sum(0).max().item()
+        assert int(stats[-4].item()) == 256
+        parts = stats[:-(-n // 256) * 128].double().view(-1, 2, 64)
+        assert (parts[:, 0].sum(0) - yd.sum(0)).abs().max().item() <= 1e-5 * yd.abs().sum(0).max().item()
+        assert (parts[:, 1].sum(0) - (yd * yd).sum(0)).abs().max().item() <= 1e-5 * (yd * yd).sum(0).max().item()
     finally:
         L.set_tuning("precise", -1)
