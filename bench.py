@@ -326,9 +326,14 @@ def run_b200(args):
     barrier()
 
     # ---- timed region 1: inputs resident in HBM
+    ncu_range = os.environ.get("B2S_NCU_RANGE") == "1"     # tools/gpu_ncu.sh: profile exactly these replays
+    if ncu_range:
+        torch.cuda.profiler.start()
     clocks = ClockSampler(local)
     ms_total = timed(step_from_device, devb, args.steps)
     clk = clocks.stop()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
     calls = gstep.launches_per_step * args.steps

@@ -30,10 +30,10 @@ def main(raw, manifest_path, out_path, peaks_path=None):
     for r in rows[2:]:
         name = r[idx["Kernel Name"]]
         grid = r[idx["launch__grid_size"]] if "launch__grid_size" in idx else ""
-        if name.startswith("flat_kernel") and grid.replace(",", "") in ("1", "1.0"):
+        if "flat_kernel" in name and grid.replace(",", "").split(".")[0] == "1":
             cur = []
             groups.append(cur)
-        elif cur is not None:
+        elif cur is not None and "at::" not in name:      # torch's own kernels (statistics code of the driver script)
             cur.append(r)
     inst = man["instances"]
     if len(groups) == len(inst) + 1 and not groups[-1]:
