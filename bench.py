@@ -91,7 +91,8 @@ def workload(args, cpu_plots=None):
                        f"size {w['grid']} ({w['what']}); {step}",
            "plots_per_gpu": w["plots"], "points_per_plot": w["points"], "grid_size": w["grid"],
            "optimizer": "AdaBelief lr 5e-3 wd 1e-2 clip 100 (fused flat buffer)" if w["train"] else None,
-           "parallelism": f"dp{args.gpus}",
+           "parallelism": f"dp{args.gpus}" + ("" if args.gpus == 1 else
+                                              " (plots of every global batch dealt to the ranks by voxel count)"),
            "l2": "distinct batch every step; per-step working set (activations + maps, several GB) >> 126 MB L2"}
     if cpu_plots is not None:
         cfg["plots_per_step_cpu_arm"] = cpu_plots
@@ -247,8 +248,20 @@ def run_b200(args):
     nb = min(NUM_DISTINCT_BATCHES, args.steps + args.warmup)
     keys_in = ("pos", "feats", "batch", "perm", "target") if TRAIN else ("pos", "feats", "batch", "perm")
     host, devb = [], []
+    balance = None
     for i in range(nb):
-        b = plots.synth_batch(2, (rank * nb + i) * B, B, n_points=NPTS, canopy_max_m=w["canopy"])
+        if world == 1:
+            b = plots.synth_batch(2, i * B, B, n_points=NPTS, canopy_max_m=w["canopy"])
+        else:
+            # data-parallel step i: a global batch of world x B plots, dealt to the ranks by voxel count so that the
+            # per-rank work (and with it the max-over-ranks step time) stays within ~1 % (train.shard_plots);
+            # every rank computes the same deal from the same seeds
+            ids = list(range(i * world * B, (i + 1) * world * B))
+            weights = [plots.voxel_count(plots.synth_plot(2000 + p, NPTS, w["canopy"])[0], GRID) for p in ids]
+            mine = train.shard_plots(weights, rank, world)
+            loads = [sum(weights[j] for j in train.shard_plots(weights, r, world)) for r in range(world)]
+            balance = max(loads) / (sum(loads) / world) if balance is None else max(balance, max(loads) / (sum(loads) / world))
+            b = plots.synth_batch_from_ids(2, [ids[j] for j in mine], n_points=NPTS, canopy_max_m=w["canopy"])
         h = {k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in keys_in}
         host.append(h)
         devb.append({k: v.to(dev) for k, v in h.items()})
@@ -506,7 +519,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 4 if TRAIN else 8 * B, "ms_per_step": ms_e2e / args.steps},
             "last_result": last_out[0], "gpu_launches": calls, "gpu_launches_note": "C-ABI calls into libb200sparse.so recorded in the captured "
                                                           "step graph x steps (each launches 1-4 kernels of ours)",
-            "row_capacities": caps,
+            "row_capacities": caps, "rank_work_imbalance_max_over_mean": balance,
             "roofline": roofline, "roofline_wgrad": roofline_wgrad, "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu_baseline, "breakdown_ms_per_step": breakdown}
     print(json.dumps(line), flush=True)

@@ -324,11 +324,11 @@ class ConvolutionFunction(torch.autograd.Function):
             bp = ctx.params[1]
             pre = getattr(gy, "_b2s_colsum", None)      # column sums already accumulated by the producer of gy
             if pre is not None and pre[1] == gy._version and pre[0].dim() == 2 and pre[0].shape[1] == c_out:
+                gb = bp.grad.view(1, c_out) if _direct(bp) else torch.empty((1, c_out), dtype=torch.float32,
+                                                                             device=gy.device)
+                L.call("b2s_sum_rows", pre[0], pre[0].shape[0], c_out, gb)
                 if _direct(bp):
-                    torch.sum(pre[0], 0, keepdim=True, out=bp.grad.view(1, c_out))
                     gb = None
-                else:
-                    gb = pre[0].sum(0, keepdim=True)
             else:
                 gb = bp.grad.view(1, c_out) if _direct(bp) else torch.empty((1, c_out), dtype=torch.float32,
                                                                              device=gy.device)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "b2s_conv_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),
     "b2s_conv_col_stats_elems": (_i64, [_i64, _i32]),
     "b2s_bn_bwd_colsum_rows": (_i64, [_i64, _i32]),
+    "b2s_sum_rows": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "b2s_round_tf32": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_conv_gather_gemm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i32,
                                     _vp, _vp]),

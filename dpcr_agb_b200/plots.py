@@ -76,3 +76,27 @@ def synth_batch(cfg: int, first_plot: int, num_plots: int, n_points: int = 16000
         base += p.shape[0]
     return {"pos": np.concatenate(pos), "feats": np.concatenate(feats), "batch": np.concatenate(batch),
             "target": np.stack(target), "perm": np.concatenate(perm)}
+
+
+def synth_batch_from_ids(cfg: int, plot_ids, n_points: int = 16000, canopy_max_m: float = 40.0):
+    """Like :func:`synth_batch` for an arbitrary list of plot ids (seed of plot p is ``1000*cfg + p``): the batch a
+    data-parallel rank assembles from the plots ``train.shard_plots`` dealt to it."""
+    pos, feats, batch, target, perm = [], [], [], [], []
+    base = 0
+    for b, pid in enumerate(plot_ids):
+        seed = 1000 * cfg + int(pid)
+        p, f, t = synth_plot(seed, n_points, canopy_max_m)
+        pos.append(p)
+        feats.append(f)
+        batch.append(np.full(p.shape[0], b, np.int32))
+        target.append(t)
+        perm.append(np.random.default_rng(seed + 500_000).permutation(p.shape[0]).astype(np.int32) + base)
+        base += p.shape[0]
+    return {"pos": np.concatenate(pos), "feats": np.concatenate(feats), "batch": np.concatenate(batch),
+            "target": np.stack(target), "perm": np.concatenate(perm)}
+
+
+def voxel_count(pos: np.ndarray, grid: float) -> int:
+    """Number of occupied voxels of one plot at ``grid`` (the work estimate ``train.shard_plots`` balances ranks by)."""
+    q = np.rint(pos / np.float32(grid)).astype(np.int64)
+    return int(np.unique((q[:, 2] * 4096 + q[:, 1]) * 4096 + q[:, 0]).shape[0])

@@ -342,6 +342,8 @@ B2S_API int32_t b2s_bn_bwd_reduce(const float* gy, const float* x, const float* 
                                   const float* gamma, const float* beta, int64_t n, const int32_t* n_dev, int32_t c,
                                   int32_t act, double* stats_ws, float* sums, b2s_stream_t stream);
 B2S_API int64_t b2s_bn_bwd_colsum_rows(int64_t n, int32_t c);
+/* out[c] = sum over the rows of x [rows, c]: adds the partial rows of gx_colsum (the convolution's bias gradient) */
+B2S_API int32_t b2s_sum_rows(const float* x, int64_t rows, int32_t c, float* out, b2s_stream_t stream);
 B2S_API int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float* mean, const float* invstd, const float* gamma,
                                  const float* beta, const float* sums, int64_t n, const int32_t* n_dev, int32_t c,
                                  int32_t act, int32_t training, float* gx, float* gx_tf32, float* gx_colsum,
