@@ -46,6 +46,20 @@ def plan_capacities(gs: GridSampling3D, ME, model, batches, num_plots, bounds, m
     return {ts: max(align, -(-int(n * (1.0 + margin)) // align) * align) for ts, n in seen.items()}
 
 
+class _LossHandle:
+    """Result of ``GraphStep.step_async``: the loss of one step, readable once its device -> host copy has landed.
+    At most ``len(ring) - 1`` newer steps may be launched before ``result()`` is called (the slot is then reused)."""
+
+    __slots__ = ("buf", "event")
+
+    def __init__(self, buf, event):
+        self.buf, self.event = buf, event
+
+    def result(self) -> float:
+        self.event.synchronize()
+        return float(self.buf)
+
+
 class GraphStep:
     """Captured training step.  ``load(host_batch)`` + ``step()`` per batch; ``verify()`` (one host read) checks
     that no capacity was exceeded by the steps since the last call."""
@@ -83,6 +97,8 @@ class GraphStep:
         self.status = None          # int32 device tensor: live row counts / flags recorded during capture
         self.status_meta = []
         self.launches_per_step = 0  # C-ABI calls recorded into the graph (== kernels-of-ours launches, lower bound)
+        self._stage = None          # staging copies of the inputs for the overlapped host feed (prefetch)
+        self._loss_ring = None      # pinned slots for the asynchronous loss read-back (step_async)
 
     # ------------------------------------------------------------------ the step body (captured)
     def _forward_backward(self):
@@ -172,6 +188,47 @@ class GraphStep:
             src = host_batch[k]
             assert src.shape == dst.shape, f"{k}: {tuple(src.shape)} does not match the captured shape {tuple(dst.shape)}"
             dst.copy_(src, non_blocking=non_blocking)
+
+    # ------------------------------------------------------------------ overlapped input feed
+    def prefetch(self, host_batch):
+        """Start the host -> device copies of the NEXT step's batch (pinned host tensors) on a copy stream, into a
+        staging set of device buffers, while the current step computes; ``take_prefetched()`` then moves the staged
+        batch into the captured input buffers (a 16 MB device copy, ~5 us) at the start of the next step.  The copy
+        stream waits for the previous ``take_prefetched()`` before it overwrites the staging set."""
+        if self._stage is None:
+            self._stage = {k: torch.empty_like(v) for k, v in self.inp.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._staged, self._taken = torch.cuda.Event(), torch.cuda.Event()
+            self._taken.record()
+        self._copy_stream.wait_event(self._taken)
+        with torch.cuda.stream(self._copy_stream):
+            for k, dst in self._stage.items():
+                src = host_batch[k]
+                assert src.shape == dst.shape, f"{k}: {tuple(src.shape)} does not match the captured shape"
+                dst.copy_(src, non_blocking=True)
+            self._staged.record()
+
+    def take_prefetched(self):
+        """Make the current stream wait for the staged batch and copy it into the captured input buffers."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        for k, dst in self.inp.items():
+            dst.copy_(self._stage[k], non_blocking=True)
+        self._taken.record()
+
+    def step_async(self):
+        """``step()`` + an asynchronous device -> host copy of the loss into a pinned slot; returns a handle whose
+        ``result()`` blocks until THAT step's loss is on the host.  A loop that reads the previous step's handle after
+        launching the current step keeps the device busy while the host prepares the next launch."""
+        loss = self.step()
+        if self._loss_ring is None:
+            self._loss_ring = [(torch.zeros((), dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._loss_i = 0
+        buf, ev = self._loss_ring[self._loss_i]
+        self._loss_i = (self._loss_i + 1) % len(self._loss_ring)
+        buf.copy_(loss, non_blocking=True)
+        ev.record()
+        return _LossHandle(buf, ev)
 
     def step(self):
         """Replay the captured step on the data currently in the input buffers; returns the on-device loss."""
