@@ -140,6 +140,16 @@ def _direct(p):
             and p.grad.dtype == torch.float32 and p.grad.shape == p.shape)
 
 
+def _claim(p):
+    """A backward kernel is about to OVERWRITE ``p.grad`` in place (direct mode).  A second write before the next
+    ``zero_grad`` -- a second ``backward()`` for gradient accumulation, or a parameter shared by two ops -- would
+    silently discard the first gradient, so it raises instead (``FlatAdaBelief.zero_grad`` clears the marks)."""
+    if getattr(p, "_b2s_grad_written", False):
+        raise RuntimeError("direct_param_grads(): this parameter's gradient was already written in place since the "
+                           "last zero_grad(); accumulate outside direct_param_grads() instead")
+    p._b2s_grad_written = True
+
+
 def _ws(n_in, n_out, c_in, c_out, k3, device, prerounded=False):
     nbytes = L.query("b2s_conv_workspace_bytes", n_in, n_out, c_in, c_out, k3, 1 if prerounded else 0)
     if nbytes < 0:
@@ -319,6 +329,7 @@ class ConvolutionFunction(torch.autograd.Function):
                            k3, n_out_dev=nd_out, prerounded=both,
                            out=kp.grad if _direct(kp) else None).view(kernel.shape)
             if _direct(kp):
+                _claim(kp)
                 gw = None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             bp = ctx.params[1]
@@ -328,12 +339,14 @@ class ConvolutionFunction(torch.autograd.Function):
                                                                              device=gy.device)
                 L.call("b2s_sum_rows", pre[0], pre[0].shape[0], c_out, gb)
                 if _direct(bp):
+                    _claim(bp)
                     gb = None
             else:
                 gb = bp.grad.view(1, c_out) if _direct(bp) else torch.empty((1, c_out), dtype=torch.float32,
                                                                              device=gy.device)
                 L.call("b2s_colsum", gy, n_out, nd_out, c_out, gb)
                 if _direct(bp):
+                    _claim(bp)
                     gb = None
         return gx, gw, gb, None, None, None
 
@@ -560,11 +573,13 @@ class BatchNormFunction(torch.autograd.Function):
         gw = gb = None
         if weight is not None and ctx.needs_input_grad[1]:
             if _direct(weight):
+                _claim(weight)
                 weight.grad.copy_(sums[c:])
             else:
                 gw = sums[c:].clone()
         if bias is not None and ctx.needs_input_grad[2]:
             if _direct(bias):
+                _claim(bias)
                 bias.grad.copy_(sums[:c])
             else:
                 gb = sums[:c].clone()
@@ -680,6 +695,7 @@ class SETailFunction(torch.autograd.Function):
             if prm is None:
                 outs.append(None)
             elif _direct(prm):
+                _claim(prm)
                 outs.append(prm.grad)
             else:
                 outs.append(torch.empty_like(prm, memory_format=torch.contiguous_format))

@@ -67,6 +67,8 @@ class FlatAdaBelief:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+        for p in self.params:                 # in-place gradient writes of the next backward may claim them again
+            p._b2s_grad_written = False
 
     @staticmethod
     def rectified_step(step, beta1, beta2):

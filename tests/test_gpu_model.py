@@ -367,3 +367,31 @@ def test_fused_se_tail_matches_the_unfused_chain(cuda, name):
     for n, g0 in runs[False][1].items():
         err = (runs[True][1][n] - g0).abs().max().item()
         assert err <= 2e-3 * g0.abs().max().item() + 1e-4 * gmax, f"{n}: {err:.3e}"
+
+
+def test_direct_param_grads_refuses_a_second_backward(cuda):
+    """In direct mode the backward kernels OVERWRITE ``param.grad`` (views of the trainer's zeroed flat buffer): a second
+    backward before ``zero_grad`` would silently discard the first gradient, so it raises; after ``zero_grad`` the
+    next step runs normally."""
+    from dpcr_agb_b200 import train
+    torch.manual_seed(0)
+    model = msenet.build(ME, "SENet14", drop_path=0.0).to(cuda)
+    tr = train.Trainer(model, ME, lr=1e-4)
+    b = util.make_points(2, 1500, cfg=13)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(cuda) for k, v in b.items()}
+    vox = GridSampling3D(0.04)(d["pos"], d["batch"], tensors=(d["feats"],), order=d["perm"], num_plots=2)
+
+    def loss():
+        x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"])
+        return train.reg_loss(model(x), d["target"], tr.center, tr.scale)
+
+    model.train()
+    tr.opt.zero_grad()
+    with tr.direct_grads():
+        loss().backward()
+        with pytest.raises(RuntimeError, match="already written in place"):
+            loss().backward()
+    tr.opt.zero_grad()
+    with tr.direct_grads():
+        loss().backward()
+    assert torch.isfinite(tr.opt.flat_grad).all() and tr.opt.flat_grad.abs().max() > 0
