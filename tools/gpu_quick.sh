@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1800 python -m pytest tests -q -m gpu --timeout 300 2>&1 | tail -6
-timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/quick_bench.json 2> gpurun_out/quick_bench.err; echo "bench rc=$?"
-python tools/show_bench.py gpurun_out/quick_bench.json 2>&1 | head -3; tail -3 gpurun_out/quick_bench.err
+timeout 900 python -m pytest tests/test_gpu_lines.py -q -x --timeout 300 2>&1 | tail -3
+for v in 0 1 2 3; do echo "B2S_LINES_WG=$v"; B2S_LINES_WG=$v ONLY_STEM=1 timeout 600 python tools/conv_bench.py 2>&1 | grep -E "stem|Error|error" | cut -c150-400; done
