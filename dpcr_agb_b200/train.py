@@ -36,8 +36,27 @@ class FlatAdaBelief:
     ``b2s_adabelief_step`` launch and the data-parallel exchange is a single all-reduce."""
 
     def __init__(self, params, lr=5e-3, betas=(0.9, 0.999), eps=1e-16, weight_decay=1e-2, grad_clip=100.0):
-        self.params = [p for p in params if p.requires_grad]
+        """``params``: an iterable of parameters, or of torch-style group dicts ``{"params": [...], "lr": ...,
+        "weight_decay": ..., "betas": ..., "eps": ...}`` -- what ``MinkowskiBaselineModel.get_parameter_list``
+        (models/instance/minkowski.py:54-65: head / backbone settings) hands the reference's optimiser.  A group is a
+        contiguous segment of the flat buffer with its own hyper-parameters: one kernel launch per group.  ``self.lr``
+        is the scheduled learning rate of a group whose own lr equals the constructor's ``lr``; a group with another lr
+        keeps its ratio to it, which is how torch's schedulers treat per-group base rates."""
+        params = list(params)
+        raw_groups = params if (params and isinstance(params[0], dict)) else [{"params": params}]
+        self.groups, flat = [], []
+        for gdict in raw_groups:
+            ps = [p for p in gdict["params"] if p.requires_grad]
+            if not ps:
+                continue
+            self.groups.append({"first": len(flat), "count": len(ps),
+                                "lr_ratio": float(gdict.get("lr", lr)) / float(lr),
+                                "betas": tuple(gdict.get("betas", betas)), "eps": float(gdict.get("eps", eps)),
+                                "weight_decay": float(gdict.get("weight_decay", weight_decay))})
+            flat += ps
+        self.params = flat
         assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
+        assert len({id(p) for p in self.params}) == len(self.params), "a parameter appears in two groups"
         dev = self.params[0].device
         n = sum(p.numel() for p in self.params)
         self.numel = n
@@ -54,6 +73,11 @@ class FlatAdaBelief:
                 p.grad = self.flat_grad[off:off + k].view_as(p)
                 off += k
         self.lr, self.betas, self.eps, self.weight_decay, self.grad_clip = lr, betas, eps, weight_decay, grad_clip
+        off = 0
+        for g in self.groups:                       # flat-buffer segment of every group
+            k = sum(p.numel() for p in self.params[g["first"]:g["first"] + g["count"]])
+            g["offset"], g["numel"] = off, k
+            off += k
         self.step_count = 0
         # factor applied to every gradient inside the update kernel (before the clip): 1 / world_size turns the SUM the
         # data-parallel exchange leaves in ``flat_grad`` into the mean without a separate pass over the buffer
@@ -62,8 +86,9 @@ class FlatAdaBelief:
         # device copy of the hyper-parameter block (captured-graph replays read it; see graph_step.py), fed through a
         # ring of pinned staging buffers: the host may run several replays ahead of the device, and a buffer is only
         # rewritten after the copy that read it has completed (event per slot)
-        self.hyper_dev = torch.zeros(16, dtype=torch.float32, device=dev)
-        self.hyper_ring = PinnedRing((16,), torch.float32) if torch.cuda.is_available() else None
+        ng = len(self.groups)
+        self.hyper_dev = torch.zeros((ng, 16), dtype=torch.float32, device=dev)
+        self.hyper_ring = PinnedRing((ng, 16), torch.float32) if torch.cuda.is_available() else None
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -83,12 +108,20 @@ class FlatAdaBelief:
             step_size = 1.0 / (1 - beta1 ** step)
         return sma, step_size
 
-    def hyper_values(self, inv_scale=1.0):
-        """The 16-float hyper-parameter block of ``b2s_adabelief_step`` for the CURRENT step count."""
-        b1, b2 = self.betas
+    def hyper_values(self, inv_scale=1.0, group=None):
+        """The 16-float hyper-parameter block of ``b2s_adabelief_step`` for the CURRENT step count (``group``: one of
+        ``self.groups``; default = the constructor's settings)."""
+        g = group or {"lr_ratio": 1.0, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+        b1, b2 = g["betas"]
         sma, step_size = self.rectified_step(self.step_count, b1, b2)
-        return [self.lr, b1, b2, self.eps, self.weight_decay, step_size, 1.0 if sma >= 5 else 0.0, inv_scale,
-                self.grad_clip, 0, 0, 0, 0, 0, 0, 0]
+        return [self.lr * g["lr_ratio"], b1, b2, g["eps"], g["weight_decay"], step_size, 1.0 if sma >= 5 else 0.0,
+                inv_scale, self.grad_clip, 0, 0, 0, 0, 0, 0, 0]
+
+    def _segments(self):
+        for i, g in enumerate(self.groups):
+            o, k = g["offset"], g["numel"]
+            yield i, g, (self.flat_param[o:o + k], self.flat_grad[o:o + k], self.exp_avg[o:o + k],
+                         self.exp_avg_var[o:o + k], k)
 
     def step(self, inv_scale=1.0, check_inf=False):
         self.step_count += 1
@@ -97,15 +130,15 @@ class FlatAdaBelief:
         if check_inf:
             L.call("b2s_grad_check", self.flat_grad, self.numel, float(inv_scale), self.found_inf)
             found = self.found_inf
-        hyper = L.host_f32(*self.hyper_values(inv_scale))
-        L.call("b2s_adabelief_step", self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_var, self.numel,
-               hyper, None, found)
+        for _, g, (p, gr, m, v, k) in self._segments():
+            L.call("b2s_adabelief_step", p, gr, m, v, k, L.host_f32(*self.hyper_values(inv_scale, g)), None, found)
 
     def upload_hyper(self, inv_scale=1.0):
         """Advance the step count and copy this step's hyper-parameters to the device (stream-ordered); the
         captured graph's ``step_from_device`` launch reads them."""
         self.step_count += 1
-        self.hyper_ring.upload(torch.tensor(self.hyper_values(float(inv_scale) * self.grad_scale), dtype=torch.float32),
+        sc = float(inv_scale) * self.grad_scale
+        self.hyper_ring.upload(torch.tensor([self.hyper_values(sc, g) for g in self.groups], dtype=torch.float32),
                                self.hyper_dev)
 
     def state_dict(self):
@@ -118,9 +151,10 @@ class FlatAdaBelief:
             state[i] = {"step": self.step_count, "exp_avg": self.exp_avg[off:off + k].view_as(p).clone(),
                         "exp_avg_var": self.exp_avg_var[off:off + k].view_as(p).clone()}
             off += k
-        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
-                 "grad_clip": self.grad_clip, "params": list(range(len(self.params)))}
-        return {"state": state, "param_groups": [group]}
+        groups = [{"lr": self.lr * g["lr_ratio"], "betas": g["betas"], "eps": g["eps"],
+                   "weight_decay": g["weight_decay"], "grad_clip": self.grad_clip,
+                   "params": list(range(g["first"], g["first"] + g["count"]))} for g in self.groups]
+        return {"state": state, "param_groups": groups}
 
     def load_state_dict(self, sd):
         off = 0
@@ -132,15 +166,21 @@ class FlatAdaBelief:
                 self.exp_avg_var[off:off + k].copy_(st["exp_avg_var"].reshape(-1))
                 self.step_count = int(st["step"])
             off += k
-        g = sd["param_groups"][0]
-        self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]
-        self.weight_decay, self.grad_clip = g["weight_decay"], g.get("grad_clip", self.grad_clip)
+        saved = sd["param_groups"]
+        assert len(saved) == len(self.groups), "checkpoint and optimiser disagree on the parameter groups"
+        ref = next((i for i, g in enumerate(self.groups) if g["lr_ratio"] == 1.0), 0)
+        self.lr = saved[ref]["lr"] / self.groups[ref]["lr_ratio"]
+        for g, sg in zip(self.groups, saved):
+            g["betas"], g["eps"], g["weight_decay"] = tuple(sg["betas"]), sg["eps"], sg["weight_decay"]
+            g["lr_ratio"] = sg["lr"] / self.lr if self.lr else g["lr_ratio"]
+        self.betas, self.eps, self.weight_decay = self.groups[ref]["betas"], self.groups[ref]["eps"], self.groups[ref]["weight_decay"]
+        self.grad_clip = saved[0].get("grad_clip", self.grad_clip)
 
     def step_from_device(self, skip_flag=True):
         """AdaBelief update with the hyper-parameters read from ``hyper_dev`` (capturable).  ``found_inf`` (device
         float, nonzero = skip the update) is honoured: the captured step sets it when a capacity check failed."""
-        L.call("b2s_adabelief_step", self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_var, self.numel,
-               None, self.hyper_dev, self.found_inf if skip_flag else None)
+        for i, _, (p, gr, m, v, k) in self._segments():
+            L.call("b2s_adabelief_step", p, gr, m, v, k, None, self.hyper_dev[i], self.found_inf if skip_flag else None)
 
 
 class PinnedRing:

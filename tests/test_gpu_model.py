@@ -232,6 +232,44 @@ def test_fused_adabelief_matches_oracle(cuda):
     assert torch.equal(before, ogpu.flat_param)
 
 
+def test_fused_adabelief_parameter_groups(cuda):
+    """Head / backbone parameter groups with their own lr and weight decay (the reference's
+    ``MinkowskiBaselineModel.get_parameter_list``, models/instance/minkowski.py:54-65): every group is a segment of the
+    flat buffer updated with its own hyper-parameters; checked against one oracle optimiser per group, eager
+    (host hyper-parameters) and through the device-side hyper block the captured step reads, with a scheduled lr."""
+    torch.manual_seed(1)
+    shapes = [(27, 8, 16), (16,), (5, 7), (7,)]
+    ps_ref = [torch.randn(s) for s in shapes]
+    ps_gpu = [p.clone().to(cuda).requires_grad_() for p in ps_ref]
+    for p in ps_ref:
+        p.requires_grad_()
+    head_ref, back_ref = ps_ref[2:], ps_ref[:2]
+    o_head = otrain.AdaBelief(head_ref, lr=1e-2, weight_decay=0.0)
+    o_back = otrain.AdaBelief(back_ref, lr=5e-3, weight_decay=1e-2)
+    ogpu = train.FlatAdaBelief([{"params": ps_gpu[2:], "lr": 1e-2, "weight_decay": 0.0}, {"params": ps_gpu[:2]}],
+                               lr=5e-3, weight_decay=1e-2, grad_clip=100.0)
+    assert [g["numel"] for g in ogpu.groups] == [42, 27 * 8 * 16 + 16]
+    order = ps_ref[2:] + ps_ref[:2]                      # flat-buffer order: group by group
+    for step in range(8):
+        factor = 1.0 - 0.1 * step                        # a scheduler scales every group's lr by the same factor
+        o_head.lr, o_back.lr, ogpu.lr = 1e-2 * factor, 5e-3 * factor, 5e-3 * factor
+        for pr, pg in zip(order, ogpu.params):
+            g = torch.randn(pr.shape)
+            pr.grad = g.clone()
+            pg.grad.copy_(g.to(cuda))
+        o_head.step()
+        o_back.step()
+        if step % 2 == 0:
+            ogpu.step()
+        else:                                            # the captured step's form: hyper-parameters from device memory
+            ogpu.upload_hyper()
+            ogpu.step_from_device(skip_flag=False)
+        for pr, pg in zip(order, ogpu.params):
+            util.assert_close(pg, pr, tol=2e-6, what=f"param after step {step}")
+    sd = ogpu.state_dict()
+    assert [len(g["params"]) for g in sd["param_groups"]] == [2, 2] and sd["param_groups"][0]["weight_decay"] == 0.0
+
+
 def test_trainer_steps_reduce_loss(cuda):
     """Three optimisation steps on one small batch through the public Trainer; loss must go down and stay
     finite (the functional smoke of the whole path: quantise -> hash -> maps -> convs -> optimiser)."""
