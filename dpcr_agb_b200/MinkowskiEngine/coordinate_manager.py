@@ -14,6 +14,8 @@ All state lives in torch CUDA tensors owned by this object; every kernel is a C-
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from dpcr_agb_b200 import lib as L
@@ -26,6 +28,9 @@ USE_LINES = True         # tests flip this to compare the x-line convolution ker
 # kernel map 16 N_out + 8 P, strided map 16 N_in + 16 N_out + 4 N_in); pair counts cost a host sync per map, so this
 # is only ever enabled in an untimed statistics pass
 MAP_STATS = None
+
+# prebuild(): consumers wait for the side-stream operation they need instead of for the whole side stream
+PER_OP_JOIN = os.environ.get("B2S_PER_OP_JOIN", "1") == "1"
 
 
 def _map_account(name, nbytes):
@@ -155,7 +160,7 @@ class KernelMap:
     @property
     def inv(self):
         """Transposed table ``[K^3, N_in]``: ``inv[k, i] = o`` iff ``nbr[k, o] = i`` (strided maps only)."""
-        self.manager._join(("inv", id(self)))
+        self.manager._join(("inv", self.in_key, self.out_key, self.kernel_size))
         if self._inv is None:
             cm = self.manager
             cm._note(("inv", self.in_key, self.out_key, self.kernel_size))
@@ -166,7 +171,7 @@ class KernelMap:
     def parity_plan(self):
         """(perm, bounds) of ``b2s_parity_plan`` for the fine (input) rows of a stride-2 map, or None when the map is
         not a stride-2 map with kernel sizes 1 or 3 (dgrad then takes the dense transposed table)."""
-        self.manager._join(("plan", id(self)))
+        self.manager._join(("plan", self.in_key, self.out_key, self.kernel_size))
         if getattr(self, "_plan", None) is None:
             cm = self.manager
             cm._note(("plan", self.in_key, self.out_key, self.kernel_size))
@@ -239,6 +244,8 @@ class CoordinateManager:
         # sitting between the layers.  _side: the stream whose work the first consumer of a prebuilt map must join.
         self.journal = []
         self._side = None
+        self._side_events = {}      # prebuild: event recorded behind every side-stream operation, by _join key
+        self._side_done = set()     # ... and the keys whose event a consumer has already waited for
         self._replaying = False
         self._main_built = set()
         self.capacities = dict(capacities) if capacities is not None else None
@@ -254,11 +261,34 @@ class CoordinateManager:
             self.journal.append(op)
 
     def _join(self, what):
-        """Called by every map accessor: the first request for anything that was not built on the caller's stream
-        makes that stream wait for the side stream."""
-        if self._side is not None and not self._replaying and what not in self._main_built:
-            torch.cuda.current_stream().wait_stream(self._side)
-            self._side = None
+        """Called by every map accessor: a request for something the side stream built makes the caller's stream wait
+        for THAT operation (an event recorded behind it on the side stream; the journal is replayed in order of first
+        use, so the first consumer waits for the first few operations only, not for every map of the step); anything
+        else that was not built on the caller's stream waits for the whole side stream."""
+        if self._side is None or self._replaying or what in self._main_built:
+            return
+        ev = self._side_events.pop(what, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            return
+        if what in self._side_done:
+            return
+        torch.cuda.current_stream().wait_stream(self._side)
+        self._side_events.clear()
+        self._side = None
+
+    @staticmethod
+    def _what_of(op):
+        """The ``_join`` key of a journal operation."""
+        kind = op[0]
+        if kind == "stride":
+            ts = tuple(a * b for a, b in zip(op[1].tensor_stride, _triple(op[2])))
+            return ("map", CoordinateMapKey(ts, op[1].tag))
+        if kind == "kmap":
+            return ("kmap", (op[1], op[2], op[3], op[4]))
+        if kind in ("inv", "plan"):
+            return (kind, op[1], op[2], op[3])
+        return (kind, op[1])
 
     def _replay(self, op):
         kind = op[0]
@@ -293,6 +323,12 @@ class CoordinateManager:
             with torch.cuda.stream(side_stream):
                 for op in journal[main_first:]:
                     self._replay(op)
+                    if PER_OP_JOIN:
+                        ev = torch.cuda.Event()
+                        ev.record(side_stream)
+                        what = self._what_of(op)
+                        self._side_events[what] = ev
+                        self._side_done.add(what)
         finally:
             self._replaying = False
         self._side = side_stream
@@ -301,6 +337,7 @@ class CoordinateManager:
         """Make the current stream wait for any outstanding prebuild work (end of a step)."""
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
+            self._side_events.clear()
             self._side = None
 
     def capacity_of(self, tensor_stride):
