@@ -41,6 +41,9 @@ def _account(kind, nbr, n_rows, c_in, c_out, k3, n_dev=None, kmap=None):
     st["bytes"] += 4 * (n_rows * (c_in + c_out)) + 4 * k3 * c_in * c_out + 8 * pairs
 
 
+import contextlib  # noqa: E402
+
+_NULL_CTX = contextlib.nullcontext()
 _fwd = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
 _bwd = custom_bwd(device_type="cuda")
 
@@ -133,6 +136,30 @@ class direct_param_grads:
     def __exit__(self, *exc):
         global DIRECT_PARAM_GRADS
         DIRECT_PARAM_GRADS = self.old
+
+
+# ---- weight gradients beside the dgrad chain ---------------------------------------------------------------------
+# Inside ``with side_wgrad(stream):`` (and direct_param_grads) the weight-gradient kernels are launched on ``stream``:
+# they are leaves of the backward pass -- nothing but the optimiser waits for them -- while the chain
+# bn_bwd -> dgrad -> bn_bwd -> ... is the critical path, and the two use different resources (wgrad: shared-memory
+# bandwidth, batch norm: HBM).  Every launch waits for the main stream's position (its operands are ready), the context
+# exit makes the main stream wait for the side stream.
+WGRAD_STREAM = None
+
+
+class side_wgrad:
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        global WGRAD_STREAM
+        self.old, WGRAD_STREAM = WGRAD_STREAM, self.stream
+
+    def __exit__(self, *exc):
+        global WGRAD_STREAM
+        WGRAD_STREAM = self.old
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
 
 
 def _direct(p):
@@ -322,12 +349,20 @@ class ConvolutionFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             both = wg_ok                                  # feats is the operand-form copy saved by forward
             kp = ctx.params[0]
-            if ctx.lines and wg_ok:
-                gw = lines_wgrad(feats, gyr, kmap, c_in, c_out, out=kp.grad if _direct(kp) else None).view(kernel.shape)
-            else:
-                gw = wgrad(feats, gyr if both else gy, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out,
-                           k3, n_out_dev=nd_out, prerounded=both,
-                           out=kp.grad if _direct(kp) else None).view(kernel.shape)
+            g_op = gyr if both else gy
+            side = WGRAD_STREAM if (_direct(kp) and WGRAD_STREAM is not None and WORK_STATS is None) else None
+            if side is not None:                          # in-place gradient on the side stream (see side_wgrad)
+                side.wait_stream(torch.cuda.current_stream())
+                feats.record_stream(side)
+                g_op.record_stream(side)
+            with (torch.cuda.stream(side) if side is not None else _NULL_CTX):
+                if ctx.lines and wg_ok:
+                    gw = lines_wgrad(feats, gyr, kmap, c_in, c_out,
+                                     out=kp.grad if _direct(kp) else None).view(kernel.shape)
+                else:
+                    gw = wgrad(feats, g_op, None if kmap is None else kmap.nbr, n_in, n_out, c_in, c_out,
+                               k3, n_out_dev=nd_out, prerounded=both,
+                               out=kp.grad if _direct(kp) else None).view(kernel.shape)
             if _direct(kp):
                 _claim(kp)
                 gw = None

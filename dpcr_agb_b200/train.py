@@ -263,6 +263,7 @@ class Trainer:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.opt.grad_scale = 1.0 / self.world     # the exchange sums; the update kernel applies the mean
         self.num_batches = 0
+        self._wgrad_stream = None
         # Gradient exchange overlapped with the backward pass: the parameters of the last stage and the head (85 % of
         # MSENet's weights) sit at the END of the flat buffer and their gradients are complete EARLY in the backward
         # pass -- as soon as the gradient of the last stage's input exists.  A tensor hook there starts the all-reduce
@@ -329,11 +330,19 @@ class Trainer:
         return contextlib.nullcontext()
 
     def direct_grads(self):
-        fn = getattr(self.ME, "MinkowskiFunctional", None)
-        if fn is not None and hasattr(fn, "direct_param_grads"):
-            return fn.direct_param_grads()
+        """Context of the backward pass: parameter gradients written in place into the flat buffer, and (on a GPU, unless
+        B2S_SIDE_WGRAD=0) the weight-gradient kernels on a second stream beside the dgrad chain."""
         import contextlib
-        return contextlib.nullcontext()
+        fn = getattr(self.ME, "MinkowskiFunctional", None)
+        if fn is None or not hasattr(fn, "direct_param_grads"):
+            return contextlib.nullcontext()
+        stack = contextlib.ExitStack()
+        stack.enter_context(fn.direct_param_grads())
+        if hasattr(fn, "side_wgrad") and self.opt.flat_param.is_cuda and os.environ.get("B2S_SIDE_WGRAD", "1") == "1":
+            if self._wgrad_stream is None:
+                self._wgrad_stream = torch.cuda.Stream()
+            stack.enter_context(fn.side_wgrad(self._wgrad_stream))
+        return stack
 
     def broadcast_parameters(self):
         if self.world > 1:
