@@ -245,7 +245,6 @@ class CoordinateManager:
         self.journal = []
         self._side = None
         self._side_events = {}      # prebuild: event recorded behind every side-stream operation, by _join key
-        self._side_done = set()     # ... and the keys whose event a consumer has already waited for
         self._replaying = False
         self._main_built = set()
         self.capacities = dict(capacities) if capacities is not None else None
@@ -267,15 +266,11 @@ class CoordinateManager:
         else that was not built on the caller's stream waits for the whole side stream."""
         if self._side is None or self._replaying or what in self._main_built:
             return
-        ev = self._side_events.pop(what, None)
-        if ev is not None:
+        ev = self._side_events.get(what)
+        if ev is not None:                 # kept: a consumer on another stream (a branch of the network) waits again
             torch.cuda.current_stream().wait_event(ev)
             return
-        if what in self._side_done:
-            return
         torch.cuda.current_stream().wait_stream(self._side)
-        self._side_events.clear()
-        self._side = None
 
     @staticmethod
     def _what_of(op):
@@ -328,7 +323,6 @@ class CoordinateManager:
                         ev.record(side_stream)
                         what = self._what_of(op)
                         self._side_events[what] = ev
-                        self._side_done.add(what)
         finally:
             self._replaying = False
         self._side = side_stream

@@ -138,6 +138,65 @@ class direct_param_grads:
         DIRECT_PARAM_GRADS = self.old
 
 
+# ---- weight images built ahead -----------------------------------------------------------------------------------
+# The tensor-core convolution kernels read the weights as a split, swizzled K-major image that every call used to build
+# at the head of its workspace: 22 small launches per MSENet14 step on the critical path (0.2 ms).  Weights change once
+# per optimiser step, so a trainer builds the images of all layers -- forward layout and dgrad layout -- at the start of
+# the step on a side stream (``prepare_weight_images``); a convolution that finds a current image passes it as its
+# workspace with w_layout bit 4 set and launches its main kernel only.  Without a current image nothing changes.
+IMG_EPOCH = 0
+_IMG_EVENTS = {}          # "fwd" / "bwd" -> event recorded behind the images of the current epoch
+
+
+def conv_image_specs(model):
+    """(kernel parameter, c_in, c_out, k3, dgrad w_layout) of every convolution of ``model`` whose shape the tensor-core
+    kernels cover (the module class is looked up by name: this file must not import modules.py)."""
+    specs = []
+    for m in model.modules():
+        if type(m).__name__ != "MinkowskiConvolution" or getattr(m, "is_transpose", False):
+            continue
+        c_in, c_out, k3 = m.in_channels, m.out_channels, m.kernel_volume
+        if L.query("b2s_conv_weight_image_bytes", c_in, c_out, k3) <= 0 or \
+                L.query("b2s_conv_weight_image_bytes", c_out, c_in, k3) <= 0:
+            continue
+        symmetric = k3 > 1 and all(s == 1 for s in m.stride) and all(k % 2 == 1 for k in m.kernel_size)
+        specs.append((m.kernel, c_in, c_out, k3, 3 if symmetric else 1))
+    return specs
+
+
+def prepare_weight_images(specs, stream):
+    """Build the forward and dgrad weight images of ``specs`` on ``stream`` (forked from the current stream here)."""
+    global IMG_EPOCH
+    IMG_EPOCH += 1
+    cur = torch.cuda.current_stream()
+    stream.wait_stream(cur)
+    with torch.cuda.stream(stream):
+        for phase in ("fwd", "bwd"):
+            for kernel, c_in, c_out, k3, dl in specs:
+                layout, ci, co = (0, c_in, c_out) if phase == "fwd" else (dl, c_out, c_in)
+                imgs = kernel.__dict__.setdefault("_b2s_img", {})
+                ent = imgs.get(layout)
+                if ent is None:
+                    nbytes = L.query("b2s_conv_weight_image_bytes", ci, co, k3)
+                    ent = imgs[layout] = [torch.empty(nbytes, dtype=torch.uint8, device=kernel.device), -1]
+                L.call("b2s_conv_weight_image", kernel, ci, co, k3, layout, ent[0], ent[0].numel())
+                ent[1] = IMG_EPOCH
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            _IMG_EVENTS[phase] = ev
+
+
+def weight_image(kernel, layout):
+    """The current prebuilt image of ``kernel`` in ``layout`` (the caller's stream is made to wait for it), or None."""
+    ent = getattr(kernel, "_b2s_img", {}).get(layout)
+    if ent is None or ent[1] != IMG_EPOCH:
+        return None
+    ev = _IMG_EVENTS.get("fwd" if layout == 0 else "bwd")
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+    return ent[0]
+
+
 # ---- weight gradients beside the dgrad chain ---------------------------------------------------------------------
 # Inside ``with side_wgrad(stream):`` (and direct_param_grads) the weight-gradient kernels are launched on ``stream``:
 # they are leaves of the backward pass -- nothing but the optimiser waits for them -- while the chain
@@ -184,16 +243,19 @@ def _ws(n_in, n_out, c_in, c_out, k3, device, prerounded=False):
     return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device), nbytes
 
 
-def dgrad_strided(gy, w, kmap, c_gy, c_x):
+def dgrad_strided(gy, w, kmap, c_gy, c_x, wimg=None):
     """gx[i] = sum_k gy[inv[k,i]] @ W[k]^T for a stride-2 map through the parity plan (C ABI
-    ``b2s_conv_dgrad_strided``); ``gy`` must be TF32-rounded."""
+    ``b2s_conv_dgrad_strided``); ``gy`` must be TF32-rounded.  ``wimg``: prebuilt weight image (layout 1)."""
     perm, bounds = kmap.parity_plan
     gx = torch.empty((kmap.n_in, c_x), dtype=torch.float32, device=gy.device)
     _account("dgrad", kmap.inv, kmap.n_in, c_gy, c_x, kmap.k3, kmap.n_in_dev)
     nbytes = L.query("b2s_conv_dgrad_strided_workspace_bytes", c_gy, c_x, kmap.k3)
-    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=gy.device)
+    if wimg is not None and wimg.numel() >= nbytes:
+        ws, flags = wimg, 1
+    else:
+        ws, flags = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=gy.device), 0
     L.call("b2s_conv_dgrad_strided", gy, w, kmap.inv, perm, bounds, kmap.n_in, kmap.n_in_dev, c_gy, c_x,
-           L.host_i32(*kmap.kernel_size), gx, ws, nbytes)
+           L.host_i32(*kmap.kernel_size), gx, ws, ws.numel() if flags else nbytes, flags)
     return gx
 
 
@@ -216,12 +278,17 @@ def _wg_tc_ok(c_in, c_out, has_map):
 
 
 def gather_gemm(x, w, bias, nbr, n_in, n_out, c_in, c_out, k3, w_layout, impl=None, n_out_dev=None,
-                prerounded=False, col_stats=None):
+                prerounded=False, col_stats=None, wimg=None):
     """y[o] = bias + sum_k x[nbr[k,o]] @ B_k  (C ABI ``b2s_conv_gather_gemm``).  ``n_out_dev``: device row count
     (then ``n_out`` is the capacity / pitch of ``nbr``).  ``prerounded``: x is already TF32-representable.
     ``col_stats``: float64 [2 c_out + 1] that receives the column sums / sums of squares of y."""
     y = torch.empty((n_out, c_out), dtype=torch.float32, device=x.device)
     _account("dgrad" if (w_layout & 1) else "fwd", nbr, n_out, c_in, c_out, k3, n_out_dev)
+    if wimg is not None and prerounded and c_in > 4 and (CONV_IMPL if impl is None else impl) != 1:
+        # ``wimg``: the prebuilt weight image of (w, w_layout) -- it IS the workspace of a pre-rounded call
+        L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout | 4 | 16, y,
+               wimg, wimg.numel(), CONV_IMPL if impl is None else impl, col_stats)
+        return y
     ws, nbytes = _ws(n_in, n_out, c_in, c_out, k3, x.device, prerounded)
     L.call("b2s_conv_gather_gemm", x, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3,
            w_layout | (4 if prerounded else 0), y, ws, nbytes, CONV_IMPL if impl is None else impl, col_stats)
@@ -306,7 +373,7 @@ class ConvolutionFunction(torch.autograd.Function):
         if pre:
             feats = rounded_operand(feats, nd_in)
         out = gather_gemm(feats, kernel, b, nbr, n_in, n_out, c_in, c_out, k3, 0, n_out_dev=nd_out, prerounded=pre,
-                          col_stats=col_stats)
+                          col_stats=col_stats, wimg=weight_image(kernel, 0) if pre else None)
         if pre and not _wg_tc_ok(c_in, c_out, kmap is not None):   # wgrad will run on the SIMT kernel: keep plain x
             feats, pre = raw, False
         ctx.pre = pre
@@ -334,18 +401,20 @@ class ConvolutionFunction(torch.autograd.Function):
         gyr = rounded_operand(gy, nd_out) if (dg_ok or wg_ok) else gy
         if ctx.needs_input_grad[0]:
             gd, pre_gy = (gyr, True) if dg_ok else (gy, False)
+            dl = 3 if (kmap is not None and kmap.symmetric) else 1
+            img = weight_image(ctx.params[0], dl) if pre_gy else None
             if kmap is None:
                 gx = gather_gemm(gd, kernel, None, None, n_out, n_in, c_out, c_in, 1, 1, n_out_dev=nd_in,
-                                 prerounded=pre_gy)
+                                 prerounded=pre_gy, wimg=img)
             elif kmap.symmetric:      # transposed map == same table with the kernel index reversed
                 gx = gather_gemm(gd, kernel, None, kmap.nbr, n_out, n_in, c_out, c_in, k3, 1 | 2, n_out_dev=nd_in,
-                                 prerounded=pre_gy)
+                                 prerounded=pre_gy, wimg=img)
             elif (USE_PARITY_DGRAD and pre_gy and CONV_IMPL == 0 and c_out % 32 == 0 and c_in % 64 == 0
                   and kmap.parity_plan is not None):
-                gx = dgrad_strided(gd, kernel, kmap, c_out, c_in)
+                gx = dgrad_strided(gd, kernel, kmap, c_out, c_in, wimg=img)
             else:
                 gx = gather_gemm(gd, kernel, None, kmap.inv, n_out, n_in, c_out, c_in, k3, 1, n_out_dev=nd_in,
-                                 prerounded=pre_gy)
+                                 prerounded=pre_gy, wimg=img)
         if ctx.needs_input_grad[1]:
             both = wg_ok                                  # feats is the operand-form copy saved by forward
             kp = ctx.params[0]

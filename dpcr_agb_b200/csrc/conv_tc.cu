@@ -1155,6 +1155,13 @@ static void launch_prep_weights(const float* w, int c_in, int c_out, int k3, int
         w, c_in, c_out, k3, w_layout, small ? 1 : 0, T, precise, img);
 }
 
+// the weight image of one convolution (what b2s_conv_gather_gemm builds at the head of its workspace), built ahead
+int b2s_conv_weight_image_tc(const float* w, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* img,
+                             cudaStream_t st) {
+  launch_prep_weights(w, c_in, c_out, k3, w_layout & 3, false, iterations(c_in, k3), img, st);
+  return 0;
+}
+
 int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                             int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
                             void* workspace, int64_t workspace_bytes, cudaStream_t st, float* col_stats,
@@ -1164,7 +1171,7 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   const bool small = c_in <= 4;
   const int T = iterations(c_in, k3);
   float* img = reinterpret_cast<float*>(workspace);
-  launch_prep_weights(w, c_in, c_out, k3, w_layout, small, T, img, st);
+  if (!(w_layout & 16)) launch_prep_weights(w, c_in, c_out, k3, w_layout & 3, small, T, img, st);   // bit 4: image prebuilt
   const float* xin = x;
   if (small) {
     float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + b2s_conv_tc_image_bytes(c_in, c_out, k3));
@@ -1226,7 +1233,7 @@ int b2s_conv_dgrad_perm_tc(const float* x, const float* w, const int32_t* nbr, i
   const int k3 = ksize[0] * ksize[1] * ksize[2];
   const int T = iterations(c_in, k3);
   float* img = reinterpret_cast<float*>(workspace);
-  launch_prep_weights(w, c_in, c_out, k3, w_layout, false, T, img, st);
+  if (!(w_layout & 16)) launch_prep_weights(w, c_in, c_out, k3, w_layout & 3, false, T, img, st);
   PermArgs pa{};
   pa.perm = perm;
   pa.bounds = bounds;

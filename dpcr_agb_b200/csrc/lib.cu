@@ -116,7 +116,9 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
                                         int64_t workspace_bytes, int32_t impl, float* col_stats,
                                         b2s_stream_t stream) {
   B2S_CHECK_ARG(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && k3 > 0, "bad sizes");
-  B2S_CHECK_ARG(w_layout >= 0 && w_layout <= 7, "w_layout must be in 0..7");
+  B2S_CHECK_ARG(w_layout >= 0 && w_layout <= 31 && (w_layout & 8) == 0, "w_layout: bits 0-2 and 4");
+  B2S_CHECK_ARG(!(w_layout & 16) || ((w_layout & 4) && c_in > 4),
+                "a prebuilt weight image (bit 4) needs pre-rounded operands (bit 2) and c_in > 4");
   B2S_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0, 1 or 2");
   B2S_CHECK_ARG(nbr || (k3 == 1 && n_in == n_out), "nbr may be null only for the identity map (k3 == 1)");
   if (n_out == 0) return B2S_OK;
@@ -142,7 +144,11 @@ extern "C" int32_t b2s_conv_gather_gemm(const float* x, const float* w, const fl
       xin = xr;
     }
     int stats_rows = 0;
-    if (b2s_conv_gather_gemm_tc(xin, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout & 3, y, workspace,
+    if ((w_layout & 16) && !tc_ok) {
+      b2s_set_error("b2s_conv_gather_gemm: prebuilt weight image for a shape the tcgen05 kernel does not cover");
+      return B2S_EINVAL;
+    }
+    if (b2s_conv_gather_gemm_tc(xin, w, bias, nbr, n_in, n_out, n_out_dev, c_in, c_out, k3, w_layout & 19, y, workspace,
                                 workspace_bytes, st, col_stats, &stats_rows))
       return B2S_ECUDA;
     if (col_stats && stats_rows == 0) b2s_launch_col_partials(y, n_out, n_out_dev, c_out, col_stats, st);
@@ -163,6 +169,25 @@ int b2s_conv_dgrad_perm_tc(const float* x, const float* w, const int32_t* nbr, i
                            int32_t c_in, int32_t c_out, const int32_t* ksize, int32_t w_layout, const int32_t* perm,
                            const int32_t* bounds, float* y, void* workspace, cudaStream_t st);
 int64_t b2s_conv_tc_image_bytes(int32_t c_in, int32_t c_out, int32_t k3);
+int b2s_conv_weight_image_tc(const float* w, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* img,
+                             cudaStream_t st);
+
+extern "C" int64_t b2s_conv_weight_image_bytes(int32_t c_in, int32_t c_out, int32_t k3) {
+  if (c_in <= 4 || c_in % 32 != 0 || c_out % 64 != 0 || k3 <= 0) return -1;   // shapes of the tcgen05 kernels only
+  return al256(b2s_conv_tc_image_bytes(c_in, c_out, k3));
+}
+
+extern "C" int32_t b2s_conv_weight_image(const float* w, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout,
+                                         void* img, int64_t img_bytes, b2s_stream_t stream) {
+  B2S_CHECK_ARG(w && img && w_layout >= 0 && w_layout <= 3, "bad arguments");
+  const int64_t need = b2s_conv_weight_image_bytes(c_in, c_out, k3);
+  B2S_CHECK_ARG(need > 0 && img_bytes >= need && (reinterpret_cast<uintptr_t>(img) & 255) == 0,
+                "shape not covered, or image buffer too small / misaligned");
+  if (b2s_conv_weight_image_tc(w, c_in, c_out, k3, w_layout, reinterpret_cast<float*>(img), as_stream(stream)))
+    return B2S_ECUDA;
+  B2S_LAUNCH_CHECK();
+  return B2S_OK;
+}
 
 extern "C" int64_t b2s_conv_dgrad_strided_workspace_bytes(int32_t c_gy, int32_t c_x, int32_t k3) {
   if (c_gy <= 0 || c_x <= 0 || k3 <= 0) return -1;
@@ -172,7 +197,8 @@ extern "C" int64_t b2s_conv_dgrad_strided_workspace_bytes(int32_t c_gy, int32_t 
 extern "C" int32_t b2s_conv_dgrad_strided(const float* gy, const float* w, const int32_t* inv_nbr, const int32_t* perm,
                                           const int32_t* bounds, int64_t n_fine, const int32_t* n_fine_dev,
                                           int32_t c_gy, int32_t c_x, const int32_t* kernel_size_host, float* gx,
-                                          void* workspace, int64_t workspace_bytes, b2s_stream_t stream) {
+                                          void* workspace, int64_t workspace_bytes, int32_t flags,
+                                          b2s_stream_t stream) {
   B2S_CHECK_ARG(n_fine >= 0 && c_gy > 0 && c_x > 0 && kernel_size_host, "bad sizes");
   const int k3 = kernel_size_host[0] * kernel_size_host[1] * kernel_size_host[2];
   B2S_CHECK_ARG(k3 >= 1 && k3 <= 27, "kernel volume must be 1..27");
@@ -182,8 +208,8 @@ extern "C" int32_t b2s_conv_dgrad_strided(const float* gy, const float* w, const
   B2S_CHECK_ARG(workspace && workspace_bytes >= b2s_conv_dgrad_strided_workspace_bytes(c_gy, c_x, k3) &&
                     (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
                 "workspace too small or misaligned");
-  if (b2s_conv_dgrad_perm_tc(gy, w, inv_nbr, n_fine, n_fine_dev, c_gy, c_x, kernel_size_host, 1, perm, bounds, gx,
-                             workspace, as_stream(stream)))
+  if (b2s_conv_dgrad_perm_tc(gy, w, inv_nbr, n_fine, n_fine_dev, c_gy, c_x, kernel_size_host, 1 | ((flags & 1) ? 16 : 0),
+                             perm, bounds, gx, workspace, as_stream(stream)))
     return B2S_ECUDA;
   B2S_LAUNCH_CHECK();
   return B2S_OK;

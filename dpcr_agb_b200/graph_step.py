@@ -107,6 +107,7 @@ class GraphStep:
                       num_plots=self.B, bounds=self.bounds, capacity=self.capacities[1],
                       n_points_dev=self.n_points_dev)
         tr.opt.zero_grad()
+        tr.prepare_weight_images()           # all weight images of this step, on a side stream beside quantiser + stem
         x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"], num_rows=vox["num_rows"],
                             capacities=self.capacities, num_batches=self.B, dense_index=vox["index"])
         cm = x.coordinate_manager
@@ -118,6 +119,7 @@ class GraphStep:
         loss = T.reg_loss(pred, self.inp["target"], tr.center, tr.scale)
         with tr.direct_grads():
             loss.backward()
+        tr.join_weight_images()
         cm.join_side()
         if self.map_journal is None:
             self.map_journal = list(cm.journal)

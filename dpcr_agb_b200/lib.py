@@ -43,6 +43,8 @@ SIGNATURES = {
     "b2s_kernel_map_pairs_fill": (_i32, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "b2s_conv_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),
     "b2s_conv_col_stats_elems": (_i64, [_i64, _i32]),
+    "b2s_conv_weight_image_bytes": (_i64, [_i32, _i32, _i32]),
+    "b2s_conv_weight_image": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "b2s_bn_bwd_colsum_rows": (_i64, [_i64, _i32]),
     "b2s_sum_rows": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "b2s_round_tf32": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
@@ -56,7 +58,7 @@ SIGNATURES = {
     "b2s_parity_plan_rows": (_i64, [_i64]),
     "b2s_parity_plan": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2s_conv_dgrad_strided_workspace_bytes": (_i64, [_i32, _i32, _i32]),
-    "b2s_conv_dgrad_strided": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "b2s_conv_dgrad_strided": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "b2s_colsum": (_i32, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "b2s_maxpool_fwd": (_i32, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b2s_maxpool_bwd": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _vp, _vp]),

@@ -81,6 +81,11 @@ def _is_gelu(ME, act):
     return isinstance(act, ME.MinkowskiNonlinearity.MinkowskiGELU)
 
 
+# Stream for the downsample branch of strided residual blocks (see SEResidualBlock._residual_branch); None = off.
+# dpcr_agb_b200.train.Trainer sets it for the step it drives (B2S_BRANCH_STREAM=1).
+BRANCH_STREAM = None
+
+
 class ConvNormAct(nn.Module):
     def __init__(self, ME, cin, cout, kernel_size, stride, norm_layer, act, bias, fuse=False):
         super().__init__()
@@ -137,7 +142,33 @@ class SEResidualBlock(nn.Module):
         self.drop_path = DropPath(ME, drop_path) if drop_path > 0.0 else nn.Identity()
         self.se = SqueezeExcite(ME, planes * self.expansion, act)
 
+    def _residual_branch(self, x):
+        """The downsample branch (k1 convolution + norm of the first block of a stage) is independent of the main
+        branch until the residual join: on a GPU it runs on ``BRANCH_STREAM`` beside conv1 .. norm2 (forward, and --
+        autograd replays every op on its forward stream -- backward).  Returns (residual, stream to join or None)."""
+        side = BRANCH_STREAM
+        if side is None or isinstance(self.downsample, nn.Identity) or not x.F.is_cuda:
+            return self.downsample(x), None
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        x.F.record_stream(side)
+        twin = getattr(x.F, "_b2s_tf32", None)
+        if twin is not None:
+            twin[0].record_stream(side)
+        with torch.cuda.stream(side):
+            res = self.downsample(x)
+        return res, side
+
+    @staticmethod
+    def _join_branch(res, side):
+        if side is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(side)
+            res.F.record_stream(cur)
+        return res
+
     def forward(self, x):
+        res, side = self._residual_branch(x) if self._fuse else (None, None)
         out = x
         for i in range(1, self.num_convs + 1):
             conv, norm = getattr(self, f"conv{i}"), getattr(self, f"norm{i}")
@@ -148,10 +179,10 @@ class SEResidualBlock(nn.Module):
                 out = norm(conv(out))
         if self._se_tail is not None:
             keep = self.drop_path.mask(out) if isinstance(self.drop_path, DropPath) else None
-            return self._se_tail[0](out, self.downsample(x), self.se.fc[0], self.se.fc[2], keep, self.out_tf32)
+            return self._se_tail[0](out, self._join_branch(res, side), self.se.fc[0], self.se.fc[2], keep, self.out_tf32)
         out = self.se(out)
         if self._fuse:
-            return self._add_act[0](self.drop_path(out), self.downsample(x), self.out_tf32)
+            return self._add_act[0](self.drop_path(out), self._join_branch(res, side), self.out_tf32)
         out = self.drop_path(out) + self.downsample(x)
         return self.relu(out)
 

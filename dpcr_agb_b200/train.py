@@ -264,6 +264,10 @@ class Trainer:
         self.opt.grad_scale = 1.0 / self.world     # the exchange sums; the update kernel applies the mean
         self.num_batches = 0
         self._wgrad_stream = None
+        self._img_stream, self._img_specs = None, None
+        if os.environ.get("B2S_BRANCH_STREAM", "0") == "1" and self.opt.flat_param.is_cuda:
+            from . import msenet as _msenet          # residual downsample branches on their own stream (opt-in)
+            _msenet.BRANCH_STREAM = torch.cuda.Stream()
         # Gradient exchange overlapped with the backward pass: the parameters of the last stage and the head (85 % of
         # MSENet's weights) sit at the END of the flat buffer and their gradients are complete EARLY in the backward
         # pass -- as soon as the gradient of the last stage's input exists.  A tensor hook there starts the all-reduce
@@ -344,6 +348,22 @@ class Trainer:
             stack.enter_context(fn.side_wgrad(self._wgrad_stream))
         return stack
 
+    def prepare_weight_images(self):
+        """Start building the weight images of every tensor-core convolution for THIS step on a side stream (call after
+        the previous optimiser step, before the forward pass); ``join_weight_images`` after the backward pass."""
+        fn = getattr(self.ME, "MinkowskiFunctional", None)
+        if (fn is None or not hasattr(fn, "prepare_weight_images") or not self.opt.flat_param.is_cuda
+                or os.environ.get("B2S_PREBUILT_IMAGES", "1") != "1" or fn.CONV_IMPL == 1 or fn.WORK_STATS is not None):
+            return
+        if self._img_stream is None:
+            self._img_stream = torch.cuda.Stream()
+            self._img_specs = fn.conv_image_specs(self.model)
+        fn.prepare_weight_images(self._img_specs, self._img_stream)
+
+    def join_weight_images(self):
+        if self._img_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._img_stream)
+
     def broadcast_parameters(self):
         if self.world > 1:
             dist.broadcast(self.opt.flat_param, src=0)
@@ -354,6 +374,7 @@ class Trainer:
         Returns the (detached, on-device) loss."""
         self.model.train()
         self.opt.zero_grad()
+        self.prepare_weight_images()
         kw = {"dense_index": dense_index} if dense_index is not None else {}
         x = self.ME.SparseTensor(features=feats, coordinates=coords, **kw)
         with self.deferred_counters():
@@ -361,6 +382,7 @@ class Trainer:
         loss = reg_loss(pred, target, self.center, self.scale)
         with self.direct_grads():            # .grad = views of the flat buffer zeroed above: kernels write in place
             loss.backward()
+        self.join_weight_images()
         self.exchange_gradients()            # == DDP's all-reduce: two buckets, the big one overlapped with backward
         # the reference updates with the current lr, THEN steps the scheduler with the un-incremented batch counter
         # (base_model.py:219-226, 246-256): batch 0 and 1 run at base_lr, batch k at lr_at((k - 1) / batches_per_epoch)

@@ -189,6 +189,10 @@ B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_
  *     w_layout bit 1 set  : B_k is taken from w[K3-1-k] -- for point-symmetric maps (stride 1, odd K) the
  *                           transposed table is the forward table with k reversed, so dgrad reuses nbr.
  *     w_layout bit 2 set  : x is already TF32-representable (see b2s_round_tf32) -- skip the internal rounding pass.
+ *     w_layout bit 4 set  : `workspace` already holds the weight image of this (w, w_layout bits 0-1), built ahead
+ *                           with b2s_conv_weight_image (needs bit 2 and c_in > 4): the call launches the convolution
+ *                           kernel only.  Weights change once per optimiser step, so a trainer builds the images of
+ *                           every layer at the start of the step on a side stream, off the critical path.
  *     k3 == 1 and nbr == NULL means the identity map (the K=1, stride=1 `use_mm` case).
  *     impl: 0 = auto, 1 = SIMT fp32 reference kernel, 2 = tcgen05 kind::tf32 kernel.
  * b2s_conv_wgrad       : gw[k] = sum_o x[nbr[k,o],:]^T gy[o,:]   (gw fp32 [K3, c_in, c_out]);
@@ -212,6 +216,9 @@ B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_
 B2S_API int64_t b2s_conv_workspace_bytes(int64_t n_in, int64_t n_out, int32_t c_in, int32_t c_out, int32_t k3,
                                          int32_t prerounded);
 B2S_API int64_t b2s_conv_col_stats_elems(int64_t n_out, int32_t c_out);
+B2S_API int64_t b2s_conv_weight_image_bytes(int32_t c_in, int32_t c_out, int32_t k3);   /* -1: shape not covered */
+B2S_API int32_t b2s_conv_weight_image(const float* w, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout,
+                                      void* img, int64_t img_bytes, b2s_stream_t stream);
 B2S_API int32_t b2s_round_tf32(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* y, b2s_stream_t stream);
 B2S_API int32_t b2s_conv_gather_gemm(const float* x, const float* w, const float* bias, const int32_t* nbr, int64_t n_in,
                                      int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3,
@@ -247,7 +254,8 @@ B2S_API int32_t b2s_conv_lines_wgrad(const float* x, const float* gy, const uint
  * 128-row tile of every class, [8] = number of tiles), scratch16 = 16 ints.  b2s_conv_dgrad_strided then walks, per
  * tile, only the offsets of its class.  gy must be TF32-representable (b2s_round_tf32); w is the forward kernel
  * [K3, c_x, c_gy]; inv_nbr is the transposed table [K3, n_fine] (b2s_kernel_map with sign = -1).  Same result as
- * b2s_conv_gather_gemm with w_layout = 1 on inv_nbr. */
+ * b2s_conv_gather_gemm with w_layout = 1 on inv_nbr.  flags bit 0: `workspace` already holds the weight image
+ * (b2s_conv_weight_image(w, c_gy, c_x, k3, 1, ...)). */
 B2S_API int64_t b2s_parity_plan_rows(int64_t n);
 B2S_API int32_t b2s_parity_plan(const int32_t* coords, int64_t n, const int32_t* n_dev, const int32_t* ts_coarse_host,
                                 int32_t* perm, int32_t* bounds, int32_t* scratch16, b2s_stream_t stream);
@@ -255,7 +263,7 @@ B2S_API int64_t b2s_conv_dgrad_strided_workspace_bytes(int32_t c_gy, int32_t c_x
 B2S_API int32_t b2s_conv_dgrad_strided(const float* gy, const float* w, const int32_t* inv_nbr, const int32_t* perm,
                                        const int32_t* bounds, int64_t n_fine, const int32_t* n_fine_dev, int32_t c_gy,
                                        int32_t c_x, const int32_t* kernel_size_host, float* gx, void* workspace,
-                                       int64_t workspace_bytes, b2s_stream_t stream);
+                                       int64_t workspace_bytes, int32_t flags, b2s_stream_t stream);
 B2S_API int32_t b2s_colsum(const float* x, int64_t n, const int32_t* n_dev, int32_t c, float* out, b2s_stream_t stream);
 
 /* ---------------------------------------------------------------- (a9) max pooling -----------
