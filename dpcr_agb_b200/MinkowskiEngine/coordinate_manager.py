@@ -113,9 +113,11 @@ class KernelMap:
     def nbr(self):
         """Neighbour table ``[K^3, N_out]``.  Maps that have the x-line form (``lines_ok``) build it on first use only:
         the k7 stem never asks for it."""
+        self.manager._sync_builds()
         if self._nbr is None:
             cm = self.manager
             self._nbr = cm._probe(cm.maps[self.out_key], cm.maps[self.in_key], self.kernel_size, self.step, +1)
+            cm._mark_built()
         return self._nbr
 
     @nbr.setter
@@ -133,6 +135,7 @@ class KernelMap:
     @property
     def lines(self):
         """uint32-in-int32 ``[K1*K2, N]`` line words ``(base << 8) | mask`` (include/b200sparse.h), built on first use."""
+        self.manager._sync_builds()
         if self._lines is None:
             assert self.lines_ok
             cm = self.manager
@@ -144,6 +147,7 @@ class KernelMap:
                    L.host_i32(*self.kernel_size), L.host_i32(*self.step), self._lines)
             if MAP_STATS is not None:
                 _map_account("b2s_kernel_map_lines", 16 * m.n + 8 * self.num_pairs())
+            cm._mark_built()
         return self._lines
 
     def num_pairs(self, n_rows=None):
@@ -165,6 +169,7 @@ class KernelMap:
             cm = self.manager
             cm._note(("inv", self.in_key, self.out_key, self.kernel_size))
             self._inv = cm._probe(cm.maps[self.in_key], cm.maps[self.out_key], self.kernel_size, self.step, -1)
+            cm._mark_built()
         return self._inv
 
     @property
@@ -194,6 +199,7 @@ class KernelMap:
                 L.call("b2s_parity_plan", imap.coords, imap.n, imap.n_dev, L.host_i32(*tout), perm, bounds, scratch)
                 self._plan = (perm, bounds)
                 cm.parity_plans[(self.in_key, self.out_key)] = self._plan
+                cm._mark_built()
         return self._plan or None
 
     def transposed(self):
@@ -245,6 +251,7 @@ class CoordinateManager:
         self.journal = []
         self._side = None
         self._side_events = {}      # prebuild: event recorded behind every side-stream operation, by _join key
+        self._built = {}            # stream id -> event behind the latest map build on that stream
         self._replaying = False
         self._main_built = set()
         self.capacities = dict(capacities) if capacities is not None else None
@@ -259,11 +266,32 @@ class CoordinateManager:
         if not self._replaying:
             self.journal.append(op)
 
+    # ------------------------------------------------------------------ builds on more than one stream
+    # A network may run a branch on its own stream (dpcr_agb_b200.msenet.BRANCH_STREAM); whichever stream asks first
+    # builds a map that the other one then finds in the cache.  Every build is followed by an event on its stream
+    # (_mark_built) and every accessor first makes its stream wait for the builds of the OTHER streams (_sync_builds).
+    def _mark_built(self):
+        if self._replaying:              # prebuild(): the per-operation events of the side stream cover these
+            return
+        s = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(s)
+        self._built[s.cuda_stream] = ev
+
+    def _sync_builds(self):
+        if not self._built:
+            return
+        cur = torch.cuda.current_stream()
+        for sid, ev in self._built.items():
+            if sid != cur.cuda_stream:
+                cur.wait_event(ev)
+
     def _join(self, what):
         """Called by every map accessor: a request for something the side stream built makes the caller's stream wait
         for THAT operation (an event recorded behind it on the side stream; the journal is replayed in order of first
         use, so the first consumer waits for the first few operations only, not for every map of the step); anything
         else that was not built on the caller's stream waits for the whole side stream."""
+        self._sync_builds()
         if self._side is None or self._replaying or what in self._main_built:
             return
         ev = self._side_events.get(what)
@@ -379,6 +407,7 @@ class CoordinateManager:
             cmap.table, cmap.capacity, cmap.info = table, hcap, info
             if self.static:
                 self.checks.append(("coordinate range flag", 0, info[1:2]))
+            self._mark_built()
         return cmap.table
 
     # ------------------------------------------------------------------ map construction
@@ -438,6 +467,7 @@ class CoordinateManager:
             else:
                 cmap, _, _ = self._build(self.maps[in_key].coords, ts, want_in2out=False)
                 self.maps[out_key] = cmap
+            self._mark_built()
         return out_key
 
     def _build_static(self, imap: CoordMap, ts):
@@ -514,6 +544,7 @@ class CoordinateManager:
             km = KernelMap(self, in_key, out_key, kernel_size, step, None, imap.n, omap.n, imap.n_dev, omap.n_dev)
             if not km.lines_ok:          # maps with an x-line form build either table on first use (KernelMap.nbr / .lines)
                 km.nbr = self._probe(omap, imap, kernel_size, step, +1)
+                self._mark_built()
             self.kernel_maps[ck] = km
         return km
 
@@ -553,6 +584,7 @@ class CoordinateManager:
             L.call("b2s_batch_counts", m.coords, 4, m.n, m.n_dev, self.num_batches, counts)
             m._inv_counts = 1.0 / counts.clamp(min=1).float()
             m._counts_host = None
+            self._mark_built()
         return m._inv_counts
 
     def rows_per_batch(self, key):

@@ -65,7 +65,7 @@ def round_tf32(x, n_dev=None):
 # b2s_round_tf32 pass.  A tensor that IS the rounded result (no plain copy was written) is marked ``_b2s_is_tf32``.
 # Nothing depends on the attribute surviving: without it the convolution rounds as before.
 TWINS = True
-FUSE_BIAS_GRAD = True   # bn_bwd_apply accumulates the column sums of its gx (the bias gradient of the conv in front)
+FUSE_BIAS_GRAD = os.environ.get("B2S_FUSE_BIAS", "1") == "1"   # bn_bwd_apply also leaves the column sums of its gx
 # A convolution's epilogue can accumulate the column sums / sums of squares of its output -- the statistics of the batch
 # norm behind it (C ABI: col_stats of b2s_conv_gather_gemm / _lines_fwd).  OFF by default: measured on the B200 the
 # transposing reduction in the (not overlapped) epilogue adds 0.27 ms to the convolutions of an MSENet14 step while the

