@@ -299,7 +299,12 @@ def run_b200(args):
         t = torch.tensor([caps[k] for k in keys], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         caps = {k: int(v) for k, v in zip(keys, t.tolist())}
-    if TRAIN:
+    # training: the step pipelined across batches (the coordinate graph of batch i+1 replays beside the training graph
+    # of batch i: graph_step.PipelinedGraphStep); B2S_PIPELINE=0 selects the single-graph step
+    PIPE = TRAIN and os.environ.get("B2S_PIPELINE", "1") == "1"
+    if PIPE:
+        gstep = graph_step.PipelinedGraphStep(trainer, gs, B, B * NPTS, BOUNDS, caps).capture()
+    elif TRAIN:
         gstep = graph_step.GraphStep(trainer, gs, B, B * NPTS, BOUNDS, caps).capture()
     else:
         gstep = graph_step.GraphForward(model, ME, gs, B, B * NPTS, BOUNDS, caps).capture()
@@ -307,6 +312,24 @@ def run_b200(args):
     def step_from_device(d):
         gstep.load(d)
         return gstep.step()
+
+    def run_pipelined(items, steps, read_loss):
+        """steps training steps, every batch fed one step ahead; with ``read_loss`` the host reads the loss of step
+        i-1 after launching step i (every step's loss is read before the function returns)."""
+        gstep.reset_feed()
+        gstep.feed(items[0])
+        pending = None
+        for i in range(steps):
+            gstep.feed(items[(i + 1) % len(items)])
+            if read_loss:
+                handle = gstep.step_async()
+                if pending is not None:
+                    last_out[0] = pending.result()
+                pending = handle
+            else:
+                gstep.step()
+        if pending is not None:
+            last_out[0] = pending.result()
 
     last_out = [None]
 
@@ -333,9 +356,25 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # max over ranks, timed on the device
         return float(ms.item())
 
+    def timed_pipelined(items, steps, read_loss):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_pipelined(items, steps, read_loss)
+        torch.cuda.current_stream().wait_stream(gstep.prep_stream)      # the one coordinate graph fed ahead of the end
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
     # ---- warm-up
-    for i in range(args.warmup):
-        step_from_device(devb[i % nb])
+    if PIPE:
+        run_pipelined(devb, args.warmup, False)
+    else:
+        for i in range(args.warmup):
+            step_from_device(devb[i % nb])
     barrier()
 
     # ---- timed region 1: inputs resident in HBM
@@ -343,7 +382,7 @@ def run_b200(args):
     if ncu_range:
         torch.cuda.profiler.start()
     clocks = ClockSampler(local)
-    ms_total = timed(step_from_device, devb, args.steps)
+    ms_total = timed_pipelined(devb, args.steps, False) if PIPE else timed(step_from_device, devb, args.steps)
     clk = clocks.stop()
     if ncu_range:
         torch.cuda.profiler.stop()
@@ -357,9 +396,16 @@ def run_b200(args):
     #      copy stream, into staging buffers) while step i computes (GraphStep.prefetch / take_prefetched), and the
     #      host reads the loss of step i-1 after launching step i (GraphStep.step_async): the host never runs more than
     #      one step ahead, and every step's inputs and result cross PCIe inside the timed region
-    for i in range(min(2, args.warmup)):
-        step_from_host(host[i % nb])
-    if TRAIN:
+    if PIPE:
+        run_pipelined(host, min(2, args.warmup), True)
+        ms_e2e = timed_pipelined(host, args.steps, True)
+        h2d_bytes = h2d_bytes * (args.steps + 1) / args.steps     # one more batch is fed than steps are run
+    else:
+        for i in range(min(2, args.warmup)):
+            step_from_host(host[i % nb])
+    if PIPE:
+        pass
+    elif TRAIN:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -543,9 +589,14 @@ def run_b200(args):
             "config": workload(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4 if TRAIN else 8 * B, "ms_per_step": ms_e2e / args.steps,
-                    "how": ("pinned host batch -> staging buffers on a copy stream while the previous step computes -> "
-                            "captured step -> loss copied to pinned host memory, read by the host one step later")
-                           if TRAIN else "pinned host batch -> captured forward -> predictions read back (blocking)"},
+                    "how": ("pinned host batch of step i+1 -> input buffers of the other buffer set + its coordinate graph "
+                            "on a second stream while step i trains -> training graph -> loss copied to pinned host "
+                            "memory, read by the host one step later") if PIPE else
+                           (("pinned host batch -> staging buffers on a copy stream while the previous step computes -> "
+                             "captured step -> loss copied to pinned host memory, read by the host one step later")
+                            if TRAIN else "pinned host batch -> captured forward -> predictions read back (blocking)")},
+            "step_form": "pipelined across batches (coordinate graph of batch i+1 beside the training graph of batch i)"
+                         if PIPE else "single captured graph",
             "last_result": last_out[0], "gpu_launches": calls, "gpu_launches_note": "C-ABI calls into libb200sparse.so recorded in the captured "
                                                           "step graph x steps (each launches 1-4 kernels of ours)",
             "row_capacities": caps, "rank_work_imbalance_max_over_mean": balance,

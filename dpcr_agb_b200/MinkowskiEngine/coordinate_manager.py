@@ -139,6 +139,7 @@ class KernelMap:
         if self._lines is None:
             assert self.lines_ok
             cm = self.manager
+            cm._note(("lines", self.in_key, self.out_key, self.kernel_size))
             m = cm.maps[self.in_key]
             ws, lo, dims, num_plots = m.dense
             nl = self.kernel_size[1] * self.kernel_size[2]
@@ -309,7 +310,7 @@ class CoordinateManager:
             return ("map", CoordinateMapKey(ts, op[1].tag))
         if kind == "kmap":
             return ("kmap", (op[1], op[2], op[3], op[4]))
-        if kind in ("inv", "plan"):
+        if kind in ("inv", "plan", "lines"):
             return (kind, op[1], op[2], op[3])
         return (kind, op[1])
 
@@ -319,11 +320,11 @@ class CoordinateManager:
             self.stride(op[1], op[2])
         elif kind == "kmap":
             self.kernel_map(op[1], op[2], op[3], op[4])
-        elif kind in ("inv", "plan"):
+        elif kind in ("inv", "plan", "lines"):
             km = next((k for k in self.kernel_maps.values()
                        if (k.in_key, k.out_key, k.kernel_size) == (op[1], op[2], op[3])), None)
             if km is not None:
-                _ = km.inv if kind == "inv" else km.parity_plan
+                _ = km.inv if kind == "inv" else (km.parity_plan if kind == "plan" else km.lines)
         elif kind == "invc":
             self.inv_counts(op[1])
 
@@ -354,6 +355,18 @@ class CoordinateManager:
         finally:
             self._replaying = False
         self._side = side_stream
+
+    def build_all(self, journal):
+        """Replay a previous step's whole map journal on the CURRENT stream and leave no stream bookkeeping behind: the
+        form a separately captured "coordinate pipeline" graph uses (graph_step.PipelinedGraphStep) -- its consumers
+        run in another graph, ordered behind it by an event between the two replays."""
+        self._replaying = True
+        try:
+            for op in journal:
+                self._replay(op)
+        finally:
+            self._replaying = False
+        self._side, self._side_events, self._built = None, {}, {}
 
     def join_side(self):
         """Make the current stream wait for any outstanding prebuild work (end of a step)."""

@@ -366,3 +366,172 @@ class GraphForward:
     def release(self):
         torch.cuda.synchronize()
         self.graph = None
+
+
+class _Slot:
+    """One of the two buffer sets of :class:`PipelinedGraphStep`: input buffers, the coordinate structures built from
+    them, the two captured graphs and the events that order them."""
+
+    def __init__(self, proto, n_points):
+        self.inp = {k: torch.zeros_like(v) for k, v in proto.items()}
+        self.inp["perm"] = proto["perm"].clone()
+        self.n_points_dev = torch.full((1,), n_points, dtype=torch.int32, device=proto["pos"].device)
+        self.x = None
+        self.g_pre = self.g_main = None
+        self.prep_done, self.train_done = torch.cuda.Event(), torch.cuda.Event()
+
+
+class PipelinedGraphStep(GraphStep):
+    """The captured step split in two graphs per buffer set and software-pipelined ACROSS steps: the coordinate
+    pipeline of batch i+1 (voxel quantisation, coordinate hash, every strided / kernel map, the stem's x-line table --
+    everything that depends on the points only) replays on a second stream while batch i trains (forward, backward,
+    exchange, optimiser).  Nothing is cached across steps -- every batch still builds all of its structures from its
+    own points; they are built one step early, into the other of two buffer sets.
+
+        step.feed(batch)                     # host / device -> input buffers of the next set + its coordinate graph
+        for nxt in batches: step.feed(nxt); loss = step.step()      # train the set fed one call earlier
+
+    Same kernels, same operands, same results as :class:`GraphStep` (tests/test_gpu_graph.py)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.slots = [_Slot(self.inp, self.n_points), _Slot(self.inp, self.n_points)]
+        self.prep_stream = torch.cuda.Stream()
+        self._fed, self._cur = 0, 0          # slot the next feed() fills / the next step() trains
+
+    # ---- the two halves of GraphStep._forward_backward
+    def _prep(self, slot):
+        tr, ME = self.tr, self.tr.ME
+        i = slot.inp
+        vox = self.gs(i["pos"], i["batch"], tensors=(i["feats"],), order=i["perm"], num_plots=self.B,
+                      bounds=self.bounds, capacity=self.capacities[1], n_points_dev=slot.n_points_dev)
+        x = ME.SparseTensor(features=vox["tensors"][0], coordinates=vox["coords"], num_rows=vox["num_rows"],
+                            capacities=self.capacities, num_batches=self.B, dense_index=vox["index"])
+        if self.map_journal is not None:
+            x.coordinate_manager.build_all(self.map_journal)
+        slot.x, slot.vox = x, vox
+
+    def _train(self, slot):
+        tr = self.tr
+        tr.opt.zero_grad()
+        tr.prepare_weight_images()
+        x = slot.x
+        cm = x.coordinate_manager
+        with tr.deferred_counters():
+            pred = tr.model(x)
+        loss = T.reg_loss(pred, slot.inp["target"], tr.center, tr.scale)
+        with tr.direct_grads():
+            loss.backward()
+        tr.join_weight_images()
+        if self.map_journal is None:
+            self.map_journal = list(cm.journal)
+        cm._side, cm._side_events, cm._built = None, {}, {}
+        self.loss.copy_(loss.detach())
+        self.status_meta = [(what, cap) for what, cap, _ in cm.checks]
+        status = torch.cat([t.reshape(-1)[:1] for _, _, t in cm.checks])
+        if self.status is None:
+            self.status = torch.zeros_like(status)
+            self.status_min = torch.zeros_like(status)
+            self.caps_dev = torch.tensor([cap for _, cap in self.status_meta], dtype=torch.int32, device=status.device)
+        torch.maximum(self.status, status, out=self.status)
+        torch.minimum(self.status_min, status, out=self.status_min)
+        bad = (status < 0) | torch.where(self.caps_dev > 0, status > self.caps_dev, status != 0)
+        tr.opt.found_inf.copy_(bad.any().to(torch.float32).reshape(1))
+        if self.capture_collective:
+            self._tail()
+
+    def capture(self, warmup=2):
+        tr = self.tr
+        tr.model.train()
+        tr.opt.upload_hyper()
+        tr.opt.step_count -= 1
+        snapshot = [t.clone() for t in (tr.opt.flat_param, tr.opt.exp_avg, tr.opt.exp_avg_var)]
+        buffers = [(b, b.clone()) for b in tr.model.buffers()]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                for slot in self.slots:
+                    self._prep(slot)
+                    self._train(slot)
+                    if not self.capture_collective:
+                        self._tail()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for dst, src in zip((tr.opt.flat_param, tr.opt.exp_avg, tr.opt.exp_avg_var), snapshot):
+            dst.copy_(src)
+        for b, saved in buffers:
+            b.copy_(saved)
+        self.status.zero_()
+        self.status_min.zero_()
+        calls0 = L.launch_count
+        for slot in self.slots:                      # the coordinate graphs first: the training graphs read their tensors
+            slot.g_pre = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(slot.g_pre):
+                self._prep(slot)
+        for slot in self.slots:
+            slot.g_main = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(slot.g_main):
+                self._train(slot)
+        self.launches_per_step = (L.launch_count - calls0) // 2
+        if not self.capture_collective:
+            self.graph_tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_tail):
+                self.tr.opt.step_from_device()
+        torch.cuda.synchronize()
+        for slot in self.slots:
+            slot.train_done.record()
+        self.graph = True                            # truthy: captured
+        return self
+
+    # ---- replay
+    def feed(self, batch, non_blocking=True):
+        """Copy ``batch`` (pinned host or device tensors) into the next buffer set and replay its coordinate graph on
+        the prep stream -- beside whatever the main stream is training."""
+        slot = self.slots[self._fed]
+        self._fed ^= 1
+        ps = self.prep_stream
+        ps.wait_event(slot.train_done)               # the step that last trained on this set has finished with it
+        with torch.cuda.stream(ps):
+            for k, dst in slot.inp.items():
+                src = batch[k]
+                assert src.shape == dst.shape, f"{k}: {tuple(src.shape)} does not match the captured shape {tuple(dst.shape)}"
+                dst.copy_(src, non_blocking=non_blocking)
+            slot.g_pre.replay()
+            slot.prep_done.record(ps)
+
+    def load(self, host_batch, non_blocking=True):
+        self.feed(host_batch, non_blocking)
+
+    def reset_feed(self):
+        """Forget a batch that was fed but not trained (end of a loop that feeds one ahead)."""
+        self._fed = self._cur
+
+    def step(self):
+        """Train the set fed by the oldest outstanding ``feed``; returns the on-device loss."""
+        tr = self.tr
+        slot = self.slots[self._cur]
+        self._cur ^= 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(slot.prep_done)
+        tr.opt.upload_hyper()
+        if self.drops:
+            vals = [m.draw(self.B) if tr.model.training else [1.0] * self.B for m in self.drops]
+            self.drop_ring.upload(torch.tensor(vals, dtype=torch.float32), self.drop_dev)
+        slot.g_main.replay()
+        if not self.capture_collective:
+            tr.exchange_gradients()
+            self.graph_tail.replay()
+        slot.train_done.record(cur)
+        tr.opt.lr = tr.sched.lr_at(tr.num_batches / tr.batches_per_epoch)
+        tr.num_batches += 1
+        return self.loss
+
+    def release(self):
+        torch.cuda.synchronize()
+        for slot in self.slots:
+            slot.g_pre = slot.g_main = None
+        self.graph_tail = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()

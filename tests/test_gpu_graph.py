@@ -153,3 +153,35 @@ def test_prefetched_host_feed_equals_direct_load(cuda):
     # same inputs, same parameters: only the order of the fp32 atomics differs between two runs of the same graph
     np.testing.assert_allclose(losses[1], losses[0], rtol=2e-3)
     assert len(set(losses[0])) == 3                    # three different batches gave three different losses
+
+
+def test_pipelined_step_equals_single_graph_step(cuda):
+    """PipelinedGraphStep (coordinate graph of batch i+1 replayed on a second stream while batch i trains, two buffer
+    sets) trains on the same inputs with the same kernels as GraphStep: same losses step by step, same parameters."""
+    plots, n_points = 2, 2000
+    batches = _batches(cuda, 5, plots, n_points)
+    gs = GridSampling3D(SIZE)
+    out, params = [], []
+    for cls in (graph_step.GraphStep, graph_step.PipelinedGraphStep):
+        m = _model(cuda, drop_path=0.0)
+        t = train.Trainer(m, ME, lr=1e-3)
+        caps = graph_step.plan_capacities(gs, ME, m, batches, plots, BOUNDS)
+        g = cls(t, gs, plots, plots * n_points, BOUNDS, caps).capture()
+        losses = []
+        if cls is graph_step.GraphStep:
+            for d in batches:
+                g.load(d)
+                losses.append(float(g.step()))
+        else:
+            g.feed(batches[0])
+            for i in range(len(batches)):
+                if i + 1 < len(batches):
+                    g.feed(batches[i + 1])                 # one batch ahead, beside the training graph
+                losses.append(float(g.step()))
+        seen = g.verify()
+        assert all(v <= caps[int(k.split()[-1])] for k, v in seen.items() if k.startswith("rows"))
+        out.append(losses)
+        params.append(t.opt.flat_param.clone())
+    assert len(set(out[0])) == len(batches)
+    np.testing.assert_allclose(out[1], out[0], rtol=3e-3)
+    util.assert_close(params[1], params[0], tol=1e-3, what="parameters after 5 steps")
