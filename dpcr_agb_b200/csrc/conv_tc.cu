@@ -18,7 +18,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-extern int g_b2s_tc_rot, g_b2s_tc_ca, g_b2s_tc_occ1, g_b2s_tc_m256;   // lib.cu (b2s_set_tuning)
+extern int g_b2s_tc_rot, g_b2s_tc_ca, g_b2s_tc_occ1, g_b2s_tc_m256, g_b2s_tc_ta;   // lib.cu (b2s_set_tuning)
 
 namespace {
 
@@ -44,6 +44,11 @@ constexpr int SMALL_NB = 3;        // weight images per stage of the small-c_in 
 //            (it*3 + j): j = 0 [H | H], j = 1 [M | M], j = 2 [L | 0] with W = H + M + L (24 bits: the k7 stem's
 //            weights need more than the 16-17 bits of a pair, and the l*M cross term, measured end to end: without
 //            them the stem kernel's own gradient is off by 4e-3 at BASELINE plot size).
+// Image rows for the kernel that keeps the A operand in tensor memory (gather_gemm_ta_kernel, precise == 2): position
+// p of the 64 bf16 of a row ([H | L], 16 per MMA k-step) holds channel 8 ((p % 16) / 4) + 4 ((p / 16) % 2) + p % 4 of the
+// 32-channel chunk -- the order in which that kernel's row fragments land in tensor memory.
+__device__ __forceinline__ int ta_channel(int p) { return 8 * ((p & 15) >> 2) + 4 * ((p >> 4) & 1) + (p & 3); }
+
 __device__ __forceinline__ float weight_at(const float* __restrict__ w, int c_in, int c_out, int k3, int w_layout, int k,
                                            int ci, int n) {
   if (k >= k3 || ci >= c_in) return 0.f;
@@ -76,7 +81,8 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(const float* __restri
           out[q] = j == 0 ? h : (j == 1 ? m : (s8 < 4 ? l : 0u));
         } else {
           const int kc = c_in / BK;
-          split_bf16(weight_at(w, c_in, c_out, k3, w_layout, it / kc, (it % kc) * BK + (kq & 31), n), h, l);
+          const int ch = precise == 2 ? ta_channel(kq) : (kq & 31);
+          split_bf16(weight_at(w, c_in, c_out, k3, w_layout, it / kc, (it % kc) * BK + ch, n), h, l);
           out[q] = kq < 32 ? h : l;
         }
       }
@@ -127,8 +133,9 @@ __global__ void __launch_bounds__(256) prep_weights_t_kernel(const float* __rest
     if (precise) {
       const int k16 = chunk * 8 + (tx & 3) * 2;   // [H(32) | L(32)]: the two bf16 of this slot
       uint32_t h0, l0, h1, l1;
-      split_bf16(t[k16 & 31][y], h0, l0);
-      split_bf16(t[(k16 + 1) & 31][y], h1, l1);
+      const int ch = precise == 2 ? ta_channel(k16) : (k16 & 31);   // k16 is even: its partner is channel ch + 1
+      split_bf16(t[ch][y], h0, l0);
+      split_bf16(t[ch + 1][y], h1, l1);
       r = k16 < 32 ? (h0 | (h1 << 16)) : (l0 | (l1 << 16));
     } else {
       const int kk = chunk * 4 + (tx & 3);
@@ -480,7 +487,7 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
     for (int it = 0; it < T; ++it) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t a_desc = smem_desc_sw128(a_base + s * A_STAGE_BYTES, 16, 1024);
         const uint64_t b_desc = smem_desc_sw128(b_base + s * L::B_STAGE_BYTES, 16, 1024);
         if (!precise) {
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__((PW + 1) * 32, 1)
         ph ^= 1u;
       }
     }
-    if (lane == 0) mma_commit(accum_bar);
+    if (elect_one()) mma_commit(accum_bar);
     __syncwarp();
   }
   __syncthreads();
@@ -733,7 +740,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
     for (int it = 0; it < T; ++it) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t b_desc = smem_desc_sw128(b_base + s * L::B_STAGE_BYTES, 16, 1024);
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
@@ -760,7 +767,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
         ph ^= 1u;
       }
     }
-    if (lane == 0) mma_commit(accum_bar);
+    if (elect_one()) mma_commit(accum_bar);
     __syncwarp();
   }
   __syncthreads();
@@ -908,7 +915,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int it = 0; it < T; ++it) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t a_desc = smem_desc_sw128(a_base + s * A_STAGE_BYTES, 16, 1024);
         const uint64_t b_desc = smem_desc_sw128(b_base + s * L::B_STAGE_BYTES, 16, 1024);
 #pragma unroll
@@ -922,7 +929,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         ph ^= 1u;
       }
     }
-    if (lane == 0) mma_commit(accum_bar);
+    if (elect_one()) mma_commit(accum_bar);
     __syncwarp();
   }
   __syncthreads();
@@ -999,6 +1006,224 @@ int launch_tma(const float* x, int64_t n_in, const float* wimg, const float* bia
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// A operand in TENSOR MEMORY (split-bf16 mode, c_in a power-of-two multiple of 32, no split-K, no permutation).
+// The shared-memory kernels above are bound by the L1 / shared-memory data pipe, not by the tensor cores: per
+// (128-row tile, kernel offset) of a 64 -> 64 layer the LDGSTS gather writes 32 KB (in 64-byte beats), the six MMAs
+// per stage read the A stage three times (72 KB with the weights) and the tensor pipe idles at 31 %.  Here the
+// gathered rows never touch shared memory: four lanes load one row chunk (2 x LDG.128 each, a quad covers 64
+// contiguous bytes per instruction) straight into the register fragment of tcgen05.st.16x256b, the MMAs take A from
+// tensor memory (tcgen05.mma [d], [a], b-desc) and shared memory carries the weights only.
+//   CTA = 256 out rows (two accumulators, every weight stage is used by both) x BN channels, 10 warps:
+//   warps 0-7  producers + epilogue: warp w owns lanes 32 (w % 4) .. + 31 of tile w / 4 -- the quarter of tensor memory
+//              a warp may address; per stage a thread loads 4 rows x 32 bytes and issues two 16-lane stores
+//   warp 8     MMA issuer: per stage and tile 6 x (M 128, N BN, K 16): h*H (k-steps 0,1), l*H (2,3 x 0,1), h*L (0,1 x 2,3)
+//   warp 9     weight loader: one bulk copy per stage
+// Tensor memory: accumulators in columns [0, 2 BN), A ring (2 stages x 2 tiles x 32 columns) behind them.
+// The k-step positions of a row fragment are a fixed permutation of the chunk's channels (ta_channel); the weight
+// image is built with the same permutation, so the products pair up unchanged.
+// ---------------------------------------------------------------------------------------------
+constexpr int TA_THREADS = 320;
+template <int BN, int SB, int TA_SA>
+struct SmemTA {
+  static constexpr int B_STAGE = BN * 128;
+  static constexpr int B_OFF = 0;
+  static constexpr int BAR_OFF = SB * B_STAGE;
+  static constexpr int NBAR = 2 * TA_SA + 2 * SB + 2;
+  static constexpr int TOTAL = BAR_OFF + NBAR * 8;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+template <int BN, int SB, int DEPTH, int TA_SA>
+__global__ void __launch_bounds__(TA_THREADS, 1)
+    gather_gemm_ta_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
+                          const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
+                          int c_out, int k3, int kc_shift, float* __restrict__ y) {
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_out_dev);
+  const int64_t m0 = (int64_t)blockIdx.x * 256;
+  if (m0 >= n_out) return;                       // uniform across the CTA
+  const int n0 = blockIdx.y * BN;
+  using L = SmemTA<BN, SB, TA_SA>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t b_base = base + L::B_OFF, bar_base = base + L::BAR_OFF;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (TA_SA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * TA_SA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * TA_SA + SB + s); };
+  const uint32_t accum_bar = bar_base + 8u * (2 * TA_SA + 2 * SB);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * TA_SA + 2 * SB + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + 8 * (2 * TA_SA + 2 * SB + 1));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = k3 << kc_shift;
+
+  if (tid == 0) {
+    for (int s = 0; s < TA_SA; ++s) {
+      mbar_init(a_full(s), 256);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  constexpr int TCOLS = 2 * BN + TA_SA * 64 <= 256 ? 256 : 512;
+  constexpr uint32_t A_COL = 2 * BN;
+  if (warp == 8) tmem_alloc<TCOLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot_ptr;
+
+  if (warp < 8) {
+    // ===================== producers =====================
+    const int tile = warp >> 2, quarter = warp & 3, qd = lane & 3;
+    const int64_t r0 = m0 + tile * 128 + quarter * 32 + (lane >> 2);      // this thread's rows: r0 + {0, 8, 16, 24}
+    const uint32_t t_quarter = tmem_d + ((uint32_t)(quarter * 32) << 16);
+    const int kcm = (1 << kc_shift) - 1;
+    auto ldidx = [&](int it, int (&ix)[4]) {
+      const int k = it >> kc_shift;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t o = r0 + 8 * q;
+        ix[q] = (it < T && o < n_out) ? __ldg(nbr + (int64_t)k * pitch + o) : -1;
+      }
+    };
+    auto ldrows = [&](int it, const int (&ix)[4], uint4 (&v)[8]) {
+      const int cc = it & kcm;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (ix[q] >= 0) {          // bytes [16 qd, + 16) of the h half and of the l half of the 128-byte row chunk
+          const uint4* p = reinterpret_cast<const uint4*>(x + (int64_t)ix[q] * c_in + cc * BK) + qd;
+          v[2 * q] = __ldg(p);
+          v[2 * q + 1] = __ldg(p + 4);
+        } else {
+          v[2 * q] = make_uint4(0u, 0u, 0u, 0u);
+          v[2 * q + 1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    };
+    auto store = [&](uint32_t taddr, const uint4 (&v)[8]) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {   // lanes 16 g .. 16 g + 15 of the quarter: rows r0 + 16 g (a) and r0 + 16 g + 8 (b)
+        const uint4 &a0 = v[4 * g], &a1 = v[4 * g + 1], &b0 = v[4 * g + 2], &b1 = v[4 * g + 3];
+        const uint32_t r[16] = {a0.x, a0.y, b0.x, b0.y, a0.z, a0.w, b0.z, b0.w,
+                                a1.x, a1.y, b1.x, b1.y, a1.z, a1.w, b1.z, b1.w};
+        tmem_st_16x256b_x4(taddr + ((uint32_t)(g * 16) << 16), r);
+      }
+    };
+    uint4 d[DEPTH][8];
+    int wq[DEPTH][4];
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) ldidx(j, wq[j]);
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) {
+      ldrows(j, wq[j], d[j]);
+      ldidx(j + DEPTH, wq[j]);
+    }
+#pragma unroll 1
+    for (int it0 = 0; it0 < T; it0 += DEPTH) {
+#pragma unroll
+      for (int j = 0; j < DEPTH; ++j) {
+        const int it = it0 + j;
+        if (it < T) {
+          const int sa = it % TA_SA;
+          mbar_wait(a_empty(sa), (((uint32_t)(it / TA_SA)) & 1u) ^ 1u);
+          tc_fence_after();
+          store(t_quarter + A_COL + (uint32_t)((sa * 2 + tile) * 32), d[j]);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(a_full(sa));
+          ldrows(it + DEPTH, wq[j], d[j]);       // stage it + DEPTH (indices past the last stage are -1: no loads)
+          ldidx(it + 2 * DEPTH, wq[j]);
+        }
+      }
+    }
+    // ===================== epilogue: warp = (tile, lane quarter) =====================
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int64_t orow = m0 + tile * 128 + quarter * 32 + lane;
+    const uint32_t t_lane = t_quarter + (uint32_t)(tile * BN);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (orow < n_out) {
+        float* dst = y + orow * c_out + n0 + c0;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          float4 r;
+          r.x = __uint_as_float(v[e]) + (bias ? __ldg(&bias[n0 + c0 + e]) : 0.f);
+          r.y = __uint_as_float(v[e + 1]) + (bias ? __ldg(&bias[n0 + c0 + e + 1]) : 0.f);
+          r.z = __uint_as_float(v[e + 2]) + (bias ? __ldg(&bias[n0 + c0 + e + 2]) : 0.f);
+          r.w = __uint_as_float(v[e + 3]) + (bias ? __ldg(&bias[n0 + c0 + e + 3]) : 0.f);
+          *reinterpret_cast<float4*>(dst + e) = r;
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC = idesc_bf16(128, BN, 0, 0);
+    int sb = 0;
+    uint32_t phb = 0;
+    for (int it = 0; it < T; ++it) {
+      const int sa = it % TA_SA;
+      mbar_wait(b_full(sb), phb);
+      mbar_wait(a_full(sa), ((uint32_t)(it / TA_SA)) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t b_desc = smem_desc_sw128(b_base + sb * L::B_STAGE, 16, 1024);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t a_t = tmem_d + A_COL + (uint32_t)((sa * 2 + t) * 32);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {          // K = 16 bf16 = 8 columns of tensor memory / 32 bytes of the image row
+            const int ak = q < 4 ? q : q - 4, bk = q < 2 ? q : q - 2;
+            mma_bf16_ta(tmem_d + (uint32_t)(t * BN), a_t + (uint32_t)(ak * 8), b_desc + (uint64_t)(bk * 2), IDESC,
+                        (it | q) ? 1u : 0u);
+          }
+        }
+        mma_commit(a_empty(sa));
+        mma_commit(b_empty(sb));
+      }
+      __syncwarp();
+      if (++sb == SB) {
+        sb = 0;
+        phb ^= 1u;
+      }
+    }
+    if (elect_one()) mma_commit(accum_bar);
+    __syncwarp();
+  } else if (elect_one()) {
+    // ===================== weight loader (warp 9, one lane) =====================
+    int sb = 0;
+    uint32_t phb = 0;
+    for (int it = 0; it < T; ++it) {
+      mbar_wait(b_empty(sb), phb ^ 1u);
+      mbar_arrive_expect_tx(b_full(sb), L::B_STAGE);
+      bulk_g2s(b_base + sb * L::B_STAGE, wimg + ((int64_t)it * c_out + n0) * BK, L::B_STAGE, b_full(sb));
+      if (++sb == SB) {
+        sb = 0;
+        phb ^= 1u;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<TCOLS>(tmem_d);
+  }
+}
 
 int tc_knob(int global, const char* env_name, int dflt) {
   if (global >= 0) return global;
@@ -1082,6 +1307,41 @@ int launch_tc2(const float* x, const float* wimg, const float* bias, const int* 
 }
 
 int tc_m256() { return tc_knob(g_b2s_tc_m256, "B2S_TC_M256", 1); }
+// "tc_ta": 0 = off, 1 = 64-wide output tiles take the A operand from tensor memory (default), 2 = 128-wide ones too,
+// 3 = as 2 and also maps with fewer CTAs than SMs (tests)
+int tc_ta() { return tc_knob(g_b2s_tc_ta, "B2S_TC_TA", 1); }
+
+// shapes gather_gemm_ta_kernel covers: split-bf16 operands, c_in = 32 * 2^s, at least one 256-row CTA per SM (no
+// split-K in that kernel), a neighbour table, no statistics epilogue
+bool ta_applies(int c_in, int c_out, int64_t n_out, bool has_nbr, bool stats) {
+  const int mode = tc_ta();
+  if (!mode || !b2s_precise() || !has_nbr || stats || c_in < BK || c_in % BK != 0) return false;
+  const int kc = c_in / BK;
+  if (kc & (kc - 1)) return false;
+  const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
+  if (!(bn == 64 || (bn == 128 && mode >= 2))) return false;
+  return mode >= 3 || ceil_div64(n_out, 2 * BM) * (c_out / bn) >= B2S_NUM_SMS;
+}
+
+template <int BN, int SB, int DEPTH, int SA>
+int launch_ta(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
+              int c_in, int c_out, int k3, float* y, cudaStream_t st) {
+  using L = SmemTA<BN, SB, SA>;
+  auto kern = gather_gemm_ta_kernel<BN, SB, DEPTH, SA>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
+      b2s_set_error("conv_tc: cannot opt in to %d bytes of shared memory", L::DYN_BYTES);
+      return -1;
+    }
+    attr_set = true;
+  }
+  int sh = 0;
+  while ((BK << sh) < c_in) ++sh;
+  dim3 grid((unsigned)ceil_div64(n_out, 2 * BM), (unsigned)(c_out / BN), 1);
+  kern<<<grid, TA_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, sh, y);
+  return 0;
+}
 
 template <int BN, int STAGES, bool SMALL, int LAG = 2, int NB = 1, int PW = 4>
 int launch_tc(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
@@ -1140,13 +1400,23 @@ int64_t b2s_conv_tc_image_bytes(int32_t c_in, int32_t c_out, int32_t k3) {   // 
   return align256((int64_t)iterations(c_in, k3) * (c_in <= 4 ? SMALL_NB : 1) * c_out * 128);
 }
 
+// A prebuilt image (b2s_conv_weight_image) does not know the row count of the call that will use it, hence not which
+// kernel: for the shapes gather_gemm_ta_kernel may take it holds both forms back to back.
+static bool ta_shape(int c_in, int c_out) {
+  const int kc = c_in / BK;
+  return c_in >= BK && c_in % BK == 0 && !(kc & (kc - 1)) && c_out % 64 == 0 && c_out % 256 != 0;
+}
+int64_t b2s_conv_tc_prebuilt_image_bytes(int32_t c_in, int32_t c_out, int32_t k3) {
+  return b2s_conv_tc_image_bytes(c_in, c_out, k3) * (ta_shape(c_in, c_out) ? 2 : 1);
+}
+
 int64_t b2s_conv_tc_workspace_bytes(int32_t c_in, int32_t c_out, int32_t k3, int64_t n_in) {
   return b2s_conv_tc_image_bytes(c_in, c_out, k3) + (c_in <= 4 ? align256(n_in * 16) : 0);
 }
 
 static void launch_prep_weights(const float* w, int c_in, int c_out, int k3, int w_layout, bool small, int T, float* img,
-                                cudaStream_t st) {
-  const int precise = b2s_precise();
+                                cudaStream_t st, bool ta = false) {
+  const int precise = b2s_precise() ? (ta ? 2 : 1) : 0;     // 2: rows in the channel order of gather_gemm_ta_kernel
   if (!small && !(w_layout & 1) && c_in % BK == 0 && c_out % 32 == 0)
     prep_weights_t_kernel<<<dim3((unsigned)T, (unsigned)(c_out / 32)), 256, 0, st>>>(w, c_in, c_out, k3, w_layout,
                                                                                      precise, img);
@@ -1159,6 +1429,9 @@ static void launch_prep_weights(const float* w, int c_in, int c_out, int k3, int
 int b2s_conv_weight_image_tc(const float* w, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* img,
                              cudaStream_t st) {
   launch_prep_weights(w, c_in, c_out, k3, w_layout & 3, false, iterations(c_in, k3), img, st);
+  if (ta_shape(c_in, c_out) && b2s_precise())
+    launch_prep_weights(w, c_in, c_out, k3, w_layout & 3, false, iterations(c_in, k3),
+                        img + b2s_conv_tc_image_bytes(c_in, c_out, k3) / sizeof(float), st, true);
   return 0;
 }
 
@@ -1166,12 +1439,14 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
                             int64_t n_out, const int32_t* n_out_dev, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* y,
                             void* workspace, int64_t workspace_bytes, cudaStream_t st, float* col_stats,
                             int* stats_rows) {
-  (void)workspace_bytes;
   if (stats_rows) *stats_rows = 0;
   const bool small = c_in <= 4;
   const int T = iterations(c_in, k3);
   float* img = reinterpret_cast<float*>(workspace);
-  if (!(w_layout & 16)) launch_prep_weights(w, c_in, c_out, k3, w_layout & 3, small, T, img, st);   // bit 4: image prebuilt
+  bool ta = !small && ta_applies(c_in, c_out, n_out, nbr != nullptr, col_stats != nullptr);
+  if ((w_layout & 16) && workspace_bytes < b2s_conv_tc_prebuilt_image_bytes(c_in, c_out, k3)) ta = false;   // one form only
+  if (!(w_layout & 16)) launch_prep_weights(w, c_in, c_out, k3, w_layout & 3, small, T, img, st, ta);   // bit 4: image prebuilt
+  else if (ta) img += b2s_conv_tc_image_bytes(c_in, c_out, k3) / sizeof(float);   // ... in both forms: the second one
   const float* xin = x;
   if (small) {
     float4* x4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + b2s_conv_tc_image_bytes(c_in, c_out, k3));
@@ -1179,6 +1454,10 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
     xin = reinterpret_cast<const float*>(x4);
   }
   const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
+  if (ta) {
+    if (bn == 128) return launch_ta<128, 5, 3, 4>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, y, st);
+    return launch_ta<64, 8, 3, 4>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, y, st);
+  }
   if (small && b2s_precise()) {   // three weight images per stage: one CTA per SM, deeper ring
     if (bn == 256) return launch_tc<256, 2, true, 1, SMALL_NB, 8>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
     if (bn == 128) return launch_tc<128, 3, true, 2, SMALL_NB, 8>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);

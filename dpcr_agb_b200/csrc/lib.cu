@@ -32,7 +32,7 @@ extern "C" int32_t b2s_device_check(void) {
 // launch-tuning knobs (wgrad_tc.cu / conv_tc.cu read them at every launch)
 int g_b2s_wg_nbp = -1, g_b2s_wg_lag = -1, g_b2s_wg_occ2 = -1, g_b2s_tc_rot = -1;
 int g_b2s_tc_ca = -1, g_b2s_tc_occ1 = -1, g_b2s_wg_ca = -1;
-int g_b2s_wg_wv = -1, g_b2s_tc_m256 = -1;
+int g_b2s_wg_wv = -1, g_b2s_tc_m256 = -1, g_b2s_tc_ta = -1;
 int g_b2s_cr_v4 = -1, g_b2s_cr_cap = -1, g_b2s_cr_unroll = -1;
 int g_b2s_precise = -1;
 
@@ -59,6 +59,7 @@ extern "C" int32_t b2s_set_tuning(const char* key, int32_t value) {
   else if (!strcmp(key, "wg_ca")) g_b2s_wg_ca = value;
   else if (!strcmp(key, "wg_wv")) g_b2s_wg_wv = value;
   else if (!strcmp(key, "tc_m256")) g_b2s_tc_m256 = value;
+  else if (!strcmp(key, "tc_ta")) g_b2s_tc_ta = value;
   else if (!strcmp(key, "cr_v4")) g_b2s_cr_v4 = value;
   else if (!strcmp(key, "cr_cap")) g_b2s_cr_cap = value;
   else if (!strcmp(key, "cr_unroll")) g_b2s_cr_unroll = value;
@@ -169,12 +170,13 @@ int b2s_conv_dgrad_perm_tc(const float* x, const float* w, const int32_t* nbr, i
                            int32_t c_in, int32_t c_out, const int32_t* ksize, int32_t w_layout, const int32_t* perm,
                            const int32_t* bounds, float* y, void* workspace, cudaStream_t st);
 int64_t b2s_conv_tc_image_bytes(int32_t c_in, int32_t c_out, int32_t k3);
+int64_t b2s_conv_tc_prebuilt_image_bytes(int32_t c_in, int32_t c_out, int32_t k3);
 int b2s_conv_weight_image_tc(const float* w, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout, float* img,
                              cudaStream_t st);
 
 extern "C" int64_t b2s_conv_weight_image_bytes(int32_t c_in, int32_t c_out, int32_t k3) {
   if (c_in <= 4 || c_in % 32 != 0 || c_out % 64 != 0 || k3 <= 0) return -1;   // shapes of the tcgen05 kernels only
-  return al256(b2s_conv_tc_image_bytes(c_in, c_out, k3));
+  return al256(b2s_conv_tc_prebuilt_image_bytes(c_in, c_out, k3));
 }
 
 extern "C" int32_t b2s_conv_weight_image(const float* w, int32_t c_in, int32_t c_out, int32_t k3, int32_t w_layout,

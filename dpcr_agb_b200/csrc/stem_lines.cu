@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
     for (int it = 0; it < T; ++it) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t b_desc = smem_desc_sw128(b_base + s * LF_B_STAGE, 16, 1024);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1)
         ph ^= 1u;
       }
     }
-    if (lane == 0) mma_commit(accum_bar);
+    if (elect_one()) mma_commit(accum_bar);
     __syncwarp();
   }
   __syncthreads();
@@ -279,18 +279,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint4 (&d)[8]) {
       "r"(d[6].x), "r"(d[6].y), "r"(d[6].z), "r"(d[6].w), "r"(d[7].x), "r"(d[7].y), "r"(d[7].z), "r"(d[7].w)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] * B[smem desc], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void mma_bf16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 template <int SB>
 struct LtSmem {
   static constexpr int B_OFF = 0;
@@ -446,7 +434,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
       mbar_wait(b_full(sb), phb);
       mbar_wait(a_full(sa), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t b_desc = smem_desc_sw128(b_base + sb * LF_B_STAGE, 16, 1024);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -465,10 +453,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1)
         phb ^= 1u;
       }
     }
-    if (lane == 0) mma_commit(accum_bar);
+    if (elect_one()) mma_commit(accum_bar);
     __syncwarp();
-  } else if (lane == 0) {
-    // ===================== weight loader =====================
+  } else if (elect_one()) {
+    // ===================== weight loader (warp 9, one lane) =====================
     int sb = 0;
     uint32_t phb = 0;
     for (int it = 0; it < T; ++it) {
@@ -657,7 +645,7 @@ __global__ void __launch_bounds__(LW_THREADS, 1)
     for (int it = 0; it < T; ++it) {
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_stage = base + (uint32_t)s * LW_STAGE, b_stage = a_stage + LW_A_STAGE;
 #pragma unroll
         for (int k16 = 0; k16 < LW_ROWS / 16; ++k16) {
@@ -675,7 +663,7 @@ __global__ void __launch_bounds__(LW_THREADS, 1)
         ph ^= 1u;
       }
     }
-    if (lane == 0) mma_commit(accum_bar);
+    if (elect_one()) mma_commit(accum_bar);
     __syncwarp();
   }
   __syncthreads();

@@ -97,6 +97,21 @@ __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  Single-thread tcgen05 instructions (mma, commit) are uniform-datapath
+// instructions: under a data-dependent branch such as `lane == 0` the compiler wraps every one of them in a
+// divergence loop (ELECT / BRA.U.ANY, about 140 clocks per MMA measured with tools/mma_rate_probe.cu, which caps a
+// CTA at one N = 64 MMA per 140 clocks whatever the operands do); under the predicate of elect.sync it issues them
+// back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ tcgen05 ------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_slot) {  // whole warp
@@ -150,6 +165,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc], bf16 inputs, fp32 accumulate: the A operand (128 lanes = rows, 8 columns = 16
+// bf16 of K per instruction) is read from tensor memory instead of shared memory
+__device__ __forceinline__ void mma_bf16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 lanes x 128 bytes (32 columns) per warp instruction, fragment layout of the 16x256b shape repeated four times
+// along the columns: thread t holds, for j = 0..3, columns 8 j + 2 (t % 4) + {0, 1} of lane t / 4 in r[4 j + {0, 1}]
+// and of lane t / 4 + 8 in r[4 j + {2, 3}].  The lane field of taddr is the first of the 16 lanes (a multiple of 16
+// inside the warp's own 32-lane quarter).
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 
 // ------------------------------------------------------------------ descriptors --------------
 // Shared-memory matrix descriptor (64-bit):

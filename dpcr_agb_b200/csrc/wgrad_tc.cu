@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
       const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_stage = base + (uint32_t)s * stage_bytes, b_stage = a_stage + a_stage_bytes;
         for (int mt = 0; mt < p.MT; ++mt) {
           if (p.precise) {
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(G_THREADS, MINB)
       }
       __syncwarp();
     }
-    if (lane == 0) mma_commit(accum_bar);
+    if (elect_one()) mma_commit(accum_bar);
     __syncwarp();
   }
   __syncthreads();
@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      if (lane == 0 && precise) {
+      const bool issuer = elect_one();
+      if (issuer && precise) {
 #pragma unroll
         for (int g = 0; g < WG_ROWS / 16; ++g) {      // K = 16 rows per MMA; A terms gh, gl against [xh | xl]
           const uint64_t b_desc = smem_desc_sw128(b_base + s * SM_B_STAGE + g * 2048, 4096, 1024);
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
             mma_bf16(tmem_d, smem_desc_sw128(a_base + s * WG_A_STAGE + 8192 + g * 2048, 4096, 1024), b_desc, IDESC16, 1u);
         }
         mma_commit(empty_bar(s));
-      } else if (lane == 0) {
+      } else if (issuer) {
 #pragma unroll
         for (int g = 0; g < WG_ROWS / 8; ++g) {
           const uint64_t a_desc = smem_desc_sw128_base32(a_base + s * WG_A_STAGE + g * ATOM_BYTES, LBO_BYTES, SBO_BYTES);
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
       }
       __syncwarp();
     }
-    if (lane == 0) mma_commit(accum_bar);
+    if (elect_one()) mma_commit(accum_bar);
     __syncwarp();
   }
   __syncthreads();

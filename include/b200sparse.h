@@ -58,7 +58,9 @@ B2S_API int32_t b2s_device_check(void);
  * producer run-ahead in stages, 1 = two CTAs per SM), "wg_wv" (half-waves of CTAs the row range is split over),
  * "wg_ca" / "tc_ca" (1 = L1-allocating gathers), "tc_occ1" (1 = one CTA per SM), "tc_rot" (1 = every output tile
  * starts its kernel-offset loop at a different offset), "tc_m256" (0 off, 1 = M = 256 tiles for 128-wide output tiles,
- * 2 = wherever they can run, 3 = 64- and 128-wide), "cr_v4" / "cr_cap" (column reductions: 0 = scalar kernel; CTAs
+ * 2 = wherever they can run, 3 = 64- and 128-wide), "tc_ta" (split-bf16 mode: 0 = A operand always staged in shared
+ * memory, 1 = 64-wide output tiles of maps with >= 148 x 256 rows gather it into tensor memory, 2 = 128-wide tiles
+ * too, 3 = as 2 for maps of any size), "cr_v4" / "cr_cap" (column reductions: 0 = scalar kernel; CTAs
  * per SM).  A value < 0 restores the default.  B2S_EINVAL for an unknown key.  Not part of the reference-facing
  * surface. */
 B2S_API int32_t b2s_set_tuning(const char* key, int32_t value);

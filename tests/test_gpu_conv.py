@@ -269,6 +269,60 @@ def test_conv_m256_tiles(cuda, n, cin, cout):
     util.assert_close(gx, x32.grad, tol=TF32_MODEL_TOL, what="M=256 dgrad vs tf32 model")
 
 
+@pytest.mark.parametrize("n,cin,cout", [(700, 64, 64), (1300, 128, 64), (257, 64, 128), (900, 256, 64),
+                                        (300, 128, 128), (520, 64, 192)])
+def test_conv_operand_in_tensor_memory(cuda, n, cin, cout, opmode):
+    """gather_gemm_ta_kernel (split-bf16 mode: gathered rows go registers -> tensor memory, weight image rows in the
+    matching channel order; chosen automatically for 64-wide tiles of maps with >= 148 x 256 rows, forced here):
+    forward with bias and dgrad against the oracle's precision model and against the shared-memory kernel, through a
+    workspace image and through a prebuilt image (which holds both forms), incl. a partial last tile."""
+    if opmode != "bf16x2":
+        pytest.skip("split-bf16 operand mode only")
+    c, out, nbr = _maps(n, seed=17)
+    rng = np.random.default_rng(18)
+    x = rng.standard_normal((c.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) * 0.05).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    gy = rng.standard_normal((out.shape[0], cout)).astype(np.float32)
+    x32 = torch.from_numpy(x).requires_grad_()
+    with tf32_model():
+        ref = oo.conv(x32, torch.from_numpy(w), nbr, torch.from_numpy(b))
+        ref.backward(torch.from_numpy(gy))
+    ng, wg, bg = torch.from_numpy(nbr).to(cuda), torch.from_numpy(w).to(cuda), torch.from_numpy(b).to(cuda)
+    xg, gg = torch.from_numpy(x).to(cuda), torch.from_numpy(gy).to(cuda)
+    n_in, n_out = c.shape[0], out.shape[0]
+
+    def both(img_f=None, img_d=None):
+        pre = img_f is not None
+        xo, go = (Fn.round_tf32(xg), Fn.round_tf32(gg)) if pre else (xg, gg)
+        y = Fn.gather_gemm(xo, wg, bg, ng, n_in, n_out, cin, cout, 27, 0, impl=TC, prerounded=pre, wimg=img_f)
+        gx = Fn.gather_gemm(go, wg, None, ng, n_out, n_in, cout, cin, 27, 3, impl=TC, prerounded=pre, wimg=img_d)
+        return y, gx
+
+    L.set_tuning("tc_ta", 0)
+    try:
+        y0, gx0 = both()
+        L.set_tuning("tc_ta", 3)
+        y1, gx1 = both()
+        imgs = []
+        for layout, ci, co in ((0, cin, cout), (3, cout, cin)):
+            nbytes = L.query("b2s_conv_weight_image_bytes", ci, co, 27)
+            img = torch.empty(nbytes, dtype=torch.uint8, device=cuda)
+            L.call("b2s_conv_weight_image", wg, ci, co, 27, layout, img, img.numel())
+            imgs.append(img)
+        y2, gx2 = both(*imgs)
+        L.set_tuning("tc_ta", 0)
+        y3, gx3 = both(*imgs)                        # the same prebuilt images serve the shared-memory kernel
+    finally:
+        L.set_tuning("tc_ta", -1)
+    util.assert_close(y1, ref.detach(), tol=TF32_MODEL_TOL, what="forward vs precision model")
+    util.assert_close(gx1, x32.grad, tol=TF32_MODEL_TOL, what="dgrad vs precision model")
+    for what, a, r in (("forward", y1, y0), ("dgrad", gx1, gx0), ("forward, prebuilt image", y2, y0),
+                       ("dgrad, prebuilt image", gx2, gx0), ("forward, prebuilt image, smem kernel", y3, y0),
+                       ("dgrad, prebuilt image, smem kernel", gx3, gx0)):
+        util.assert_close(a, r, tol=5e-6, what=what + " vs shared-memory kernel")   # same products, fp32 order only
+
+
 @pytest.mark.parametrize("n,cin,cout,K", [
     (3000, 64, 64, 3),        # M = 128 kernel, 64-wide tiles
     (3000, 64, 128, 3),       # M = 256 kernel (two row tiles per CTA)

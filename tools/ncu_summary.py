@@ -21,6 +21,17 @@ KEYS = [
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput %"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard / issue"),
     ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait / issue"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard / issue"),
+    ("smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio", "stall tex_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "stall membar / issue"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "L1 global load requests"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "L1 global load sectors"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "LSU smem wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts.sum", "LSU wavefronts"),
+    ("sm__cycles_elapsed.max", "SM cycles"),
 ]
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}
 
