@@ -146,5 +146,8 @@ def test_checkpoint_with_optimiser_state_resumes(cuda, tmp_path):
     b.opt.lr = a.opt.lr
     la, lb = a.step(cg, fg, target), b.step(cg, fg, target)
     torch.cuda.synchronize()
-    assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(la))
+    # Not bit-equal by design: on a batch this small the convolutions run split-K with fp32 reductions in arrival order
+    # and the coarse batch norms see a handful of rows -- the SAME model's loss on this batch spreads by 1.6e-5 run to
+    # run (tools/noise_check.py), so the bar is 1e-4 here and 1e-5 on the parameters after the step.
+    assert abs(float(la) - float(lb)) <= 1e-4 * abs(float(la))
     util.assert_close(b.opt.flat_param, a.opt.flat_param, tol=1e-5, what="parameters after the resumed step")
