@@ -1024,7 +1024,8 @@ int launch_tma(const float* x, int64_t n_in, const float* wimg, const float* bia
 // The k-step positions of a row fragment are a fixed permutation of the chunk's channels (ta_channel); the weight
 // image is built with the same permutation, so the products pair up unchanged.
 // ---------------------------------------------------------------------------------------------
-constexpr int TA_THREADS = 320;
+// TILES: 128-row accumulator tiles per CTA.  2 = one CTA per SM whose tiles share every weight stage; 1 = two CTAs per
+// SM (6 warps, 168 registers), the prologue / epilogue of one overlapping the main loop of the other.
 template <int BN, int SB, int TA_SA>
 struct SmemTA {
   static constexpr int B_STAGE = BN * 128;
@@ -1035,14 +1036,14 @@ struct SmemTA {
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
-template <int BN, int SB, int DEPTH, int TA_SA>
-__global__ void __launch_bounds__(TA_THREADS, 1)
+template <int BN, int SB, int DEPTH, int TA_SA, int TILES>
+__global__ void __launch_bounds__(TILES * 128 + 64, 3 - TILES)
     gather_gemm_ta_kernel(const float* __restrict__ x, const float* __restrict__ wimg, const float* __restrict__ bias,
                           const int* __restrict__ nbr, int64_t n_out, const int* __restrict__ n_out_dev, int c_in,
                           int c_out, int k3, int kc_shift, float* __restrict__ y) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_out_dev);
-  const int64_t m0 = (int64_t)blockIdx.x * 256;
+  const int64_t m0 = (int64_t)blockIdx.x * (TILES * 128);
   if (m0 >= n_out) return;                       // uniform across the CTA
   const int n0 = blockIdx.y * BN;
   using L = SmemTA<BN, SB, TA_SA>;
@@ -1064,7 +1065,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1)
 
   if (tid == 0) {
     for (int s = 0; s < TA_SA; ++s) {
-      mbar_init(a_full(s), 256);
+      mbar_init(a_full(s), TILES * 128);
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < SB; ++s) {
@@ -1074,15 +1075,17 @@ __global__ void __launch_bounds__(TA_THREADS, 1)
     mbar_init(accum_bar, 1);
     fence_mbar_init();
   }
-  constexpr int TCOLS = 2 * BN + TA_SA * 64 <= 256 ? 256 : 512;
-  constexpr uint32_t A_COL = 2 * BN;
-  if (warp == 8) tmem_alloc<TCOLS>(tmem_slot);
+  constexpr int TNEED = TILES * (BN + TA_SA * 32);
+  constexpr int TCOLS = TNEED <= 128 ? 128 : (TNEED <= 256 ? 256 : 512);
+  constexpr uint32_t A_COL = TILES * BN;
+  constexpr int MMA_WARP = TILES * 4;
+  if (warp == MMA_WARP) tmem_alloc<TCOLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot_ptr;
 
-  if (warp < 8) {
+  if (warp < MMA_WARP) {
     // ===================== producers =====================
     const int tile = warp >> 2, quarter = warp & 3, qd = lane & 3;
     const int64_t r0 = m0 + tile * 128 + quarter * 32 + (lane >> 2);      // this thread's rows: r0 + {0, 8, 16, 24}
@@ -1137,7 +1140,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1)
           const int sa = it % TA_SA;
           mbar_wait(a_empty(sa), (((uint32_t)(it / TA_SA)) & 1u) ^ 1u);
           tc_fence_after();
-          store(t_quarter + A_COL + (uint32_t)((sa * 2 + tile) * 32), d[j]);
+          store(t_quarter + A_COL + (uint32_t)((sa * TILES + tile) * 32), d[j]);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(a_full(sa));
@@ -1170,7 +1173,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1)
       }
     }
     tc_fence_before();
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC = idesc_bf16(128, BN, 0, 0);
     int sb = 0;
@@ -1183,8 +1186,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1)
       if (elect_one()) {
         const uint64_t b_desc = smem_desc_sw128(b_base + sb * L::B_STAGE, 16, 1024);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const uint32_t a_t = tmem_d + A_COL + (uint32_t)((sa * 2 + t) * 32);
+        for (int t = 0; t < TILES; ++t) {
+          const uint32_t a_t = tmem_d + A_COL + (uint32_t)((sa * TILES + t) * 32);
 #pragma unroll
           for (int q = 0; q < 6; ++q) {          // K = 16 bf16 = 8 columns of tensor memory / 32 bytes of the image row
             const int ak = q < 4 ? q : q - 4, bk = q < 2 ? q : q - 2;
@@ -1218,7 +1221,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1)
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<TCOLS>(tmem_d);
@@ -1323,11 +1326,11 @@ bool ta_applies(int c_in, int c_out, int64_t n_out, bool has_nbr, bool stats) {
   return mode >= 3 || ceil_div64(n_out, 2 * BM) * (c_out / bn) >= B2S_NUM_SMS;
 }
 
-template <int BN, int SB, int DEPTH, int SA>
+template <int BN, int SB, int DEPTH, int SA, int TILES>
 int launch_ta(const float* x, const float* wimg, const float* bias, const int* nbr, int64_t n_out, const int* n_out_dev,
               int c_in, int c_out, int k3, float* y, cudaStream_t st) {
   using L = SmemTA<BN, SB, SA>;
-  auto kern = gather_gemm_ta_kernel<BN, SB, DEPTH, SA>;
+  auto kern = gather_gemm_ta_kernel<BN, SB, DEPTH, SA, TILES>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) != cudaSuccess) {
@@ -1338,8 +1341,8 @@ int launch_ta(const float* x, const float* wimg, const float* bias, const int* n
   }
   int sh = 0;
   while ((BK << sh) < c_in) ++sh;
-  dim3 grid((unsigned)ceil_div64(n_out, 2 * BM), (unsigned)(c_out / BN), 1);
-  kern<<<grid, TA_THREADS, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, sh, y);
+  dim3 grid((unsigned)ceil_div64(n_out, TILES * BM), (unsigned)(c_out / BN), 1);
+  kern<<<grid, TILES * 128 + 64, L::DYN_BYTES, st>>>(x, wimg, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, sh, y);
   return 0;
 }
 
@@ -1455,8 +1458,15 @@ int b2s_conv_gather_gemm_tc(const float* x, const float* w, const float* bias, c
   }
   const int bn = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
   if (ta) {
-    if (bn == 128) return launch_ta<128, 5, 3, 4>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, y, st);
-    return launch_ta<64, 8, 3, 4>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, y, st);
+    static int tiles = -1;
+    if (tiles < 0) {
+      const char* e = getenv("B2S_TA_TILES");
+      tiles = e ? atoi(e) : 1;
+    }
+    if (bn == 128) return launch_ta<128, 5, 3, 4, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, y, st);
+    if (tiles == 2) return launch_ta<64, 8, 3, 4, 2>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, y, st);
+    if (tiles == 12) return launch_ta<64, 6, 3, 2, 1>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, y, st);
+    return launch_ta<64, 6, 3, 4, 1>(xin, img, bias, nbr, n_out, n_out_dev, c_in, c_out, k3, y, st);
   }
   if (small && b2s_precise()) {   // three weight images per stage: one CTA per SM, deeper ring
     if (bn == 256) return launch_tc<256, 2, true, 1, SMALL_NB, 8>(xin, img, bias, nbr, n_out, n_out_dev, 4, c_out, k3, T, y, st);
