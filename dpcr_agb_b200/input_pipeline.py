@@ -81,7 +81,7 @@ class NFIInputPipeline:
 
     # ---- the whole chain --------------------------------------------------------------------------------------
     def __call__(self, raw_pos, plot, num_plots, order=None, max_points_rank=None, flips=None, shifts=None,
-                 bounds=None, capacity=None, n_points_dev=None):
+                 bounds=None, capacity=None, n_points_dev=None, resort=True, aug_bounds=None):
         """raw_pos float32 [n,3] in metres, plot int32 [n] (plots contiguous).  ``order``: GridSampling3D's shuffle
         over the SURVIVING points (see :class:`GridSampling3D`); ``max_points_rank``: enables MaxPoints.  With
         ``bounds`` + ``capacity`` nothing synchronises with the host (captured-graph form).  Returns the quantiser's
@@ -105,5 +105,12 @@ class NFIInputPipeline:
             shifts = shifts if shifts is not None else torch.zeros((num_plots, 3), dtype=torch.int32)
             self.augment_coords(vox["coords"], num_plots, flips, shifts, vox["num_rows"] if static else None)
             vox["index"] = None              # the occupancy index describes the un-augmented coordinates
+            # The reference leaves the rows in the quantiser's order with the changed coordinates (the network is
+            # indifferent to the row order).  ``resort``: bring them back into (plot, z, y, x) order with a fresh
+            # occupancy index, which keeps the x-line stem kernels and the dense kernel maps on the augmented batch
+            # (otherwise the hash-probed [343, N] table path: +1.1 ms per 32-plot step).  Static mode needs the box of
+            # the augmented coordinates (``aug_bounds``); without it the rows stay as they are.
+            if resort and (not static or aug_bounds is not None):
+                vox = self.gs.resort(vox, num_plots, aug_bounds, capacity)
         vox["num_points"] = count
         return vox

@@ -69,6 +69,27 @@ class GridSampling3D:
             lo, hi = b[:3], b[3:]
         else:
             lo, hi = [int(v) for v in bounds[0]], [int(v) for v in bounds[1]]
+        coords, src, m, m_arg, m_dev, index = self._cells(q, batch, order, n, n_points_dev, num_plots, lo, hi, capacity)
+
+        def gather(t):
+            t = t.contiguous()
+            t2 = t.view(n, -1).float()
+            out = torch.empty((m, t2.shape[1]), dtype=torch.float32, device=dev)
+            L.call("b2s_gather_rows", t2, src, m, m_arg, t2.shape[1], out)
+            return out
+
+        return {"coords": coords, "src": src, "pos": gather(pos), "tensors": [gather(t) for t in tensors],
+                "grid_size": self._grid_size, "num_rows": m_dev,
+                # the occupancy bitmap + popcount prefix of this batch: rank(cell) == output row, so the coordinate
+                # manager can resolve neighbours of THIS map without hash probes (b2s_kernel_map_dense)
+                "index": index}
+
+    @staticmethod
+    def _cells(q, batch, order, n, n_points_dev, num_plots, lo, hi, capacity):
+        """Occupied cells of integer coordinates ``q`` [n,3]: rows sorted by (plot, z, y, x), the representative point
+        of every cell (LAST in ``order``) and the occupancy index.  Returns (coords, src, m, m_arg, m_dev, index)."""
+        dev = q.device
+        static = capacity is not None
         dims = [max(h - l + 1, 1) for l, h in zip(lo, hi)]
         lo_h, dims_h = L.host_i32(*lo), L.host_i32(*dims)
         ws_bytes = L.query("b2s_quantize_workspace_bytes", num_plots, dims_h)
@@ -86,19 +107,36 @@ class GridSampling3D:
         coords = torch.empty((m, 4), dtype=torch.int32, device=dev)
         src = torch.empty(m, dtype=torch.int32, device=dev)
         L.call("b2s_quantize_fill", q, batch, order, n, n_points_dev, num_plots, lo_h, dims_h, ws, m, m_arg, coords, src)
+        return coords, src, m, m_arg, m_dev, (ws, tuple(lo), tuple(dims), int(num_plots))
 
-        def gather(t):
-            t = t.contiguous()
-            t2 = t.view(n, -1).float()
-            out = torch.empty((m, t2.shape[1]), dtype=torch.float32, device=dev)
-            L.call("b2s_gather_rows", t2, src, m, m_arg, t2.shape[1], out)
-            return out
+    def resort(self, vox, num_plots, bounds=None, capacity=None):
+        """Rows of ``vox`` (this class's result whose ``coords`` were changed in place by a one-to-one integer map:
+        RandomCoordsFlip / ShiftVoxels) back into (plot, z, y, x) order with a fresh occupancy index, every per-row
+        tensor permuted along -- what the x-line stem kernels and the dense kernel maps need.  ``bounds`` must hold the
+        CHANGED coordinates (measured here when None: one host sync); static mode as in ``__call__``."""
+        coords = vox["coords"]
+        static = capacity is not None
+        n = coords.shape[0]
+        n_dev = vox["num_rows"] if static else None
+        q = coords[:, 1:4].contiguous()
+        plot = coords[:, 0].contiguous()
+        if bounds is None:
+            assert not static, "static mode needs bounds"
+            lo, hi = q.amin(0).tolist(), q.amax(0).tolist()
+        else:
+            lo, hi = [int(v) for v in bounds[0]], [int(v) for v in bounds[1]]
+        new_coords, perm, m, m_arg, m_dev, index = self._cells(q, plot, None, n, n_dev, num_plots, lo, hi, capacity)
 
-        return {"coords": coords, "src": src, "pos": gather(pos), "tensors": [gather(t) for t in tensors],
-                "grid_size": self._grid_size, "num_rows": m_dev,
-                # the occupancy bitmap + popcount prefix of this batch: rank(cell) == output row, so the coordinate
-                # manager can resolve neighbours of THIS map without hash probes (b2s_kernel_map_dense)
-                "index": (ws, tuple(lo), tuple(dims), int(num_plots))}
+        def gather(t, as_int=False):
+            t2 = t.contiguous().view(n, -1)
+            out = torch.empty((m, t2.shape[1]), dtype=torch.float32, device=t.device)
+            L.call("b2s_gather_rows", t2.view(torch.float32) if as_int else t2.float(), perm, m, m_arg, t2.shape[1], out)
+            return out.view(torch.int32) if as_int else out
+
+        out = dict(vox)
+        out.update(coords=new_coords, src=gather(vox["src"], True).view(-1), pos=gather(vox["pos"]),
+                   tensors=[gather(t) for t in vox["tensors"]], num_rows=m_dev, index=index, row_perm=perm)
+        return out
 
     def __repr__(self):
         return "{}(grid_size={}, quantize_coords={}, mode={})".format(

@@ -82,7 +82,7 @@ def test_coordinate_augmentations(cuda):
     base = pipe(raw_all, plot_all, 4)
     flips = torch.tensor([[1, 0], [0, 1], [1, 1], [0, 0]])
     shifts = torch.tensor([[3, 99, 0], [0, 0, 0], [57, 1, 20], [7, 7, 7]])
-    aug = pipe(raw_all, plot_all, 4, flips=flips, shifts=shifts)
+    aug = pipe(raw_all, plot_all, 4, flips=flips, shifts=shifts, resort=False)
     c0, c1 = base["coords"].cpu().numpy(), aug["coords"].cpu().numpy()
     assert aug["index"] is None and base["index"] is not None
     for p in range(4):
@@ -90,6 +90,50 @@ def test_coordinate_augmentations(cuda):
         ref = ot.shift_voxels(ot.coords_flip(c0[sel][:, 1:], bool(flips[p, 0]), bool(flips[p, 1])), shifts[p].numpy())
         assert np.array_equal(c1[sel][:, 1:], ref) and np.all(c1[sel][:, 0] == p)
     assert torch.equal(aug["tensors"][0], base["tensors"][0])          # features untouched, same row order
+
+    # resort=True (default): the same voxels in (plot, z, y, x) order with a fresh occupancy index
+    srt = pipe(raw_all, plot_all, 4, flips=flips, shifts=shifts)
+    c2 = srt["coords"].cpu().numpy()
+    order = np.lexsort((c1[:, 1], c1[:, 2], c1[:, 3], c1[:, 0]))
+    assert np.array_equal(c2, c1[order])
+    assert np.array_equal(srt["row_perm"].cpu().numpy(), order)
+    for k in ("pos", "src"):
+        assert torch.equal(srt[k].cpu(), aug[k].cpu()[torch.from_numpy(order)])
+    assert torch.equal(srt["tensors"][0].cpu(), aug["tensors"][0].cpu()[torch.from_numpy(order)])
+    assert srt["index"] is not None
+    # static form (no host sync): same rows, given the box of the augmented coordinates
+    n_dev = torch.tensor([raw_all.shape[0]], dtype=torch.int32, device=cuda)
+    lo, hi = c1[:, 1:].min(0), c1[:, 1:].max(0)
+    sta = pipe(raw_all, plot_all, 4, flips=flips, shifts=shifts, bounds=((-80, -80, 0), (80, 80, 100)),
+               capacity=c1.shape[0] + 100, n_points_dev=n_dev, aug_bounds=(tuple(lo - 1), tuple(hi + 1)))
+    m = int(sta["num_rows"].item())
+    assert m == c2.shape[0] and np.array_equal(sta["coords"][:m].cpu().numpy(), c2)
+    assert torch.equal(sta["tensors"][0][:m], srt["tensors"][0])
+
+
+def test_augmented_batch_keeps_the_x_line_stem(cuda):
+    """The network on an augmented batch: re-sorted rows + occupancy index (x-line stem, dense maps) give the same
+    per-plot predictions as the rows left in the quantiser's order (hash-probed maps, table-driven stem)."""
+    from dpcr_agb_b200 import MinkowskiEngine as ME
+    from dpcr_agb_b200 import msenet
+    from dpcr_agb_b200.MinkowskiEngine import functional as Fn
+    plots = _raw_plots(3, 5000, seed=11)
+    pipe = NFIInputPipeline()
+    raw_all = torch.from_numpy(np.concatenate(plots)).to(cuda)
+    plot_all = torch.cat([torch.full((p.shape[0],), i, dtype=torch.int32) for i, p in enumerate(plots)]).to(cuda)
+    flips = torch.tensor([[1, 1], [0, 1], [1, 0]])
+    shifts = torch.tensor([[5, 0, 2], [0, 9, 0], [1, 1, 1]])
+    plain = pipe(raw_all, plot_all, 3, flips=flips, shifts=shifts, resort=False)
+    srt = pipe(raw_all, plot_all, 3, flips=flips, shifts=shifts)
+    torch.manual_seed(0)
+    net = msenet.build(ME, "SENet14", drop_path=0.0).to(cuda).eval()
+    x1 = ME.SparseTensor(features=srt["tensors"][0], coordinates=srt["coords"], dense_index=srt["index"])
+    km = x1.coordinate_manager.kernel_map(x1.coordinate_map_key, x1.coordinate_map_key, 7)
+    assert Fn.lines_path(km, 3, 64)                                   # the stem takes the x-line kernels
+    y1 = net(x1)
+    y0 = net(ME.SparseTensor(features=plain["tensors"][0], coordinates=plain["coords"]))
+    err = ((y1 - y0).abs().max() / y0.abs().max()).item()
+    assert err <= 1e-4, err
 
 
 def test_pipeline_feeds_the_network(cuda):

@@ -1,6 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for z in 0 1; do
-echo "B2S_TC_ZST=$z"
-B2S_TC_ZST=$z TA_MODES=0 timeout 120 python tools/ta_bench.py 2>&1 | grep -v Warning | tail -4
-done
+timeout 300 python -m pytest tests/test_gpu_input_pipeline.py tests/test_gpu_coords.py -q -x --timeout 120 2>&1 | tail -12
