@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(PW_THREADS) maxpool_fwd_kernel(const float* __
                                                                  const int* __restrict__ nbr, int64_t n_out,
                                                                  const int* __restrict__ n_dev, int c, int k3,
                                                                  float* __restrict__ y, int* __restrict__ arg,
-                                                                 float* __restrict__ y_tf32, int opm) {
+                                                                 float* __restrict__ y_tf32, int opm, int batched) {
   const int64_t pitch = n_out;
   n_out = b2s_rows(n_out, n_dev);
   const RowMap m = row_map<VEC>(c);
@@ -153,26 +153,130 @@ __global__ void __launch_bounds__(PW_THREADS) maxpool_fwd_kernel(const float* __
       int bi[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) bi[j] = -1;
-      for (int k = 0; k < k3; ++k) {
-        const int i = __ldg(&nbr[(int64_t)k * pitch + o]);
-        if (i < 0) continue;
-        const V<VEC> v = ldgv<VEC>(x + (int64_t)i * c + ch);
+      // nine kernel offsets at a time: their table entries, then the rows of the existing neighbours, are all in
+      // flight before the first comparison (one offset after the other made every row a dependent pair of loads:
+      // 0.19 ms for the k3 s2 pool of a 32-plot batch, 3x its HBM time)
+      if (!batched) {
+        for (int k = 0; k < k3; ++k) {
+          const int i = __ldg(&nbr[(int64_t)k * pitch + o]);
+          if (i < 0) continue;
+          const V<VEC> v = ldgv<VEC>(x + (int64_t)i * c + ch);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          if (bi[j] < 0 || v.v[j] > best.v[j] || (v.v[j] == best.v[j] && i < bi[j])) {
-            best.v[j] = v.v[j];
-            bi[j] = i;
+          for (int j = 0; j < VEC; ++j) {
+            if (bi[j] < 0 || v.v[j] > best.v[j] || (v.v[j] == best.v[j] && i < bi[j])) {
+              best.v[j] = v.v[j];
+              bi[j] = i;
+            }
+          }
+        }
+      } else
+      for (int k0 = 0; k0 < k3; k0 += 9) {
+        int idx[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) idx[q] = k0 + q < k3 ? __ldg(&nbr[(int64_t)(k0 + q) * pitch + o]) : -1;
+        V<VEC> v[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q)
+          if (idx[q] >= 0) v[q] = ldgv<VEC>(x + (int64_t)idx[q] * c + ch);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const int i = idx[q];
+          if (i < 0) continue;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            if (bi[j] < 0 || v[q].v[j] > best.v[j] || (v[q].v[j] == best.v[j] && i < bi[j])) {
+              best.v[j] = v[q].v[j];
+              bi[j] = i;
+            }
           }
         }
       }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
+      for (int j = 0; j < VEC; ++j)
         if (bi[j] < 0) best.v[j] = 0.f;
-        arg[o * c + ch + j] = bi[j];
-      }
+      if (VEC == 4) *reinterpret_cast<int4*>(arg + o * c + ch) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+      else
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) arg[o * c + ch + j] = bi[j];
       stv<VEC>(y + o * c + ch, best);
       if (y_tf32) st_operand<VEC>(y_tf32, o, c, ch, best, opm);
     }
+  }
+}
+
+// Max pooling with a WARP per 32 consecutive out rows (c = 4 * TPR, TPR threads per row, k3 <= 27).  The kernel above
+// reads its 27 table entries per row group as 27 separate sectors with 8 useful bytes each and then walks the offsets
+// one dependent (entry -> row) load pair at a time.  Here the warp first stages the entries of its 32 rows coalesced
+// (one 128-byte line per offset, all offsets in flight) in shared memory together with a presence mask per row; a row
+// then visits only the offsets that exist, four row loads in flight at a time.  Same comparisons in the same
+// (ascending offset) order: identical values and arg-max rows.
+constexpr int MP_WARPS = 8;
+template <int TPR>
+__global__ void __launch_bounds__(MP_WARPS * 32) maxpool_fwd_warp_kernel(const float* __restrict__ x,
+                                                                         const int* __restrict__ nbr, int64_t n_out,
+                                                                         const int* __restrict__ n_dev, int c, int k3,
+                                                                         float* __restrict__ y, int* __restrict__ arg,
+                                                                         float* __restrict__ y_tf32, int opm) {
+  __shared__ int s_idx[MP_WARPS][27][32];
+  const int64_t pitch = n_out;
+  n_out = b2s_rows(n_out, n_dev);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int RPP = 32 / TPR;                 // rows per pass
+  const int sub = lane / TPR, ch = (lane % TPR) * 4;
+  for (int64_t o0 = ((int64_t)blockIdx.x * MP_WARPS + warp) * 32; o0 < n_out; o0 += (int64_t)gridDim.x * MP_WARPS * 32) {
+    const int64_t ol = o0 + lane;
+    unsigned mymask = 0;
+#pragma unroll 9
+    for (int k = 0; k < k3; ++k) {
+      const int i = ol < n_out ? __ldg(nbr + (int64_t)k * pitch + ol) : -1;
+      s_idx[warp][k][lane] = i;
+      mymask |= (i >= 0 ? 1u : 0u) << k;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int p = 0; p < 32 / RPP; ++p) {
+      const int r = p * RPP + sub;
+      const int64_t o = o0 + r;
+      unsigned mask = __shfl_sync(0xffffffffu, mymask, r);
+      V<4> best = splat<4>(-INFINITY);
+      int bi[4] = {-1, -1, -1, -1};
+      while (mask) {
+        int ii[4];
+        V<4> vv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          ii[q] = -1;
+          if (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            ii[q] = s_idx[warp][k][r];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (ii[q] >= 0) vv[q] = ldgv<4>(x + (int64_t)ii[q] * c + ch);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (ii[q] < 0) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (bi[j] < 0 || vv[q].v[j] > best.v[j] || (vv[q].v[j] == best.v[j] && ii[q] < bi[j])) {
+              best.v[j] = vv[q].v[j];
+              bi[j] = ii[q];
+            }
+          }
+        }
+      }
+      if (o < n_out) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (bi[j] < 0) best.v[j] = 0.f;
+        *reinterpret_cast<int4*>(arg + o * c + ch) = make_int4(bi[0], bi[1], bi[2], bi[3]);
+        stv<4>(y + o * c + ch, best);
+        if (y_tf32) st_operand<4>(y_tf32, o, c, ch, best, opm);
+      }
+    }
+    __syncwarp();                               // the next 32 rows overwrite the staged entries
   }
 }
 
@@ -1107,12 +1211,33 @@ extern "C" int32_t b2s_maxpool_fwd(const float* x, const int32_t* nbr, int64_t n
   if (n_out == 0) return B2S_OK;
   B2S_CHECK_ARG(x && nbr && y && arg, "null pointer");
   cudaStream_t st = as_stream(stream);
+  static int batched = -1;
+  if (batched < 0) {
+    const char* e = getenv("B2S_POOL_BATCH");
+    batched = e ? atoi(e) : 2;                 // 0: one offset after the other, 1: nine at a time, 2: warp per 32 rows
+  }
+  if (batched >= 2 && vec_of(c, x, y, y_tf32) == 4 && k3 <= 27 && (c == 32 || c == 64 || c == 128) &&
+      (reinterpret_cast<uintptr_t>(arg) & 15) == 0) {
+    const int64_t blocks64 = (n_out + MP_WARPS * 32 - 1) / (MP_WARPS * 32);
+    const int blocks = (int)(blocks64 < (int64_t)B2S_NUM_SMS * 8 ? blocks64 : (int64_t)B2S_NUM_SMS * 8);
+    if (c == 32)
+      maxpool_fwd_warp_kernel<8><<<blocks, MP_WARPS * 32, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg, y_tf32,
+                                                                   operand_mode(c));
+    else if (c == 64)
+      maxpool_fwd_warp_kernel<16><<<blocks, MP_WARPS * 32, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg, y_tf32,
+                                                                    operand_mode(c));
+    else
+      maxpool_fwd_warp_kernel<32><<<blocks, MP_WARPS * 32, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg, y_tf32,
+                                                                    operand_mode(c));
+    B2S_LAUNCH_CHECK();
+    return B2S_OK;
+  }
   if (vec_of(c, x, y, y_tf32) == 4)
     maxpool_fwd_kernel<4><<<rows_grid(n_out, c, 4), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg,
-                                                                         y_tf32, operand_mode(c));
+                                                                         y_tf32, operand_mode(c), batched);
   else
     maxpool_fwd_kernel<1><<<rows_grid(n_out, c, 1), PW_THREADS, 0, st>>>(x, nbr, n_out, n_out_dev, c, k3, y, arg,
-                                                                         y_tf32, operand_mode(c));
+                                                                         y_tf32, operand_mode(c), batched);
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }

@@ -21,14 +21,17 @@ def _setup(cuda, n=4000, nb=3, seed=0):
     return rng, c, cm, key
 
 
-def test_maxpool_fwd_bwd(cuda):
+@pytest.mark.parametrize("ch", [64, 32, 128, 48, 3])
+def test_maxpool_fwd_bwd(cuda, ch):
+    """ch = 32 / 64 / 128: the warp-per-32-rows kernel (table entries staged coalesced, only existing neighbours
+    visited); 48 and 3: the row-loop kernel (vector / scalar)."""
     rng, c, cm, key = _setup(cuda)
     out_key = cm.stride(key, 2)
     out_c = cm.coords(out_key).cpu().numpy()
     nbr = oc.kernel_map_table(c, out_c, 3, (1, 1, 1))
-    x = rng.standard_normal((c.shape[0], 64)).astype(np.float32)
+    x = rng.standard_normal((c.shape[0], ch)).astype(np.float32)
     x[:50] = 0.25                                   # ties -> lowest in-row
-    gy = rng.standard_normal((out_c.shape[0], 64)).astype(np.float32)
+    gy = rng.standard_normal((out_c.shape[0], ch)).astype(np.float32)
     xr = torch.from_numpy(x).double().requires_grad_()
     yr = oo.max_pool(xr, nbr)
     yr.backward(torch.from_numpy(gy).double())
