@@ -398,6 +398,7 @@ class PipelinedGraphStep(GraphStep):
         self.slots = [_Slot(self.inp, self.n_points), _Slot(self.inp, self.n_points)]
         self.prep_stream = torch.cuda.Stream()
         self._fed, self._cur = 0, 0          # slot the next feed() fills / the next step() trains
+        self._outstanding = 0                # batches fed and not yet trained (0, 1 or 2)
 
     # ---- the two halves of GraphStep._forward_backward
     def _prep(self, slot):
@@ -488,8 +489,12 @@ class PipelinedGraphStep(GraphStep):
     def feed(self, batch, non_blocking=True):
         """Copy ``batch`` (pinned host or device tensors) into the next buffer set and replay its coordinate graph on
         the prep stream -- beside whatever the main stream is training."""
+        if self._outstanding >= 2:
+            raise RuntimeError("PipelinedGraphStep.feed(): both buffer sets hold a batch that has not been trained; "
+                               "call step() first")
         slot = self.slots[self._fed]
         self._fed ^= 1
+        self._outstanding += 1
         ps = self.prep_stream
         ps.wait_event(slot.train_done)               # the step that last trained on this set has finished with it
         with torch.cuda.stream(ps):
@@ -506,10 +511,14 @@ class PipelinedGraphStep(GraphStep):
     def reset_feed(self):
         """Forget a batch that was fed but not trained (end of a loop that feeds one ahead)."""
         self._fed = self._cur
+        self._outstanding = 0
 
     def step(self):
         """Train the set fed by the oldest outstanding ``feed``; returns the on-device loss."""
         tr = self.tr
+        if self._outstanding == 0:
+            raise RuntimeError("PipelinedGraphStep.step(): no batch has been fed (feed() one batch ahead of step())")
+        self._outstanding -= 1
         slot = self.slots[self._cur]
         self._cur ^= 1
         cur = torch.cuda.current_stream()

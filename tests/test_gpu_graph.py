@@ -185,3 +185,37 @@ def test_pipelined_step_equals_single_graph_step(cuda):
     assert len(set(out[0])) == len(batches)
     np.testing.assert_allclose(out[1], out[0], rtol=3e-3)
     util.assert_close(params[1], params[0], tol=1e-3, what="parameters after 5 steps")
+
+
+def test_pipelined_step_flags_a_point_outside_the_box_and_skips_the_update(cuda):
+    """A point outside the quantiser's bounds in ONE batch of the pipelined step: that step's optimiser update is
+    skipped on the device (parameters unchanged), ``verify()`` raises, and the protocol errors (step without feed,
+    three feeds in a row) are caught on the host."""
+    plots, n_points = 2, 2000
+    good, bad = _batches(cuda, 2, plots, n_points)
+    bad = dict(bad)
+    bad["pos"] = bad["pos"].clone()
+    bad["pos"][7, 0] = 1e4                                     # far outside BOUNDS
+    gs = GridSampling3D(SIZE)
+    m = _model(cuda, drop_path=0.0)
+    t = train.Trainer(m, ME, lr=1e-3)
+    caps = graph_step.plan_capacities(gs, ME, m, [good], plots, BOUNDS)
+    g = graph_step.PipelinedGraphStep(t, gs, plots, plots * n_points, BOUNDS, caps).capture()
+    with pytest.raises(RuntimeError):
+        g.step()
+    g.feed(good)
+    g.feed(bad)
+    with pytest.raises(RuntimeError):
+        g.feed(good)
+    g.step()
+    g.verify()                                                 # the good batch: clean
+    before = t.opt.flat_param.clone()
+    g.step()                                                   # the bad batch
+    torch.cuda.synchronize()
+    assert torch.equal(t.opt.flat_param, before)               # update skipped on the device
+    with pytest.raises(lib.B2SError):
+        g.verify()
+    g.feed(good)
+    g.step()
+    g.verify()
+    assert not torch.equal(t.opt.flat_param, before)           # training goes on
