@@ -124,6 +124,19 @@ __device__ __forceinline__ RowMap row_map(int c) {
 #define B2S_ROW_LOOP(m, n, r)                                                                       \
   for (int64_t r = (int64_t)blockIdx.x * (m).rpb + (m).tr; r < (n); r += (int64_t)gridDim.x * (m).rpb)
 
+// rows per pass of the unrolled row-streaming kernels (loads of all rows of a pass issued first); B2S_PW_UNROLL=1
+// selects the one-row-per-pass form.  Measured (tools/bn_bench.py, graph replays): +5-10 % on the 256 k- and 422 k-row
+// layers, -10-25 % below ~4 M elements (too few rows per thread), hence the size threshold.
+constexpr int64_t PW_UNROLL_MIN = (int64_t)1 << 22;
+static int pw_unroll() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2S_PW_UNROLL");
+    v = e ? atoi(e) : 4;
+  }
+  return v;
+}
+
 static inline int rows_grid(int64_t n, int c, int vec) {
   const int cv = c / vec;
   const int tpr = cv < PW_THREADS ? cv : PW_THREADS;
@@ -744,7 +757,7 @@ __global__ void double_to_float_kernel(const double* __restrict__ in, float* __r
   if (i < m) out[i] = (float)in[i];
 }
 
-template <int VEC>
+template <int VEC, int PW_U>
 __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __restrict__ x,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ invstd,
@@ -760,16 +773,28 @@ __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __res
     const int ch = v0 * VEC;
     const V<VEC> mu = ldgv<VEC>(mean + ch), is = ldgv<VEC>(invstd + ch);
     const V<VEC> ga = ldparam<VEC>(gamma, ch, 1.f), be = ldparam<VEC>(beta, ch, 0.f);
-    B2S_ROW_LOOP(m, n, r) {
-      V<VEC> v = ldv<VEC>(x + r * c + ch);
+    // PW_U rows per pass with all of their loads issued first: one 16-byte load per thread and pass kept 16 KB in
+    // flight per SM (1 024 resident threads), a third of what HBM needs; the kernel ran at half of the copy bandwidth
+    const int64_t stride = (int64_t)gridDim.x * m.rpb;
+    for (int64_t r0 = (int64_t)blockIdx.x * m.rpb + m.tr; r0 < n; r0 += stride * PW_U) {
+      V<VEC> vu[PW_U];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        float t = (v.v[j] - mu.v[j]) * is.v[j];
-        t = t * ga.v[j] + be.v[j];
-        v.v[j] = act == 1 ? gelu_f(t) : t;
+      for (int u = 0; u < PW_U; ++u)
+        if (r0 + u * stride < n) vu[u] = ldv<VEC>(x + (r0 + u * stride) * c + ch);
+#pragma unroll
+      for (int u = 0; u < PW_U; ++u) {
+        const int64_t r = r0 + u * stride;
+        if (r >= n) break;
+        V<VEC> v = vu[u];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float t = (v.v[j] - mu.v[j]) * is.v[j];
+          t = t * ga.v[j] + be.v[j];
+          v.v[j] = act == 1 ? gelu_f(t) : t;
+        }
+        if (y) stv<VEC>(y + r * c + ch, v);
+        if (y_tf32) st_operand<VEC>(y_tf32, r, c, ch, v, opm);
       }
-      if (y) stv<VEC>(y + r * c + ch, v);
-      if (y_tf32) st_operand<VEC>(y_tf32, r, c, ch, v, opm);
     }
   }
 }
@@ -779,7 +804,7 @@ __global__ void __launch_bounds__(PW_THREADS) bn_apply_kernel(const float* __res
 // tree over the row lanes of the block, one partial ROW per block (row blockIdx.x of colsum; the consumer adds the
 // rows -- ~1 000 same-address atomics per channel serialised in L2 and cost more than the pass they replaced).  Needs
 // every thread of the block active and the same number of channel passes for all of them (the launcher checks).
-template <int VEC, bool COLSUM>
+template <int VEC, bool COLSUM, int PW_U>
 __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -800,20 +825,34 @@ __global__ void __launch_bounds__(PW_THREADS) bn_bwd_apply_kernel(
       s0 = ldgv<VEC>(sums + ch);
       s1 = ldgv<VEC>(sums + c + ch);
     }
-    B2S_ROW_LOOP(m, n, r) {
-      const V<VEC> xv = ldv<VEC>(x + r * c + ch);
-      V<VEC> g = ldv<VEC>(gy + r * c + ch);
+    const int64_t stride = (int64_t)gridDim.x * m.rpb;           // PW_U rows per pass, loads first (see bn_apply_kernel)
+    for (int64_t r0 = (int64_t)blockIdx.x * m.rpb + m.tr; r0 < n; r0 += stride * PW_U) {
+      V<VEC> xu[PW_U], gu[PW_U];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
-        float t = g.v[j];
-        if (act == 1) t *= gelu_grad_f(xh * ga.v[j] + be.v[j]);
-        if (training) t = t - s0.v[j] * inv_n - xh * s1.v[j] * inv_n;
-        g.v[j] = t * ga.v[j] * is.v[j];
-        if (COLSUM) cs.v[j] += g.v[j];
+      for (int u = 0; u < PW_U; ++u) {
+        if (r0 + u * stride < n) {
+          xu[u] = ldv<VEC>(x + (r0 + u * stride) * c + ch);
+          gu[u] = ldv<VEC>(gy + (r0 + u * stride) * c + ch);
+        }
       }
-      stv<VEC>(gx + r * c + ch, g);
-      if (gx_tf32) st_operand<VEC>(gx_tf32, r, c, ch, g, opm);
+#pragma unroll
+      for (int u = 0; u < PW_U; ++u) {
+        const int64_t r = r0 + u * stride;
+        if (r >= n) break;
+        const V<VEC> xv = xu[u];
+        V<VEC> g = gu[u];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float xh = (xv.v[j] - mu.v[j]) * is.v[j];
+          float t = g.v[j];
+          if (act == 1) t *= gelu_grad_f(xh * ga.v[j] + be.v[j]);
+          if (training) t = t - s0.v[j] * inv_n - xh * s1.v[j] * inv_n;
+          g.v[j] = t * ga.v[j] * is.v[j];
+          if (COLSUM) cs.v[j] += g.v[j];
+        }
+        stv<VEC>(gx + r * c + ch, g);
+        if (gx_tf32) st_operand<VEC>(gx_tf32, r, c, ch, g, opm);
+      }
     }
     if (COLSUM) {
       __syncthreads();                     // the previous channel pass has read its sums
@@ -1536,12 +1575,17 @@ extern "C" int32_t b2s_bn_apply(const float* x, const float* mean, const float* 
   if (n == 0) return B2S_OK;
   B2S_CHECK_ARG(x && mean && invstd && (y || y_tf32), "null pointer");
   cudaStream_t st = as_stream(stream);
-  if (vec_of(c, x, y, mean, invstd) == 4 && vec_of(c, gamma, beta, y_tf32) == 4)
-    bn_apply_kernel<4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
-                                                                  y_tf32, operand_mode(c));
-  else
-    bn_apply_kernel<1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
-                                                                  y_tf32, operand_mode(c));
+  if (vec_of(c, x, y, mean, invstd) == 4 && vec_of(c, gamma, beta, y_tf32) == 4) {
+    if (pw_unroll() > 1 && n * c >= PW_UNROLL_MIN)
+      bn_apply_kernel<4, 4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
+                                                                       y_tf32, operand_mode(c));
+    else
+      bn_apply_kernel<4, 1><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
+                                                                       y_tf32, operand_mode(c));
+  } else {
+    bn_apply_kernel<1, 1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(x, mean, invstd, gamma, beta, n, n_dev, c, act, y,
+                                                                     y_tf32, operand_mode(c));
+  }
   B2S_LAUNCH_CHECK();
   return B2S_OK;
 }
@@ -1613,15 +1657,19 @@ extern "C" int32_t b2s_bn_bwd_apply(const float* gy, const float* x, const float
     // the fused column sums need all threads active, equal channel passes and a power-of-two tree over the row lanes
     if (gx_colsum && PW_THREADS % tpr == 0 && cv % tpr == 0 && (rpb & (rpb - 1)) == 0 &&
         (reinterpret_cast<uintptr_t>(gx_colsum) & 3) == 0) {
-      bn_bwd_apply_kernel<4, true><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(
-          gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), gx_colsum);
+      if (pw_unroll() > 1 && n * c >= PW_UNROLL_MIN)
+        bn_bwd_apply_kernel<4, true, 4><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(
+            gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), gx_colsum);
+      else
+        bn_bwd_apply_kernel<4, true, 1><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(
+            gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), gx_colsum);
       colsum_done = true;
     } else {
-      bn_bwd_apply_kernel<4, false><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(
+      bn_bwd_apply_kernel<4, false, 1><<<rows_grid(n, c, 4), PW_THREADS, 0, st>>>(
           gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), nullptr);
     }
   } else {
-    bn_bwd_apply_kernel<1, false><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(
+    bn_bwd_apply_kernel<1, false, 1><<<rows_grid(n, c, 1), PW_THREADS, 0, st>>>(
         gy, x, mean, invstd, gamma, beta, sums, n, n_dev, c, act, training, gx, gx_tf32, operand_mode(c), nullptr);
   }
   if (gx_colsum && !colsum_done) {     // shapes the fused form does not cover: the separate column reduction into row 0
