@@ -194,7 +194,11 @@ B2S_API int32_t b2s_kernel_map_pairs_fill(const int32_t* nbr, int32_t k3, int64_
  *     w_layout bit 4 set  : `workspace` already holds the weight image of this (w, w_layout bits 0-1), built ahead
  *                           with b2s_conv_weight_image (needs bit 2 and c_in > 4): the call launches the convolution
  *                           kernel only.  Weights change once per optimiser step, so a trainer builds the images of
- *                           every layer at the start of the step on a side stream, off the critical path.
+ *                           every layer at the start of the step on a side stream, off the critical path.  For
+ *                           shapes that the tensor-memory-operand kernel may take (c_in = 32 * 2^s, c_out a
+ *                           multiple of 64 but not of 256) a prebuilt image holds two forms back to back -- the
+ *                           plain one and the one in that kernel's channel order -- because the builder does not
+ *                           know the row count of the call that will use it; b2s_conv_weight_image_bytes counts both.
  *     k3 == 1 and nbr == NULL means the identity map (the K=1, stride=1 `use_mm` case).
  *     impl: 0 = auto, 1 = SIMT fp32 reference kernel, 2 = tcgen05 kind::tf32 kernel.
  * b2s_conv_wgrad       : gw[k] = sum_o x[nbr[k,o],:]^T gy[o,:]   (gw fp32 [K3, c_in, c_out]);
