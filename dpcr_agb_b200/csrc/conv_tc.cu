@@ -1011,16 +1011,21 @@ int launch_tma(const float* x, int64_t n_in, const float* wimg, const float* bia
 // A operand in TENSOR MEMORY (split-bf16 mode, c_in a power-of-two multiple of 32, no split-K, no permutation).
 // The shared-memory kernels above are bound by the L1 / shared-memory data pipe, not by the tensor cores: per
 // (128-row tile, kernel offset) of a 64 -> 64 layer the LDGSTS gather writes 32 KB (in 64-byte beats), the six MMAs
-// per stage read the A stage three times (72 KB with the weights) and the tensor pipe idles at 31 %.  Here the
+// per stage read 6 KB of operands each (48 clocks at 128 B / clk against 32 clocks of tensor time: 72 KB per tile and
+// offset) and the tensor pipe idles at 31 %.  Here the
 // gathered rows never touch shared memory: four lanes load one row chunk (2 x LDG.128 each, a quad covers 64
 // contiguous bytes per instruction) straight into the register fragment of tcgen05.st.16x256b, the MMAs take A from
 // tensor memory (tcgen05.mma [d], [a], b-desc) and shared memory carries the weights only.
-//   CTA = 256 out rows (two accumulators, every weight stage is used by both) x BN channels, 10 warps:
-//   warps 0-7  producers + epilogue: warp w owns lanes 32 (w % 4) .. + 31 of tile w / 4 -- the quarter of tensor memory
-//              a warp may address; per stage a thread loads 4 rows x 32 bytes and issues two 16-lane stores
-//   warp 8     MMA issuer: per stage and tile 6 x (M 128, N BN, K 16): h*H (k-steps 0,1), l*H (2,3 x 0,1), h*L (0,1 x 2,3)
-//   warp 9     weight loader: one bulk copy per stage
-// Tensor memory: accumulators in columns [0, 2 BN), A ring (2 stages x 2 tiles x 32 columns) behind them.
+//   CTA = TILES x 128 out rows x BN channels, 4 TILES + 2 warps:
+//   warps 0 .. 4 TILES - 1  producers + epilogue: warp w owns lanes 32 (w % 4) .. + 31 of tile w / 4 -- the quarter of
+//              tensor memory a warp may address; per stage a thread loads 4 rows x 32 bytes and issues two 16-lane stores
+//   next warp  MMA issuer (elect.sync lane): per stage and tile 6 x (M 128, N BN, K 16): h*H (k-steps 0,1),
+//              l*H (2,3 x 0,1), h*L (0,1 x 2,3)
+//   last warp  weight loader: one bulk copy per stage
+// Tensor memory: accumulators in columns [0, TILES * BN), A ring (TA_SA stages x TILES tiles x 32 columns) behind them.
+// Measured (tools/ta_bench.py, profiles/r02_ta_kernel_*.txt): L2 -> L1 traffic 1.84 -> 0.80 GB and 4 % less time than
+// the shared-memory kernel on the 64 -> 64 layers; what holds it is the producers (row-load latency + instructions per
+// gathered byte), not a saturated unit.
 // The k-step positions of a row fragment are a fixed permutation of the chunk's channels (ta_channel); the weight
 // image is built with the same permutation, so the products pair up unchanged.
 // ---------------------------------------------------------------------------------------------
