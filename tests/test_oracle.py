@@ -239,3 +239,33 @@ def test_kernel_map_lines_hand_case():
     shuffled = c[[1, 0, 2]]
     with pytest.raises(AssertionError):
         oc.kernel_map_lines(oc.kernel_map_table(shuffled, shuffled, (3, 1, 1), (1, 1, 1)), (3, 1, 1))
+
+
+def test_tensor_memory_fragment_channel_order():
+    """Layout contract of gather_gemm_ta_kernel (csrc/conv_tc.cu), restated: four lanes q = 0..3 of a row load bytes
+    [16 q, 16 q + 16) of the h half and of the l half of a 128-byte operand row chunk ([h(32 bf16) | l(32 bf16)]) and
+    store them as their pieces j = 0..3 of tcgen05.st.16x256b.x4, which puts piece j of lane q at tensor-memory columns
+    8 j + 2 q + {0, 1} (two bf16 per column).  The k-step s = column // 8 of the MMA then holds, at position
+    p = 2 (column % 8) + half, the channel the weight image must carry at the same position: ``ta_channel``."""
+    def ta_channel(p):                                   # csrc/conv_tc.cu
+        return 8 * ((p & 15) >> 2) + 4 * ((p >> 4) & 1) + (p & 3)
+
+    pos_to_src = {}
+    for q in range(4):                                   # lane of the quad
+        loads = [(0, 16 * q), (64, 16 * q)]              # (half base, byte offset): v0 from h, v1 from l
+        pieces = []                                      # piece j -> (source byte of its first bf16)
+        for base, off in loads:
+            pieces += [base + off, base + off + 8]       # .xy and .zw of the 16-byte load
+        for j, byte in enumerate(pieces):
+            for w in range(2):                           # 32-bit word of the piece = one tensor-memory column
+                col = 8 * j + 2 * q + w
+                for half in range(2):
+                    p = 2 * col + half                   # bf16 position in the 64-element K row
+                    pos_to_src[p] = (byte + 4 * w + 2 * half) // 2      # source bf16 index: 0..31 = h, 32..63 = l
+    assert sorted(pos_to_src) == list(range(64)) and sorted(pos_to_src.values()) == list(range(64))
+    for p, src in pos_to_src.items():
+        assert (src >= 32) == (p >= 32)                  # k-steps 0, 1 carry h, k-steps 2, 3 carry l
+        assert src % 32 == ta_channel(p)                 # same channel order in both halves, as the image builder uses
+    # the h k-step s and the l k-step s + 2 hold the same channels: h*H, l*H and h*L pair up step by step
+    for p in range(32):
+        assert ta_channel(p) == ta_channel(p + 32)
